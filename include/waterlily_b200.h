@@ -1,0 +1,156 @@
+/*
+ * waterlily_b200.h — C ABI of libwaterlily_b200.so
+ *
+ * Drop-in boundary for the per-timestep hot path of WaterLily.jl
+ * (`mom_step!(::Flow, ::MultiLevelPoisson)`, reference src/Flow.jl:153-169 and everything it
+ * calls).  The reference selects its backend by array type (`mem=Array|CuArray`,
+ * src/WaterLily.jl:66-78) and has no FFI of its own; these are the entry points a Julia
+ * extension module binds with `ccall` (see INTEGRATION.md and julia/WaterLilyB200.jl) and that
+ * the Python host mirror in waterlily_b200/ binds with ctypes.
+ *
+ * Conventions
+ *  - plain C types only; every function returns 0 on success or a negative wl_status code and
+ *    never throws across the ABI; wl_last_error() returns the message of the last failure on
+ *    the calling thread (the reference's own assertion texts are reproduced verbatim).
+ *  - all fields are Float32 (`T=Float32`, src/WaterLily.jl:69).  Host layout is the reference's:
+ *    padded (one ghost layer per side) column-major arrays, x fastest, components last:
+ *    scalar (Ng...), vector (Ng...,D), tensor (Ng...,D,D).
+ *  - the library owns all device memory behind the opaque handle.  Level-1 multigrid arrays
+ *    alias the flow arrays exactly as in the reference: x ≡ p, L ≡ μ₀, z ≡ σ
+ *    (src/WaterLily.jl:77).
+ *  - perdir is passed as D 0/1 flags (flag[j]=1 ⇔ j+1 ∈ perdir of the reference).
+ *  - one host thread per handle; calls are synchronous from the caller's view.
+ *
+ * The identical ABI, with the prefix `wlo_`, is exported by the CPU oracle (oracle/), which is
+ * test infrastructure only and is never loaded by this library or the package.
+ */
+#ifndef WATERLILY_B200_H
+#define WATERLILY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct wl_sim wl_sim;
+
+enum wl_status {
+  WL_OK = 0,
+  WL_ERR_ARG = -1,      /* bad argument (AssertionError in the reference) */
+  WL_ERR_CUDA = -2,     /* CUDA runtime failure (sticky per handle) */
+  WL_ERR_NCCL = -3,     /* NCCL failure (sticky per handle) */
+  WL_ERR_STATE = -4     /* call not valid for this handle (e.g. wrong pois_kind) */
+};
+
+/* Flow fields, reference src/Flow.jl:92-109 */
+enum wl_field {
+  WL_U = 0,     /* u   (Ng...,D)   velocity                      */
+  WL_U0 = 1,    /* u⁰  (Ng...,D)   previous velocity             */
+  WL_F = 2,     /* f   (Ng...,D)   force / RHS                   */
+  WL_P = 3,     /* p   (Ng...)     pressure  (≡ levels[1].x)     */
+  WL_SIGMA = 4, /* σ   (Ng...)     divergence scratch (≡ levels[1].z, ≡ Φ of conv_diff!) */
+  WL_V = 5,     /* V   (Ng...,D)   body velocity                 */
+  WL_MU0 = 6,   /* μ₀  (Ng...,D)   zeroth moment (≡ levels[1].L) */
+  WL_MU1 = 7    /* μ₁  (Ng...,D,D) first moment                  */
+};
+
+/* Poisson level fields, reference src/Poisson.jl:21-30 */
+enum wl_level_field {
+  WL_LVL_L = 0, WL_LVL_D = 1, WL_LVL_ID = 2, WL_LVL_X = 3,
+  WL_LVL_EPS = 4, WL_LVL_R = 5, WL_LVL_Z = 6
+};
+
+/* which AbstractPoisson the handle owns (reference src/Poisson.jl:21, src/MultiLevelPoisson.jl:44) */
+enum wl_pois_kind { WL_POIS_MULTILEVEL = 0, WL_POIS_SINGLE = 1 };
+
+/* ---- lifetime ------------------------------------------------------------------------- */
+
+/* Flow(N,U;Δt,ν,perdir,exitBC,T=Float32) + [MultiLevel]Poisson(p,μ₀,σ;perdir)
+ * (src/Flow.jl:110-121, src/WaterLily.jl:75-77, src/MultiLevelPoisson.jl:51-59).
+ * N = interior cells per dimension (D entries, D = 2 or 3).  Fields start as the reference's
+ * constructor leaves them before apply!/measure!: u=u⁰=f=p=σ=V=μ₁=0, μ₀=1 with BC!(μ₀,0).
+ * WL_POIS_MULTILEVEL fails with "MultiLevelPoisson requires size=a2ⁿ, where n>2"
+ * (src/MultiLevelPoisson.jl:56-57) when fewer than 3 levels can be built.
+ * device: CUDA ordinal (ignored by the oracle). */
+int wl_create(wl_sim** out, int D, const int* N, double nu, double dt0,
+              const int* perdir, int exitBC, int pois_kind, int device);
+int wl_destroy(wl_sim* s);
+const char* wl_last_error(void);
+/* cudaStream_t on which all work of this handle is issued (NULL = handle's own stream). */
+int wl_set_stream(wl_sim* s, void* cuda_stream);
+int wl_sync(wl_sim* s);
+
+/* ---- field transfer: B200Array(::Array) / Array(::B200Array) ---------------------------- */
+int wl_field_count(wl_sim* s, int field, int64_t* count);
+int wl_upload(wl_sim* s, int field, const float* host, int64_t count);
+int wl_download(wl_sim* s, int field, float* host, int64_t count);
+int wl_nlevels(wl_sim* s);
+int wl_level_dims(wl_sim* s, int level, int* Ng);            /* padded size, D entries; level is 0-based */
+int wl_level_upload(wl_sim* s, int level, int lfield, const float* host, int64_t count);
+int wl_level_download(wl_sim* s, int level, int lfield, float* host, int64_t count);
+
+/* ---- boundary conditions (src/util.jl:192-231) ----------------------------------------- */
+/* BC!(a,A,saveexit,perdir) on a vector field of the handle; perdir==NULL → the handle's own. */
+int wl_bc(wl_sim* s, int field, const double* A, int saveexit, const int* perdir);
+/* exitBC!(u,u⁰,U,Δt) */
+int wl_exit_bc(wl_sim* s, const double* U, double dt);
+/* perBC!(a,perdir) on a scalar field (WL_P or WL_SIGMA) */
+int wl_per_bc(wl_sim* s, int field, const int* perdir);
+
+/* ---- momentum pieces (src/Flow.jl) — exported so that each reference function has a parity
+ *      test of its own; wl_mom_step runs the fused sequence ---------------------------------- */
+/* conv_diff!(f, src, σ; ν, perdir), src = WL_U or WL_U0 (src/Flow.jl:36-60) */
+int wl_conv_diff(wl_sim* s, int src_field);
+/* accelerate!: f[..,i] += g[i] (src/Flow.jl:68-73) */
+int wl_accelerate(wl_sim* s, const double* g);
+/* BDIM!(a) (src/Flow.jl:131-135) */
+int wl_bdim(wl_sim* s);
+/* scale_u!(a,scale) (src/Flow.jl:170) */
+int wl_scale_u(wl_sim* s, double scale);
+/* project!(a,b,w) (src/Flow.jl:137-145); n = V-cycles (or PCG sweeps) used */
+int wl_project(wl_sim* s, double w, int* n);
+/* CFL(a) (src/Flow.jl:172-175); does not push to Δt */
+int wl_cfl(wl_sim* s, double* dt);
+
+/* ---- pressure solver (src/Poisson.jl, src/MultiLevelPoisson.jl) ------------------------- */
+/* update!(pois): set_diag! on level 1, restrictL!+set_diag! on the coarser levels */
+int wl_pois_update(wl_sim* s);
+/* mult!(pois,x): z = A x with perBC!(x) and zero ghosts; x is levels[1].x */
+int wl_pois_mult(wl_sim* s);
+/* residual!(levels[level]); r2 = L₂ = r⋅r afterwards */
+int wl_pois_residual(wl_sim* s, int level, double* r2);
+/* Jacobi!(levels[level];it) */
+int wl_pois_jacobi(wl_sim* s, int level, int it);
+/* pcg!(levels[level];it) */
+int wl_pois_pcg(wl_sim* s, int level, int it);
+/* Vcycle!(ml;l=level+1) */
+int wl_pois_vcycle(wl_sim* s, int level);
+/* solver!(pois;tol,itmx): MultiLevelPoisson (tol=1e-4,itmx=32) or Poisson (tol=1e-4,itmx=1e3);
+ * pass tol<0 / itmx<0 for the reference defaults.  n = iterations, also appended to the log. */
+int wl_pois_solve(wl_sim* s, double tol, int itmx, int* n);
+
+/* ---- the hot path --------------------------------------------------------------------- */
+/* mom_step!(a,b) (src/Flow.jl:153-169).
+ * U       : BCTuple(a.U,a.Δt,N) evaluated by the host at t+Δt (D entries)
+ * g_pred  : uniform acceleration gᵢ(+dUᵢ/dt) at t, or NULL for `nothing` (src/Flow.jl:158)
+ * g_corr  : the same at t+Δt (src/Flow.jl:165)
+ * dt_next : CFL(a), already pushed onto the handle's Δt history
+ * n_pred, n_corr : the two entries pushed onto pois.n */
+int wl_mom_step(wl_sim* s, const double* U, const double* g_pred, const double* g_corr,
+                double* dt_next, int* n_pred, int* n_corr);
+/* Δt[end] */
+int wl_get_dt(wl_sim* s, double* dt);
+int wl_set_dt(wl_sim* s, double dt);
+/* number of kernels launched by this handle since creation (bench.py's gpu_launches) */
+int64_t wl_launch_count(wl_sim* s);
+/* device time of the dominant kernels accumulated with CUDA events while profiling is on:
+ * which = 0 momentum (conv_diff+BDIM), 1 fine-level smoother (pcg! level 1), 2 whole solver.
+ * Returns milliseconds and launches since wl_profile(s,1). */
+int wl_profile(wl_sim* s, int on);
+int wl_profile_read(wl_sim* s, int which, double* ms, int64_t* launches, double* bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WATERLILY_B200_H */

@@ -1,0 +1,49 @@
+"""Python handle on the CPU oracle (oracle/wl_oracle.cpp) — TEST INFRASTRUCTURE ONLY.
+
+Importers: tests/, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference``
+legs.  It binds ``liboracle.so`` through the same ctypes table as the product (prefix ``wlo_``) and
+re-uses the package's host logic, so a parity test drives both sides with identical calls.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+from waterlily_b200._cabi import CABI, Engine
+from waterlily_b200.sim import _SimulationBase
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "liboracle.so")
+_lib = None
+
+
+def build(force=False):
+    src = os.path.join(HERE, "wl_oracle.cpp")
+    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", HERE, "-B", "liboracle.so"], stdout=subprocess.DEVNULL)
+
+
+def load() -> CABI:
+    global _lib
+    if _lib is None:
+        build()
+        _lib = CABI(LIB_PATH, "wlo_")
+        _lib.lib.wlo_num_threads.restype = ctypes.c_int
+    return _lib
+
+
+def num_threads() -> int:
+    return int(load().lib.wlo_num_threads())
+
+
+def engine(dims, **kw) -> Engine:
+    return Engine(load(), dims, **kw)
+
+
+class OracleSimulation(_SimulationBase):
+    """The reference's ``Simulation`` with ``mem=Array`` semantics, computed by the oracle."""
+
+    @classmethod
+    def _lib(cls):
+        return load()

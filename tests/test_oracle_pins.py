@@ -1,0 +1,195 @@
+"""Pins the CPU oracle against the known-answer assertions of the reference's own test-suite
+(/root/reference/test/maintests.jl; the line of each ported assertion is quoted).  The reference
+stores no golden arrays, so these are all the pins that exist for the mom_step! path."""
+import numpy as np
+import pytest
+
+from oracle import oracle
+from oracle.oracle import OracleSimulation
+from waterlily_b200 import _cabi, sim_step, sim_time, AutoBody
+from waterlily_b200.body import mu0_of, mu1_of
+from helpers import L2, poisson_setup
+
+import torch
+
+
+def test_bc_pins():
+    # maintests.jl:32-56
+    Ng, D, U = (6, 6), 2, (1.0, 0.5)
+    rng = np.random.default_rng(1)
+    e = oracle.engine((4, 4), pois_kind=_cabi.POIS_SINGLE)
+    e.upload("u", rng.random(Ng + (D,)).astype(np.float32))
+    sg = rng.random(Ng).astype(np.float32)
+    e.bc("u", U, False, ())
+    u = e.download("u")
+    assert (u[0, :, 0] == U[0]).all() and (u[1, :, 0] == U[0]).all() and (u[-1, :, 0] == U[0]).all()      # :36
+    assert (u[2:-1, 0, 0] == u[2:-1, 1, 0]).all() and (u[2:-1, -1, 0] == u[2:-1, -2, 0]).all()            # :37
+    assert (u[:, 0, 1] == U[1]).all() and (u[:, 1, 1] == U[1]).all() and (u[:, -1, 1] == U[1]).all()      # :38
+    assert (u[0, 2:-1, 1] == u[1, 2:-1, 1]).all() and (u[-1, 2:-1, 1] == u[-2, 2:-1, 1]).all()            # :39
+    u[-1, :, 0] = 3
+    e.upload("u", u)
+    e.bc("u", U, True, ())                                                                                # :42
+    assert (e.download("u")[-1, :, 0] == 3).all()                                                         # :43
+    e.upload("u0", e.download("u"))
+    e.exit_bc(U, 0.0)                                                                                     # :45
+    assert (e.download("u")[-1, 1:-1, 0] == np.float32(U[0])).all()                                       # :46
+    e.bc("u", U, True, (2,))                                                                              # :48
+    u = e.download("u")
+    assert (u[:, 0:2, 0] == u[:, -2:, 0]).all() and (u[:, 0:2, 1] == u[:, -2:, 1]).all()                  # :49
+    e.upload("sigma", sg)
+    e.per_bc("sigma", (1, 2))                                                                             # :50
+    s = e.download("sigma")
+    assert (s[0, 1:-1] == s[-2, 1:-1]).all() and (s[1:-1, 0] == s[1:-1, -2]).all()                        # :51
+    e.upload("u", rng.random(Ng + (D,)).astype(np.float32))
+    e.bc("u", U, True, (1,))                                                                              # :54
+    u = e.download("u")
+    assert (u[0:2, :, 0] == u[-2:, :, 0]).all() and (u[0:2, :, 1] == u[-2:, :, 1]).all()                  # :55
+    assert (u[:, 0, 1] == U[1]).all() and (u[:, 1, 1] == U[1]).all() and (u[:, -1, 1] == U[1]).all()      # :56
+
+
+def test_poisson_pins():
+    # maintests.jl:81-94
+    err, n, e = poisson_setup(oracle.engine, _cabi.POIS_SINGLE, (5, 5))
+    Dm = np.array([[0, 0, 0, 0, 0], [0, -2, -3, -2, 0], [0, -3, -4, -3, 0], [0, -2, -3, -2, 0], [0, 0, 0, 0, 0]], dtype=np.float32)
+    assert (e.level_download(0, "D") == Dm).all()                                                         # :84
+    iD = np.where(Dm == 0, 0, 1 / np.where(Dm == 0, 1, Dm)).astype(np.float32)
+    assert np.allclose(e.level_download(0, "iD"), iD, rtol=1e-6)                                          # :85
+    assert err < 1e-5                                                                                     # :86
+    err, n, _ = poisson_setup(oracle.engine, _cabi.POIS_SINGLE, (66, 66))
+    assert err < 1e-6 and n < 310                                                                         # :88-89
+    err, n, _ = poisson_setup(oracle.engine, _cabi.POIS_SINGLE, (18, 18, 18))
+    assert err < 1e-6 and n < 35                                                                          # :91-92
+
+
+def test_multilevel_pins():
+    # maintests.jl:96-117
+    with pytest.raises(_cabi.WLError, match="MultiLevelPoisson requires size=a2ⁿ, where n>2"):            # :99
+        poisson_setup(oracle.engine, _cabi.POIS_MULTILEVEL, (15 + 2, 3 ** 4 + 2))
+    err, n, e = poisson_setup(oracle.engine, _cabi.POIS_MULTILEVEL, (10, 10))
+    D3 = np.array([[0, 0, 0, 0], [0, -2, -2, 0], [0, -2, -2, 0], [0, 0, 0, 0]], dtype=np.float32)
+    assert (e.level_download(2, "D") == D3).all()                                                         # :102
+    assert err < 1e-5                                                                                     # :103
+    L = e.level_download(0, "L")
+    L[4:6, :, 0] = 0                                                                                      # :105
+    e.level_upload(0, "L", L)
+    e.pois_update()                                                                                       # :106
+    assert (e.level_download(2, "D") == D3 / 2).all()                                                     # :107
+    err, n, _ = poisson_setup(oracle.engine, _cabi.POIS_MULTILEVEL, (66, 66))
+    assert err < 1e-6 and n <= 3                                                                          # :111-112
+    err, n, _ = poisson_setup(oracle.engine, _cabi.POIS_MULTILEVEL, (18, 18, 18))
+    assert err < 1e-6 and n <= 3                                                                          # :114-115
+
+
+def test_impulsive_box():
+    # maintests.jl:172-180: Flow(N,U;T=Float32); mom_step!(a, MultiLevelPoisson(a.p,a.μ₀,a.σ))
+    U = (2 / 3, -1 / 3)
+    sim = OracleSimulation((16, 16), U, 16)
+    sim_step(sim, remeasure=False)
+    u = sim.flow.u.numpy()
+    assert L2(u[:, :, 0] - U[0]) < 2e-5                                                                   # :178
+    assert L2(u[:, :, 1] - U[1]) < 1e-5                                                                   # :179
+
+
+def tgv_sim(cls, Re=1e8, L=64):
+    # TGVsim — maintests.jl:232-243
+    kappa = 2 * np.pi / L
+    nu = 1 / (kappa * Re)
+
+    def TGV(i, xy, t):
+        x, y = xy[..., 0] * kappa, xy[..., 1] * kappa
+        if i == 1:
+            return -np.sin(x) * np.cos(y) * np.exp(-2 * kappa ** 2 * nu * t)
+        return np.cos(x) * np.sin(y) * np.exp(-2 * kappa ** 2 * nu * t)
+    return cls((L, L), (0, 0), L, U=1, ulam=lambda i, x: TGV(i, x, 0.0), nu=nu, perdir=(1, 2)), TGV
+
+
+def test_tgv_periodic():
+    # maintests.jl:244-253
+    from waterlily_b200.body import loc_grid
+    sim, TGV = tgv_sim(OracleSimulation)
+    sim_step(sim, np.pi / 100)
+    t = sim.flow.time()
+    u = sim.flow.u.numpy()
+    for i in (1, 2):
+        ue = TGV(i, loc_grid(i, u.shape[:-1]), t).astype(np.float32)
+        assert L2(u[..., i - 1] - ue) < 1e-4                                                              # :250-251
+    # regression anchor (not a reference pin): V-cycle counts; SURVEY.md Appendix B's independent
+    # numpy restatement gave [2,1,1,1,1,1] — the last solve sits at the tol=1e-4 threshold
+    assert sim.pois.n[:5] == [2, 1, 1, 1, 1] and sim.pois.n[5] in (1, 2)
+
+
+def test_accelerating_flow():
+    # maintests.jl:280-302 (T=Float64 there; this build is Float32-only, so the tolerance is the
+    # Float32 one the same test would need)
+    N, jerk = 8, 4
+    sim = OracleSimulation((N, N), (np.sqrt(N), 0.0), N, nu=0.001, g=lambda i, t: t * jerk if i == 1 else 0.0, dt=0.001, perdir=(1,))
+    sim_step(sim, 1.0)
+    u = sim.flow.u.numpy()
+    uFinal = np.sqrt(N) + 0.5 * jerk * sim.flow.time() ** 2
+    assert L2(u[:, :, 0] - uFinal) < 1e-4 and L2(u[:, :, 1]) < 1e-4                                       # :297-300
+
+
+def test_body_kernel_pins():
+    # maintests.jl:183-187
+    assert mu0_of(3, 6) == mu0_of(0.5, 1)
+    assert mu0_of(0, 1) == 0.5
+    assert np.isclose(mu1_of(0, 2), 2 * (1 / 4 - 1 / np.pi ** 2))
+
+
+def _circle(radius):
+    return lambda x, t: torch.sqrt(((x - 2 * radius) ** 2).sum(-1)) - radius
+
+
+@pytest.mark.parametrize("exitBC", [True, False])
+def test_moving_bodies(exitBC):
+    # maintests.jl:372-413
+    radius = 8
+    nu = radius / 250
+    nm = (4 * radius, 4 * radius)
+    circle = _circle(radius)
+    e1 = torch.tensor([1.0, 0.0])
+    move = lambda x, t: x - e1 * t
+    accel = lambda x, t: x - e1 * (2 * t ** 2)
+    # remeasure works perfectly when V = U = 1                                                          # :393-395
+    sim = OracleSimulation(nm, (1, 0), radius, body=AutoBody(circle, move), nu=nu, exitBC=exitBC)
+    sim_step(sim)
+    assert np.allclose(sim.flow.u.numpy()[:, radius - 1, 0], 1, rtol=1e-5)
+    # accelerating from U=0 to U=1                                                                      # :398-401
+    sim = OracleSimulation(nm, (0, 0), radius, U=1, body=AutoBody(circle, accel), nu=nu, exitBC=exitBC)
+    sim_step(sim)
+    assert sim.pois.n == [2, 1]
+    assert sim.flow.u.numpy().max() > sim.flow.V.numpy().max() > 0
+
+    # non-uniform V (rotating plate)                                                                    # :403-406
+    def plate(x, t):
+        cx = torch.clamp(x[..., 0], -radius + 2, radius - 2)
+        return torch.sqrt((x[..., 0] - cx) ** 2 + x[..., 1] ** 2) - 2
+
+    def rotate(x, t):
+        a = t / radius + 1
+        s, c = torch.sin(a), torch.cos(a)
+        y = x - 2 * radius
+        return torch.stack([c * y[..., 0] + s * y[..., 1], -s * y[..., 0] + c * y[..., 1]], -1)
+    sim = OracleSimulation(nm, (0, 0), radius, U=1, body=AutoBody(plate, rotate), nu=nu, exitBC=exitBC)
+    sim_step(sim)
+    assert sim.pois.n == [2, 1]
+    assert 1 > sim.flow.dt[-1] > 0.5
+
+    # divergent V (bending plate)                                                                       # :408-411
+    def bend(xy, t):
+        x, y = xy[..., 0] - 2 * radius, xy[..., 1] - 2 * radius
+        k = 2 * t / radius ** 2 + 0.2 / radius
+        return torch.stack([x + x ** 3 * k ** 2 / 6, y - x ** 2 * k / 2], -1)
+    sim = OracleSimulation(nm, (0, 0), radius, U=1, body=AutoBody(plate, bend), nu=nu, exitBC=exitBC)
+    sim_step(sim)
+    assert sim.pois.n == [2, 1]
+    assert 1.2 > sim.flow.dt[-1] > 0.8
+
+
+def test_sim_time_stopping():
+    # maintests.jl:387-390
+    radius = 8
+    sim = OracleSimulation((4 * radius, 4 * radius), (1, 0), radius, body=AutoBody(_circle(radius)), nu=radius / 250)
+    assert sim_time(sim) == 0
+    sim_step(sim, 0.1, remeasure=False)
+    assert sim_time(sim) >= 0.1 > float(np.sum(sim.flow.dt[:-2])) * sim.U / sim.L
