@@ -144,10 +144,13 @@ int wl_get_dt(wl_sim* s, double* dt);
 int wl_set_dt(wl_sim* s, double dt);
 /* number of kernels launched by this handle since creation (bench.py's gpu_launches) */
 int64_t wl_launch_count(wl_sim* s);
-/* device time of the dominant kernels accumulated with CUDA events while profiling is on:
- * which = 0 momentum (conv_diff+BDIM), 1 fine-level smoother (pcg! level 1), 2 whole solver.
- * Returns milliseconds and launches since wl_profile(s,1). */
+/* Per-kernel-class device time, measured with CUDA events on the handle's stream while profiling
+ * is on.  Classes 0..wl_profile_count()-1 are named by wl_profile_name(); read returns the summed
+ * milliseconds, the number of launches that did work (kernels of an exited pcg! are predicated off
+ * on the device and not counted) and their algorithmic bytes. */
 int wl_profile(wl_sim* s, int on);
+int wl_profile_count(void);
+const char* wl_profile_name(int which);
 int wl_profile_read(wl_sim* s, int which, double* ms, int64_t* launches, double* bytes);
 
 #ifdef __cplusplus

@@ -679,6 +679,8 @@ int wlo_profile_read(wl_sim*, int, double* ms, int64_t* launches, double* bytes)
   if (bytes) *bytes = 0;
   return WL_OK;
 }
+int wlo_profile_count(void) { return 0; }
+const char* wlo_profile_name(int) { return ""; }
 int wlo_num_threads(void) {
   int n = 1;
 #ifdef _OPENMP

@@ -1,0 +1,271 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle, function by function and for
+whole mom_step! runs, on identical seeded inputs.  Tolerances are the north star's: per-field
+relative L2 ≤ 1e-5 after one step, ≤ 1e-4 after many, V-cycle counts within ±1."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle
+from oracle.oracle import OracleSimulation
+from waterlily_b200 import _cabi, lib, sim_step, AutoBody, Simulation
+from helpers import L2, poisson_setup, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+FIELDS_V = ("u", "u0", "f", "V", "mu0")
+
+
+def cuda_engine(dims, **kw):
+    return _cabi.Engine(lib.load(), dims, **kw)
+
+
+def pair(dims, perdir=(), exitBC=False, nu=0.01, dt=0.25, kind=_cabi.POIS_SINGLE, seed=0, random_fields=("u", "u0", "f", "p", "sigma", "V")):
+    eo = oracle.engine(dims, nu=nu, dt0=dt, perdir=perdir, exitBC=exitBC, pois_kind=kind)
+    ec = cuda_engine(dims, nu=nu, dt0=dt, perdir=perdir, exitBC=exitBC, pois_kind=kind)
+    rng = np.random.default_rng(seed)
+    for name in random_fields:
+        a = (rng.random(eo.shape(_cabi.FIELD_IDS[name])) * 2 - 1).astype(np.float32)
+        eo.upload(name, a)
+        ec.upload(name, a)
+    return eo, ec
+
+
+DIMS = [((8, 12), ()), ((8, 12), (1,)), ((8, 12), (2,)), ((8, 12), (1, 2)),
+        ((8, 6, 10), ()), ((8, 6, 10), (3,)), ((8, 6, 10), (1, 2, 3)), ((8, 6, 10), (2,))]
+
+
+@pytest.mark.parametrize("dims,perdir", DIMS)
+@pytest.mark.parametrize("saveexit", [False, True])
+def test_bc_bit_exact(dims, perdir, saveexit):
+    eo, ec = pair(dims, perdir)
+    A = (1.0, 0.5, -0.25)[:len(dims)]
+    for e in (eo, ec):
+        e.bc("u", A, saveexit, None)
+    assert np.array_equal(eo.download("u"), ec.download("u"))
+    for e in (eo, ec):
+        e.per_bc("sigma", None)
+    assert np.array_equal(eo.download("sigma"), ec.download("sigma"))
+
+
+@pytest.mark.parametrize("dims", [(8, 12), (8, 6, 10)])
+def test_exit_bc(dims):
+    eo, ec = pair(dims, exitBC=True)
+    U = (1.0, 0.0, 0.0)[:len(dims)]
+    for e in (eo, ec):
+        e.exit_bc(U, 0.3)
+    assert np.allclose(eo.download("u"), ec.download("u"), rtol=0, atol=2e-7)
+
+
+@pytest.mark.parametrize("dims,perdir", DIMS + [((32, 32, 32), (1, 2, 3)), ((48, 24, 24), ())])
+def test_conv_diff(dims, perdir):
+    eo, ec = pair(dims, perdir, nu=0.05)
+    for e in (eo, ec):
+        e.conv_diff("u")
+    fo, fc = eo.download("f"), ec.download("f")
+    assert rel_l2(fc, fo) < 2e-7
+    assert np.abs(fc - fo).max() < 5e-6
+    # σ ≡ Φ: the ghost layer must hold the same stale fluxes; the interior is scratch
+    so, sc = eo.download("sigma"), ec.download("sigma")
+    shell = np.ones(so.shape, bool)
+    shell[tuple(slice(1, -1) for _ in dims)] = False
+    assert np.abs(so[shell] - sc[shell]).max() < 5e-6
+
+
+@pytest.mark.parametrize("dims,perdir", [((8, 12), ()), ((8, 6, 10), (3,))])
+def test_bdim_accelerate_scale(dims, perdir):
+    D = len(dims)
+    eo, ec = pair(dims, perdir, random_fields=("u", "u0", "f", "V"))
+    rng = np.random.default_rng(5)
+    mu0 = rng.random(eo.shape(_cabi.MU0)).astype(np.float32)
+    mu1 = (rng.random(eo.shape(_cabi.MU1)) - 0.5).astype(np.float32)
+    for e in (eo, ec):
+        e.upload("mu0", mu0)
+        e.upload("mu1", mu1)
+        e.accelerate((0.3, -0.2, 0.1)[:D])
+        e.bdim()
+        e.scale_u(0.5)
+    assert rel_l2(ec.download("f"), eo.download("f")) < 2e-7
+    assert rel_l2(ec.download("u"), eo.download("u")) < 2e-7
+
+
+def _random_pois(dims, perdir, kind, seed=3):
+    eo, ec = pair(dims, perdir, kind=kind, seed=seed, random_fields=("p", "sigma"))
+    rng = np.random.default_rng(seed + 1)
+    L = rng.random(eo.shape(_cabi.MU0)).astype(np.float32)
+    # solid patch: L=0 makes D=0 → iD=0 cells
+    L[tuple(slice(2, 4) for _ in dims)] = 0
+    for e in (eo, ec):
+        e.upload("mu0", L)
+        e.bc("mu0", (0.0,) * len(dims), False, None)
+        e.pois_update()
+    return eo, ec
+
+
+@pytest.mark.parametrize("dims,perdir", [((16, 32), ()), ((16, 32), (1,)), ((16, 8, 24), ()), ((16, 8, 24), (1, 2, 3))])
+def test_poisson_pieces(dims, perdir):
+    eo, ec = _random_pois(dims, perdir, _cabi.POIS_MULTILEVEL)
+    assert eo.nlevels() == ec.nlevels() >= 3
+    for l in range(eo.nlevels()):
+        assert eo.level_dims(l) == ec.level_dims(l)
+        for f in ("L", "D", "iD"):
+            assert np.allclose(ec.level_download(l, f), eo.level_download(l, f), rtol=1e-6, atol=1e-7), (l, f)
+    r2o, r2c = eo.pois_residual(0), ec.pois_residual(0)
+    assert abs(r2c - r2o) <= 1e-5 * abs(r2o)
+    assert rel_l2(ec.level_download(0, "r"), eo.level_download(0, "r")) < 1e-6
+    for e in (eo, ec):
+        e.pois_jacobi(0, 2)
+    for f in ("r", "x", "eps"):
+        assert rel_l2(ec.level_download(0, f), eo.level_download(0, f)) < 1e-6, f
+    for e in (eo, ec):
+        e.pois_pcg(0, 6)
+    for f in ("r", "x", "eps"):
+        assert rel_l2(ec.level_download(0, f), eo.level_download(0, f)) < 1e-5, f
+    for e in (eo, ec):
+        e.pois_vcycle(0)
+    for l in range(eo.nlevels()):
+        for f in ("r", "x"):
+            assert rel_l2(ec.level_download(l, f), eo.level_download(l, f)) < 2e-5, (l, f)
+    for e in (eo, ec):
+        e.pois_mult()
+    assert rel_l2(ec.download("sigma"), eo.download("sigma")) < 1e-6
+
+
+@pytest.mark.parametrize("kind,Ng,nmax", [(_cabi.POIS_SINGLE, (5, 5), 10**6), (_cabi.POIS_SINGLE, (66, 66), 310), (_cabi.POIS_SINGLE, (18, 18, 18), 35),
+                                          (_cabi.POIS_MULTILEVEL, (66, 66), 4), (_cabi.POIS_MULTILEVEL, (18, 18, 18), 4)])
+def test_reference_poisson_pins_on_cuda(kind, Ng, nmax):
+    # test/maintests.jl:81-94,109-116 through the CUDA library
+    err, n, _ = poisson_setup(cuda_engine, kind, Ng)
+    erro, no, _ = poisson_setup(oracle.engine, kind, Ng)
+    assert err < (1e-5 if Ng == (5, 5) else 1e-6) and n < nmax
+    assert abs(n - no) <= 1
+
+
+def test_reference_multilevel_pins_on_cuda():
+    # test/maintests.jl:101-107
+    err, n, e = poisson_setup(cuda_engine, _cabi.POIS_MULTILEVEL, (10, 10))
+    D3 = np.array([[0, 0, 0, 0], [0, -2, -2, 0], [0, -2, -2, 0], [0, 0, 0, 0]], dtype=np.float32)
+    assert (e.level_download(2, "D") == D3).all() and err < 1e-5
+    L = e.level_download(0, "L")
+    L[4:6, :, 0] = 0
+    e.level_upload(0, "L", L)
+    e.pois_update()
+    assert (e.level_download(2, "D") == D3 / 2).all()
+
+
+def compare_sims(so, sc, tol, fields=("u", "p", "f")):
+    out = {}
+    for f in fields:
+        a, b = getattr(sc.flow, f).numpy(), getattr(so.flow, f).numpy()
+        out[f] = rel_l2(a, b)
+        assert out[f] <= tol, (f, out[f])
+    return out
+
+
+def run_pair(make, steps, tol1=1e-5, tolN=1e-4):
+    so, sc = make(OracleSimulation), make(Simulation)
+    compare_sims(so, sc, 1e-7, fields=("u", "mu0"))
+    for k in range(steps):
+        sim_step(so, remeasure=False)
+        sim_step(sc, remeasure=False)
+        compare_sims(so, sc, tol1 if k == 0 else tolN)
+        assert abs(float(so.flow.dt[-1]) - float(sc.flow.dt[-1])) <= tolN * float(so.flow.dt[-1])
+    assert len(so.pois.n) == len(sc.pois.n)
+    assert all(abs(a - b) <= 1 for a, b in zip(so.pois.n, sc.pois.n)), (so.pois.n, sc.pois.n)
+    return so, sc
+
+
+def tgv3d(cls, N, Re=1600.0):
+    # BASELINE.json config "3D Taylor-Green vortex N³ periodic" 
+    kappa = 2 * np.pi / N
+    nu = 1 / (kappa * Re)
+
+    def ulam(i, x):
+        X, Y, Z = x[..., 0] * kappa, x[..., 1] * kappa, x[..., 2] * kappa
+        if i == 1:
+            return -np.sin(X) * np.cos(Y) * np.cos(Z)
+        if i == 2:
+            return np.cos(X) * np.sin(Y) * np.cos(Z)
+        return np.zeros_like(X)
+    return cls((N, N, N), (0, 0, 0), N, U=1, nu=nu, ulam=ulam, perdir=(1, 2, 3))
+
+
+def circle2d(cls, n=3 * 2 ** 5, m=2 ** 6, Re=100):
+    # README example
+    radius, center = m / 8, m / 2 - 1
+    sdf = lambda x, t: torch.sqrt(((x - center) ** 2).sum(-1)) - radius
+    return cls((n, m), (1, 0), 2 * radius, nu=2 * radius / Re, body=AutoBody(sdf))
+
+
+def sphere3d(cls, n=64, m=32, exitBC=True):
+    # SURVEY.md §8d C3 at reduced size
+    radius, center = m / 8, m / 2 - 1
+    sdf = lambda x, t: torch.sqrt(((x - center) ** 2).sum(-1)) - radius
+    return cls((n, m, m), (1, 0, 0), 2 * radius, nu=2 * radius / 3700, body=AutoBody(sdf), exitBC=exitBC)
+
+
+def test_mom_step_circle_2d():
+    run_pair(circle2d, 20)
+
+
+def test_mom_step_tgv_32():
+    run_pair(lambda cls: tgv3d(cls, 32), 6)
+
+
+def test_mom_step_tgv_64():
+    run_pair(lambda cls: tgv3d(cls, 64), 3)
+
+
+@pytest.mark.parametrize("exitBC", [True, False])
+def test_mom_step_sphere(exitBC):
+    run_pair(lambda cls: sphere3d(cls, exitBC=exitBC), 5)
+
+
+def test_mom_step_100_circle():
+    # north star: ≤1e-4 after 100 steps
+    so, sc = circle2d(OracleSimulation), circle2d(Simulation)
+    for _ in range(100):
+        sim_step(so, remeasure=False)
+        sim_step(sc, remeasure=False)
+    compare_sims(so, sc, 1e-4, fields=("u", "p"))
+    assert sum(abs(a - b) for a, b in zip(so.pois.n, sc.pois.n)) <= 2
+
+
+def test_accelerating_flow_and_g():
+    # test/maintests.jl:280-302 on the CUDA path: g(i,t) and periodic x
+    N, jerk = 8, 4
+    make = lambda cls: cls((N, N), (np.sqrt(N), 0.0), N, nu=0.001, g=lambda i, t: t * jerk if i == 1 else 0.0, dt=0.001, perdir=(1,))
+    so, sc = make(OracleSimulation), make(Simulation)
+    sim_step(so, 1.0)
+    sim_step(sc, 1.0)
+    u = sc.flow.u.numpy()
+    uFinal = np.sqrt(N) + 0.5 * jerk * sc.flow.time() ** 2
+    assert L2(u[:, :, 0] - uFinal) < 1e-4 and L2(u[:, :, 1]) < 1e-4
+    assert rel_l2(u, so.flow.u.numpy()) < 1e-5
+
+
+def test_moving_body_pins_on_cuda():
+    # test/maintests.jl:398-400: accelerating circle, pois.n == [2,1]
+    radius = 8
+    e1 = torch.tensor([1.0, 0.0])
+    circle = lambda x, t: torch.sqrt(((x - 2 * radius) ** 2).sum(-1)) - radius
+    accel = lambda x, t: x - e1 * (2 * t ** 2)
+    for exitBC in (True, False):
+        sim = Simulation((4 * radius, 4 * radius), (0, 0), radius, U=1, body=AutoBody(circle, accel), nu=radius / 250, exitBC=exitBC)
+        sim_step(sim)
+        assert sim.pois.n == [2, 1]
+        assert sim.flow.u.numpy().max() > sim.flow.V.numpy().max() > 0
+
+
+def test_full_size_properties_tgv128():
+    # BASELINE config C2 at full size: size-independent properties (the oracle is too slow to step 128³ in a test)
+    sim = tgv3d(Simulation, 128)
+    for _ in range(3):
+        sim_step(sim, remeasure=False)
+    u = sim.flow.u.numpy().astype(np.float64)
+    div = (u[2:, 1:-1, 1:-1, 0] - u[1:-1, 1:-1, 1:-1, 0]) + (u[1:-1, 2:, 1:-1, 1] - u[1:-1, 1:-1, 1:-1, 1]) + (u[1:-1, 1:-1, 2:, 2] - u[1:-1, 1:-1, 1:-1, 2])
+    assert (div ** 2).sum() < 5e-4          # solver tolerance: Σr² < 1e-4 per projection (scaled by dt)
+    assert np.array_equal(u[0], u[-2]) and np.array_equal(u[-1], u[1])   # periodic ghosts
+    ke = 0.5 * (u[1:-1, 1:-1, 1:-1] ** 2).sum() / 128 ** 3
+    assert 0.115 < ke < 0.126              # TGV kinetic energy 1/8 at t=0, decaying slowly
+    assert all(1 <= n <= 32 for n in sim.pois.n)
+    assert 0.5 < float(sim.flow.dt[-1]) < 1.1

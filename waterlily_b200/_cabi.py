@@ -51,6 +51,8 @@ SIGNATURES = {
     "set_dt": (C.c_int, [H, C.c_double]),
     "launch_count": (C.c_int64, [H]),
     "profile": (C.c_int, [H, C.c_int]),
+    "profile_count": (C.c_int, []),
+    "profile_name": (C.c_char_p, [C.c_int]),
     "profile_read": (C.c_int, [H, C.c_int, c_dbl_p, c_i64_p, c_dbl_p]),
 }
 
@@ -262,6 +264,9 @@ class Engine:
 
     def profile(self, on=True):
         self.cabi.check(self.cabi.profile(self.h, int(on)))
+
+    def profile_classes(self):
+        return [self.cabi.profile_name(i).decode() for i in range(self.cabi.profile_count())]
 
     def profile_read(self, which):
         ms, n, b = C.c_double(0), C.c_int64(0), C.c_double(0)

@@ -141,6 +141,26 @@ def loc_grid(i, Ng, dtype=np.float32):
     return X.astype(dtype)
 
 
+class LocLazy:
+    """``loc(i,I)`` for every cell without materialising the ``(Ng...,D)`` array: ``x[..., k]`` is a
+    broadcastable 1-D coordinate, so ``uλ`` closures written with ``x[..., k]`` cost O(N) memory
+    until their final broadcast (a 512³ initial condition would otherwise need several GB)."""
+
+    def __init__(self, i, Ng, dtype=np.float32):
+        self.shape = tuple(Ng) + (len(Ng),)
+        self._ax = []
+        for k, n in enumerate(Ng):
+            a = np.arange(1, n + 1, dtype=np.float64) - 1.5 - (0.5 if (k == i - 1) else 0.0)
+            shp = [1] * len(Ng)
+            shp[k] = n
+            self._ax.append(a.astype(dtype).reshape(shp))
+
+    def __getitem__(self, idx):
+        if isinstance(idx, tuple) and len(idx) == 2 and idx[0] is Ellipsis and isinstance(idx[1], int):
+            return self._ax[idx[1]]
+        return np.stack(np.broadcast_arrays(*self._ax), axis=-1)[idx]
+
+
 def measure_fields(body, Ng, t=0.0, eps=1.0, dtype=np.float32):
     """The cell loop of ``measure!(flow,body;t,ϵ)`` — reference src/Body.jl:31-50.
 

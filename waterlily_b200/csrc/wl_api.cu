@@ -1,0 +1,412 @@
+// wl_api.cu — the C ABI of include/waterlily_b200.h: handle lifetime, field transfer, and thin
+// exports of each reference function on the path.  Every export catches its own errors and
+// returns a status; nothing throws across the boundary.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "wl_internal.h"
+
+namespace {
+thread_local std::string g_err;
+}
+
+int wl_fail(int code, const std::string& msg) { g_err = msg; return code; }
+int wl_cuda_check(Sim& s, cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return s.sticky;
+  if (!s.sticky) s.sticky = WL_ERR_CUDA;
+  return wl_fail(WL_ERR_CUDA, std::string("CUDA error in ") + what + ": " + cudaGetErrorString(e));
+}
+
+dim3 wl_pick_block(const GridD& g) {
+  const int nx = g.n[0];
+  const int bx = nx >= 96 ? 128 : nx >= 48 ? 64 : nx >= 24 ? 32 : nx >= 12 ? 16 : 8;
+  if (g.D == 2) return dim3(bx, 256 / bx, 1);
+  switch (bx) {
+    case 128: return dim3(128, 2, 1);
+    case 64: return dim3(64, 2, 2);
+    case 32: return dim3(32, 4, 2);
+    case 16: return dim3(16, 4, 4);
+    default: return dim3(8, 8, 4);
+  }
+}
+int wl_grid_for(const Sim& s, int64_t ntiles) {
+  const int64_t cap = std::min<int64_t>((int64_t)s.nsm * 8, WL_MAXBLOCKS);
+  return (int)std::max<int64_t>(1, std::min(ntiles, cap));
+}
+
+void wl_prof_begin(Sim& s, int cls) {
+  if (!s.profiling) return;
+  ProfClass& p = s.prof[cls];
+  if (p.used + 2 > p.ev.size()) {
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    p.ev.push_back(a); p.ev.push_back(b);
+  }
+  cudaEventRecord(p.ev[p.used], s.stream);
+}
+void wl_prof_end(Sim& s, int cls, double bytes) {
+  if (!s.profiling) return;
+  ProfClass& p = s.prof[cls];
+  cudaEventRecord(p.ev[p.used + 1], s.stream);
+  p.used += 2;
+  p.launches += 1;
+  p.bytes += bytes;
+}
+
+namespace {
+__global__ void k_fill(float* p, float v, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+void grid_set(GridD& g, int D, const int* Ng, const int* per) {
+  g.D = D;
+  for (int k = 0; k < 3; ++k) { g.n[k] = k < D ? Ng[k] : 1; g.per[k] = (k < D && per) ? (per[k] != 0) : 0; }
+  const int64_t pitch = ((int64_t)g.n[0] + WL_OX + 3) / 4 * 4;  // rows start 16-byte aligned at i=1
+  g.s[0] = 1; g.s[1] = pitch; g.s[2] = pitch * g.n[1];
+  g.comp = ((WL_OX + pitch * g.n[1] * g.n[2] + 8) + 3) / 4 * 4;
+  g.interior = 1;
+  for (int k = 0; k < D; ++k) g.interior *= g.n[k] - 2;
+}
+
+float* dev_alloc(Sim& s, int64_t floats, int* rc) {
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, sizeof(float) * (size_t)floats);
+  if (e == cudaSuccess) e = cudaMemsetAsync(p, 0, sizeof(float) * (size_t)floats, s.stream);
+  if (e != cudaSuccess) { *rc = wl_cuda_check(s, e, "cudaMalloc"); return nullptr; }
+  s.allocs.push_back(p);
+  return (float*)p + WL_OX;
+}
+
+float* field_ptr(Sim& s, int field, int* ncomp) {
+  const int D = s.D;
+  switch (field) {
+    case WL_U: *ncomp = D; return s.u;
+    case WL_U0: *ncomp = D; return s.u0;
+    case WL_F: *ncomp = D; return s.f;
+    case WL_P: *ncomp = 1; return s.p;
+    case WL_SIGMA: *ncomp = 1; return s.sigma;
+    case WL_V: *ncomp = D; return s.V;
+    case WL_MU0: *ncomp = D; return s.mu0;
+    case WL_MU1: *ncomp = D * D; return s.mu1;
+  }
+  return nullptr;
+}
+float* level_ptr(Sim& s, int level, int lf, int* ncomp) {
+  if (level < 0 || level >= (int)s.levels.size()) return nullptr;
+  Lvl& l = s.levels[level];
+  *ncomp = 1;
+  switch (lf) {
+    case WL_LVL_L: *ncomp = s.D; return l.L;
+    case WL_LVL_D: return l.Dg;
+    case WL_LVL_ID: return l.iD;
+    case WL_LVL_X: return l.x;
+    case WL_LVL_EPS: return l.eps;
+    case WL_LVL_R: return l.r;
+    case WL_LVL_Z: return l.z;
+  }
+  return nullptr;
+}
+// host (dense, column-major, padded) <-> device (re-pitched rows)
+int copy_field(Sim& s, const GridD& g, float* dev, float* host, int ncomp, bool to_device) {
+  const size_t w = sizeof(float) * (size_t)g.n[0];
+  const size_t rows = (size_t)g.n[1] * g.n[2];
+  const int64_t dense = (int64_t)g.n[0] * g.n[1] * g.n[2];
+  for (int c = 0; c < ncomp; ++c) {
+    float* d = dev + c * g.comp;
+    float* h = host + c * dense;
+    cudaError_t e = to_device ? cudaMemcpy2DAsync(d, sizeof(float) * g.s[1], h, w, w, rows, cudaMemcpyHostToDevice, s.stream)
+                              : cudaMemcpy2DAsync(h, w, d, sizeof(float) * g.s[1], w, rows, cudaMemcpyDeviceToHost, s.stream);
+    if (e != cudaSuccess) return wl_cuda_check(s, e, "cudaMemcpy2DAsync");
+  }
+  return wl_cuda_check(s, cudaStreamSynchronize(s.stream), "cudaStreamSynchronize");
+}
+inline bool divisible(int N) { return N % 2 == 0 && N > 4; }  // MultiLevelPoisson.jl:36
+}  // namespace
+
+int wl_fill(Sim& s, float* p, float v, int64_t n) {
+  k_fill<<<(int)std::min<int64_t>((n + 255) / 256, s.nsm * 8), 256, 0, s.stream>>>(p, v, n);
+  ++s.launches;
+  return wl_cuda_check(s, cudaGetLastError(), "k_fill");
+}
+int wl_read_scalars(Sim& s, const void* dptr, size_t bytes) {
+  cudaError_t e = cudaMemcpyAsync(s.h_pinned, dptr, bytes, cudaMemcpyDeviceToHost, s.stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
+  return wl_cuda_check(s, e, "scalar readback");
+}
+
+#define S (*(Sim*)s)
+#define GUARD(s)                                                         \
+  if (!(s)) return wl_fail(WL_ERR_ARG, "null handle");                   \
+  if (S.sticky) return wl_fail(S.sticky, "handle is in a failed state: " + g_err); \
+  cudaSetDevice(S.device)
+
+extern "C" {
+
+int wl_create(wl_sim** out, int D, const int* N, double nu, double dt0, const int* perdir, int exitBC, int pois_kind, int device) {
+  if (!out || !N || (D != 2 && D != 3)) return wl_fail(WL_ERR_ARG, "wl_create: D must be 2 or 3");
+  for (int k = 0; k < D; ++k) if (N[k] < 1) return wl_fail(WL_ERR_ARG, "wl_create: N must be positive");
+  // the MultiLevelPoisson size assertion comes first, as in the reference constructor
+  int Ng[3] = {1, 1, 1};
+  for (int k = 0; k < D; ++k) Ng[k] = N[k] + 2;
+  std::vector<std::vector<int>> dims;
+  dims.push_back({Ng[0], Ng[1], Ng[2]});
+  if (pois_kind == WL_POIS_MULTILEVEL) {
+    auto div_ok = [&](const std::vector<int>& n) { for (int k = 0; k < D; ++k) if (!divisible(n[k])) return false; return true; };
+    while (div_ok(dims.back()) && (int)dims.size() <= 10) {  // MultiLevelPoisson.jl:53
+      std::vector<int> c(3, 1);
+      for (int k = 0; k < D; ++k) c[k] = 1 + dims.back()[k] / 2;  // restrictML :20
+      dims.push_back(c);
+    }
+    if (dims.size() <= 2) return wl_fail(WL_ERR_ARG, "MultiLevelPoisson requires size=a2ⁿ, where n>2");
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return wl_fail(WL_ERR_CUDA, "wl_create: no CUDA device available (libwaterlily_b200 has no CPU fallback)");
+  if (device < 0 || device >= ndev) return wl_fail(WL_ERR_ARG, "wl_create: bad device ordinal");
+  Sim* sp = new (std::nothrow) Sim;
+  if (!sp) return wl_fail(WL_ERR_ARG, "out of host memory");
+  Sim& a = *sp;
+  a.D = D; a.device = device; a.nu = (float)nu; a.dt.push_back((float)dt0); a.exitBC = exitBC != 0; a.pois_kind = pois_kind;
+  int rc = 0;
+  cudaDeviceProp prop;
+  if ((rc = wl_cuda_check(a, cudaSetDevice(device), "cudaSetDevice")) ||
+      (rc = wl_cuda_check(a, cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties"))) { delete sp; return rc; }
+  a.nsm = prop.multiProcessorCount;
+  if ((rc = wl_cuda_check(a, cudaStreamCreateWithFlags(&a.stream, cudaStreamNonBlocking), "cudaStreamCreate"))) { delete sp; return rc; }
+  a.own_stream = true;
+  grid_set(a.g, D, Ng, perdir);
+  const int64_t c = a.g.comp;
+  a.u = dev_alloc(a, c * D, &rc); a.u0 = dev_alloc(a, c * D, &rc); a.f = dev_alloc(a, c * D, &rc);
+  a.p = dev_alloc(a, c, &rc); a.sigma = dev_alloc(a, c, &rc); a.V = dev_alloc(a, c * D, &rc);
+  a.mu0 = dev_alloc(a, c * D, &rc); a.mu1 = dev_alloc(a, c * D * D, &rc);
+  // solver scalars, reduction workspace, pinned readback
+  void* tmp = nullptr;
+  if (!rc && cudaMalloc(&tmp, sizeof(LevelScalars) * dims.size()) == cudaSuccess) { a.allocs.push_back(tmp); a.d_scalars = (LevelScalars*)tmp; cudaMemsetAsync(tmp, 0, sizeof(LevelScalars) * dims.size(), a.stream); } else if (!rc) rc = wl_fail(WL_ERR_CUDA, "cudaMalloc scalars");
+  if (!rc && cudaMalloc(&tmp, sizeof(MiscScalars)) == cudaSuccess) { a.allocs.push_back(tmp); a.d_misc = (MiscScalars*)tmp; cudaMemsetAsync(tmp, 0, sizeof(MiscScalars), a.stream); } else if (!rc) rc = wl_fail(WL_ERR_CUDA, "cudaMalloc misc");
+  if (!rc && cudaMalloc(&tmp, sizeof(double) * (WL_MAXBLOCKS * WL_MAXRED + 8)) == cudaSuccess) { a.allocs.push_back(tmp); a.ws.partials = (double*)tmp; } else if (!rc) rc = wl_fail(WL_ERR_CUDA, "cudaMalloc partials");
+  if (!rc && cudaMalloc(&tmp, 64) == cudaSuccess) { a.allocs.push_back(tmp); a.ws.ticket = (unsigned int*)tmp; cudaMemsetAsync(tmp, 0, 64, a.stream); } else if (!rc) rc = wl_fail(WL_ERR_CUDA, "cudaMalloc ticket");
+  if (!rc && cudaMallocHost((void**)&a.h_pinned, 64 * sizeof(float)) != cudaSuccess) rc = wl_fail(WL_ERR_CUDA, "cudaMallocHost");
+  if (rc) { wl_destroy((wl_sim*)sp); return rc; }
+  // levels[1] aliases the flow arrays (WaterLily.jl:77); r, ϵ, D, iD are its own (Poisson.jl:33-34)
+  for (size_t l = 0; l < dims.size() && !rc; ++l) {
+    Lvl lv{};
+    int n3[3] = {dims[l][0], dims[l][1], dims[l][2]};
+    grid_set(lv.g, D, n3, perdir);
+    lv.sc = a.d_scalars + l;
+    if (l == 0) { lv.x = a.p; lv.L = a.mu0; lv.z = a.sigma; }
+    else { lv.L = dev_alloc(a, lv.g.comp * D, &rc); lv.x = dev_alloc(a, lv.g.comp, &rc); lv.z = dev_alloc(a, lv.g.comp, &rc); }
+    lv.r = dev_alloc(a, lv.g.comp, &rc); lv.eps = dev_alloc(a, lv.g.comp, &rc);
+    lv.Dg = dev_alloc(a, lv.g.comp, &rc); lv.iD = dev_alloc(a, lv.g.comp, &rc);
+    a.levels.push_back(lv);
+  }
+  if (rc) { wl_destroy((wl_sim*)sp); return rc; }
+  // μ₀ = 1, BC!(μ₀,0) (Flow.jl:118-119); then the Poisson constructors' set_diag!/restrictL!
+  const double zero[3] = {0, 0, 0};
+  rc = wl_fill(a, a.mu0 - WL_OX, 1.f, c * D);
+  if (!rc) rc = bc_vec(a, a.g, a.mu0, zero, false, a.g.per);
+  if (!rc) rc = pois_update(a);
+  if (!rc) rc = wl_cuda_check(a, cudaStreamSynchronize(a.stream), "wl_create sync");
+  if (rc) { wl_destroy((wl_sim*)sp); return rc; }
+  *out = (wl_sim*)sp;
+  return WL_OK;
+}
+
+int wl_destroy(wl_sim* s) {
+  if (!s) return WL_OK;
+  Sim& a = S;
+  cudaSetDevice(a.device);
+  if (a.stream) cudaStreamSynchronize(a.stream);
+  for (void* p : a.allocs) cudaFree(p);
+  if (a.h_pinned) cudaFreeHost(a.h_pinned);
+  for (auto& pc : a.prof) for (cudaEvent_t e : pc.ev) cudaEventDestroy(e);
+  if (a.own_stream && a.stream) cudaStreamDestroy(a.stream);
+  delete &a;
+  return WL_OK;
+}
+const char* wl_last_error(void) { return g_err.c_str(); }
+int wl_set_stream(wl_sim* s, void* stream) {
+  GUARD(s);
+  cudaStreamSynchronize(S.stream);
+  if (S.own_stream && S.stream) cudaStreamDestroy(S.stream);
+  S.own_stream = false;
+  S.stream = (cudaStream_t)stream;
+  return WL_OK;
+}
+int wl_sync(wl_sim* s) { GUARD(s); return wl_cuda_check(S, cudaStreamSynchronize(S.stream), "wl_sync"); }
+
+int wl_field_count(wl_sim* s, int field, int64_t* count) {
+  GUARD(s);
+  int nc; if (!field_ptr(S, field, &nc)) return wl_fail(WL_ERR_ARG, "bad field");
+  *count = (int64_t)S.g.n[0] * S.g.n[1] * S.g.n[2] * nc;
+  return WL_OK;
+}
+int wl_upload(wl_sim* s, int field, const float* host, int64_t count) {
+  GUARD(s);
+  int nc; float* d = field_ptr(S, field, &nc);
+  if (!d || count != (int64_t)S.g.n[0] * S.g.n[1] * S.g.n[2] * nc) return wl_fail(WL_ERR_ARG, "wl_upload: bad field or size");
+  return copy_field(S, S.g, d, const_cast<float*>(host), nc, true);
+}
+int wl_download(wl_sim* s, int field, float* host, int64_t count) {
+  GUARD(s);
+  int nc; float* d = field_ptr(S, field, &nc);
+  if (!d || count != (int64_t)S.g.n[0] * S.g.n[1] * S.g.n[2] * nc) return wl_fail(WL_ERR_ARG, "wl_download: bad field or size");
+  return copy_field(S, S.g, d, host, nc, false);
+}
+int wl_nlevels(wl_sim* s) { return s ? (int)S.levels.size() : 0; }
+int wl_level_dims(wl_sim* s, int level, int* Ng) {
+  GUARD(s);
+  if (level < 0 || level >= (int)S.levels.size()) return wl_fail(WL_ERR_ARG, "bad level");
+  for (int k = 0; k < S.D; ++k) Ng[k] = S.levels[level].g.n[k];
+  return WL_OK;
+}
+int wl_level_upload(wl_sim* s, int level, int lf, const float* host, int64_t count) {
+  GUARD(s);
+  int nc; float* d = level_ptr(S, level, lf, &nc);
+  if (!d) return wl_fail(WL_ERR_ARG, "wl_level_upload: bad level/field");
+  const GridD& g = S.levels[level].g;
+  if (count != (int64_t)g.n[0] * g.n[1] * g.n[2] * nc) return wl_fail(WL_ERR_ARG, "wl_level_upload: bad size");
+  return copy_field(S, g, d, const_cast<float*>(host), nc, true);
+}
+int wl_level_download(wl_sim* s, int level, int lf, float* host, int64_t count) {
+  GUARD(s);
+  int nc; float* d = level_ptr(S, level, lf, &nc);
+  if (!d) return wl_fail(WL_ERR_ARG, "wl_level_download: bad level/field");
+  const GridD& g = S.levels[level].g;
+  if (count != (int64_t)g.n[0] * g.n[1] * g.n[2] * nc) return wl_fail(WL_ERR_ARG, "wl_level_download: bad size");
+  return copy_field(S, g, d, host, nc, false);
+}
+
+static void per_flags(Sim& a, const int* perdir, int* out) {
+  for (int k = 0; k < 3; ++k) out[k] = perdir ? (k < a.D && perdir[k] != 0) : a.g.per[k];
+}
+int wl_bc(wl_sim* s, int field, const double* A, int saveexit, const int* perdir) {
+  GUARD(s);
+  int nc; float* d = field_ptr(S, field, &nc);
+  if (!d || nc != S.D) return wl_fail(WL_ERR_ARG, "wl_bc: not a vector field");
+  int per[3]; per_flags(S, perdir, per);
+  int rc = bc_vec(S, S.g, d, A, saveexit != 0, per);
+  return rc ? rc : wl_sync(s);
+}
+int wl_exit_bc(wl_sim* s, const double* U, double dt) {
+  GUARD(s);
+  int rc = bc_exit(S, U, (float)dt);
+  return rc ? rc : wl_sync(s);
+}
+int wl_per_bc(wl_sim* s, int field, const int* perdir) {
+  GUARD(s);
+  int nc; float* d = field_ptr(S, field, &nc);
+  if (!d || nc != 1) return wl_fail(WL_ERR_ARG, "wl_per_bc: not a scalar field");
+  int per[3]; per_flags(S, perdir, per);
+  int rc = bc_per(S, S.g, d, per);
+  return rc ? rc : wl_sync(s);
+}
+int wl_conv_diff(wl_sim* s, int src) {
+  GUARD(s);
+  if (src != WL_U && src != WL_U0) return wl_fail(WL_ERR_ARG, "wl_conv_diff: src must be WL_U or WL_U0");
+  int rc = mom_conv_diff(S, src == WL_U ? S.u : S.u0, false, nullptr);
+  return rc ? rc : wl_sync(s);
+}
+int wl_accelerate(wl_sim* s, const double* g) { GUARD(s); int rc = mom_accelerate(S, g); return rc ? rc : wl_sync(s); }
+int wl_bdim(wl_sim* s) {
+  GUARD(s);
+  int rc = mom_bdim1(S);
+  if (!rc) rc = mom_bdim2(S, true, 1.f);
+  return rc ? rc : wl_sync(s);
+}
+int wl_scale_u(wl_sim* s, double scale) { GUARD(s); int rc = mom_scale_u(S, scale); return rc ? rc : wl_sync(s); }
+int wl_project(wl_sim* s, double w, int* n) { GUARD(s); int rc = mom_project(S, w, n); return rc ? rc : wl_sync(s); }
+int wl_cfl(wl_sim* s, double* dt) { GUARD(s); return mom_cfl(S, dt); }
+
+int wl_pois_update(wl_sim* s) { GUARD(s); int rc = pois_update(S); return rc ? rc : wl_sync(s); }
+int wl_pois_mult(wl_sim* s) { GUARD(s); int rc = pois_mult(S); return rc ? rc : wl_sync(s); }
+int wl_pois_residual(wl_sim* s, int level, double* r2) {
+  GUARD(s);
+  if (level < 0 || level >= (int)S.levels.size()) return wl_fail(WL_ERR_ARG, "bad level");
+  int rc = pois_residual(S, S.levels[level]);
+  if (!rc && r2) rc = pois_dot_rr(S, S.levels[level], r2);
+  return rc ? rc : wl_sync(s);
+}
+int wl_pois_jacobi(wl_sim* s, int level, int it) {
+  GUARD(s);
+  if (level < 0 || level >= (int)S.levels.size()) return wl_fail(WL_ERR_ARG, "bad level");
+  int rc = pois_jacobi(S, S.levels[level], it);
+  return rc ? rc : wl_sync(s);
+}
+int wl_pois_pcg(wl_sim* s, int level, int it) {
+  GUARD(s);
+  if (level < 0 || level >= (int)S.levels.size()) return wl_fail(WL_ERR_ARG, "bad level");
+  int rc = pois_pcg(S, level, it);
+  return rc ? rc : wl_sync(s);
+}
+int wl_pois_vcycle(wl_sim* s, int level) {
+  GUARD(s);
+  if (level < 0 || level + 1 >= (int)S.levels.size()) return wl_fail(WL_ERR_ARG, "bad level");
+  int rc = pois_vcycle(S, level);
+  return rc ? rc : wl_sync(s);
+}
+int wl_pois_solve(wl_sim* s, double tol, int itmx, int* n) {
+  GUARD(s);
+  if (tol < 0) tol = 1e-4;
+  if (itmx < 0) itmx = S.pois_kind == WL_POIS_MULTILEVEL ? 32 : 1000;
+  int rc = pois_solve(S, tol, itmx, n);
+  return rc ? rc : wl_sync(s);
+}
+int wl_mom_step(wl_sim* s, const double* U, const double* gp, const double* gc, double* dt_next, int* n_pred, int* n_corr) {
+  GUARD(s);
+  if (!U) return wl_fail(WL_ERR_ARG, "wl_mom_step: U is required");
+  return mom_step(S, U, gp, gc, dt_next, n_pred, n_corr);
+}
+int wl_get_dt(wl_sim* s, double* dt) { GUARD(s); *dt = (double)S.dt.back(); return WL_OK; }
+int wl_set_dt(wl_sim* s, double dt) { GUARD(s); S.dt.back() = (float)dt; return WL_OK; }
+int64_t wl_launch_count(wl_sim* s) { return s ? S.launches : 0; }
+int wl_profile(wl_sim* s, int on) {
+  GUARD(s);
+  S.profiling = on != 0;
+  for (auto& p : S.prof) { p.used = 0; p.ms = 0; p.launches = 0; p.bytes = 0; p.d_counter = nullptr; }
+  // pcg! kernels can be predicated off on the device: their traffic is counted from device counters
+  LevelScalars* sc = S.levels[0].sc;
+  const double cb = 4.0 * (double)S.g.interior;
+  S.prof[WL_PROF_PCG_MULT].d_counter = &sc->cnt_mult;     S.prof[WL_PROF_PCG_MULT].bytes_per_active = 6 * cb;
+  S.prof[WL_PROF_PCG_UPDATE].d_counter = &sc->cnt_update; S.prof[WL_PROF_PCG_UPDATE].bytes_per_active = 7 * cb;
+  S.prof[WL_PROF_PCG_DIR].d_counter = &sc->cnt_dir;       S.prof[WL_PROF_PCG_DIR].bytes_per_active = 4 * cb;
+  int rc = wl_read_scalars(S, sc, sizeof(LevelScalars));
+  if (rc) return rc;
+  LevelScalars h; memcpy(&h, S.h_pinned, sizeof(h));
+  S.prof[WL_PROF_PCG_MULT].counter_base = h.cnt_mult;
+  S.prof[WL_PROF_PCG_UPDATE].counter_base = h.cnt_update;
+  S.prof[WL_PROF_PCG_DIR].counter_base = h.cnt_dir;
+  return WL_OK;
+}
+int wl_profile_read(wl_sim* s, int which, double* ms, int64_t* launches, double* bytes) {
+  GUARD(s);
+  if (which < 0 || which >= WL_PROF_N) return wl_fail(WL_ERR_ARG, "bad profile class");
+  int rc = wl_cuda_check(S, cudaStreamSynchronize(S.stream), "profile sync");
+  if (rc) return rc;
+  ProfClass& p = S.prof[which];
+  for (size_t i = 0; i + 1 < p.used; i += 2) {
+    float t = 0;
+    if (cudaEventElapsedTime(&t, p.ev[i], p.ev[i + 1]) == cudaSuccess) p.ms += t;
+  }
+  p.used = 0;
+  if (p.d_counter) {  // active launches only
+    if ((rc = wl_read_scalars(S, p.d_counter, sizeof(int)))) return rc;
+    int c; memcpy(&c, S.h_pinned, sizeof(int));
+    p.launches = c - p.counter_base;
+    p.bytes = p.bytes_per_active * (double)p.launches;
+  }
+  if (ms) *ms = p.ms;
+  if (launches) *launches = p.launches;
+  if (bytes) *bytes = p.bytes;
+  return WL_OK;
+}
+
+int wl_profile_count(void) { return WL_PROF_N; }
+const char* wl_profile_name(int which) {
+  static const char* names[WL_PROF_N] = {"conv_diff+bdim1", "bdim2", "pcg_mult", "pcg_update", "pcg_dir", "pcg_init",
+                                         "increment", "residual", "project_misc", "solver", "mom_step"};
+  return (which >= 0 && which < WL_PROF_N) ? names[which] : "";
+}
+
+}  // extern "C"

@@ -1,0 +1,166 @@
+// wl_bc.cu — boundary-condition kernels: BC!, perBC!, exitBC! (reference src/util.jl:192-231).
+//
+// The reference applies BC! as D² sequential passes (component i outer, direction j inner) of
+// three tiny launches each, and relies on the pass order to fill edges and corners transitively.
+// Here ONE kernel per BC! resolves every ghost cell directly: walking the directions from the
+// last to the first, a cell written by pass j takes the value its source cell had when pass j
+// ran, which only earlier passes (smaller j) can have changed — so the source is resolved
+// recursively over smaller j until a cell no pass writes (or a Dirichlet constant) is reached.
+// All reads therefore hit cells the kernel never writes: no ordering hazards, same values.
+#include "wl_internal.h"
+
+namespace {
+
+struct BCArgs {
+  float A[3];
+  int per[3];
+  int saveexit;
+};
+
+// threads enumerate, for every direction j, the planes c[j] ∈ {0,1,n-1} in full (edge cells are
+// visited more than once and receive the same value each time)
+__device__ __forceinline__ bool planes_decode(const GridD& g, int64_t idx, int nplanes, int c[3]) {
+  c[0] = c[1] = c[2] = 0;
+  for (int j = 0; j < g.D; ++j) {
+    int64_t other = 1;
+    for (int k = 0; k < g.D; ++k) if (k != j) other *= g.n[k];
+    const int64_t cnt = nplanes * other;
+    if (idx < cnt) {
+      const int pl = (int)(idx / other);
+      int64_t q = idx % other;
+      for (int k = 0; k < g.D; ++k) {
+        if (k == j) continue;
+        c[k] = (int)(q % g.n[k]);
+        q /= g.n[k];
+      }
+      c[j] = nplanes == 3 ? (pl == 0 ? 0 : (pl == 1 ? 1 : g.n[j] - 1)) : (pl == 0 ? 0 : g.n[j] - 1);
+      return true;
+    }
+    idx -= cnt;
+  }
+  return false;
+}
+__host__ int64_t planes_count(const GridD& g, int nplanes) {
+  int64_t tot = 0;
+  for (int j = 0; j < g.D; ++j) {
+    int64_t other = 1;
+    for (int k = 0; k < g.D; ++k) if (k != j) other *= g.n[k];
+    tot += nplanes * other;
+  }
+  return tot;
+}
+
+// BC!(a,A,saveexit,perdir) (util.jl:192-210)
+__global__ void __launch_bounds__(256) k_bc_vec(GridD g, float* __restrict__ a, BCArgs args, int64_t count) {
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < count; idx += (int64_t)gridDim.x * blockDim.x) {
+    int c0[3];
+    if (!planes_decode(g, idx, 3, c0)) continue;
+    for (int i = 0; i < g.D; ++i) {
+      int c[3] = {c0[0], c0[1], c0[2]};
+      bool written = false, constant = false;
+      for (int j = g.D - 1; j >= 0; --j) {
+        const int n = g.n[j];
+        if (args.per[j]) {
+          if (c[j] == 0) { c[j] = n - 2; written = true; }
+          else if (c[j] == n - 1) { c[j] = 1; written = true; }
+        } else if (i == j) {
+          if (c[j] <= 1 || (c[j] == n - 1 && !(args.saveexit && i == 0))) { constant = true; written = true; break; }
+        } else {
+          if (c[j] == 0) { c[j] = 1; written = true; }
+          else if (c[j] == n - 1) { c[j] = n - 2; written = true; }
+        }
+      }
+      if (!written) continue;
+      float* ai = a + i * g.comp;
+      const float v = constant ? args.A[i] : ai[c[0] + c[1] * g.s[1] + c[2] * g.s[2]];
+      ai[c0[0] + c0[1] * g.s[1] + c0[2] * g.s[2]] = v;
+    }
+  }
+}
+
+// perBC!(a,perdir) (util.jl:227-231); `active` (may be null) predicates the launch on a running pcg!
+__global__ void __launch_bounds__(256) k_per_bc(GridD g, float* __restrict__ a, int p0, int p1, int p2, int64_t count, const int* active) {
+  if (active && !*active) return;
+  const int per[3] = {p0, p1, p2};
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < count; idx += (int64_t)gridDim.x * blockDim.x) {
+    int c0[3];
+    if (!planes_decode(g, idx, 2, c0)) continue;
+    int c[3] = {c0[0], c0[1], c0[2]};
+    bool written = false;
+    for (int j = g.D - 1; j >= 0; --j) {
+      if (!per[j]) continue;
+      if (c[j] == 0) { c[j] = g.n[j] - 2; written = true; }
+      else if (c[j] == g.n[j] - 1) { c[j] = 1; written = true; }
+    }
+    if (written) a[c0[0] + c0[1] * g.s[1] + c0[2] * g.s[2]] = a[c[0] + c[1] * g.s[1] + c[2] * g.s[2]];
+  }
+}
+
+// exitBC! (util.jl:216-222): 1-D convective update of the exit plane + its mean
+__global__ void __launch_bounds__(256) k_exit1(GridD g, float* __restrict__ u, const float* __restrict__ u0, double Udt, double U0,
+                                               ReduceWS ws, MiscScalars* misc) {
+  const int ny = g.n[1] - 2, nz = g.D > 2 ? g.n[2] - 2 : 1;
+  const int64_t count = (int64_t)ny * nz;
+  const int i = g.n[0] - 1;
+  float acc[1] = {0.f};
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < count; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int j = 1 + (int)(idx % ny), k = g.D > 2 ? 1 + (int)(idx / ny) : 0;
+    const int64_t I = i + j * g.s[1] + k * g.s[2];
+    const float v = (float)((double)u0[I] - Udt * (double)(u0[I] - u0[I - 1]));
+    u[I] = v;
+    acc[0] += v;
+  }
+  double tot[1];
+  if (grid_reduce<1>(acc, ws, tot)) {
+    const float mean = (float)tot[0] / (float)count;
+    misc->exit_mean_minus_U = (float)((double)mean - U0);
+  }
+}
+__global__ void __launch_bounds__(256) k_exit2(GridD g, float* __restrict__ u, const MiscScalars* misc) {
+  const int ny = g.n[1] - 2, nz = g.D > 2 ? g.n[2] - 2 : 1;
+  const int64_t count = (int64_t)ny * nz;
+  const int i = g.n[0] - 1;
+  const double du = (double)misc->exit_mean_minus_U;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < count; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int j = 1 + (int)(idx % ny), k = g.D > 2 ? 1 + (int)(idx / ny) : 0;
+    const int64_t I = i + j * g.s[1] + k * g.s[2];
+    u[I] = (float)((double)u[I] - du);
+  }
+}
+
+inline int flat_grid(int64_t count, int cap) {
+  int64_t b = (count + 255) / 256;
+  if (b < 1) b = 1;
+  return (int)(b > cap ? cap : b);
+}
+
+}  // namespace
+
+int bc_vec(Sim& s, const GridD& g, float* a, const double* A, bool saveexit, const int* per) {
+  BCArgs args;
+  for (int k = 0; k < 3; ++k) { args.A[k] = k < g.D ? (float)A[k] : 0.f; args.per[k] = k < g.D ? per[k] : 0; }
+  args.saveexit = saveexit ? 1 : 0;
+  const int64_t cnt = planes_count(g, 3);
+  k_bc_vec<<<flat_grid(cnt, s.nsm * 8), 256, 0, s.stream>>>(g, a, args, cnt);
+  ++s.launches;
+  return wl_cuda_check(s, cudaGetLastError(), "k_bc_vec");
+}
+
+int bc_per(Sim& s, const GridD& g, float* a, const int* per, const int* active) {
+  bool any = false;
+  for (int k = 0; k < g.D; ++k) any |= per[k] != 0;
+  if (!any) return 0;  // perBC!(a,::Tuple{}) = nothing
+  const int64_t cnt = planes_count(g, 2);
+  k_per_bc<<<flat_grid(cnt, s.nsm * 8), 256, 0, s.stream>>>(g, a, per[0], g.D > 1 ? per[1] : 0, g.D > 2 ? per[2] : 0, cnt, active);
+  ++s.launches;
+  return wl_cuda_check(s, cudaGetLastError(), "k_per_bc");
+}
+
+int bc_exit(Sim& s, const double* U, float dt) {
+  const GridD& g = s.g;
+  const int64_t cnt = (int64_t)(g.n[1] - 2) * (g.D > 2 ? g.n[2] - 2 : 1);
+  k_exit1<<<flat_grid(cnt, 256), 256, 0, s.stream>>>(g, s.u, s.u0, U[0] * (double)dt, U[0], s.ws, s.d_misc);
+  k_exit2<<<flat_grid(cnt, 256), 256, 0, s.stream>>>(g, s.u, s.d_misc);
+  s.launches += 2;
+  return wl_cuda_check(s, cudaGetLastError(), "k_exit");
+}

@@ -1,0 +1,203 @@
+// wl_common.cuh — shared device/host definitions of libwaterlily_b200.so (sm_100a only).
+//
+// Data layout in HBM: every field keeps the reference's padded, x-fastest,
+// component-last (SoA) layout, but rows are re-pitched so that the first interior cell of each
+// row is 16-byte aligned (float4 loads) — cell (i,j,k) (0-based, ghosts at 0 and n-1) of a scalar
+// field lives at  base + i + j*s1 + k*s2,  base = alloc + OX, s1 = pitch (multiple of 4),
+// s2 = s1*n[1].  Component c of a vector field starts at c*comp floats.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define WL_OX 3  // row offset: interior cell i=1 lands on a 16-byte boundary
+
+struct GridD {
+  int D;
+  int n[3];        // padded size (1 for dims >= D)
+  int per[3];      // periodic flags
+  int64_t s[3];    // strides in floats: 1, pitch, pitch*n[1]
+  int64_t comp;    // floats per scalar field (allocation, incl. WL_OX and row padding)
+  int64_t interior;  // product of (n-2) over the D dims
+};
+
+// device-resident solver scalars of one Poisson level (src/Poisson.jl:123-144 keeps these on the
+// host; here every data-dependent decision of pcg! is taken on the device)
+struct LevelScalars {
+  float rho;        // r⋅z
+  float alpha;
+  float beta;
+  float r2;         // L₂ = r⋅r, refreshed by every kernel that writes r
+  float rsum;       // mean of r in residual!
+  float ghost_dot;  // Σ over the ghost shell of z·ϵ (level 1 only: z ≡ σ holds stale Φ)
+  int active;       // pcg! still iterating
+  int need_sub;     // residual!: |s| > 2eps → subtract the mean
+  int cnt_mult, cnt_update, cnt_dir;  // pcg! kernels that actually ran (not predicated off)
+};
+
+struct Lvl {
+  GridD g;
+  float *L, *Dg, *iD, *x, *eps, *r, *z;
+  LevelScalars* sc;
+};
+
+// scratch for deterministic two-stage reductions: per-block partials + a ticket
+struct ReduceWS {
+  double* partials;   // [maxBlocks * WL_MAXRED]
+  unsigned int* ticket;
+};
+#define WL_MAXRED 4
+#define WL_MAXBLOCKS 4096
+
+#ifdef __CUDACC__
+
+#define WL_EPS32 1.1920929e-07f
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Block-level sum of NR per-thread float accumulators (warp shuffles, then one smem hop),
+// followed by a grid-level combine through per-block partials: the LAST block to arrive (ticket)
+// adds the partials in a fixed order in double and returns true on its thread 0 with the totals.
+// Deterministic for a fixed launch geometry.  All threads of the block must call it.
+template <int NR, bool MAX = false>
+__device__ __forceinline__ bool grid_reduce(const float (&v)[NR], ReduceWS ws, double (&tot)[NR]) {
+  __shared__ double sm[NR][32];
+  __shared__ bool last;
+  const int tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+  const int nthr = blockDim.x * blockDim.y * blockDim.z;
+  const int lane = tid & 31, warp = tid >> 5, nwarp = (nthr + 31) >> 5;
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    const float w = MAX ? warp_max(v[r]) : warp_sum(v[r]);
+    if (lane == 0) sm[r][warp] = (double)w;
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      double a = lane < nwarp ? sm[r][lane] : (MAX ? -1e300 : 0.0);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double b = __shfl_xor_sync(0xffffffffu, a, o);
+        a = MAX ? fmax(a, b) : a + b;
+      }
+      if (lane == 0) ws.partials[(size_t)blockIdx.x * WL_MAXRED + r] = a;
+    }
+  }
+  if (tid == 0) {
+    __threadfence();
+    const unsigned int t = atomicAdd(ws.ticket, 1u);
+    last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!last) return false;
+  __threadfence();
+  // last block: fixed-order combine of gridDim.x partials
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    double a = MAX ? -1e300 : 0.0;
+    for (unsigned int b = tid; b < gridDim.x; b += nthr) {
+      const double p = ((volatile double*)ws.partials)[(size_t)b * WL_MAXRED + r];
+      a = MAX ? fmax(a, p) : a + p;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double b = __shfl_xor_sync(0xffffffffu, a, o);
+      a = MAX ? fmax(a, b) : a + b;
+    }
+    __syncthreads();
+    if (lane == 0) sm[r][warp] = a;
+  }
+  __syncthreads();
+  if (tid == 0) {
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      double a = MAX ? -1e300 : 0.0;
+      for (int w = 0; w < nwarp; ++w) a = MAX ? fmax(a, sm[r][w]) : a + sm[r][w];
+      tot[r] = a;
+    }
+    *ws.ticket = 0u;  // re-arm for the next launch on this stream
+    return true;
+  }
+  return false;
+}
+
+#endif  // __CUDACC__
+
+#ifdef __CUDACC__
+// Walk the cell box [lo,hi] (0-based, inclusive, per dim) with a persistent grid: tiles of
+// blockDim cells, grid-stride over tiles, threadIdx.x along x (coalesced rows).
+struct Box { int lo[3], hi[3]; };
+__host__ __device__ inline Box box_interior(const GridD& g) {
+  Box b;
+  for (int k = 0; k < 3; ++k) { b.lo[k] = k < g.D ? 1 : 0; b.hi[k] = k < g.D ? g.n[k] - 2 : 0; }
+  return b;
+}
+__host__ __device__ inline Box box_all(const GridD& g) {
+  Box b;
+  for (int k = 0; k < 3; ++k) { b.lo[k] = 0; b.hi[k] = g.n[k] - 1; }
+  return b;
+}
+__host__ inline int64_t box_tiles(const Box& b, dim3 blk) {
+  const int e[3] = {b.hi[0] - b.lo[0] + 1, b.hi[1] - b.lo[1] + 1, b.hi[2] - b.lo[2] + 1};
+  const int bd[3] = {(int)blk.x, (int)blk.y, (int)blk.z};
+  int64_t n = 1;
+  for (int k = 0; k < 3; ++k) n *= (e[k] + bd[k] - 1) / bd[k];
+  return n;
+}
+template <class F>
+__device__ __forceinline__ void for_cells(const GridD& g, const Box& b, F&& f) {
+  const int ntx = (b.hi[0] - b.lo[0] + blockDim.x) / blockDim.x;
+  const int nty = (b.hi[1] - b.lo[1] + blockDim.y) / blockDim.y;
+  const int ntz = (b.hi[2] - b.lo[2] + blockDim.z) / blockDim.z;
+  const int64_t ntiles = (int64_t)ntx * nty * ntz;
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int tx = (int)(t % ntx);
+    const int64_t q = t / ntx;
+    const int ty = (int)(q % nty), tz = (int)(q / nty);
+    const int i = b.lo[0] + tx * blockDim.x + threadIdx.x;
+    const int j = b.lo[1] + ty * blockDim.y + threadIdx.y;
+    const int k = b.lo[2] + tz * blockDim.z + threadIdx.z;
+    if (i <= b.hi[0] && j <= b.hi[1] && k <= b.hi[2]) f(i, j, k, (int64_t)i + j * g.s[1] + k * g.s[2]);
+  }
+}
+// unique enumeration of the ghost shell: last dim's two planes in full, then the next dim's
+// planes restricted to the interior of the dims above it, ...
+__device__ __forceinline__ bool shell_decode(const GridD& g, int64_t idx, int c[3]) {
+  c[0] = c[1] = c[2] = 0;
+  for (int d = g.D - 1; d >= 0; --d) {
+    int64_t below = 1, above = 1;
+    for (int k = 0; k < d; ++k) below *= g.n[k];
+    for (int k = d + 1; k < g.D; ++k) above *= g.n[k] - 2;
+    const int64_t cnt = 2 * below * above;
+    if (idx < cnt) {
+      const int64_t half = below * above;
+      c[d] = idx < half ? 0 : g.n[d] - 1;
+      int64_t q = idx < half ? idx : idx - half;
+      for (int k = 0; k < d; ++k) { c[k] = (int)(q % g.n[k]); q /= g.n[k]; }
+      for (int k = d + 1; k < g.D; ++k) { c[k] = 1 + (int)(q % (g.n[k] - 2)); q /= (g.n[k] - 2); }
+      return true;
+    }
+    idx -= cnt;
+  }
+  return false;
+}
+__host__ __device__ inline int64_t shell_count(const GridD& g) {
+  int64_t all = 1, in = 1;
+  for (int k = 0; k < g.D; ++k) { all *= g.n[k]; in *= g.n[k] - 2; }
+  return all - in;
+}
+#endif

@@ -1,0 +1,115 @@
+// wl_internal.h — host-side state of one wl_sim handle and the launch functions shared by the
+// translation units of libwaterlily_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/waterlily_b200.h"
+#include "wl_common.cuh"
+
+// profiled kernel classes (wl_profile_read `which`)
+enum {
+  WL_PROF_CONVDIFF = 0,   // conv_diff!+accelerate!+BDIM! stage 1 (one kernel)
+  WL_PROF_BDIM2,          // BDIM! stage 2 (+scale_u!)
+  WL_PROF_PCG_MULT,       // fine level: z = Aϵ, z⋅ϵ
+  WL_PROF_PCG_UPDATE,     // fine level: x += αϵ, r -= αz, r⋅z, r⋅r
+  WL_PROF_PCG_DIR,        // fine level: ϵ = βϵ + r·iD
+  WL_PROF_PCG_INIT,       // fine level: ϵ = r·iD, r⋅z
+  WL_PROF_INCREMENT,      // fine level: increment! (r -= Aϵ, x += ϵ)
+  WL_PROF_RESIDUAL,       // fine level: residual!
+  WL_PROF_PROJECT,        // div, x scaling, pressure correction
+  WL_PROF_SOLVER,         // whole solver! call (all levels)
+  WL_PROF_STEP,           // whole mom_step!
+  WL_PROF_N
+};
+
+struct ProfClass {
+  std::vector<cudaEvent_t> ev;  // start/stop pairs
+  size_t used = 0;
+  double ms = 0;
+  int64_t launches = 0;
+  double bytes = 0;
+  const int* d_counter = nullptr;  // device-side count of launches that were not predicated off
+  double bytes_per_active = 0;     // algorithmic bytes of one active launch (with d_counter)
+  int counter_base = 0;
+};
+
+// device scratch scalars shared by the momentum kernels
+struct MiscScalars {
+  float exit_mean_minus_U;  // ∮u of exitBC!
+  float cfl_max;            // max over padded σ
+  float pad[6];
+};
+
+struct Sim {
+  int D = 0;
+  GridD g{};
+  int device = 0;
+  int nsm = 148;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  // flow fields (pointers already offset by WL_OX); u/u0 are swapped by mom_step
+  float *u = nullptr, *u0 = nullptr, *f = nullptr, *p = nullptr, *sigma = nullptr, *V = nullptr, *mu0 = nullptr, *mu1 = nullptr;
+  std::vector<void*> allocs;
+  float nu = 0.f;
+  std::vector<float> dt;
+  bool exitBC = false;
+  int pois_kind = WL_POIS_MULTILEVEL;
+  std::vector<Lvl> levels;
+  LevelScalars* d_scalars = nullptr;  // one per level
+  MiscScalars* d_misc = nullptr;
+  ReduceWS ws{};
+  float* h_pinned = nullptr;  // pinned readback buffer (64 floats)
+  std::vector<int> n_log;
+  int64_t launches = 0;
+  int sticky = 0;  // first CUDA error, sticky per handle
+  bool profiling = false;
+  ProfClass prof[WL_PROF_N];
+};
+
+int wl_fail(int code, const std::string& msg);
+int wl_cuda_check(Sim& s, cudaError_t e, const char* what);
+#define WL_CUDA(s, call) do { int _rc = wl_cuda_check((s), (call), #call); if (_rc) return _rc; } while (0)
+
+// launch geometry
+dim3 wl_pick_block(const GridD& g);
+int wl_grid_for(const Sim& s, int64_t ntiles);
+
+// profiling brackets (no-ops unless wl_profile(s,1))
+void wl_prof_begin(Sim& s, int cls);
+void wl_prof_end(Sim& s, int cls, double bytes);
+
+// ---- wl_bc.cu ----
+int bc_vec(Sim& s, const GridD& g, float* a, const double* A, bool saveexit, const int* per);
+int bc_per(Sim& s, const GridD& g, float* a, const int* per, const int* active = nullptr);
+int bc_exit(Sim& s, const double* U, float dt);
+
+// ---- wl_poisson.cu ----
+int pois_set_diag(Sim& s, Lvl& l);
+int pois_restrictL(Sim& s, Lvl& coarse, const Lvl& fine);
+int pois_update(Sim& s);
+int pois_mult(Sim& s);
+int pois_residual(Sim& s, Lvl& l);
+int pois_jacobi(Sim& s, Lvl& l, int it);
+int pois_pcg(Sim& s, int level, int it);
+int pois_vcycle(Sim& s, int level);
+int pois_solve(Sim& s, double tol, int itmx, int* n);
+int pois_dot_rr(Sim& s, Lvl& l, double* out);
+
+// ---- wl_momentum.cu ----
+int mom_conv_diff(Sim& s, const float* src, bool fuse_bdim1, const double* g);
+int mom_accelerate(Sim& s, const double* g);
+int mom_bdim1(Sim& s);
+int mom_bdim2(Sim& s, bool accumulate, float scale);
+int mom_scale_u(Sim& s, double scale);
+int mom_project(Sim& s, double w, int* n);
+int mom_cfl(Sim& s, double* dt);
+int mom_step(Sim& s, const double* U, const double* gp, const double* gc, double* dt_next, int* n_pred, int* n_corr);
+
+// generic helpers (wl_api.cu)
+int wl_fill(Sim& s, float* p, float v, int64_t n);
+int wl_scale_all(Sim& s, float* p, const GridD& g, double factor, bool divide, bool f32);
+int wl_read_scalars(Sim& s, const void* dptr, size_t bytes);  // → h_pinned, synchronises the stream

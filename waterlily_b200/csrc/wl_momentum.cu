@@ -1,0 +1,365 @@
+// wl_momentum.cu — momentum-step kernels (reference src/Flow.jl): conv_diff! (QUICK/central flux
+// stencil), accelerate!, BDIM!, scale_u!, project! (div / pressure correction), CFL, mom_step!.
+//
+// Fusion relative to the reference's pass structure:
+//  * conv_diff!'s 1+4D² single-statement launches are ONE kernel that, per cell and component,
+//    accumulates the 2D face fluxes in the reference's order; `accelerate!` and BDIM! stage 1
+//    (f = u⁰ + Δt·f − V) are applied in the same kernel before the only store of f;
+//  * `u⁰ .= u` is a pointer swap and `scale_u!` is folded into BDIM! stage 2;
+//  * the reference's ghost-layer side effects are reproduced: r/f on the upper ghost layer (Q0)
+//    and the stale flux Φ left in σ's ghosts (Q1/Q2) — the kernel covers the padded box and
+//    evaluates exactly the passes that reach each ghost cell.
+// Float64 sub-expressions follow Julia's promotion rules.
+#include <algorithm>
+
+#include "wl_internal.h"
+
+namespace {
+
+// median (Flow.jl:25-34)
+__device__ __forceinline__ float median3(float a, float b, float c) {
+  if (a > b) { if (b >= c) return b; if (a > c) return c; }
+  else { if (b <= c) return b; if (a < c) return c; }
+  return a;
+}
+// quick (Flow.jl:4)
+__device__ __forceinline__ float quick(float u, float c, float d) { return median3((5 * c + 2 * d - u) / 6, c, median3(10 * c - 9 * u, c, d)); }
+
+struct CDArgs {
+  GridD g;
+  const float* u;    // field being differenced (u⁰ in the predictor, u in the corrector)
+  const float* u0;   // BDIM stage 1 operands
+  const float* V;
+  float* f;
+  float* sigma;      // Φ scratch ≡ flow.σ: only its ghost layer is materialised
+  float nu, dt;
+  double gacc[3];
+  int has_g;
+  int fuse_bdim1;
+};
+
+// Φ[I] of the inner loop (Flow.jl:45) / periodic lower boundary (:58-59); `upup` is the offset of the
+// upwind-upwind sample (−2sj, or the periodic wrap to N[j]-2).
+__device__ __forceinline__ float phi_face(const float* __restrict__ ui, const float* __restrict__ uj, int64_t I, int64_t si, int64_t sj,
+                                          int64_t upup, float nu) {
+  const float uf = (uj[I] + uj[I - si]) * 0.5f;  // ϕ(i,CI(I,j),u): exact in Float32
+  const float c = ui[I], m = ui[I - sj];
+  const float q = uf > 0 ? quick(ui[I + upup], m, c) : quick(ui[I + sj], c, m);
+  return (float)((double)uf * (double)q - (double)(nu * (c - m)));
+}
+
+template <int D>
+__device__ __forceinline__ void convdiff_cell(const CDArgs& a, const int (&c)[3], int64_t I, float (&r)[D]) {
+  const GridD& g = a.g;
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    const float* ui = a.u + i * g.comp;
+    const int64_t si = g.s[i];
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      const int n = g.n[j], cj = c[j];
+      if (cj < 1 || cj > n - 2) continue;  // no pass of direction j reaches a j-ghost cell
+      const float* uj = a.u + j * g.comp;
+      const int64_t sj = g.s[j];
+      // flux through the lower j-face: lowerBoundary! (Flow.jl:54,58) or inner loop (:45-46)
+      if (cj == 1) {
+        if (g.per[j]) {
+          acc += phi_face(ui, uj, I, si, sj, (int64_t)(n - 4) * sj, a.nu);
+        } else {  // ϕuL, accumulated in Float64
+          const double uf = (double)(uj[I] + uj[I - si]) * 0.5;
+          const double fl = uf > 0 ? uf * ((double)(ui[I] + ui[I - sj]) * 0.5) : uf * (double)quick(ui[I + sj], ui[I], ui[I - sj]);
+          acc = (float)((double)acc + (fl - (double)(a.nu * (ui[I] - ui[I - sj]))));
+        }
+      } else {
+        acc += phi_face(ui, uj, I, si, sj, -2 * sj, a.nu);
+      }
+      // flux through the upper j-face: inner loop (:47) or upperBoundary! (:55,60)
+      if (cj == n - 2) {
+        if (g.per[j]) {
+          acc -= phi_face(ui, uj, I + (int64_t)(1 - cj) * sj, si, sj, (int64_t)(n - 4) * sj, a.nu);
+        } else {  // ϕuR
+          const int64_t J = I + sj;
+          const double uf = (double)(uj[J] + uj[J - si]) * 0.5;
+          const double fl = uf < 0 ? uf * ((double)(ui[J] + ui[J - sj]) * 0.5) : uf * (double)quick(ui[J - 2 * sj], ui[J - sj], ui[J]);
+          acc = (float)((double)acc + (-fl + (double)(a.nu * (ui[J] - ui[J - sj]))));
+        }
+      } else {
+        acc -= phi_face(ui, uj, I + sj, si, sj, -2 * sj, a.nu);
+      }
+    }
+    r[i] = acc;
+  }
+}
+
+// conv_diff! (+ accelerate! + BDIM! stage 1) over the padded box
+template <int D>
+__global__ void __launch_bounds__(256) k_conv_diff(CDArgs a) {
+  const GridD& g = a.g;
+  const Box b = box_all(g);
+  for_cells(g, b, [&](int i0, int j0, int k0, int64_t I) {
+    const int c[3] = {i0, j0, k0};
+    float r[D];
+    bool lowghost = false, ghost = false;
+#pragma unroll
+    for (int k = 0; k < D; ++k) { lowghost |= c[k] == 0; ghost |= c[k] == g.n[k] - 1; }
+    if (lowghost) {
+#pragma unroll
+      for (int i = 0; i < D; ++i) r[i] = 0.f;  // index-1 ghosts are never written (r .= 0)
+    } else {
+      convdiff_cell<D>(a, c, I, r);
+      if (ghost) {
+        // stale Φ: last pass (i=D, largest j) that covers this upper-ghost cell
+        for (int j = D - 1; j >= 0; --j) {
+          const int lo = g.per[j] ? 1 : 2;
+          if (c[j] >= lo && c[j] <= g.n[j] - 2) {
+            const int64_t sj = g.s[j];
+            a.sigma[I] = phi_face(a.u + (D - 1) * g.comp, a.u + j * g.comp, I, g.s[D - 1], sj,
+                                  c[j] == 1 ? (int64_t)(g.n[j] - 4) * sj : -2 * sj, a.nu);
+            break;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      float v = r[i];
+      if (a.has_g) v = (float)((double)v + a.gacc[i]);          // accelerate! (Flow.jl:68-70)
+      if (a.fuse_bdim1) v = a.u0[I + i * g.comp] + a.dt * v - a.V[I + i * g.comp];  // BDIM! stage 1 (:133)
+      a.f[I + i * g.comp] = v;
+    }
+  });
+}
+
+// accelerate! alone (API parity hook)
+__global__ void __launch_bounds__(256) k_accelerate(GridD g, float* f, double g0, double g1, double g2) {
+  const double ga[3] = {g0, g1, g2};
+  const Box b = box_all(g);
+  for_cells(g, b, [&](int, int, int, int64_t I) {
+    for (int i = 0; i < g.D; ++i) f[I + i * g.comp] = (float)((double)f[I + i * g.comp] + ga[i]);
+  });
+}
+// BDIM! stage 1 alone (API parity hook)
+__global__ void __launch_bounds__(256) k_bdim1(GridD g, float* f, const float* u0, const float* V, float dt) {
+  const Box b = box_all(g);
+  for_cells(g, b, [&](int, int, int, int64_t I) {
+    for (int i = 0; i < g.D; ++i) { const int64_t Ii = I + i * g.comp; f[Ii] = u0[Ii] + dt * f[Ii] - V[Ii]; }
+  });
+}
+
+// BDIM! stage 2 (Flow.jl:134) with μddn (:18-24); `accumulate`=0 folds the predictor's
+// scale_u!(a,0), `scale` folds the corrector's scale_u!(a,0.5)
+template <int D>
+__global__ void __launch_bounds__(256) k_bdim2(GridD g, float* __restrict__ u, const float* __restrict__ f, const float* __restrict__ V,
+                                               const float* __restrict__ mu0, const float* __restrict__ mu1, int accumulate, float scale) {
+  const Box b = box_interior(g);
+  for_cells(g, b, [&](int, int, int, int64_t I) {
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      const int64_t Ii = I + i * g.comp;
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < D; ++j) s += mu1[I + (i + D * j) * g.comp] * (f[Ii + g.s[j]] - f[Ii - g.s[j]]);
+      const double add = (0.5 * (double)s + (double)V[Ii]) + (double)(mu0[Ii] * f[Ii]);
+      const float un = (float)((accumulate ? (double)u[Ii] : 0.0) + add);
+      u[Ii] = un * scale;
+    }
+  });
+}
+__global__ void __launch_bounds__(256) k_scale_u(GridD g, float* u, double scale) {
+  const Box b = box_interior(g);
+  for_cells(g, b, [&](int, int, int, int64_t I) {
+    for (int i = 0; i < g.D; ++i) u[I + i * g.comp] = (float)((double)u[I + i * g.comp] * scale);
+  });
+}
+
+// project!: z = div(u) (Flow.jl:139, :11-17)
+template <int D>
+__global__ void __launch_bounds__(256) k_div(GridD g, const float* __restrict__ u, float* __restrict__ z) {
+  const Box b = box_interior(g);
+  for_cells(g, b, [&](int, int, int, int64_t I) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < D; ++i) s += u[I + g.s[i] + i * g.comp] - u[I + i * g.comp];
+    z[I] = s;
+  });
+}
+// project!: u[I,i] -= L[I,i]*∂(i,I,x) (Flow.jl:141-143)
+template <int D>
+__global__ void __launch_bounds__(256) k_project_correct(GridD g, float* __restrict__ u, const float* __restrict__ L, const float* __restrict__ x) {
+  const Box b = box_interior(g);
+  for_cells(g, b, [&](int, int, int, int64_t I) {
+    const float xc = x[I];
+#pragma unroll
+    for (int i = 0; i < D; ++i) u[I + i * g.comp] -= L[I + i * g.comp] * (xc - x[I - g.s[i]]);
+  });
+}
+// x .*= dt / x ./= dt over the padded array (Flow.jl:139,144)
+__global__ void __launch_bounds__(256) k_scale_all(GridD g, float* x, float f32v, double f64v, int divide, int f32) {
+  const Box b = box_all(g);
+  for_cells(g, b, [&](int, int, int, int64_t I) {
+    const float v = x[I];
+    x[I] = f32 ? (divide ? v / f32v : v * f32v) : (divide ? (float)((double)v / f64v) : (float)((double)v * f64v));
+  });
+}
+
+// CFL: σ = flux_out (Flow.jl:173,176-182) + interior max
+template <int D>
+__global__ void __launch_bounds__(256) k_cfl(GridD g, const float* __restrict__ u, float* __restrict__ sigma, ReduceWS ws, MiscScalars* misc) {
+  const Box b = box_interior(g);
+  float acc[1] = {0.f};
+  for_cells(g, b, [&](int, int, int, int64_t I) {
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < D; ++i) s += fmax(0., (double)u[I + g.s[i] + i * g.comp]) + fmax(0., (double)-u[I + i * g.comp]);
+    const float v = (float)s;
+    sigma[I] = v;
+    acc[0] = fmaxf(acc[0], v);
+  });
+  double tot[1];
+  if (grid_reduce<1, true>(acc, ws, tot)) misc->cfl_max = (float)tot[0];
+}
+// the reference takes maximum(σ) over the PADDED array (Flow.jl:174): fold in the ghost shell, which
+// holds the corrector's stale Φ.  Shell = cells with any coordinate on a boundary.
+__global__ void __launch_bounds__(256) k_shell_max(GridD g, const float* __restrict__ sigma, ReduceWS ws, MiscScalars* misc, int64_t count) {
+  float acc[1] = {-3.4e38f};
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < count; idx += (int64_t)gridDim.x * blockDim.x) {
+    int c[3];
+    if (shell_decode(g, idx, c)) acc[0] = fmaxf(acc[0], sigma[c[0] + c[1] * g.s[1] + c[2] * g.s[2]]);
+  }
+  double tot[1];
+  if (grid_reduce<1, true>(acc, ws, tot)) misc->cfl_max = fmaxf(misc->cfl_max, (float)tot[0]);
+}
+// with exitBC the exit plane of u₁ survives from step to step (saveexit); after the u/u⁰ pointer swap
+// it has to be carried over explicitly
+__global__ void __launch_bounds__(256) k_copy_exit_plane(GridD g, float* __restrict__ u, const float* __restrict__ u0) {
+  const int ny = g.n[1], nz = g.n[2];
+  const int64_t count = (int64_t)ny * nz;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < count; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t I = (g.n[0] - 1) + (idx % ny) * g.s[1] + (idx / ny) * g.s[2];
+    u[I] = u0[I];
+  }
+}
+
+}  // namespace
+
+#define LAUNCH(s, kern, ntiles, blk, ...)                                        \
+  do {                                                                            \
+    kern<<<wl_grid_for((s), (ntiles)), (blk), 0, (s).stream>>>(__VA_ARGS__);      \
+    ++(s).launches;                                                               \
+  } while (0)
+#define LAUNCH_D(s, kern, D, ntiles, blk, ...)                                   \
+  do {                                                                            \
+    if ((D) == 2) LAUNCH(s, kern<2>, ntiles, blk, __VA_ARGS__);                   \
+    else LAUNCH(s, kern<3>, ntiles, blk, __VA_ARGS__);                            \
+  } while (0)
+
+int mom_conv_diff(Sim& s, const float* src, bool fuse_bdim1, const double* gacc) {
+  CDArgs a;
+  a.g = s.g; a.u = src; a.u0 = s.u0; a.V = s.V; a.f = s.f; a.sigma = s.sigma;
+  a.nu = s.nu; a.dt = s.dt.back();
+  a.has_g = gacc ? 1 : 0;
+  for (int k = 0; k < 3; ++k) a.gacc[k] = (gacc && k < s.D) ? gacc[k] : 0.0;
+  a.fuse_bdim1 = fuse_bdim1 ? 1 : 0;
+  const dim3 blk = wl_pick_block(s.g);
+  wl_prof_begin(s, WL_PROF_CONVDIFF);
+  LAUNCH_D(s, k_conv_diff, s.D, box_tiles(box_all(s.g), blk), blk, a);
+  // algorithmic words/cell: read u (D) [+ u⁰, V (2D)], write f (D)
+  wl_prof_end(s, WL_PROF_CONVDIFF, 4.0 * (double)s.g.interior * (fuse_bdim1 ? (src == s.u0 ? 3 : 4) * s.D : 2 * s.D));
+  return wl_cuda_check(s, cudaGetLastError(), "k_conv_diff");
+}
+int mom_accelerate(Sim& s, const double* g) {
+  if (!g) return 0;
+  const dim3 blk = wl_pick_block(s.g);
+  LAUNCH(s, k_accelerate, box_tiles(box_all(s.g), blk), blk, s.g, s.f, g[0], s.D > 1 ? g[1] : 0.0, s.D > 2 ? g[2] : 0.0);
+  return wl_cuda_check(s, cudaGetLastError(), "k_accelerate");
+}
+int mom_bdim1(Sim& s) {
+  const dim3 blk = wl_pick_block(s.g);
+  LAUNCH(s, k_bdim1, box_tiles(box_all(s.g), blk), blk, s.g, s.f, s.u0, s.V, s.dt.back());
+  return wl_cuda_check(s, cudaGetLastError(), "k_bdim1");
+}
+int mom_bdim2(Sim& s, bool accumulate, float scale) {
+  const dim3 blk = wl_pick_block(s.g);
+  wl_prof_begin(s, WL_PROF_BDIM2);
+  LAUNCH_D(s, k_bdim2, s.D, box_tiles(box_interior(s.g), blk), blk, s.g, s.u, s.f, s.V, s.mu0, s.mu1, accumulate ? 1 : 0, scale);
+  // read f, V, μ₀ (3D), μ₁ (D²) [+ u (D)], write u (D)
+  wl_prof_end(s, WL_PROF_BDIM2, 4.0 * (double)s.g.interior * ((accumulate ? 5 : 4) * s.D + s.D * s.D));
+  return wl_cuda_check(s, cudaGetLastError(), "k_bdim2");
+}
+int mom_scale_u(Sim& s, double scale) {
+  const dim3 blk = wl_pick_block(s.g);
+  LAUNCH(s, k_scale_u, box_tiles(box_interior(s.g), blk), blk, s.g, s.u, scale);
+  return wl_cuda_check(s, cudaGetLastError(), "k_scale_u");
+}
+int wl_scale_all(Sim& s, float* p, const GridD& g, double factor, bool divide, bool f32) {
+  const dim3 blk = wl_pick_block(g);
+  LAUNCH(s, k_scale_all, box_tiles(box_all(g), blk), blk, g, p, (float)factor, factor, divide ? 1 : 0, f32 ? 1 : 0);
+  return wl_cuda_check(s, cudaGetLastError(), "k_scale_all");
+}
+// project!(a,b,w) (Flow.jl:137-145)
+int mom_project(Sim& s, double w, int* n) {
+  const float dt32 = s.dt.back();
+  const bool f32 = (w == 1.0);                 // dt = w*Δt: Float32 for the Int w=1, Float64 for w=0.5
+  const double dtw = f32 ? (double)dt32 : w * (double)dt32;
+  Lvl& b = s.levels[0];
+  const dim3 blk = wl_pick_block(s.g);
+  wl_prof_begin(s, WL_PROF_PROJECT);
+  LAUNCH_D(s, k_div, s.D, box_tiles(box_interior(s.g), blk), blk, s.g, s.u, b.z);
+  int rc = wl_scale_all(s, b.x, s.g, dtw, false, f32);
+  wl_prof_end(s, WL_PROF_PROJECT, 4.0 * (double)s.g.interior * (s.D + 1 + 2));
+  if (rc) return rc;
+  if ((rc = pois_solve(s, 1e-4, s.pois_kind == WL_POIS_MULTILEVEL ? 32 : 1000, n))) return rc;
+  wl_prof_begin(s, WL_PROF_PROJECT);
+  LAUNCH_D(s, k_project_correct, s.D, box_tiles(box_interior(s.g), blk), blk, s.g, s.u, b.L, b.x);
+  rc = wl_scale_all(s, b.x, s.g, dtw, true, f32);
+  wl_prof_end(s, WL_PROF_PROJECT, 4.0 * (double)s.g.interior * (3 * s.D + 1 + 2));
+  return rc;
+}
+// CFL(a) (Flow.jl:172-175)
+int mom_cfl(Sim& s, double* dt) {
+  const dim3 blk = wl_pick_block(s.g);
+  LAUNCH_D(s, k_cfl, s.D, box_tiles(box_interior(s.g), blk), blk, s.g, s.u, s.sigma, s.ws, s.d_misc);
+  {
+    const int64_t cnt = shell_count(s.g);
+    k_shell_max<<<(int)std::min<int64_t>((cnt + 255) / 256, 256), 256, 0, s.stream>>>(s.g, s.sigma, s.ws, s.d_misc, cnt);
+    ++s.launches;
+  }
+  int rc = wl_read_scalars(s, &s.d_misc->cfl_max, sizeof(float));
+  if (rc) return rc;
+  const float m = s.h_pinned[0] + 5 * s.nu;
+  const float v = 1.f / m;
+  *dt = (double)(v < 10.f ? v : 10.f);
+  return 0;
+}
+// mom_step!(a,b) (Flow.jl:153-169)
+int mom_step(Sim& s, const double* U, const double* gp, const double* gc, double* dt_next, int* n_pred, int* n_corr) {
+  int rc;
+  wl_prof_begin(s, WL_PROF_STEP);
+  // a.u⁰ .= a.u; scale_u!(a,0): pointer swap; every cell of the new u is rewritten below before it is read
+  float* t = s.u; s.u = s.u0; s.u0 = t;
+  if (s.exitBC) {
+    const int64_t cnt = (int64_t)s.g.n[1] * s.g.n[2];
+    k_copy_exit_plane<<<(int)std::min<int64_t>((cnt + 255) / 256, 256), 256, 0, s.stream>>>(s.g, s.u, s.u0);
+    ++s.launches;
+  }
+  // predictor u → u'
+  if ((rc = mom_conv_diff(s, s.u0, true, gp))) return rc;
+  if ((rc = mom_bdim2(s, false, 1.f))) return rc;
+  if ((rc = bc_vec(s, s.g, s.u, U, s.exitBC, s.g.per))) return rc;
+  if (s.exitBC && (rc = bc_exit(s, U, s.dt.back()))) return rc;
+  if ((rc = mom_project(s, 1.0, n_pred))) return rc;
+  if ((rc = bc_vec(s, s.g, s.u, U, s.exitBC, s.g.per))) return rc;
+  // corrector u → u¹
+  if ((rc = mom_conv_diff(s, s.u, true, gc))) return rc;
+  if ((rc = mom_bdim2(s, true, 0.5f))) return rc;
+  if ((rc = bc_vec(s, s.g, s.u, U, s.exitBC, s.g.per))) return rc;
+  if ((rc = mom_project(s, 0.5, n_corr))) return rc;
+  if ((rc = bc_vec(s, s.g, s.u, U, s.exitBC, s.g.per))) return rc;
+  double dt;
+  if ((rc = mom_cfl(s, &dt))) return rc;
+  wl_prof_end(s, WL_PROF_STEP, 0.0);
+  s.dt.push_back((float)dt);
+  if (dt_next) *dt_next = dt;
+  return 0;
+}

@@ -30,7 +30,7 @@ import numpy as np
 
 from . import _cabi
 from ._cabi import Engine
-from .body import AbstractBody, NoBody, loc_grid, measure_fields
+from .body import AbstractBody, LocLazy, NoBody, measure_fields
 
 
 class DeviceField:
@@ -109,7 +109,7 @@ class Flow:
         u = np.zeros(Ng + (self.D,), dtype=np.float32, order="F")
         if ulam is not None:
             for i in range(1, self.D + 1):
-                u[..., i - 1] = np.asarray(ulam(i, loc_grid(i, Ng)), dtype=np.float32)
+                u[..., i - 1] = np.asarray(ulam(i, LocLazy(i, Ng)), dtype=np.float32)
         U0 = BCTuple(U, [0.0], self.D)
         eng.upload(_cabi.U, u)
         eng.bc(_cabi.U, U0, exitBC, None)
