@@ -97,12 +97,21 @@ inline void loop(const Grid& g, const Range& R, F&& f) {
 }
 
 // ------------------------------------------------------------------------------------------
-// reductions.  Float32 accumulation like sdot / Base.sum, in a fixed chunked order so the result
-// does not depend on the OpenMP thread count (needed for committed golden vectors).
+// reductions (`⋅` → BLAS sdot, `sum` → Base pairwise sum in the reference).
+//
+// The reference's summation ORDER is library-defined (OpenBLAS kernel / Base.mapreduce blocking)
+// and unpinned, and it matters: z⋅ϵ = ϵᵀAϵ in pcg! (Poisson.jl:131) cancels heavily, so two legal
+// Float32 orders give α's that differ by 1e-6…1e-5.  The oracle therefore defines every reduction
+// canonically as the correctly rounded Float32 of the exact sum (products and accumulation in
+// Float64), which is order-independent; the CUDA path does the same.  Mode 1 (wlo_set_sum_mode)
+// switches to a BLAS-like Float32 accumulation (8 interleaved lanes per 4096-element chunk, chunks
+// combined pairwise) and is used by tests/ to measure that reproducibility floor of the reference.
+// Both modes use a fixed chunking, so results do not depend on the OpenMP thread count.
 // ------------------------------------------------------------------------------------------
 constexpr int64_t CHUNK = 4096;
+int g_sum_mode = 0;  // 0: canonical (exact, rounded once)   1: Float32 BLAS-like accumulation
 template <class F>
-float chunked_sum(int64_t n, F&& term) {
+float chunked_sum_f32(int64_t n, F&& term) {
   const int64_t nch = (n + CHUNK - 1) / CHUNK;
   std::vector<float> part(nch);
 #pragma omp parallel for schedule(static) if (n > 65536)
@@ -111,22 +120,42 @@ float chunked_sum(int64_t n, F&& term) {
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int64_t i = a;
     for (; i + 8 <= b; i += 8)
-      for (int l = 0; l < 8; ++l) acc[l] += term(i + l);
+      for (int l = 0; l < 8; ++l) acc[l] += (float)term(i + l);
     float t = ((acc[0] + acc[4]) + (acc[2] + acc[6])) + ((acc[1] + acc[5]) + (acc[3] + acc[7]));
-    for (; i < b; ++i) t += term(i);
+    for (; i < b; ++i) t += (float)term(i);
     part[c] = t;
   }
-  // pairwise combine of chunk partials
   int64_t m = nch;
-  while (m > 1) {
+  while (m > 1) {  // pairwise combine of chunk partials
     const int64_t h = (m + 1) / 2;
     for (int64_t c = 0; c + h < m; ++c) part[c] += part[c + h];
     m = h;
   }
   return nch ? part[0] : 0.f;
 }
-float dot(const float* a, const float* b, int64_t n) { return chunked_sum(n, [=](int64_t i) { return a[i] * b[i]; }); }
-float sum(const float* a, int64_t n) { return chunked_sum(n, [=](int64_t i) { return a[i]; }); }
+template <class F>
+float chunked_sum_f64(int64_t n, F&& term) {
+  const int64_t nch = (n + CHUNK - 1) / CHUNK;
+  std::vector<double> part(nch);
+#pragma omp parallel for schedule(static) if (n > 65536)
+  for (int64_t c = 0; c < nch; ++c) {
+    const int64_t a = c * CHUNK, b = std::min(n, a + CHUNK);
+    double t = 0.0;
+    for (int64_t i = a; i < b; ++i) t += term(i);
+    part[c] = t;
+  }
+  double t = 0.0;
+  for (int64_t c = 0; c < nch; ++c) t += part[c];
+  return (float)t;
+}
+float dot(const float* a, const float* b, int64_t n) {
+  if (g_sum_mode == 1) return chunked_sum_f32(n, [=](int64_t i) { return a[i] * b[i]; });
+  return chunked_sum_f64(n, [=](int64_t i) { return (double)a[i] * (double)b[i]; });
+}
+float sum(const float* a, int64_t n) {
+  if (g_sum_mode == 1) return chunked_sum_f32(n, [=](int64_t i) { return a[i]; });
+  return chunked_sum_f64(n, [=](int64_t i) { return (double)a[i]; });
+}
 float maximum(const float* a, int64_t n) {
   float m = a[0];
 #pragma omp parallel for reduction(max : m) schedule(static) if (n > 65536)
@@ -679,6 +708,7 @@ int wlo_profile_read(wl_sim*, int, double* ms, int64_t* launches, double* bytes)
   if (bytes) *bytes = 0;
   return WL_OK;
 }
+int wlo_set_sum_mode(int mode) { g_sum_mode = mode; return WL_OK; }
 int wlo_profile_count(void) { return 0; }
 const char* wlo_profile_name(int) { return ""; }
 int wlo_num_threads(void) {

@@ -102,13 +102,13 @@ __global__ void __launch_bounds__(256) k_exit1(GridD g, float* __restrict__ u, c
   const int ny = g.n[1] - 2, nz = g.D > 2 ? g.n[2] - 2 : 1;
   const int64_t count = (int64_t)ny * nz;
   const int i = g.n[0] - 1;
-  float acc[1] = {0.f};
+  double acc[1] = {0.0};
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < count; idx += (int64_t)gridDim.x * blockDim.x) {
     const int j = 1 + (int)(idx % ny), k = g.D > 2 ? 1 + (int)(idx / ny) : 0;
     const int64_t I = i + j * g.s[1] + k * g.s[2];
     const float v = (float)((double)u0[I] - Udt * (double)(u0[I] - u0[I - 1]));
     u[I] = v;
-    acc[0] += v;
+    acc[0] += (double)v;
   }
   double tot[1];
   if (grid_reduce<1>(acc, ws, tot)) {

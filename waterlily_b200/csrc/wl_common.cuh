@@ -23,12 +23,12 @@ struct GridD {
 // device-resident solver scalars of one Poisson level (src/Poisson.jl:123-144 keeps these on the
 // host; here every data-dependent decision of pcg! is taken on the device)
 struct LevelScalars {
+  double ghost_dot; // Σ over the ghost shell of z·ϵ (level 1 only: z ≡ σ holds stale Φ)
   float rho;        // r⋅z
   float alpha;
   float beta;
   float r2;         // L₂ = r⋅r, refreshed by every kernel that writes r
   float rsum;       // mean of r in residual!
-  float ghost_dot;  // Σ over the ghost shell of z·ϵ (level 1 only: z ≡ σ holds stale Φ)
   int active;       // pcg! still iterating
   int need_sub;     // residual!: |s| > 2eps → subtract the mean
   int cnt_mult, cnt_update, cnt_dir;  // pcg! kernels that actually ran (not predicated off)
@@ -62,18 +62,19 @@ __device__ __forceinline__ double warp_sum(double v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-__device__ __forceinline__ float warp_max(float v) {
+__device__ __forceinline__ double warp_max(double v) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
 
-// Block-level sum of NR per-thread float accumulators (warp shuffles, then one smem hop),
+// Block-level sum of NR per-thread Float64 accumulators (warp shuffles, then one smem hop),
 // followed by a grid-level combine through per-block partials: the LAST block to arrive (ticket)
 // adds the partials in a fixed order in double and returns true on its thread 0 with the totals.
-// Deterministic for a fixed launch geometry.  All threads of the block must call it.
+// Reductions are canonical: products and sums in Float64, rounded to Float32 once by the caller
+// (see oracle/wl_oracle.cpp "reductions" for why).  All threads of the block must call it.
 template <int NR, bool MAX = false>
-__device__ __forceinline__ bool grid_reduce(const float (&v)[NR], ReduceWS ws, double (&tot)[NR]) {
+__device__ __forceinline__ bool grid_reduce(const double (&v)[NR], ReduceWS ws, double (&tot)[NR]) {
   __shared__ double sm[NR][32];
   __shared__ bool last;
   const int tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
@@ -81,8 +82,8 @@ __device__ __forceinline__ bool grid_reduce(const float (&v)[NR], ReduceWS ws, d
   const int lane = tid & 31, warp = tid >> 5, nwarp = (nthr + 31) >> 5;
 #pragma unroll
   for (int r = 0; r < NR; ++r) {
-    const float w = MAX ? warp_max(v[r]) : warp_sum(v[r]);
-    if (lane == 0) sm[r][warp] = (double)w;
+    const double w = MAX ? warp_max(v[r]) : warp_sum(v[r]);
+    if (lane == 0) sm[r][warp] = w;
   }
   __syncthreads();
   if (warp == 0) {

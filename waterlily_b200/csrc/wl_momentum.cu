@@ -207,14 +207,14 @@ __global__ void __launch_bounds__(256) k_scale_all(GridD g, float* x, float f32v
 template <int D>
 __global__ void __launch_bounds__(256) k_cfl(GridD g, const float* __restrict__ u, float* __restrict__ sigma, ReduceWS ws, MiscScalars* misc) {
   const Box b = box_interior(g);
-  float acc[1] = {0.f};
+  double acc[1] = {0.0};
   for_cells(g, b, [&](int, int, int, int64_t I) {
     double s = 0.0;
 #pragma unroll
     for (int i = 0; i < D; ++i) s += fmax(0., (double)u[I + g.s[i] + i * g.comp]) + fmax(0., (double)-u[I + i * g.comp]);
     const float v = (float)s;
     sigma[I] = v;
-    acc[0] = fmaxf(acc[0], v);
+    acc[0] = fmax(acc[0], (double)v);
   });
   double tot[1];
   if (grid_reduce<1, true>(acc, ws, tot)) misc->cfl_max = (float)tot[0];
@@ -222,10 +222,10 @@ __global__ void __launch_bounds__(256) k_cfl(GridD g, const float* __restrict__ 
 // the reference takes maximum(σ) over the PADDED array (Flow.jl:174): fold in the ghost shell, which
 // holds the corrector's stale Φ.  Shell = cells with any coordinate on a boundary.
 __global__ void __launch_bounds__(256) k_shell_max(GridD g, const float* __restrict__ sigma, ReduceWS ws, MiscScalars* misc, int64_t count) {
-  float acc[1] = {-3.4e38f};
+  double acc[1] = {-1e300};
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < count; idx += (int64_t)gridDim.x * blockDim.x) {
     int c[3];
-    if (shell_decode(g, idx, c)) acc[0] = fmaxf(acc[0], sigma[c[0] + c[1] * g.s[1] + c[2] * g.s[2]]);
+    if (shell_decode(g, idx, c)) acc[0] = fmax(acc[0], (double)sigma[c[0] + c[1] * g.s[1] + c[2] * g.s[2]]);
   }
   double tot[1];
   if (grid_reduce<1, true>(acc, ws, tot)) misc->cfl_max = fmaxf(misc->cfl_max, (float)tot[0]);

@@ -69,12 +69,12 @@ __global__ void __launch_bounds__(256) k_restrictL(Lvl c, Lvl f) {
 template <int D>
 __global__ void __launch_bounds__(256) k_residual(Lvl l, ReduceWS ws) {
   const Box b = box_interior(l.g);
-  float acc[2] = {0.f, 0.f};
+  double acc[2] = {0.0, 0.0};
   for_cells(l.g, b, [&](int, int, int, int64_t I) {
     const float r = l.iD[I] == 0.f ? 0.f : l.z[I] - mult_at<D>(l, I, l.x);
     l.r[I] = r;
-    acc[0] += r;
-    acc[1] += r * r;
+    acc[0] += (double)r;
+    acc[1] += (double)r * (double)r;
   });
   double tot[2];
   if (grid_reduce<2>(acc, ws, tot)) {
@@ -89,11 +89,11 @@ __global__ void __launch_bounds__(256) k_sub_mean(Lvl l, ReduceWS ws) {
   if (!l.sc->need_sub) return;
   const float s = l.sc->rsum;
   const Box b = box_interior(l.g);
-  float acc[1] = {0.f};
+  double acc[1] = {0.0};
   for_cells(l.g, b, [&](int, int, int, int64_t I) {
     const float r = l.r[I] - s;
     l.r[I] = r;
-    acc[0] += r * r;
+    acc[0] += (double)r * (double)r;
   });
   double tot[1];
   if (grid_reduce<1>(acc, ws, tot)) l.sc->r2 = (float)tot[0];
@@ -116,12 +116,12 @@ __global__ void __launch_bounds__(256) k_jacobi_eps(Lvl l) {
 template <int D>
 __global__ void __launch_bounds__(256) k_increment(Lvl l, ReduceWS ws) {
   const Box b = box_interior(l.g);
-  float acc[1] = {0.f};
+  double acc[1] = {0.0};
   for_cells(l.g, b, [&](int, int, int, int64_t I) {
     const float r = l.r[I] - mult_at<D>(l, I, l.eps);
     l.r[I] = r;
     l.x[I] = l.x[I] + l.eps[I];
-    acc[0] += r * r;
+    acc[0] += (double)r * (double)r;
   });
   double tot[1];
   if (grid_reduce<1>(acc, ws, tot)) l.sc->r2 = (float)tot[0];
@@ -160,12 +160,12 @@ __global__ void __launch_bounds__(256) k_prolongate(Lvl f, Lvl c) {
 // any read, so only ϵ is stored)
 __global__ void __launch_bounds__(256) k_pcg_init(Lvl l, ReduceWS ws) {
   const Box b = box_interior(l.g);
-  float acc[1] = {0.f};
+  double acc[1] = {0.0};
   for_cells(l.g, b, [&](int, int, int, int64_t I) {
     const float r = l.r[I];
     const float e = r * l.iD[I];
     l.eps[I] = e;
-    acc[0] += r * e;
+    acc[0] += (double)r * (double)e;
   });
   double tot[1];
   if (grid_reduce<1>(acc, ws, tot)) {
@@ -180,16 +180,16 @@ template <int D>
 __global__ void __launch_bounds__(256) k_pcg_mult(Lvl l, ReduceWS ws) {
   if (!l.sc->active) return;
   const Box b = box_interior(l.g);
-  float acc[1] = {0.f};
+  double acc[1] = {0.0};
   for_cells(l.g, b, [&](int, int, int, int64_t I) {
     const float z = mult_at<D>(l, I, l.eps);
     l.z[I] = z;
-    acc[0] += z * l.eps[I];
+    acc[0] += (double)z * (double)l.eps[I];
   });
   double tot[1];
   if (grid_reduce<1>(acc, ws, tot)) {
     ++l.sc->cnt_mult;
-    const float ze = (float)(tot[0] + (double)l.sc->ghost_dot);
+    const float ze = (float)(tot[0] + l.sc->ghost_dot);
     const float alpha = l.sc->rho / ze;
     l.sc->alpha = alpha;
     const double aa = fabs((double)alpha);
@@ -202,13 +202,13 @@ __global__ void __launch_bounds__(256) k_pcg_update(Lvl l, ReduceWS ws, int last
   if (!l.sc->active) return;
   const float alpha = l.sc->alpha;
   const Box b = box_interior(l.g);
-  float acc[2] = {0.f, 0.f};
+  double acc[2] = {0.0, 0.0};
   for_cells(l.g, b, [&](int, int, int, int64_t I) {
     l.x[I] += alpha * l.eps[I];
     const float r = l.r[I] - alpha * l.z[I];
     l.r[I] = r;
-    acc[0] += r * (r * l.iD[I]);
-    acc[1] += r * r;
+    acc[0] += (double)r * (double)(r * l.iD[I]);
+    acc[1] += (double)r * (double)r;
   });
   double tot[2];
   if (grid_reduce<2>(acc, ws, tot)) {
@@ -240,22 +240,22 @@ __global__ void __launch_bounds__(256) k_pcg_dir(Lvl l) {
 // layer, and ϵ's ghosts are non-zero after perBC! — reference quirk Q2, must be reproduced)
 __global__ void __launch_bounds__(256) k_shell_dot(Lvl l, ReduceWS ws, int64_t count) {
   if (!l.sc->active) return;
-  float acc[1] = {0.f};
+  double acc[1] = {0.0};
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < count; idx += (int64_t)gridDim.x * blockDim.x) {
     int c[3];
     if (shell_decode(l.g, idx, c)) {
       const int64_t I = c[0] + c[1] * l.g.s[1] + c[2] * l.g.s[2];
-      acc[0] += l.z[I] * l.eps[I];
+      acc[0] += (double)l.z[I] * (double)l.eps[I];
     }
   }
   double tot[1];
-  if (grid_reduce<1>(acc, ws, tot)) l.sc->ghost_dot = (float)tot[0];
+  if (grid_reduce<1>(acc, ws, tot)) l.sc->ghost_dot = tot[0];
 }
 
 __global__ void __launch_bounds__(256) k_dot_rr(Lvl l, ReduceWS ws, double* out) {
   const Box b = box_interior(l.g);
-  float acc[1] = {0.f};
-  for_cells(l.g, b, [&](int, int, int, int64_t I) { acc[0] += l.r[I] * l.r[I]; });
+  double acc[1] = {0.0};
+  for_cells(l.g, b, [&](int, int, int, int64_t I) { acc[0] += (double)l.r[I] * (double)l.r[I]; });
   double tot[1];
   if (grid_reduce<1>(acc, ws, tot)) *out = tot[0];
 }
