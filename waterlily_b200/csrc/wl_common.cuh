@@ -175,30 +175,31 @@ __device__ __forceinline__ void for_cells(const GridD& g, const Box& b, F&& f) {
     if (i <= b.hi[0] && j <= b.hi[1] && k <= b.hi[2]) f(i, j, k, (int64_t)i + j * g.s[1] + k * g.s[2]);
   }
 }
-// unique enumeration of the ghost shell: last dim's two planes in full, then the next dim's
-// planes restricted to the interior of the dims above it, ...
-__device__ __forceinline__ bool shell_decode(const GridD& g, int64_t idx, int c[3]) {
+// unique enumeration of the boundary shell of thickness t (cells with any coordinate in [0,t) or
+// [n-t,n)): the last dim's 2t planes in full, then the next dim's planes restricted to the core of
+// the dims above it, ...   t=1 is the ghost layer.
+__device__ __forceinline__ bool shell_decode(const GridD& g, int64_t idx, int c[3], int t = 1) {
   c[0] = c[1] = c[2] = 0;
   for (int d = g.D - 1; d >= 0; --d) {
     int64_t below = 1, above = 1;
     for (int k = 0; k < d; ++k) below *= g.n[k];
-    for (int k = d + 1; k < g.D; ++k) above *= g.n[k] - 2;
-    const int64_t cnt = 2 * below * above;
+    for (int k = d + 1; k < g.D; ++k) above *= g.n[k] - 2 * t;
+    const int64_t plane = below * above, cnt = 2 * t * plane;
     if (idx < cnt) {
-      const int64_t half = below * above;
-      c[d] = idx < half ? 0 : g.n[d] - 1;
-      int64_t q = idx < half ? idx : idx - half;
+      const int pl = (int)(idx / plane);
+      c[d] = pl < t ? pl : g.n[d] - 2 * t + pl;
+      int64_t q = idx - (int64_t)pl * plane;
       for (int k = 0; k < d; ++k) { c[k] = (int)(q % g.n[k]); q /= g.n[k]; }
-      for (int k = d + 1; k < g.D; ++k) { c[k] = 1 + (int)(q % (g.n[k] - 2)); q /= (g.n[k] - 2); }
+      for (int k = d + 1; k < g.D; ++k) { c[k] = t + (int)(q % (g.n[k] - 2 * t)); q /= (g.n[k] - 2 * t); }
       return true;
     }
     idx -= cnt;
   }
   return false;
 }
-__host__ __device__ inline int64_t shell_count(const GridD& g) {
+__host__ __device__ inline int64_t shell_count(const GridD& g, int t = 1) {
   int64_t all = 1, in = 1;
-  for (int k = 0; k < g.D; ++k) { all *= g.n[k]; in *= g.n[k] - 2; }
+  for (int k = 0; k < g.D; ++k) { all *= g.n[k]; in *= g.n[k] - 2 * t; }
   return all - in;
 }
 #endif

@@ -11,19 +11,25 @@
 //    evaluates exactly the passes that reach each ghost cell.
 // Float64 sub-expressions follow Julia's promotion rules.
 #include <algorithm>
+#include <cstdlib>
 
 #include "wl_internal.h"
 
 namespace {
 
-// median (Flow.jl:25-34)
-__device__ __forceinline__ float median3(float a, float b, float c) {
-  if (a > b) { if (b >= c) return b; if (a > c) return c; }
-  else { if (b <= c) return b; if (a < c) return c; }
-  return a;
+// median (Flow.jl:25-34), branch-free: max(min(a,b), min(max(a,b),c)) is the same value for every
+// ordering and tie of finite inputs (only the sign of a zero can differ)
+__device__ __forceinline__ float median3(float a, float b, float c) { return fmaxf(fminf(a, b), fminf(fmaxf(a, b), c)); }
+// x/6 correctly rounded without the IEEE-division subroutine: one Newton step on q = x·RN(1/6).
+// Checked exhaustively against x/6.0f over all 2³² bit patterns: identical for 1e-30 < |x| < 1e30
+// and for ±0 (tools/check_div6.c); below 1e-30 it may differ in the last place of a number that small.
+__device__ __forceinline__ float div6(float x) {
+  const float y = 1.0f / 6.0f;
+  const float q = x * y;
+  return fmaf(fmaf(-6.0f, q, x), y, q);
 }
 // quick (Flow.jl:4)
-__device__ __forceinline__ float quick(float u, float c, float d) { return median3((5 * c + 2 * d - u) / 6, c, median3(10 * c - 9 * u, c, d)); }
+__device__ __forceinline__ float quick(float u, float c, float d) { return median3(div6(5 * c + 2 * d - u), c, median3(10 * c - 9 * u, c, d)); }
 
 struct CDArgs {
   GridD g;
@@ -92,43 +98,181 @@ __device__ __forceinline__ void convdiff_cell(const CDArgs& a, const int (&c)[3]
   }
 }
 
-// conv_diff! (+ accelerate! + BDIM! stage 1) over the padded box
+// one cell of conv_diff! (+ accelerate! + BDIM! stage 1), any position in the padded box
 template <int D>
-__global__ void __launch_bounds__(256) k_conv_diff(CDArgs a) {
+__device__ __forceinline__ void convdiff_store_cell(const CDArgs& a, const int (&c)[3], int64_t I) {
   const GridD& g = a.g;
-  const Box b = box_all(g);
-  for_cells(g, b, [&](int i0, int j0, int k0, int64_t I) {
-    const int c[3] = {i0, j0, k0};
-    float r[D];
-    bool lowghost = false, ghost = false;
+  float r[D];
+  bool lowghost = false, ghost = false;
 #pragma unroll
-    for (int k = 0; k < D; ++k) { lowghost |= c[k] == 0; ghost |= c[k] == g.n[k] - 1; }
-    if (lowghost) {
+  for (int k = 0; k < D; ++k) { lowghost |= c[k] == 0; ghost |= c[k] == g.n[k] - 1; }
+  if (lowghost) {
 #pragma unroll
-      for (int i = 0; i < D; ++i) r[i] = 0.f;  // index-1 ghosts are never written (r .= 0)
-    } else {
-      convdiff_cell<D>(a, c, I, r);
-      if (ghost) {
-        // stale Φ: last pass (i=D, largest j) that covers this upper-ghost cell
-        for (int j = D - 1; j >= 0; --j) {
-          const int lo = g.per[j] ? 1 : 2;
-          if (c[j] >= lo && c[j] <= g.n[j] - 2) {
-            const int64_t sj = g.s[j];
-            a.sigma[I] = phi_face(a.u + (D - 1) * g.comp, a.u + j * g.comp, I, g.s[D - 1], sj,
-                                  c[j] == 1 ? (int64_t)(g.n[j] - 4) * sj : -2 * sj, a.nu);
-            break;
-          }
+    for (int i = 0; i < D; ++i) r[i] = 0.f;  // index-1 ghosts are never written (r .= 0)
+  } else {
+    convdiff_cell<D>(a, c, I, r);
+    if (ghost) {
+      // stale Φ: last pass (i=D, largest j) that covers this upper-ghost cell
+      for (int j = D - 1; j >= 0; --j) {
+        const int lo = g.per[j] ? 1 : 2;
+        if (c[j] >= lo && c[j] <= g.n[j] - 2) {
+          const int64_t sj = g.s[j];
+          a.sigma[I] = phi_face(a.u + (D - 1) * g.comp, a.u + j * g.comp, I, g.s[D - 1], sj,
+                                c[j] == 1 ? (int64_t)(g.n[j] - 4) * sj : -2 * sj, a.nu);
+          break;
         }
       }
     }
+  }
 #pragma unroll
-    for (int i = 0; i < D; ++i) {
-      float v = r[i];
-      if (a.has_g) v = (float)((double)v + a.gacc[i]);          // accelerate! (Flow.jl:68-70)
-      if (a.fuse_bdim1) v = a.u0[I + i * g.comp] + a.dt * v - a.V[I + i * g.comp];  // BDIM! stage 1 (:133)
-      a.f[I + i * g.comp] = v;
-    }
+  for (int i = 0; i < D; ++i) {
+    float v = r[i];
+    if (a.has_g) v = (float)((double)v + a.gacc[i]);          // accelerate! (Flow.jl:68-70)
+    if (a.fuse_bdim1) v = a.u0[I + i * g.comp] + a.dt * v - a.V[I + i * g.comp];  // BDIM! stage 1 (:133)
+    a.f[I + i * g.comp] = v;
+  }
+}
+
+// generic path: the whole padded box (2-D and small grids)
+template <int D>
+__global__ void __launch_bounds__(256) k_conv_diff(CDArgs a) {
+  const Box b = box_all(a.g);
+  for_cells(a.g, b, [&](int i0, int j0, int k0, int64_t I) {
+    const int c[3] = {i0, j0, k0};
+    convdiff_store_cell<D>(a, c, I);
   });
+}
+// generic path on the boundary shell of thickness 2 only (the marching kernel does the core)
+template <int D>
+__global__ void __launch_bounds__(256) k_conv_diff_shell(CDArgs a, int64_t count) {
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < count; idx += (int64_t)gridDim.x * blockDim.x) {
+    int c[3];
+    if (shell_decode(a.g, idx, c, 2)) convdiff_store_cell<D>(a, c, c[0] + c[1] * a.g.s[1] + c[2] * a.g.s[2]);
+  }
+}
+
+// ---- 3-D core kernel --------------------------------------------------------------------------
+// Cells with every coordinate in [2,n-3] see only the plain inner-loop stencil (Flow.jl:45-47).
+// A block owns a 128×4 (x,y) tile and marches along z:
+//  * each thread keeps its column's five z-samples of the three components in registers, so one
+//    new plane (3 loads) per step serves the whole z-stencil;
+//  * every face flux is computed once: the z-flux of the upper face is carried to the next step in
+//    a register, x-fluxes travel between lanes by shuffle (between warps through shared memory),
+//    y-fluxes between warps through shared memory (double-buffered: one barrier per step);
+//  * Φ = uf·λ − ν∂ is one fmaf: the reference rounds the Float64 expression once (Appendix A).
+__device__ __forceinline__ float flux1(float uf, float um2, float um1, float uc, float up1, float nu) {
+  const float q = uf > 0 ? quick(um2, um1, uc) : quick(up1, uc, um1);
+  return fmaf(uf, q, -(nu * (uc - um1)));
+}
+template <int CD_TX, int CD_TY, int MINB, bool HASG, bool CORR>
+__global__ void __launch_bounds__(CD_TX * CD_TY, MINB) k_conv_diff3_march(CDArgs a, int zchunk, int ntx, int nty) {
+  __shared__ float Fx[2][3][CD_TY][CD_TX / 32];
+  __shared__ float Fy[2][3][CD_TY][CD_TX];
+  const GridD& g = a.g;
+  const int nx = g.n[0], ny = g.n[1], nz = g.n[2];
+  const int64_t s1 = g.s[1], s2 = g.s[2];
+  const int tix = threadIdx.x, tiy = threadIdx.y, lane = tix & 31, wx = tix >> 5;
+  const int bt = blockIdx.x;
+  const int tx = bt % ntx, ty = (bt / ntx) % nty, tz = bt / (ntx * nty);
+  const int x = 2 + tx * CD_TX + tix, y = 2 + ty * CD_TY + tiy;
+  const int z0 = 2 + tz * zchunk, z1 = min(z0 + zchunk, nz - 2);
+  const bool valid = x <= nx - 3 && y <= ny - 3;
+  const int xc = min(x, nx - 3), yc = min(y, ny - 3);  // clamped: out-of-range threads shadow the last cell
+  const bool extra_x = (xc == nx - 3) || (tix == CD_TX - 1);
+  const bool extra_y = (yc == ny - 3) || (tiy == CD_TY - 1);
+  const float nu = a.nu;
+  int64_t I = xc + yc * s1 + (int64_t)(z0 - 1) * s2;
+  // per-component pointers to the current cell; all neighbour offsets are 32-bit
+  const float* __restrict__ U[3] = {a.u + I, a.u + g.comp + I, a.u + 2 * g.comp + I};
+  const int o1 = (int)s1, o2 = (int)s2;
+  float w[3][5];  // w[c][k] = u_c at z-2+k
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    w[c][0] = 0.f;
+    w[c][1] = U[c][-o2];
+    w[c][2] = U[c][0];
+    w[c][3] = U[c][o2];
+  }
+  float fz_lo[3] = {0.f, 0.f, 0.f};
+  int buf = 0;
+  for (int z = z0 - 1; z < z1; ++z, I += s2, U[0] += o2, U[1] += o2, U[2] += o2) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) w[c][4] = U[c][2 * o2];
+    // upper z-face = lower z-face of cell z+1: uf = (u_z[J] + u_z[J-δi])/2, J = I+δz
+    float fz_hi[3];
+    {
+      const float uz = w[2][3];
+      const float ufx = (uz + U[2][o2 - 1]) * 0.5f, ufy = (uz + U[2][o2 - o1]) * 0.5f, ufz = (uz + w[2][2]) * 0.5f;
+      fz_hi[0] = flux1(ufx, w[0][1], w[0][2], w[0][3], w[0][4], nu);
+      fz_hi[1] = flux1(ufy, w[1][1], w[1][2], w[1][3], w[1][4], nu);
+      fz_hi[2] = flux1(ufz, w[2][1], w[2][2], w[2][3], w[2][4], nu);
+    }
+    if (z >= z0) {  // uniform per block
+      float xm2[3], xm1[3], xp1[3], ym2[3], ym1[3], yp1[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        xm2[c] = U[c][-2]; xm1[c] = U[c][-1]; xp1[c] = U[c][1];
+        ym2[c] = U[c][-2 * o1]; ym1[c] = U[c][-o1]; yp1[c] = U[c][o1];
+      }
+      float fx_lo[3], fy_lo[3], fx_hi[3], fy_hi[3];
+      {
+        const float ux = w[0][2];
+        fx_lo[0] = flux1((ux + xm1[0]) * 0.5f, xm2[0], xm1[0], w[0][2], xp1[0], nu);
+        fx_lo[1] = flux1((ux + ym1[0]) * 0.5f, xm2[1], xm1[1], w[1][2], xp1[1], nu);
+        fx_lo[2] = flux1((ux + w[0][1]) * 0.5f, xm2[2], xm1[2], w[2][2], xp1[2], nu);
+        const float uy = w[1][2];
+        fy_lo[0] = flux1((uy + xm1[1]) * 0.5f, ym2[0], ym1[0], w[0][2], yp1[0], nu);
+        fy_lo[1] = flux1((uy + ym1[1]) * 0.5f, ym2[1], ym1[1], w[1][2], yp1[1], nu);
+        fy_lo[2] = flux1((uy + w[1][1]) * 0.5f, ym2[2], ym1[2], w[2][2], yp1[2], nu);
+      }
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        if (lane == 0) Fx[buf][i][tiy][wx] = fx_lo[i];
+        Fy[buf][i][tiy][tix] = fy_lo[i];
+      }
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        fx_hi[i] = __shfl_down_sync(0xffffffffu, fx_lo[i], 1);
+        if (lane == 31 && wx < CD_TX / 32 - 1) fx_hi[i] = Fx[buf][i][tiy][wx + 1];
+        fy_hi[i] = tiy < CD_TY - 1 ? Fy[buf][i][tiy + 1][tix] : 0.f;
+      }
+      if (extra_x) {  // lower x-face of cell x+1 that no thread of the block owns
+        const float ux = xp1[0];
+        fx_hi[0] = flux1((ux + w[0][2]) * 0.5f, xm1[0], w[0][2], xp1[0], U[0][2], nu);
+        fx_hi[1] = flux1((ux + U[0][1 - o1]) * 0.5f, xm1[1], w[1][2], xp1[1], U[1][2], nu);
+        fx_hi[2] = flux1((ux + U[0][1 - o2]) * 0.5f, xm1[2], w[2][2], xp1[2], U[2][2], nu);
+      }
+      if (extra_y) {
+        const float uy = yp1[1];
+        fy_hi[0] = flux1((uy + U[1][o1 - 1]) * 0.5f, ym1[0], w[0][2], yp1[0], U[0][2 * o1], nu);
+        fy_hi[1] = flux1((uy + w[1][2]) * 0.5f, ym1[1], w[1][2], yp1[1], U[1][2 * o1], nu);
+        fy_hi[2] = flux1((uy + U[1][o1 - o2]) * 0.5f, ym1[2], w[2][2], yp1[2], U[2][2 * o1], nu);
+      }
+      if (valid) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          float v = 0.f;
+          v += fx_lo[i]; v -= fx_hi[i];
+          v += fy_lo[i]; v -= fy_hi[i];
+          v += fz_lo[i]; v -= fz_hi[i];
+          if (HASG) v = (float)((double)v + a.gacc[i]);
+          if (a.fuse_bdim1) {
+            const float u0v = CORR ? a.u0[I + i * g.comp] : w[i][2];
+            v = u0v + a.dt * v - a.V[I + i * g.comp];
+          }
+          a.f[I + i * g.comp] = v;
+        }
+      }
+      buf ^= 1;
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      w[c][0] = w[c][1]; w[c][1] = w[c][2]; w[c][2] = w[c][3]; w[c][3] = w[c][4];
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) fz_lo[i] = fz_hi[i];
+  }
 }
 
 // accelerate! alone (API parity hook)
@@ -254,6 +398,32 @@ __global__ void __launch_bounds__(256) k_copy_exit_plane(GridD g, float* __restr
     else LAUNCH(s, kern<3>, ntiles, blk, __VA_ARGS__);                            \
   } while (0)
 
+template <int TX, int TY, int MINB>
+static void launch_march_cfg(Sim& s, const CDArgs& a, int zchunk, bool corr) {
+  const GridD& g = s.g;
+  const int ntx = (g.n[0] - 4 + TX - 1) / TX, nty = (g.n[1] - 4 + TY - 1) / TY, ntz = (g.n[2] - 4 + zchunk - 1) / zchunk;
+  const dim3 blk(TX, TY, 1);
+  const int nblk = ntx * nty * ntz;
+  if (a.has_g) {
+    if (corr) k_conv_diff3_march<TX, TY, MINB, true, true><<<nblk, blk, 0, s.stream>>>(a, zchunk, ntx, nty);
+    else k_conv_diff3_march<TX, TY, MINB, true, false><<<nblk, blk, 0, s.stream>>>(a, zchunk, ntx, nty);
+  } else {
+    if (corr) k_conv_diff3_march<TX, TY, MINB, false, true><<<nblk, blk, 0, s.stream>>>(a, zchunk, ntx, nty);
+    else k_conv_diff3_march<TX, TY, MINB, false, false><<<nblk, blk, 0, s.stream>>>(a, zchunk, ntx, nty);
+  }
+  ++s.launches;
+}
+static void launch_march(Sim& s, const CDArgs& a, int variant, int zchunk, bool corr) {
+  switch (variant) {
+    case 1: launch_march_cfg<128, 4, 1>(s, a, zchunk, corr); break;
+    case 2: launch_march_cfg<64, 4, 3>(s, a, zchunk, corr); break;
+    case 3: launch_march_cfg<128, 2, 3>(s, a, zchunk, corr); break;
+    case 4: launch_march_cfg<64, 4, 4>(s, a, zchunk, corr); break;
+    case 5: launch_march_cfg<32, 8, 3>(s, a, zchunk, corr); break;
+    default: launch_march_cfg<128, 4, 2>(s, a, zchunk, corr); break;
+  }
+}
+
 int mom_conv_diff(Sim& s, const float* src, bool fuse_bdim1, const double* gacc) {
   CDArgs a;
   a.g = s.g; a.u = src; a.u0 = s.u0; a.V = s.V; a.f = s.f; a.sigma = s.sigma;
@@ -261,9 +431,23 @@ int mom_conv_diff(Sim& s, const float* src, bool fuse_bdim1, const double* gacc)
   a.has_g = gacc ? 1 : 0;
   for (int k = 0; k < 3; ++k) a.gacc[k] = (gacc && k < s.D) ? gacc[k] : 0.0;
   a.fuse_bdim1 = fuse_bdim1 ? 1 : 0;
-  const dim3 blk = wl_pick_block(s.g);
   wl_prof_begin(s, WL_PROF_CONVDIFF);
-  LAUNCH_D(s, k_conv_diff, s.D, box_tiles(box_all(s.g), blk), blk, a);
+  const GridD& g = s.g;
+  if (s.D == 3 && g.n[0] >= 8 && g.n[1] >= 8 && g.n[2] >= 8) {
+    // core [2,n-3]³ by the marching kernel, boundary shell of thickness 2 by the generic one
+    const bool corr = src != s.u0;
+    static int variant = -1;
+    if (variant < 0) { const char* e = getenv("WL_CD_VARIANT"); variant = e ? atoi(e) : 4; }
+    static int zchunk = 0;
+    if (!zchunk) { const char* e = getenv("WL_CD_ZCHUNK"); zchunk = e ? atoi(e) : 32; }
+    launch_march(s, a, variant, zchunk, corr);
+    const int64_t cnt = shell_count(g, 2);
+    k_conv_diff_shell<3><<<(int)std::min<int64_t>((cnt + 255) / 256, s.nsm * 16), 256, 0, s.stream>>>(a, cnt);
+    ++s.launches;
+  } else {
+    const dim3 blk = wl_pick_block(s.g);
+    LAUNCH_D(s, k_conv_diff, s.D, box_tiles(box_all(s.g), blk), blk, a);
+  }
   // algorithmic words/cell: read u (D) [+ u⁰, V (2D)], write f (D)
   wl_prof_end(s, WL_PROF_CONVDIFF, 4.0 * (double)s.g.interior * (fuse_bdim1 ? (src == s.u0 ? 3 : 4) * s.D : 2 * s.D));
   return wl_cuda_check(s, cudaGetLastError(), "k_conv_diff");
