@@ -164,11 +164,11 @@ __device__ __forceinline__ void for_cells(const GridD& g, const Box& b, F&& f) {
   const int ntx = (b.hi[0] - b.lo[0] + blockDim.x) / blockDim.x;
   const int nty = (b.hi[1] - b.lo[1] + blockDim.y) / blockDim.y;
   const int ntz = (b.hi[2] - b.lo[2] + blockDim.z) / blockDim.z;
-  const int64_t ntiles = (int64_t)ntx * nty * ntz;
-  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-    const int tx = (int)(t % ntx);
-    const int64_t q = t / ntx;
-    const int ty = (int)(q % nty), tz = (int)(q / nty);
+  const int ntiles = ntx * nty * ntz;  // 32-bit on purpose: 64-bit div/mod per tile costs ~100 instructions
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int tx = t % ntx;
+    const int q = t / ntx;
+    const int ty = q % nty, tz = q / nty;
     const int i = b.lo[0] + tx * blockDim.x + threadIdx.x;
     const int j = b.lo[1] + ty * blockDim.y + threadIdx.y;
     const int k = b.lo[2] + tz * blockDim.z + threadIdx.z;

@@ -111,5 +111,4 @@ int mom_step(Sim& s, const double* U, const double* gp, const double* gc, double
 
 // generic helpers (wl_api.cu)
 int wl_fill(Sim& s, float* p, float v, int64_t n);
-int wl_scale_all(Sim& s, float* p, const GridD& g, double factor, bool divide, bool f32);
 int wl_read_scalars(Sim& s, const void* dptr, size_t bytes);  // → h_pinned, synchronises the stream

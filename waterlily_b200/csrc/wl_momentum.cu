@@ -14,6 +14,7 @@
 #include <cstdlib>
 
 #include "wl_internal.h"
+#include "wl_vec.cuh"
 
 namespace {
 
@@ -293,72 +294,126 @@ __global__ void __launch_bounds__(256) k_bdim1(GridD g, float* f, const float* u
 
 // BDIM! stage 2 (Flow.jl:134) with μddn (:18-24); `accumulate`=0 folds the predictor's
 // scale_u!(a,0), `scale` folds the corrector's scale_u!(a,0.5)
-template <int D>
-__global__ void __launch_bounds__(256) k_bdim2(GridD g, float* __restrict__ u, const float* __restrict__ f, const float* __restrict__ V,
+template <int D, int V>
+__global__ void __launch_bounds__(256) k_bdim2(GridD g, float* __restrict__ u, const float* __restrict__ f, const float* __restrict__ Vb,
                                                const float* __restrict__ mu0, const float* __restrict__ mu1, int accumulate, float scale) {
-  const Box b = box_interior(g);
-  for_cells(g, b, [&](int, int, int, int64_t I) {
+  for_rows<V>(g, [&](int, int, int, int64_t I) {
 #pragma unroll
     for (int i = 0; i < D; ++i) {
       const int64_t Ii = I + i * g.comp;
-      float s = 0.f;
+      const Pack<V> fc = ldp<V>(f + Ii);
+      Pack<V> s;
+      {
+        const Pack<V> m = ldp<V>(mu1 + I + (int64_t)i * g.comp), fm = ld_xm<V>(f + Ii, fc), fp = ld_xp<V>(f + Ii, fc);
 #pragma unroll
-      for (int j = 0; j < D; ++j) s += mu1[I + (i + D * j) * g.comp] * (f[Ii + g.s[j]] - f[Ii - g.s[j]]);
-      const double add = (0.5 * (double)s + (double)V[Ii]) + (double)(mu0[Ii] * f[Ii]);
-      const float un = (float)((accumulate ? (double)u[Ii] : 0.0) + add);
-      u[Ii] = un * scale;
+        for (int q = 0; q < V; ++q) s.v[q] = 0.f + m.v[q] * (fp.v[q] - fm.v[q]);
+      }
+#pragma unroll
+      for (int j = 1; j < D; ++j) {
+        const Pack<V> m = ldp<V>(mu1 + I + (int64_t)(i + D * j) * g.comp), fm = ldp<V>(f + Ii - g.s[j]), fp = ldp<V>(f + Ii + g.s[j]);
+#pragma unroll
+        for (int q = 0; q < V; ++q) s.v[q] += m.v[q] * (fp.v[q] - fm.v[q]);
+      }
+      const Pack<V> vb = ldp<V>(Vb + Ii), m0 = ldp<V>(mu0 + Ii);
+      Pack<V> un;
+#pragma unroll
+      for (int q = 0; q < V; ++q) un.v[q] = 0.f;
+      if (accumulate) un = ldp<V>(u + Ii);
+#pragma unroll
+      for (int q = 0; q < V; ++q) {
+        const double add = (0.5 * (double)s.v[q] + (double)vb.v[q]) + (double)(m0.v[q] * fc.v[q]);
+        un.v[q] = (float)((accumulate ? (double)un.v[q] : 0.0) + add) * scale;
+      }
+      stp<V>(u + Ii, un);
     }
   });
 }
+template <int D, int V>
 __global__ void __launch_bounds__(256) k_scale_u(GridD g, float* u, double scale) {
-  const Box b = box_interior(g);
-  for_cells(g, b, [&](int, int, int, int64_t I) {
-    for (int i = 0; i < g.D; ++i) u[I + i * g.comp] = (float)((double)u[I + i * g.comp] * scale);
+  for_rows<V>(g, [&](int, int, int, int64_t I) {
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      Pack<V> a = ldp<V>(u + I + i * g.comp);
+#pragma unroll
+      for (int q = 0; q < V; ++q) a.v[q] = (float)((double)a.v[q] * scale);
+      stp<V>(u + I + i * g.comp, a);
+    }
   });
 }
 
-// project!: z = div(u) (Flow.jl:139, :11-17)
-template <int D>
-__global__ void __launch_bounds__(256) k_div(GridD g, const float* __restrict__ u, float* __restrict__ z) {
-  const Box b = box_interior(g);
-  for_cells(g, b, [&](int, int, int, int64_t I) {
-    float s = 0.f;
+// project!: z = div(u) (Flow.jl:139, :11-17) fused with x .*= dt on the interior (the periodic
+// ghosts of x are refreshed by residual!'s perBC!, all other ghosts of x are never written)
+template <int D, int V>
+__global__ void __launch_bounds__(256) k_project_pre(GridD g, const float* __restrict__ u, float* __restrict__ z, float* __restrict__ x,
+                                                     float f32v, double f64v, int f32) {
+  for_rows<V>(g, [&](int, int, int, int64_t I) {
+    Pack<V> s;
+    {
+      const Pack<V> uc = ldp<V>(u + I), up = ld_xp<V>(u + I, uc);
 #pragma unroll
-    for (int i = 0; i < D; ++i) s += u[I + g.s[i] + i * g.comp] - u[I + i * g.comp];
-    z[I] = s;
+      for (int q = 0; q < V; ++q) s.v[q] = 0.f + (up.v[q] - uc.v[q]);
+    }
+#pragma unroll
+    for (int i = 1; i < D; ++i) {
+      const Pack<V> uc = ldp<V>(u + I + i * g.comp), up = ldp<V>(u + I + g.s[i] + i * g.comp);
+#pragma unroll
+      for (int q = 0; q < V; ++q) s.v[q] += up.v[q] - uc.v[q];
+    }
+    stp<V>(z + I, s);
+    Pack<V> xv = ldp<V>(x + I);
+#pragma unroll
+    for (int q = 0; q < V; ++q) xv.v[q] = f32 ? xv.v[q] * f32v : (float)((double)xv.v[q] * f64v);
+    stp<V>(x + I, xv);
   });
 }
 // project!: u[I,i] -= L[I,i]*∂(i,I,x) (Flow.jl:141-143)
-template <int D>
+template <int D, int V>
 __global__ void __launch_bounds__(256) k_project_correct(GridD g, float* __restrict__ u, const float* __restrict__ L, const float* __restrict__ x) {
-  const Box b = box_interior(g);
-  for_cells(g, b, [&](int, int, int, int64_t I) {
-    const float xc = x[I];
+  for_rows<V>(g, [&](int, int, int, int64_t I) {
+    const Pack<V> xc = ldp<V>(x + I);
 #pragma unroll
-    for (int i = 0; i < D; ++i) u[I + i * g.comp] -= L[I + i * g.comp] * (xc - x[I - g.s[i]]);
+    for (int i = 0; i < D; ++i) {
+      const Pack<V> xm = i == 0 ? ld_xm<V>(x + I, xc) : ldp<V>(x + I - g.s[i]);
+      const Pack<V> Lc = ldp<V>(L + I + i * g.comp);
+      Pack<V> uc = ldp<V>(u + I + i * g.comp);
+#pragma unroll
+      for (int q = 0; q < V; ++q) uc.v[q] -= Lc.v[q] * (xc.v[q] - xm.v[q]);
+      stp<V>(u + I + i * g.comp, uc);
+    }
   });
 }
-// x .*= dt / x ./= dt over the padded array (Flow.jl:139,144)
-__global__ void __launch_bounds__(256) k_scale_all(GridD g, float* x, float f32v, double f64v, int divide, int f32) {
-  const Box b = box_all(g);
-  for_cells(g, b, [&](int, int, int, int64_t I) {
-    const float v = x[I];
-    x[I] = f32 ? (divide ? v / f32v : v * f32v) : (divide ? (float)((double)v / f64v) : (float)((double)v * f64v));
+// project!: x ./= dt (Flow.jl:144) on the interior; perBC! afterwards restores the periodic ghosts
+template <int D, int V>
+__global__ void __launch_bounds__(256) k_unscale(GridD g, float* __restrict__ x, float f32v, double f64v, int f32) {
+  for_rows<V>(g, [&](int, int, int, int64_t I) {
+    Pack<V> xv = ldp<V>(x + I);
+#pragma unroll
+    for (int q = 0; q < V; ++q) xv.v[q] = f32 ? xv.v[q] / f32v : (float)((double)xv.v[q] / f64v);
+    stp<V>(x + I, xv);
   });
 }
 
 // CFL: σ = flux_out (Flow.jl:173,176-182) + interior max
-template <int D>
+template <int D, int V>
 __global__ void __launch_bounds__(256) k_cfl(GridD g, const float* __restrict__ u, float* __restrict__ sigma, ReduceWS ws, MiscScalars* misc) {
-  const Box b = box_interior(g);
   double acc[1] = {0.0};
-  for_cells(g, b, [&](int, int, int, int64_t I) {
-    double s = 0.0;
+  for_rows<V>(g, [&](int, int, int, int64_t I) {
+    double s[V];
+    {
+      const Pack<V> uc = ldp<V>(u + I), up = ld_xp<V>(u + I, uc);
 #pragma unroll
-    for (int i = 0; i < D; ++i) s += fmax(0., (double)u[I + g.s[i] + i * g.comp]) + fmax(0., (double)-u[I + i * g.comp]);
-    const float v = (float)s;
-    sigma[I] = v;
-    acc[0] = fmax(acc[0], (double)v);
+      for (int q = 0; q < V; ++q) s[q] = 0.0 + (fmax(0., (double)up.v[q]) + fmax(0., (double)-uc.v[q]));
+    }
+#pragma unroll
+    for (int i = 1; i < D; ++i) {
+      const Pack<V> uc = ldp<V>(u + I + i * g.comp), up = ldp<V>(u + I + g.s[i] + i * g.comp);
+#pragma unroll
+      for (int q = 0; q < V; ++q) s[q] += fmax(0., (double)up.v[q]) + fmax(0., (double)-uc.v[q]);
+    }
+    Pack<V> o;
+#pragma unroll
+    for (int q = 0; q < V; ++q) { o.v[q] = (float)s[q]; acc[0] = fmax(acc[0], (double)o.v[q]); }
+    stp<V>(sigma + I, o);
   });
   double tot[1];
   if (grid_reduce<1, true>(acc, ws, tot)) misc->cfl_max = (float)tot[0];
@@ -464,22 +519,15 @@ int mom_bdim1(Sim& s) {
   return wl_cuda_check(s, cudaGetLastError(), "k_bdim1");
 }
 int mom_bdim2(Sim& s, bool accumulate, float scale) {
-  const dim3 blk = wl_pick_block(s.g);
   wl_prof_begin(s, WL_PROF_BDIM2);
-  LAUNCH_D(s, k_bdim2, s.D, box_tiles(box_interior(s.g), blk), blk, s.g, s.u, s.f, s.V, s.mu0, s.mu1, accumulate ? 1 : 0, scale);
+  RLAUNCH(s, k_bdim2, s.g, s.g, s.u, s.f, s.V, s.mu0, s.mu1, accumulate ? 1 : 0, scale);
   // read f, V, μ₀ (3D), μ₁ (D²) [+ u (D)], write u (D)
   wl_prof_end(s, WL_PROF_BDIM2, 4.0 * (double)s.g.interior * ((accumulate ? 5 : 4) * s.D + s.D * s.D));
   return wl_cuda_check(s, cudaGetLastError(), "k_bdim2");
 }
 int mom_scale_u(Sim& s, double scale) {
-  const dim3 blk = wl_pick_block(s.g);
-  LAUNCH(s, k_scale_u, box_tiles(box_interior(s.g), blk), blk, s.g, s.u, scale);
+  RLAUNCH(s, k_scale_u, s.g, s.g, s.u, scale);
   return wl_cuda_check(s, cudaGetLastError(), "k_scale_u");
-}
-int wl_scale_all(Sim& s, float* p, const GridD& g, double factor, bool divide, bool f32) {
-  const dim3 blk = wl_pick_block(g);
-  LAUNCH(s, k_scale_all, box_tiles(box_all(g), blk), blk, g, p, (float)factor, factor, divide ? 1 : 0, f32 ? 1 : 0);
-  return wl_cuda_check(s, cudaGetLastError(), "k_scale_all");
 }
 // project!(a,b,w) (Flow.jl:137-145)
 int mom_project(Sim& s, double w, int* n) {
@@ -487,23 +535,21 @@ int mom_project(Sim& s, double w, int* n) {
   const bool f32 = (w == 1.0);                 // dt = w*Δt: Float32 for the Int w=1, Float64 for w=0.5
   const double dtw = f32 ? (double)dt32 : w * (double)dt32;
   Lvl& b = s.levels[0];
-  const dim3 blk = wl_pick_block(s.g);
   wl_prof_begin(s, WL_PROF_PROJECT);
-  LAUNCH_D(s, k_div, s.D, box_tiles(box_interior(s.g), blk), blk, s.g, s.u, b.z);
-  int rc = wl_scale_all(s, b.x, s.g, dtw, false, f32);
+  RLAUNCH(s, k_project_pre, s.g, s.g, s.u, b.z, b.x, (float)dtw, dtw, f32 ? 1 : 0);
   wl_prof_end(s, WL_PROF_PROJECT, 4.0 * (double)s.g.interior * (s.D + 1 + 2));
+  int rc = pois_solve(s, 1e-4, s.pois_kind == WL_POIS_MULTILEVEL ? 32 : 1000, n);
   if (rc) return rc;
-  if ((rc = pois_solve(s, 1e-4, s.pois_kind == WL_POIS_MULTILEVEL ? 32 : 1000, n))) return rc;
   wl_prof_begin(s, WL_PROF_PROJECT);
-  LAUNCH_D(s, k_project_correct, s.D, box_tiles(box_interior(s.g), blk), blk, s.g, s.u, b.L, b.x);
-  rc = wl_scale_all(s, b.x, s.g, dtw, true, f32);
+  RLAUNCH(s, k_project_correct, s.g, s.g, s.u, b.L, b.x);
+  RLAUNCH(s, k_unscale, s.g, s.g, b.x, (float)dtw, dtw, f32 ? 1 : 0);
+  rc = bc_per(s, s.g, b.x, s.g.per);
   wl_prof_end(s, WL_PROF_PROJECT, 4.0 * (double)s.g.interior * (3 * s.D + 1 + 2));
   return rc;
 }
 // CFL(a) (Flow.jl:172-175)
 int mom_cfl(Sim& s, double* dt) {
-  const dim3 blk = wl_pick_block(s.g);
-  LAUNCH_D(s, k_cfl, s.D, box_tiles(box_interior(s.g), blk), blk, s.g, s.u, s.sigma, s.ws, s.d_misc);
+  RLAUNCH(s, k_cfl, s.g, s.g, s.u, s.sigma, s.ws, s.d_misc);
   {
     const int64_t cnt = shell_count(s.g);
     k_shell_max<<<(int)std::min<int64_t>((cnt + 255) / 256, 256), 256, 0, s.stream>>>(s.g, s.sigma, s.ws, s.d_misc, cnt);

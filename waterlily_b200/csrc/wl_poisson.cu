@@ -12,43 +12,64 @@
 #include <cstring>
 
 #include "wl_internal.h"
+#include "wl_vec.cuh"
 
 namespace {
 
-template <int D>
-__device__ __forceinline__ float mult_at(const Lvl& l, int64_t I, const float* __restrict__ x) {
-  // mult (Poisson.jl:69-75)
-  float s = x[I] * l.Dg[I];
+// mult (Poisson.jl:69-75) for V consecutive cells starting at I; xc = x[I..I+V)
+template <int D, int V>
+__device__ __forceinline__ Pack<V> mult_row(const Lvl& l, int64_t I, const float* __restrict__ x, const Pack<V>& xc) {
+  const Pack<V> Dc = ldp<V>(l.Dg + I);
+  Pack<V> s;
 #pragma unroll
-  for (int i = 0; i < D; ++i) {
+  for (int q = 0; q < V; ++q) s.v[q] = xc.v[q] * Dc.v[q];
+  {
+    const Pack<V> Lc = ldp<V>(l.L + I), Lp = ld_xp<V>(l.L + I, Lc), xm = ld_xm<V>(x + I, xc), xp = ld_xp<V>(x + I, xc);
+#pragma unroll
+    for (int q = 0; q < V; ++q) s.v[q] += (xm.v[q] * Lc.v[q] + xp.v[q] * Lp.v[q]);
+  }
+#pragma unroll
+  for (int i = 1; i < D; ++i) {
     const int64_t st = l.g.s[i];
-    const float* Li = l.L + i * l.g.comp;
-    s += (x[I - st] * Li[I] + x[I + st] * Li[I + st]);
+    const float* __restrict__ Li = l.L + i * l.g.comp;
+    const Pack<V> Lc = ldp<V>(Li + I), Lp = ldp<V>(Li + I + st), xm = ldp<V>(x + I - st), xp = ldp<V>(x + I + st);
+#pragma unroll
+    for (int q = 0; q < V; ++q) s.v[q] += (xm.v[q] * Lc.v[q] + xp.v[q] * Lp.v[q]);
   }
   return s;
 }
 
 // set_diag! (Poisson.jl:42-45) with diag (:48-54)
-template <int D>
+template <int D, int V>
 __global__ void __launch_bounds__(256) k_set_diag(Lvl l) {
-  const Box b = box_interior(l.g);
-  for_cells(l.g, b, [&](int, int, int, int64_t I) {
-    float s = 0.f;
+  for_rows<V>(l.g, [&](int, int, int, int64_t I) {
+    Pack<V> s;
 #pragma unroll
-    for (int i = 0; i < D; ++i) {
-      const float* Li = l.L + i * l.g.comp;
-      s -= (Li[I] + Li[I + l.g.s[i]]);
+    for (int q = 0; q < V; ++q) s.v[q] = 0.f;
+    {
+      const Pack<V> Lc = ldp<V>(l.L + I), Lp = ld_xp<V>(l.L + I, Lc);
+#pragma unroll
+      for (int q = 0; q < V; ++q) s.v[q] -= (Lc.v[q] + Lp.v[q]);
     }
-    l.Dg[I] = s;
-    l.iD[I] = (s * s < 2 * WL_EPS32) ? 0.f : 1.f / s;
+#pragma unroll
+    for (int i = 1; i < D; ++i) {
+      const float* __restrict__ Li = l.L + i * l.g.comp;
+      const Pack<V> Lc = ldp<V>(Li + I), Lp = ldp<V>(Li + I + l.g.s[i]);
+#pragma unroll
+      for (int q = 0; q < V; ++q) s.v[q] -= (Lc.v[q] + Lp.v[q]);
+    }
+    Pack<V> inv;
+#pragma unroll
+    for (int q = 0; q < V; ++q) inv.v[q] = (s.v[q] * s.v[q] < 2 * WL_EPS32) ? 0.f : 1.f / s.v[q];
+    stp<V>(l.Dg + I, s);
+    stp<V>(l.iD + I, inv);
   });
 }
 
 // restrictL! interior part (MultiLevelPoisson.jl:26-30) with restrictL (:10-16), up(I,i) (:1)
-template <int D>
+template <int D, int V>
 __global__ void __launch_bounds__(256) k_restrictL(Lvl c, Lvl f) {
-  const Box b = box_interior(c.g);
-  for_cells(c.g, b, [&](int i0, int j0, int k0, int64_t I) {
+  for_rows<1>(c.g, [&](int i0, int j0, int k0, int64_t I) {
     const int cc[3] = {i0, j0, k0};
 #pragma unroll
     for (int i = 0; i < D; ++i) {
@@ -66,15 +87,19 @@ __global__ void __launch_bounds__(256) k_restrictL(Lvl c, Lvl f) {
 }
 
 // residual! first loop + sum (Poisson.jl:93-94)
-template <int D>
+template <int D, int V>
 __global__ void __launch_bounds__(256) k_residual(Lvl l, ReduceWS ws) {
-  const Box b = box_interior(l.g);
   double acc[2] = {0.0, 0.0};
-  for_cells(l.g, b, [&](int, int, int, int64_t I) {
-    const float r = l.iD[I] == 0.f ? 0.f : l.z[I] - mult_at<D>(l, I, l.x);
-    l.r[I] = r;
-    acc[0] += (double)r;
-    acc[1] += (double)r * (double)r;
+  for_rows<V>(l.g, [&](int, int, int, int64_t I) {
+    const Pack<V> xc = ldp<V>(l.x + I), ax = mult_row<D, V>(l, I, l.x, xc), zc = ldp<V>(l.z + I), id = ldp<V>(l.iD + I);
+    Pack<V> r;
+#pragma unroll
+    for (int q = 0; q < V; ++q) {
+      r.v[q] = id.v[q] == 0.f ? 0.f : zc.v[q] - ax.v[q];
+      acc[0] += (double)r.v[q];
+      acc[1] += (double)r.v[q] * (double)r.v[q];
+    }
+    stp<V>(l.r + I, r);
   });
   double tot[2];
   if (grid_reduce<2>(acc, ws, tot)) {
@@ -85,53 +110,66 @@ __global__ void __launch_bounds__(256) k_residual(Lvl l, ReduceWS ws) {
   }
 }
 // residual! second loop (Poisson.jl:96), predicated on |s| > 2eps
+template <int D, int V>
 __global__ void __launch_bounds__(256) k_sub_mean(Lvl l, ReduceWS ws) {
   if (!l.sc->need_sub) return;
   const float s = l.sc->rsum;
-  const Box b = box_interior(l.g);
   double acc[1] = {0.0};
-  for_cells(l.g, b, [&](int, int, int, int64_t I) {
-    const float r = l.r[I] - s;
-    l.r[I] = r;
-    acc[0] += (double)r * (double)r;
+  for_rows<V>(l.g, [&](int, int, int, int64_t I) {
+    Pack<V> r = ldp<V>(l.r + I);
+#pragma unroll
+    for (int q = 0; q < V; ++q) { r.v[q] = r.v[q] - s; acc[0] += (double)r.v[q] * (double)r.v[q]; }
+    stp<V>(l.r + I, r);
   });
   double tot[1];
   if (grid_reduce<1>(acc, ws, tot)) l.sc->r2 = (float)tot[0];
 }
 
 // mult! interior (Poisson.jl:66)
-template <int D>
+template <int D, int V>
 __global__ void __launch_bounds__(256) k_mult(Lvl l) {
-  const Box b = box_interior(l.g);
-  for_cells(l.g, b, [&](int, int, int, int64_t I) { l.z[I] = mult_at<D>(l, I, l.x); });
+  for_rows<V>(l.g, [&](int, int, int, int64_t I) {
+    const Pack<V> xc = ldp<V>(l.x + I);
+    stp<V>(l.z + I, mult_row<D, V>(l, I, l.x, xc));
+  });
 }
 
 // Jacobi! (Poisson.jl:111): ϵ = r·iD
+template <int D, int V>
 __global__ void __launch_bounds__(256) k_jacobi_eps(Lvl l) {
-  const Box b = box_interior(l.g);
-  for_cells(l.g, b, [&](int, int, int, int64_t I) { l.eps[I] = l.r[I] * l.iD[I]; });
+  for_rows<V>(l.g, [&](int, int, int, int64_t I) {
+    const Pack<V> r = ldp<V>(l.r + I), id = ldp<V>(l.iD + I);
+    Pack<V> e;
+#pragma unroll
+    for (int q = 0; q < V; ++q) e.v[q] = r.v[q] * id.v[q];
+    stp<V>(l.eps + I, e);
+  });
 }
 
 // increment! (Poisson.jl:101-102) + L₂
-template <int D>
+template <int D, int V>
 __global__ void __launch_bounds__(256) k_increment(Lvl l, ReduceWS ws) {
-  const Box b = box_interior(l.g);
   double acc[1] = {0.0};
-  for_cells(l.g, b, [&](int, int, int, int64_t I) {
-    const float r = l.r[I] - mult_at<D>(l, I, l.eps);
-    l.r[I] = r;
-    l.x[I] = l.x[I] + l.eps[I];
-    acc[0] += (double)r * (double)r;
+  for_rows<V>(l.g, [&](int, int, int, int64_t I) {
+    const Pack<V> ec = ldp<V>(l.eps + I), ae = mult_row<D, V>(l, I, l.eps, ec);
+    Pack<V> r = ldp<V>(l.r + I), x = ldp<V>(l.x + I);
+#pragma unroll
+    for (int q = 0; q < V; ++q) {
+      r.v[q] = r.v[q] - ae.v[q];
+      x.v[q] = x.v[q] + ec.v[q];
+      acc[0] += (double)r.v[q] * (double)r.v[q];
+    }
+    stp<V>(l.r + I, r);
+    stp<V>(l.x + I, x);
   });
   double tot[1];
   if (grid_reduce<1>(acc, ws, tot)) l.sc->r2 = (float)tot[0];
 }
 
 // restrict! (MultiLevelPoisson.jl:33) + fill!(coarse.x,0) (:75)
-template <int D>
+template <int D, int V>
 __global__ void __launch_bounds__(256) k_restrict(Lvl c, Lvl f) {
-  const Box b = box_interior(c.g);
-  for_cells(c.g, b, [&](int i0, int j0, int k0, int64_t I) {
+  for_rows<1>(c.g, [&](int i0, int j0, int k0, int64_t I) {
     const int cc[3] = {i0, j0, k0};
     int lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
 #pragma unroll
@@ -146,26 +184,29 @@ __global__ void __launch_bounds__(256) k_restrict(Lvl c, Lvl f) {
 }
 
 // prolongate! (MultiLevelPoisson.jl:34) with down(I) (:2)
-template <int D>
+template <int D, int V>
 __global__ void __launch_bounds__(256) k_prolongate(Lvl f, Lvl c) {
-  const Box b = box_interior(f.g);
-  for_cells(f.g, b, [&](int i0, int j0, int k0, int64_t I) {
-    const int64_t J = (int64_t)((i0 + 1) >> 1) + (D > 1 ? ((j0 + 1) >> 1) * c.g.s[1] : 0) + (D > 2 ? ((k0 + 1) >> 1) * c.g.s[2] : 0);
-    f.eps[I] = c.x[J];
+  for_rows<V>(f.g, [&](int i0, int j0, int k0, int64_t I) {
+    const int64_t J = (D > 1 ? ((j0 + 1) >> 1) * c.g.s[1] : 0) + (D > 2 ? ((k0 + 1) >> 1) * c.g.s[2] : 0);
+    Pack<V> e;
+#pragma unroll
+    for (int q = 0; q < V; ++q) e.v[q] = c.x[J + ((i0 + q + 1) >> 1)];
+    stp<V>(f.eps + I, e);
   });
 }
 
 // ---- pcg! (Poisson.jl:123-144) -----------------------------------------------------------
 // :125-127  z = ϵ = r·iD ; ρ = r⋅z ; |ρ|<10eps → return      (z is rewritten by k_pcg_mult before
 // any read, so only ϵ is stored)
+template <int D, int V>
 __global__ void __launch_bounds__(256) k_pcg_init(Lvl l, ReduceWS ws) {
-  const Box b = box_interior(l.g);
   double acc[1] = {0.0};
-  for_cells(l.g, b, [&](int, int, int, int64_t I) {
-    const float r = l.r[I];
-    const float e = r * l.iD[I];
-    l.eps[I] = e;
-    acc[0] += (double)r * (double)e;
+  for_rows<V>(l.g, [&](int, int, int, int64_t I) {
+    const Pack<V> r = ldp<V>(l.r + I), id = ldp<V>(l.iD + I);
+    Pack<V> e;
+#pragma unroll
+    for (int q = 0; q < V; ++q) { e.v[q] = r.v[q] * id.v[q]; acc[0] += (double)r.v[q] * (double)e.v[q]; }
+    stp<V>(l.eps + I, e);
   });
   double tot[1];
   if (grid_reduce<1>(acc, ws, tot)) {
@@ -176,15 +217,15 @@ __global__ void __launch_bounds__(256) k_pcg_init(Lvl l, ReduceWS ws) {
 }
 // :130-132  z = Aϵ ; α = ρ/(z⋅ϵ) ; |α|∉[1e-2,1e2] → return.  The dot runs over the padded arrays
 // in the reference; the ghost-shell part (non-zero only at level 1) is in sc->ghost_dot.
-template <int D>
+template <int D, int V>
 __global__ void __launch_bounds__(256) k_pcg_mult(Lvl l, ReduceWS ws) {
   if (!l.sc->active) return;
-  const Box b = box_interior(l.g);
   double acc[1] = {0.0};
-  for_cells(l.g, b, [&](int, int, int, int64_t I) {
-    const float z = mult_at<D>(l, I, l.eps);
-    l.z[I] = z;
-    acc[0] += (double)z * (double)l.eps[I];
+  for_rows<V>(l.g, [&](int, int, int, int64_t I) {
+    const Pack<V> ec = ldp<V>(l.eps + I), z = mult_row<D, V>(l, I, l.eps, ec);
+#pragma unroll
+    for (int q = 0; q < V; ++q) acc[0] += (double)z.v[q] * (double)ec.v[q];
+    stp<V>(l.z + I, z);
   });
   double tot[1];
   if (grid_reduce<1>(acc, ws, tot)) {
@@ -198,17 +239,23 @@ __global__ void __launch_bounds__(256) k_pcg_mult(Lvl l, ReduceWS ws) {
 }
 // :133-139  x += αϵ ; r -= αz ; [last sweep → return] ; z = r·iD ; ρ₂ = r⋅z ; |ρ₂|<10eps → return ;
 // β = ρ₂/ρ ; ρ = ρ₂
+template <int D, int V>
 __global__ void __launch_bounds__(256) k_pcg_update(Lvl l, ReduceWS ws, int last) {
   if (!l.sc->active) return;
   const float alpha = l.sc->alpha;
-  const Box b = box_interior(l.g);
   double acc[2] = {0.0, 0.0};
-  for_cells(l.g, b, [&](int, int, int, int64_t I) {
-    l.x[I] += alpha * l.eps[I];
-    const float r = l.r[I] - alpha * l.z[I];
-    l.r[I] = r;
-    acc[0] += (double)r * (double)(r * l.iD[I]);
-    acc[1] += (double)r * (double)r;
+  for_rows<V>(l.g, [&](int, int, int, int64_t I) {
+    const Pack<V> e = ldp<V>(l.eps + I), z = ldp<V>(l.z + I), id = ldp<V>(l.iD + I);
+    Pack<V> x = ldp<V>(l.x + I), r = ldp<V>(l.r + I);
+#pragma unroll
+    for (int q = 0; q < V; ++q) {
+      x.v[q] += alpha * e.v[q];
+      r.v[q] -= alpha * z.v[q];
+      acc[0] += (double)r.v[q] * (double)(r.v[q] * id.v[q]);
+      acc[1] += (double)r.v[q] * (double)r.v[q];
+    }
+    stp<V>(l.x + I, x);
+    stp<V>(l.r + I, r);
   });
   double tot[2];
   if (grid_reduce<2>(acc, ws, tot)) {
@@ -228,12 +275,18 @@ __global__ void __launch_bounds__(256) k_pcg_update(Lvl l, ReduceWS ws, int last
   }
 }
 // :140  ϵ = βϵ + z  with z = r·iD recomputed
+template <int D, int V>
 __global__ void __launch_bounds__(256) k_pcg_dir(Lvl l) {
   if (!l.sc->active) return;
   const float beta = l.sc->beta;
   if (blockIdx.x == 0 && threadIdx.x + threadIdx.y + threadIdx.z == 0) atomicAdd(&l.sc->cnt_dir, 1);
-  const Box b = box_interior(l.g);
-  for_cells(l.g, b, [&](int, int, int, int64_t I) { l.eps[I] = beta * l.eps[I] + l.r[I] * l.iD[I]; });
+  for_rows<V>(l.g, [&](int, int, int, int64_t I) {
+    const Pack<V> r = ldp<V>(l.r + I), id = ldp<V>(l.iD + I);
+    Pack<V> e = ldp<V>(l.eps + I);
+#pragma unroll
+    for (int q = 0; q < V; ++q) e.v[q] = beta * e.v[q] + r.v[q] * id.v[q];
+    stp<V>(l.eps + I, e);
+  });
 }
 
 // Σ_shell z·ϵ  → sc->ghost_dot  (level 1: z ≡ σ keeps the stale Φ of conv_diff! on its upper ghost
@@ -252,38 +305,28 @@ __global__ void __launch_bounds__(256) k_shell_dot(Lvl l, ReduceWS ws, int64_t c
   if (grid_reduce<1>(acc, ws, tot)) l.sc->ghost_dot = tot[0];
 }
 
+template <int D, int V>
 __global__ void __launch_bounds__(256) k_dot_rr(Lvl l, ReduceWS ws, double* out) {
-  const Box b = box_interior(l.g);
   double acc[1] = {0.0};
-  for_cells(l.g, b, [&](int, int, int, int64_t I) { acc[0] += (double)l.r[I] * (double)l.r[I]; });
+  for_rows<V>(l.g, [&](int, int, int, int64_t I) {
+    const Pack<V> r = ldp<V>(l.r + I);
+#pragma unroll
+    for (int q = 0; q < V; ++q) acc[0] += (double)r.v[q] * (double)r.v[q];
+  });
   double tot[1];
   if (grid_reduce<1>(acc, ws, tot)) *out = tot[0];
 }
 
 }  // namespace
 
-#define LAUNCH(s, kern, ntiles, blk, ...)                                        \
-  do {                                                                            \
-    kern<<<wl_grid_for((s), (ntiles)), (blk), 0, (s).stream>>>(__VA_ARGS__);      \
-    ++(s).launches;                                                               \
-  } while (0)
-#define LAUNCH_D(s, kern, D, ntiles, blk, ...)                                   \
-  do {                                                                            \
-    if ((D) == 2) LAUNCH(s, kern<2>, ntiles, blk, __VA_ARGS__);                   \
-    else LAUNCH(s, kern<3>, ntiles, blk, __VA_ARGS__);                            \
-  } while (0)
-
-static inline int64_t interior_tiles(const GridD& g, dim3 blk) { return box_tiles(box_interior(g), blk); }
 static inline double cellsB(const Lvl& l, int words) { return 4.0 * words * (double)l.g.interior; }
 
 int pois_set_diag(Sim& s, Lvl& l) {
-  const dim3 blk = wl_pick_block(l.g);
-  LAUNCH_D(s, k_set_diag, s.D, interior_tiles(l.g, blk), blk, l);
+  RLAUNCH(s, k_set_diag, l.g, l);
   return wl_cuda_check(s, cudaGetLastError(), "k_set_diag");
 }
 int pois_restrictL(Sim& s, Lvl& c, const Lvl& f) {
-  const dim3 blk = wl_pick_block(c.g);
-  LAUNCH_D(s, k_restrictL, s.D, interior_tiles(c.g, blk), blk, c, f);
+  RLAUNCH(s, k_restrictL, c.g, c, f);
   const double zero[3] = {0, 0, 0};
   return bc_vec(s, c.g, c.L, zero, false, f.g.per);  // BC!(a,0,false,perdir) (MultiLevelPoisson.jl:31)
 }
@@ -302,20 +345,17 @@ int pois_mult(Sim& s) {
   int rc = bc_per(s, l.g, l.x, l.g.per);
   if (rc) return rc;
   if ((rc = wl_fill(s, l.z - WL_OX, 0.f, l.g.comp))) return rc;
-  const dim3 blk = wl_pick_block(l.g);
-  LAUNCH_D(s, k_mult, s.D, interior_tiles(l.g, blk), blk, l);
+  RLAUNCH(s, k_mult, l.g, l);
   return wl_cuda_check(s, cudaGetLastError(), "k_mult");
 }
 // residual!(p) (Poisson.jl:91-97)
 int pois_residual(Sim& s, Lvl& l) {
   int rc = bc_per(s, l.g, l.x, l.g.per);
   if (rc) return rc;
-  const dim3 blk = wl_pick_block(l.g);
-  const int64_t nt = interior_tiles(l.g, blk);
   const bool fine = &l == &s.levels[0];
   if (fine) wl_prof_begin(s, WL_PROF_RESIDUAL);
-  LAUNCH_D(s, k_residual, s.D, nt, blk, l, s.ws);
-  LAUNCH(s, k_sub_mean, nt, blk, l, s.ws);
+  RLAUNCH(s, k_residual, l.g, l, s.ws);
+  RLAUNCH(s, k_sub_mean, l.g, l, s.ws);
   if (fine) wl_prof_end(s, WL_PROF_RESIDUAL, cellsB(l, 8));
   return wl_cuda_check(s, cudaGetLastError(), "k_residual");
 }
@@ -323,18 +363,16 @@ int pois_residual(Sim& s, Lvl& l) {
 static int pois_increment(Sim& s, Lvl& l) {
   int rc = bc_per(s, l.g, l.eps, l.g.per);
   if (rc) return rc;
-  const dim3 blk = wl_pick_block(l.g);
   const bool fine = &l == &s.levels[0];
   if (fine) wl_prof_begin(s, WL_PROF_INCREMENT);
-  LAUNCH_D(s, k_increment, s.D, interior_tiles(l.g, blk), blk, l, s.ws);
+  RLAUNCH(s, k_increment, l.g, l, s.ws);
   if (fine) wl_prof_end(s, WL_PROF_INCREMENT, cellsB(l, 9));
   return wl_cuda_check(s, cudaGetLastError(), "k_increment");
 }
 // Jacobi!(p;it) (Poisson.jl:110-113)
 int pois_jacobi(Sim& s, Lvl& l, int it) {
-  const dim3 blk = wl_pick_block(l.g);
   for (int t = 0; t < it; ++t) {
-    LAUNCH(s, k_jacobi_eps, interior_tiles(l.g, blk), blk, l);
+    RLAUNCH(s, k_jacobi_eps, l.g, l);
     const int rc = pois_increment(s, l);
     if (rc) return rc;
   }
@@ -343,13 +381,11 @@ int pois_jacobi(Sim& s, Lvl& l, int it) {
 // pcg!(p;it) (Poisson.jl:123-144) — enqueued in full; early exits are device-side predicates
 int pois_pcg(Sim& s, int level, int it) {
   Lvl& l = s.levels[level];
-  const dim3 blk = wl_pick_block(l.g);
-  const int64_t nt = interior_tiles(l.g, blk);
   const bool fine = level == 0;
   bool anyper = false;
   for (int k = 0; k < s.D; ++k) anyper |= l.g.per[k] != 0;
   if (fine) wl_prof_begin(s, WL_PROF_PCG_INIT);
-  LAUNCH(s, k_pcg_init, nt, blk, l, s.ws);
+  RLAUNCH(s, k_pcg_init, l.g, l, s.ws);
   if (fine) wl_prof_end(s, WL_PROF_PCG_INIT, cellsB(l, 3));
   for (int i = 1; i <= it; ++i) {
     if (anyper) {
@@ -362,13 +398,13 @@ int pois_pcg(Sim& s, int level, int it) {
       }
     }
     if (fine) wl_prof_begin(s, WL_PROF_PCG_MULT);
-    LAUNCH_D(s, k_pcg_mult, s.D, nt, blk, l, s.ws);
+    RLAUNCH(s, k_pcg_mult, l.g, l, s.ws);
     if (fine) { wl_prof_end(s, WL_PROF_PCG_MULT, 0); wl_prof_begin(s, WL_PROF_PCG_UPDATE); }
-    LAUNCH(s, k_pcg_update, nt, blk, l, s.ws, i == it ? 1 : 0);
+    RLAUNCH(s, k_pcg_update, l.g, l, s.ws, i == it ? 1 : 0);
     if (fine) wl_prof_end(s, WL_PROF_PCG_UPDATE, 0);
     if (i == it) break;
     if (fine) wl_prof_begin(s, WL_PROF_PCG_DIR);
-    LAUNCH(s, k_pcg_dir, nt, blk, l);
+    RLAUNCH(s, k_pcg_dir, l.g, l);
     if (fine) wl_prof_end(s, WL_PROF_PCG_DIR, 0);
   }
   return wl_cuda_check(s, cudaGetLastError(), "pcg");
@@ -379,16 +415,10 @@ int pois_vcycle(Sim& s, int level) {
   Lvl& coarse = s.levels[level + 1];
   int rc = pois_jacobi(s, fine, 1);
   if (rc) return rc;
-  {
-    const dim3 blk = wl_pick_block(coarse.g);
-    LAUNCH_D(s, k_restrict, s.D, interior_tiles(coarse.g, blk), blk, coarse, fine);
-  }
+  RLAUNCH(s, k_restrict, coarse.g, coarse, fine);
   if (level + 2 < (int)s.levels.size() && (rc = pois_vcycle(s, level + 1))) return rc;
   if ((rc = pois_pcg(s, level + 1, 6))) return rc;
-  {
-    const dim3 blk = wl_pick_block(fine.g);
-    LAUNCH_D(s, k_prolongate, s.D, interior_tiles(fine.g, blk), blk, fine, coarse);
-  }
+  RLAUNCH(s, k_prolongate, fine.g, fine, coarse);
   return pois_increment(s, fine);
 }
 // solver!(ml;tol,itmx) (MultiLevelPoisson.jl:87-99) / solver!(p::Poisson;tol,itmx) (Poisson.jl:162-172)
@@ -413,9 +443,8 @@ int pois_solve(Sim& s, double tol, int itmx, int* n_out) {
   return rc;
 }
 int pois_dot_rr(Sim& s, Lvl& l, double* out) {
-  const dim3 blk = wl_pick_block(l.g);
   double* d = s.ws.partials + (size_t)WL_MAXBLOCKS * WL_MAXRED;  // spare slot behind the partials
-  LAUNCH(s, k_dot_rr, interior_tiles(l.g, blk), blk, l, s.ws, d);
+  RLAUNCH(s, k_dot_rr, l.g, l, s.ws, d);
   int rc = wl_read_scalars(s, d, sizeof(double));
   if (rc) return rc;
   double v;

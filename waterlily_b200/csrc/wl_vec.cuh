@@ -1,0 +1,90 @@
+// wl_vec.cuh — row-vectorised iteration for the HBM-bound field kernels.
+//
+// Every field row starts 16-byte aligned at its first interior cell (WL_OX), so when the interior
+// row length is a multiple of 4 a thread owns 4 consecutive cells and moves them with one
+// 128-bit load/store per field (V=4); coarse multigrid levels with odd row lengths use V=1.
+// A block is (BX,BY): BX threads sweep a row (stride V*BX), BY rows per block; blocks stride over
+// (row-group, plane) units, so the only integer divisions are one 32-bit pair per unit — the
+// per-cell 64-bit div/mod of a flat index cost more than the stencil itself (profiles/r01).
+#pragma once
+#include "wl_common.cuh"
+
+#ifdef __CUDACC__
+template <int V> struct Pack { float v[V]; };
+
+template <int V> __device__ __forceinline__ Pack<V> ldp(const float* __restrict__ p);
+template <> __device__ __forceinline__ Pack<4> ldp<4>(const float* __restrict__ p) {
+  const float4 t = *reinterpret_cast<const float4*>(p);
+  Pack<4> r; r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w; return r;
+}
+template <> __device__ __forceinline__ Pack<1> ldp<1>(const float* __restrict__ p) { Pack<1> r; r.v[0] = *p; return r; }
+
+template <int V> __device__ __forceinline__ void stp(float* __restrict__ p, const Pack<V>& a);
+template <> __device__ __forceinline__ void stp<4>(float* __restrict__ p, const Pack<4>& a) {
+  *reinterpret_cast<float4*>(p) = make_float4(a.v[0], a.v[1], a.v[2], a.v[3]);
+}
+template <> __device__ __forceinline__ void stp<1>(float* __restrict__ p, const Pack<1>& a) { *p = a.v[0]; }
+
+// values at x-1 / x+1 of each lane, given the centre pack loaded from p
+template <int V> __device__ __forceinline__ Pack<V> ld_xm(const float* __restrict__ p, const Pack<V>& c) {
+  Pack<V> r; r.v[0] = p[-1];
+#pragma unroll
+  for (int l = 1; l < V; ++l) r.v[l] = c.v[l - 1];
+  return r;
+}
+template <int V> __device__ __forceinline__ Pack<V> ld_xp(const float* __restrict__ p, const Pack<V>& c) {
+  Pack<V> r;
+#pragma unroll
+  for (int l = 0; l < V - 1; ++l) r.v[l] = c.v[l + 1];
+  r.v[V - 1] = p[V];
+  return r;
+}
+
+// interior rows; f(i, j, k, I) is called for the first cell of each V-group
+template <int V, class F>
+__device__ __forceinline__ void for_rows(const GridD& g, F&& f) {
+  const int nj = g.D > 1 ? g.n[1] - 2 : 1, nk = g.D > 2 ? g.n[2] - 2 : 1;
+  const int njt = (nj + blockDim.y - 1) / blockDim.y;
+  const int nunits = njt * nk;
+  const int nxi = g.n[0] - 2;
+  for (int unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
+    const int kk = unit / njt, jt = unit - kk * njt;
+    const int j = 1 + jt * blockDim.y + threadIdx.y;
+    if (j > nj) continue;
+    const int k = g.D > 2 ? 1 + kk : 0;
+    const int64_t row = j * g.s[1] + k * g.s[2];
+    for (int i = 1 + V * threadIdx.x; i <= nxi; i += V * blockDim.x) f(i, j, k, row + i);
+  }
+}
+#endif
+
+// host-side launch geometry for for_rows kernels
+struct RowLaunch { int V; dim3 blk; int nunits; };
+inline RowLaunch row_launch(const GridD& g) {
+  RowLaunch r;
+  const int nxi = g.n[0] - 2;
+  r.V = (nxi % 4 == 0) ? 4 : 1;
+  const int per = nxi / r.V;
+  int bx = 8;
+  while (bx < per && bx < 128) bx <<= 1;
+  r.blk = dim3(bx, 256 / bx, 1);
+  const int nj = g.D > 1 ? g.n[1] - 2 : 1, nk = g.D > 2 ? g.n[2] - 2 : 1;
+  r.nunits = ((nj + (int)r.blk.y - 1) / (int)r.blk.y) * nk;
+  return r;
+}
+
+// launch a for_rows kernel<D,V> on the interior of grid `grd`
+#define RLAUNCH(s, KERN, grd, ...)                                                               \
+  do {                                                                                            \
+    const RowLaunch rl_ = row_launch(grd);                                                        \
+    const int gs_ = wl_grid_for((s), rl_.nunits);                                                 \
+    if ((s).D == 2) {                                                                             \
+      if (rl_.V == 4) KERN<2, 4><<<gs_, rl_.blk, 0, (s).stream>>>(__VA_ARGS__);                   \
+      else KERN<2, 1><<<gs_, rl_.blk, 0, (s).stream>>>(__VA_ARGS__);                              \
+    } else {                                                                                      \
+      if (rl_.V == 4) KERN<3, 4><<<gs_, rl_.blk, 0, (s).stream>>>(__VA_ARGS__);                   \
+      else KERN<3, 1><<<gs_, rl_.blk, 0, (s).stream>>>(__VA_ARGS__);                              \
+    }                                                                                             \
+    ++(s).launches;                                                                               \
+  } while (0)
+
