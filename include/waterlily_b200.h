@@ -81,6 +81,22 @@ const char* wl_last_error(void);
 int wl_set_stream(wl_sim* s, void* cuda_stream);
 int wl_sync(wl_sim* s);
 
+/* ---- z-slab domain decomposition over the GPUs of one box (new; the reference is single-device,
+ *      README.md:157).  One process per GPU: rank 0 makes an id with wl_dist_unique_id, the launcher
+ *      broadcasts its 128 bytes (torch.distributed, MPI, a file …), every rank calls wl_create_dist
+ *      with the GLOBAL N.  N[2] is split into N[2]/nranks planes per rank (must be even); halo
+ *      planes travel by NCCL send/recv at the reference's BC!/perBC! sites, scalar reductions by
+ *      NCCL all-reduce, and multigrid levels with fewer than 8 planes per rank are replicated on
+ *      every rank (agglomeration).  All other entry points then act on the rank's slab and are
+ *      collective: every rank must make the same calls in the same order.  Host arrays passed to
+ *      upload/download always have the GLOBAL shape; upload reads the rank's planes from it,
+ *      download fills only the planes the rank owns. ------------------------------------------- */
+int wl_dist_unique_id(char* out128);
+int wl_create_dist(wl_sim** out, int D, const int* N, double nu, double dt0,
+                   const int* perdir, int exitBC, int pois_kind, int device,
+                   int rank, int nranks, const char* nccl_id128);
+int wl_dist_info(wl_sim* s, int* rank, int* nranks, int* zoff, int* nz_local, int64_t* collectives);
+
 /* ---- field transfer: B200Array(::Array) / Array(::B200Array) ---------------------------- */
 int wl_field_count(wl_sim* s, int field, int64_t* count);
 int wl_upload(wl_sim* s, int field, const float* host, int64_t count);

@@ -612,6 +612,21 @@ int wlo_create(wl_sim** out, int D, const int* N, double nu, double dt0, const i
   }
   *out = (wl_sim*)a; return WL_OK;
 }
+// the oracle is single-process: the dist entry points exist only to keep the ABI identical
+int wlo_dist_unique_id(char* out128) { if (out128) std::memset(out128, 0, 128); return WL_OK; }
+int wlo_create_dist(wl_sim** out, int D, const int* N, double nu, double dt0, const int* perdir, int exitBC, int pois_kind, int device,
+                    int rank, int nranks, const char*) {
+  if (nranks != 1 || rank != 0) return fail(WL_ERR_ARG, "the oracle is not distributed");
+  return wlo_create(out, D, N, nu, dt0, perdir, exitBC, pois_kind, device);
+}
+int wlo_dist_info(wl_sim* s, int* rank, int* nranks, int* zoff, int* nz_local, int64_t* collectives) {
+  if (rank) *rank = 0;
+  if (nranks) *nranks = 1;
+  if (zoff) *zoff = 0;
+  if (nz_local) *nz_local = S->D == 3 ? S->g.n[2] - 2 : 1;
+  if (collectives) *collectives = 0;
+  return WL_OK;
+}
 int wlo_destroy(wl_sim* s) { delete S; return WL_OK; }
 const char* wlo_last_error(void) { return g_err.c_str(); }
 int wlo_set_stream(wl_sim*, void*) { return WL_OK; }

@@ -19,6 +19,10 @@ H = C.c_void_p
 # name -> (restype, argtypes); mirrors include/waterlily_b200.h one to one
 SIGNATURES = {
     "create": (C.c_int, [C.POINTER(H), C.c_int, c_int_p, C.c_double, C.c_double, c_int_p, C.c_int, C.c_int, C.c_int]),
+    "dist_unique_id": (C.c_int, [C.c_char_p]),
+    "create_dist": (C.c_int, [C.POINTER(H), C.c_int, c_int_p, C.c_double, C.c_double, c_int_p, C.c_int, C.c_int, C.c_int,
+                              C.c_int, C.c_int, C.c_char_p]),
+    "dist_info": (C.c_int, [H, c_int_p, c_int_p, c_int_p, c_int_p, c_i64_p]),
     "destroy": (C.c_int, [H]),
     "last_error": (C.c_char_p, []),
     "set_stream": (C.c_int, [H, C.c_void_p]),
@@ -87,6 +91,13 @@ class CABI:
             raise WLError((msg.decode("utf-8") if msg else "") + f" (status {status})")
 
 
+def nccl_unique_id(cabi: CABI) -> bytes:
+    """128-byte NCCL id made by rank 0 and broadcast by the launcher (wl_dist_unique_id)."""
+    buf = C.create_string_buffer(128)
+    cabi.check(cabi.dist_unique_id(buf))
+    return buf.raw
+
+
 def _ints(vals):
     return (C.c_int * len(vals))(*[int(v) for v in vals])
 
@@ -102,7 +113,8 @@ class Engine:
     last — represented in numpy as Fortran-ordered float32 arrays of shape ``(Ng..., D)``.
     """
 
-    def __init__(self, cabi: CABI, dims, nu=0.0, dt0=0.25, perdir=(), exitBC=False, pois_kind=POIS_MULTILEVEL, device=0):
+    def __init__(self, cabi: CABI, dims, nu=0.0, dt0=0.25, perdir=(), exitBC=False, pois_kind=POIS_MULTILEVEL, device=0, dist=None):
+        """``dist=(rank, nranks, nccl_id_bytes)`` makes this handle one z-slab of a multi-GPU job."""
         self.cabi = cabi
         self.D = len(dims)
         self.N = tuple(int(n) for n in dims)
@@ -111,8 +123,14 @@ class Engine:
         self.per_flags = [1 if (j + 1) in self.perdir else 0 for j in range(self.D)]
         self.exitBC = bool(exitBC)
         self.h = H()
-        cabi.check(cabi.create(C.byref(self.h), self.D, _ints(self.N), float(nu), float(dt0), _ints(self.per_flags),
-                               int(self.exitBC), int(pois_kind), int(device)))
+        self.dist = dist
+        if dist is None or dist[1] == 1:
+            cabi.check(cabi.create(C.byref(self.h), self.D, _ints(self.N), float(nu), float(dt0), _ints(self.per_flags),
+                                   int(self.exitBC), int(pois_kind), int(device)))
+        else:
+            rank, nranks, ident = dist
+            cabi.check(cabi.create_dist(C.byref(self.h), self.D, _ints(self.N), float(nu), float(dt0), _ints(self.per_flags),
+                                        int(self.exitBC), int(pois_kind), int(device), int(rank), int(nranks), bytes(ident)))
 
     # -- lifetime
     def close(self):
@@ -144,9 +162,14 @@ class Engine:
 
     def download(self, field):
         field = FIELD_IDS.get(field, field)
-        a = np.empty(self.shape(field), dtype=np.float32, order="F")
+        a = np.zeros(self.shape(field), dtype=np.float32, order="F")  # a slab handle fills only the planes it owns
         self.cabi.check(self.cabi.download(self.h, field, a.ctypes.data_as(c_flt_p), a.size))
         return a
+
+    def dist_info(self):
+        r, n, z, nz, c = C.c_int(0), C.c_int(1), C.c_int(0), C.c_int(0), C.c_int64(0)
+        self.cabi.check(self.cabi.dist_info(self.h, C.byref(r), C.byref(n), C.byref(z), C.byref(nz), C.byref(c)))
+        return {"rank": r.value, "nranks": n.value, "zoff": z.value, "nz_local": nz.value, "collectives": c.value}
 
     def nlevels(self):
         return int(self.cabi.nlevels(self.h))
@@ -169,7 +192,7 @@ class Engine:
 
     def level_download(self, level, lfield):
         lfield = LEVEL_IDS.get(lfield, lfield)
-        a = np.empty(self.level_shape(level, lfield), dtype=np.float32, order="F")
+        a = np.zeros(self.level_shape(level, lfield), dtype=np.float32, order="F")
         self.cabi.check(self.cabi.level_download(self.h, level, lfield, a.ctypes.data_as(c_flt_p), a.size))
         return a
 

@@ -3,6 +3,7 @@
 // returns a status; nothing throws across the boundary.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -65,18 +66,26 @@ void grid_set(GridD& g, int D, const int* Ng, const int* per) {
   for (int k = 0; k < 3; ++k) { g.n[k] = k < D ? Ng[k] : 1; g.per[k] = (k < D && per) ? (per[k] != 0) : 0; }
   const int64_t pitch = ((int64_t)g.n[0] + WL_OX + 3) / 4 * 4;  // rows start 16-byte aligned at i=1
   g.s[0] = 1; g.s[1] = pitch; g.s[2] = pitch * g.n[1];
-  g.comp = ((WL_OX + pitch * g.n[1] * g.n[2] + 8) + 3) / 4 * 4;
+  // 3-D fields carry one spare z-plane below plane 0 and above plane n-1: the depth-2 halo of u/u⁰
+  // in a z-slab decomposition lives there (QUICK reads I-2δz from the first interior plane)
+  const int64_t spare = D == 3 ? g.s[2] : 0;
+  g.lead = WL_OX + spare;
+  g.comp = ((g.lead + pitch * g.n[1] * g.n[2] + spare + 8) + 3) / 4 * 4;
   g.interior = 1;
   for (int k = 0; k < D; ++k) g.interior *= g.n[k] - 2;
+  g.interior_global = g.interior;
+  g.zlo_halo = g.zhi_halo = 0;
+  g.zoff = 0;
 }
 
-float* dev_alloc(Sim& s, int64_t floats, int* rc) {
+float* dev_alloc(Sim& s, const GridD& g, int ncomp, int* rc) {
   void* p = nullptr;
-  cudaError_t e = cudaMalloc(&p, sizeof(float) * (size_t)floats);
-  if (e == cudaSuccess) e = cudaMemsetAsync(p, 0, sizeof(float) * (size_t)floats, s.stream);
+  const size_t bytes = sizeof(float) * (size_t)g.comp * ncomp;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e == cudaSuccess) e = cudaMemsetAsync(p, 0, bytes, s.stream);
   if (e != cudaSuccess) { *rc = wl_cuda_check(s, e, "cudaMalloc"); return nullptr; }
   s.allocs.push_back(p);
-  return (float*)p + WL_OX;
+  return (float*)p + g.lead;
 }
 
 float* field_ptr(Sim& s, int field, int* ncomp) {
@@ -108,19 +117,32 @@ float* level_ptr(Sim& s, int level, int lf, int* ncomp) {
   }
   return nullptr;
 }
-// host (dense, column-major, padded) <-> device (re-pitched rows)
-int copy_field(Sim& s, const GridD& g, float* dev, float* host, int ncomp, bool to_device) {
+// host (dense, column-major, padded, GLOBAL domain) <-> device (re-pitched rows, this rank's slab).
+// `slab`: the field lives on a z-distributed grid; the host array always has the global shape.
+// Download writes only the planes this rank owns (its interior planes and global ghost planes).
+int copy_field(Sim& s, const GridD& g, float* dev, float* host, int ncomp, bool to_device, int nz_global_padded) {
   const size_t w = sizeof(float) * (size_t)g.n[0];
-  const size_t rows = (size_t)g.n[1] * g.n[2];
-  const int64_t dense = (int64_t)g.n[0] * g.n[1] * g.n[2];
+  const int64_t dense = (int64_t)g.n[0] * g.n[1] * nz_global_padded;
+  int k0 = 0, k1 = g.n[2] - 1;
+  if (!to_device) {  // planes of a neighbouring slab are not ours to report; the global ghost planes are
+    if (g.zlo_halo && g.zoff != 0) k0 = 1;
+    if (g.zhi_halo && g.zoff + g.n[2] != nz_global_padded) k1 = g.n[2] - 2;
+  }
+  const size_t rows = (size_t)g.n[1] * (k1 - k0 + 1);
   for (int c = 0; c < ncomp; ++c) {
-    float* d = dev + c * g.comp;
-    float* h = host + c * dense;
+    float* d = dev + c * g.comp + (int64_t)k0 * g.s[2];
+    float* h = host + c * dense + (int64_t)(g.zoff + k0) * g.n[0] * g.n[1];
     cudaError_t e = to_device ? cudaMemcpy2DAsync(d, sizeof(float) * g.s[1], h, w, w, rows, cudaMemcpyHostToDevice, s.stream)
                               : cudaMemcpy2DAsync(h, w, d, sizeof(float) * g.s[1], w, rows, cudaMemcpyDeviceToHost, s.stream);
     if (e != cudaSuccess) return wl_cuda_check(s, e, "cudaMemcpy2DAsync");
   }
   return wl_cuda_check(s, cudaStreamSynchronize(s.stream), "cudaStreamSynchronize");
+}
+// padded global z-size of the grid a level lives on
+int nz_padded_global(const Sim& s, int level) {
+  const GridD& g = s.levels[level].g;
+  if (s.D < 3) return 1;
+  return (s.dist.nranks > 1 && s.lvl_dist[level]) ? (g.n[2] - 2) * s.dist.nranks + 2 : g.n[2];
 }
 inline bool divisible(int N) { return N % 2 == 0 && N > 4; }  // MultiLevelPoisson.jl:36
 }  // namespace
@@ -144,13 +166,15 @@ int wl_read_scalars(Sim& s, const void* dptr, size_t bytes) {
 
 extern "C" {
 
-int wl_create(wl_sim** out, int D, const int* N, double nu, double dt0, const int* perdir, int exitBC, int pois_kind, int device) {
+static int create_impl(wl_sim** out, int D, const int* N, double nu, double dt0, const int* perdir, int exitBC, int pois_kind, int device,
+                       int rank, int nranks, const char* nccl_id) {
   if (!out || !N || (D != 2 && D != 3)) return wl_fail(WL_ERR_ARG, "wl_create: D must be 2 or 3");
   for (int k = 0; k < D; ++k) if (N[k] < 1) return wl_fail(WL_ERR_ARG, "wl_create: N must be positive");
+  if (nranks < 1 || rank < 0 || rank >= nranks) return wl_fail(WL_ERR_ARG, "wl_create_dist: bad rank/nranks");
   // the MultiLevelPoisson size assertion comes first, as in the reference constructor
   int Ng[3] = {1, 1, 1};
   for (int k = 0; k < D; ++k) Ng[k] = N[k] + 2;
-  std::vector<std::vector<int>> dims;
+  std::vector<std::vector<int>> dims;  // GLOBAL padded sizes per level
   dims.push_back({Ng[0], Ng[1], Ng[2]});
   if (pois_kind == WL_POIS_MULTILEVEL) {
     auto div_ok = [&](const std::vector<int>& n) { for (int k = 0; k < D; ++k) if (!divisible(n[k])) return false; return true; };
@@ -161,6 +185,24 @@ int wl_create(wl_sim** out, int D, const int* N, double nu, double dt0, const in
     }
     if (dims.size() <= 2) return wl_fail(WL_ERR_ARG, "MultiLevelPoisson requires size=a2ⁿ, where n>2");
   }
+  // z-slab decomposition: which levels are distributed, which replicated (coarse tail)
+  std::vector<int> lvl_dist(dims.size(), 0);
+  if (nranks > 1) {
+    if (D != 3) return wl_fail(WL_ERR_ARG, "wl_create_dist: the z-slab decomposition needs D = 3");
+    if (N[2] % nranks != 0 || (N[2] / nranks) % 2 != 0)
+      return wl_fail(WL_ERR_ARG, "wl_create_dist: N[3] must split into an even number of z-planes per rank");
+    const char* e = getenv("WL_DIST_MIN_NZ");
+    const int min_nz = e ? atoi(e) : 8;  // coarser levels are agglomerated: replicated on every rank
+    lvl_dist[0] = 1;
+    for (size_t l = 1; l < dims.size(); ++l) {
+      const int nz = dims[l][2] - 2;
+      const int nzf_loc = (dims[l - 1][2] - 2) / nranks;
+      lvl_dist[l] = lvl_dist[l - 1] && nz % nranks == 0 && nz / nranks >= min_nz && nzf_loc % 2 == 0;
+    }
+    for (size_t l = 1; l < dims.size(); ++l)
+      if (lvl_dist[l - 1] && !lvl_dist[l] && (((dims[l - 1][2] - 2) / nranks) % 2 != 0 || (dims[l][2] - 2) % nranks != 0))
+        return wl_fail(WL_ERR_ARG, "wl_create_dist: cannot agglomerate — odd number of z-planes per rank on the last distributed level");
+  }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return wl_fail(WL_ERR_CUDA, "wl_create: no CUDA device available (libwaterlily_b200 has no CPU fallback)");
@@ -169,6 +211,9 @@ int wl_create(wl_sim** out, int D, const int* N, double nu, double dt0, const in
   if (!sp) return wl_fail(WL_ERR_ARG, "out of host memory");
   Sim& a = *sp;
   a.D = D; a.device = device; a.nu = (float)nu; a.dt.push_back((float)dt0); a.exitBC = exitBC != 0; a.pois_kind = pois_kind;
+  a.lvl_dist = lvl_dist;
+  a.Nz_global = D == 3 ? N[2] : 1;
+  a.per_z_global = (D == 3 && perdir && perdir[2]) ? 1 : 0;
   int rc = 0;
   cudaDeviceProp prop;
   if ((rc = wl_cuda_check(a, cudaSetDevice(device), "cudaSetDevice")) ||
@@ -176,11 +221,31 @@ int wl_create(wl_sim** out, int D, const int* N, double nu, double dt0, const in
   a.nsm = prop.multiProcessorCount;
   if ((rc = wl_cuda_check(a, cudaStreamCreateWithFlags(&a.stream, cudaStreamNonBlocking), "cudaStreamCreate"))) { delete sp; return rc; }
   a.own_stream = true;
-  grid_set(a.g, D, Ng, perdir);
-  const int64_t c = a.g.comp;
-  a.u = dev_alloc(a, c * D, &rc); a.u0 = dev_alloc(a, c * D, &rc); a.f = dev_alloc(a, c * D, &rc);
-  a.p = dev_alloc(a, c, &rc); a.sigma = dev_alloc(a, c, &rc); a.V = dev_alloc(a, c * D, &rc);
-  a.mu0 = dev_alloc(a, c * D, &rc); a.mu1 = dev_alloc(a, c * D * D, &rc);
+  if ((rc = dist_init(a, rank, nranks, nccl_id))) { wl_destroy((wl_sim*)sp); return rc; }
+  // local grid of a level: a distributed level keeps Nz/R planes (+ghosts); z faces towards a
+  // neighbour (or the periodic wrap) become halo faces and the local grid is not z-periodic
+  auto make_grid = [&](GridD& g, const std::vector<int>& gd, bool distributed) {
+    int n3[3] = {gd[0], gd[1], gd[2]};
+    int per3[3] = {perdir ? perdir[0] : 0, (perdir && D > 1) ? perdir[1] : 0, (perdir && D > 2) ? perdir[2] : 0};
+    int64_t glob = 1;
+    for (int k = 0; k < D; ++k) glob *= gd[k] - 2;
+    if (distributed) {
+      const int nzl = (gd[2] - 2) / nranks;
+      n3[2] = nzl + 2;
+      per3[2] = 0;
+    }
+    grid_set(g, D, n3, per3);
+    g.interior_global = glob;
+    if (distributed) {
+      g.zoff = rank * (n3[2] - 2);
+      g.zlo_halo = (rank > 0 || a.per_z_global) ? 1 : 0;
+      g.zhi_halo = (rank < nranks - 1 || a.per_z_global) ? 1 : 0;
+    }
+  };
+  make_grid(a.g, dims[0], nranks > 1);
+  a.u = dev_alloc(a, a.g, D, &rc); a.u0 = dev_alloc(a, a.g, D, &rc); a.f = dev_alloc(a, a.g, D, &rc);
+  a.p = dev_alloc(a, a.g, 1, &rc); a.sigma = dev_alloc(a, a.g, 1, &rc); a.V = dev_alloc(a, a.g, D, &rc);
+  a.mu0 = dev_alloc(a, a.g, D, &rc); a.mu1 = dev_alloc(a, a.g, D * D, &rc);
   // solver scalars, reduction workspace, pinned readback
   void* tmp = nullptr;
   if (!rc && cudaMalloc(&tmp, sizeof(LevelScalars) * dims.size()) == cudaSuccess) { a.allocs.push_back(tmp); a.d_scalars = (LevelScalars*)tmp; cudaMemsetAsync(tmp, 0, sizeof(LevelScalars) * dims.size(), a.stream); } else if (!rc) rc = wl_fail(WL_ERR_CUDA, "cudaMalloc scalars");
@@ -192,19 +257,18 @@ int wl_create(wl_sim** out, int D, const int* N, double nu, double dt0, const in
   // levels[1] aliases the flow arrays (WaterLily.jl:77); r, ϵ, D, iD are its own (Poisson.jl:33-34)
   for (size_t l = 0; l < dims.size() && !rc; ++l) {
     Lvl lv{};
-    int n3[3] = {dims[l][0], dims[l][1], dims[l][2]};
-    grid_set(lv.g, D, n3, perdir);
+    make_grid(lv.g, dims[l], nranks > 1 && lvl_dist[l]);
     lv.sc = a.d_scalars + l;
     if (l == 0) { lv.x = a.p; lv.L = a.mu0; lv.z = a.sigma; }
-    else { lv.L = dev_alloc(a, lv.g.comp * D, &rc); lv.x = dev_alloc(a, lv.g.comp, &rc); lv.z = dev_alloc(a, lv.g.comp, &rc); }
-    lv.r = dev_alloc(a, lv.g.comp, &rc); lv.eps = dev_alloc(a, lv.g.comp, &rc);
-    lv.Dg = dev_alloc(a, lv.g.comp, &rc); lv.iD = dev_alloc(a, lv.g.comp, &rc);
+    else { lv.L = dev_alloc(a, lv.g, D, &rc); lv.x = dev_alloc(a, lv.g, 1, &rc); lv.z = dev_alloc(a, lv.g, 1, &rc); }
+    lv.r = dev_alloc(a, lv.g, 1, &rc); lv.eps = dev_alloc(a, lv.g, 1, &rc);
+    lv.Dg = dev_alloc(a, lv.g, 1, &rc); lv.iD = dev_alloc(a, lv.g, 1, &rc);
     a.levels.push_back(lv);
   }
   if (rc) { wl_destroy((wl_sim*)sp); return rc; }
   // μ₀ = 1, BC!(μ₀,0) (Flow.jl:118-119); then the Poisson constructors' set_diag!/restrictL!
   const double zero[3] = {0, 0, 0};
-  rc = wl_fill(a, a.mu0 - WL_OX, 1.f, c * D);
+  rc = wl_fill(a, a.mu0 - a.g.lead, 1.f, a.g.comp * D);
   if (!rc) rc = bc_vec(a, a.g, a.mu0, zero, false, a.g.per);
   if (!rc) rc = pois_update(a);
   if (!rc) rc = wl_cuda_check(a, cudaStreamSynchronize(a.stream), "wl_create sync");
@@ -213,11 +277,32 @@ int wl_create(wl_sim** out, int D, const int* N, double nu, double dt0, const in
   return WL_OK;
 }
 
+int wl_create(wl_sim** out, int D, const int* N, double nu, double dt0, const int* perdir, int exitBC, int pois_kind, int device) {
+  return create_impl(out, D, N, nu, dt0, perdir, exitBC, pois_kind, device, 0, 1, nullptr);
+}
+int wl_dist_unique_id(char* out128) { return out128 ? dist_unique_id(out128) : wl_fail(WL_ERR_ARG, "null buffer"); }
+int wl_create_dist(wl_sim** out, int D, const int* N, double nu, double dt0, const int* perdir, int exitBC, int pois_kind, int device,
+                   int rank, int nranks, const char* nccl_id128) {
+  if (nranks > 1 && !nccl_id128) return wl_fail(WL_ERR_ARG, "wl_create_dist: NCCL id required");
+  return create_impl(out, D, N, nu, dt0, perdir, exitBC, pois_kind, device, rank, nranks, nccl_id128);
+}
+int wl_dist_info(wl_sim* s, int* rank, int* nranks, int* zoff, int* nz_local, int64_t* collectives) {
+  if (!s) return wl_fail(WL_ERR_ARG, "null handle");
+  Sim& a = *(Sim*)s;
+  if (rank) *rank = a.dist.rank;
+  if (nranks) *nranks = a.dist.nranks;
+  if (zoff) *zoff = a.g.zoff;
+  if (nz_local) *nz_local = a.D == 3 ? a.g.n[2] - 2 : 1;
+  if (collectives) *collectives = a.collectives;
+  return WL_OK;
+}
+
 int wl_destroy(wl_sim* s) {
   if (!s) return WL_OK;
   Sim& a = S;
   cudaSetDevice(a.device);
   if (a.stream) cudaStreamSynchronize(a.stream);
+  dist_destroy(a);
   for (void* p : a.allocs) cudaFree(p);
   if (a.h_pinned) cudaFreeHost(a.h_pinned);
   for (auto& pc : a.prof) for (cudaEvent_t e : pc.ev) cudaEventDestroy(e);
@@ -239,26 +324,32 @@ int wl_sync(wl_sim* s) { GUARD(s); return wl_cuda_check(S, cudaStreamSynchronize
 int wl_field_count(wl_sim* s, int field, int64_t* count) {
   GUARD(s);
   int nc; if (!field_ptr(S, field, &nc)) return wl_fail(WL_ERR_ARG, "bad field");
-  *count = (int64_t)S.g.n[0] * S.g.n[1] * S.g.n[2] * nc;
+  *count = (int64_t)S.g.n[0] * S.g.n[1] * nz_padded_global(S, 0) * nc;
   return WL_OK;
 }
 int wl_upload(wl_sim* s, int field, const float* host, int64_t count) {
   GUARD(s);
   int nc; float* d = field_ptr(S, field, &nc);
-  if (!d || count != (int64_t)S.g.n[0] * S.g.n[1] * S.g.n[2] * nc) return wl_fail(WL_ERR_ARG, "wl_upload: bad field or size");
-  return copy_field(S, S.g, d, const_cast<float*>(host), nc, true);
+  const int nzg = nz_padded_global(S, 0);
+  if (!d || count != (int64_t)S.g.n[0] * S.g.n[1] * nzg * nc) return wl_fail(WL_ERR_ARG, "wl_upload: bad field or size");
+  int rc = copy_field(S, S.g, d, const_cast<float*>(host), nc, true, nzg);
+  // slab faces: refresh the halo planes from the neighbours (collective: every rank uploads the field)
+  if (!rc) rc = dist_halo(S, S.g, d, nc, (field == WL_U || field == WL_U0) ? 2 : 1);
+  return rc ? rc : wl_sync(s);
 }
 int wl_download(wl_sim* s, int field, float* host, int64_t count) {
   GUARD(s);
   int nc; float* d = field_ptr(S, field, &nc);
-  if (!d || count != (int64_t)S.g.n[0] * S.g.n[1] * S.g.n[2] * nc) return wl_fail(WL_ERR_ARG, "wl_download: bad field or size");
-  return copy_field(S, S.g, d, host, nc, false);
+  const int nzg = nz_padded_global(S, 0);
+  if (!d || count != (int64_t)S.g.n[0] * S.g.n[1] * nzg * nc) return wl_fail(WL_ERR_ARG, "wl_download: bad field or size");
+  return copy_field(S, S.g, d, host, nc, false, nzg);
 }
 int wl_nlevels(wl_sim* s) { return s ? (int)S.levels.size() : 0; }
 int wl_level_dims(wl_sim* s, int level, int* Ng) {
   GUARD(s);
   if (level < 0 || level >= (int)S.levels.size()) return wl_fail(WL_ERR_ARG, "bad level");
   for (int k = 0; k < S.D; ++k) Ng[k] = S.levels[level].g.n[k];
+  if (S.D == 3) Ng[2] = nz_padded_global(S, level);  // always the global shape
   return WL_OK;
 }
 int wl_level_upload(wl_sim* s, int level, int lf, const float* host, int64_t count) {
@@ -266,16 +357,20 @@ int wl_level_upload(wl_sim* s, int level, int lf, const float* host, int64_t cou
   int nc; float* d = level_ptr(S, level, lf, &nc);
   if (!d) return wl_fail(WL_ERR_ARG, "wl_level_upload: bad level/field");
   const GridD& g = S.levels[level].g;
-  if (count != (int64_t)g.n[0] * g.n[1] * g.n[2] * nc) return wl_fail(WL_ERR_ARG, "wl_level_upload: bad size");
-  return copy_field(S, g, d, const_cast<float*>(host), nc, true);
+  const int nzg = nz_padded_global(S, level);
+  if (count != (int64_t)g.n[0] * g.n[1] * nzg * nc) return wl_fail(WL_ERR_ARG, "wl_level_upload: bad size");
+  int rc = copy_field(S, g, d, const_cast<float*>(host), nc, true, nzg);
+  if (!rc) rc = dist_halo(S, g, d, nc, 1);
+  return rc ? rc : wl_sync(s);
 }
 int wl_level_download(wl_sim* s, int level, int lf, float* host, int64_t count) {
   GUARD(s);
   int nc; float* d = level_ptr(S, level, lf, &nc);
   if (!d) return wl_fail(WL_ERR_ARG, "wl_level_download: bad level/field");
   const GridD& g = S.levels[level].g;
-  if (count != (int64_t)g.n[0] * g.n[1] * g.n[2] * nc) return wl_fail(WL_ERR_ARG, "wl_level_download: bad size");
-  return copy_field(S, g, d, host, nc, false);
+  const int nzg = nz_padded_global(S, level);
+  if (count != (int64_t)g.n[0] * g.n[1] * nzg * nc) return wl_fail(WL_ERR_ARG, "wl_level_download: bad size");
+  return copy_field(S, g, d, host, nc, false, nzg);
 }
 
 static void per_flags(Sim& a, const int* perdir, int* out) {

@@ -55,19 +55,22 @@ __global__ void __launch_bounds__(256) k_bc_vec(GridD g, float* __restrict__ a, 
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < count; idx += (int64_t)gridDim.x * blockDim.x) {
     int c0[3];
     if (!planes_decode(g, idx, 3, c0)) continue;
+    // z-planes owned by a neighbouring slab are filled by the halo exchange, not by BC!
+    if (g.D > 2 && ((c0[2] == 0 && g.zlo_halo) || (c0[2] == g.n[2] - 1 && g.zhi_halo))) continue;
     for (int i = 0; i < g.D; ++i) {
       int c[3] = {c0[0], c0[1], c0[2]};
       bool written = false, constant = false;
       for (int j = g.D - 1; j >= 0; --j) {
         const int n = g.n[j];
+        const bool lo = !(j == 2 && g.zlo_halo), hi = !(j == 2 && g.zhi_halo);  // physical boundary on that side?
         if (args.per[j]) {
-          if (c[j] == 0) { c[j] = n - 2; written = true; }
-          else if (c[j] == n - 1) { c[j] = 1; written = true; }
+          if (c[j] == 0 && lo) { c[j] = n - 2; written = true; }
+          else if (c[j] == n - 1 && hi) { c[j] = 1; written = true; }
         } else if (i == j) {
-          if (c[j] <= 1 || (c[j] == n - 1 && !(args.saveexit && i == 0))) { constant = true; written = true; break; }
+          if ((c[j] <= 1 && lo) || (c[j] == n - 1 && hi && !(args.saveexit && i == 0))) { constant = true; written = true; break; }
         } else {
-          if (c[j] == 0) { c[j] = 1; written = true; }
-          else if (c[j] == n - 1) { c[j] = n - 2; written = true; }
+          if (c[j] == 0 && lo) { c[j] = 1; written = true; }
+          else if (c[j] == n - 1 && hi) { c[j] = n - 2; written = true; }
         }
       }
       if (!written) continue;
@@ -85,6 +88,7 @@ __global__ void __launch_bounds__(256) k_per_bc(GridD g, float* __restrict__ a, 
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < count; idx += (int64_t)gridDim.x * blockDim.x) {
     int c0[3];
     if (!planes_decode(g, idx, 2, c0)) continue;
+    if (g.D > 2 && ((c0[2] == 0 && g.zlo_halo) || (c0[2] == g.n[2] - 1 && g.zhi_halo))) continue;
     int c[3] = {c0[0], c0[1], c0[2]};
     bool written = false;
     for (int j = g.D - 1; j >= 0; --j) {
@@ -97,8 +101,7 @@ __global__ void __launch_bounds__(256) k_per_bc(GridD g, float* __restrict__ a, 
 }
 
 // exitBC! (util.jl:216-222): 1-D convective update of the exit plane + its mean
-__global__ void __launch_bounds__(256) k_exit1(GridD g, float* __restrict__ u, const float* __restrict__ u0, double Udt, double U0,
-                                               ReduceWS ws, MiscScalars* misc) {
+__global__ void __launch_bounds__(256) k_exit1(GridD g, float* __restrict__ u, const float* __restrict__ u0, double Udt, ReduceWS ws, FinArgs fa) {
   const int ny = g.n[1] - 2, nz = g.D > 2 ? g.n[2] - 2 : 1;
   const int64_t count = (int64_t)ny * nz;
   const int i = g.n[0] - 1;
@@ -111,10 +114,7 @@ __global__ void __launch_bounds__(256) k_exit1(GridD g, float* __restrict__ u, c
     acc[0] += (double)v;
   }
   double tot[1];
-  if (grid_reduce<1>(acc, ws, tot)) {
-    const float mean = (float)tot[0] / (float)count;
-    misc->exit_mean_minus_U = (float)((double)mean - U0);
-  }
+  if (grid_reduce<1>(acc, ws, tot)) finish_reduction(FIN_EXIT, fa, tot[0], 0.0);
 }
 __global__ void __launch_bounds__(256) k_exit2(GridD g, float* __restrict__ u, const MiscScalars* misc) {
   const int ny = g.n[1] - 2, nz = g.D > 2 ? g.n[2] - 2 : 1;
@@ -136,31 +136,42 @@ inline int flat_grid(int64_t count, int cap) {
 
 }  // namespace
 
-int bc_vec(Sim& s, const GridD& g, float* a, const double* A, bool saveexit, const int* per) {
+int bc_vec(Sim& s, const GridD& g, float* a, const double* A, bool saveexit, const int* per, int halo_depth) {
   BCArgs args;
   for (int k = 0; k < 3; ++k) { args.A[k] = k < g.D ? (float)A[k] : 0.f; args.per[k] = k < g.D ? per[k] : 0; }
   args.saveexit = saveexit ? 1 : 0;
   const int64_t cnt = planes_count(g, 3);
   k_bc_vec<<<flat_grid(cnt, s.nsm * 8), 256, 0, s.stream>>>(g, a, args, cnt);
   ++s.launches;
-  return wl_cuda_check(s, cudaGetLastError(), "k_bc_vec");
+  int rc = wl_cuda_check(s, cudaGetLastError(), "k_bc_vec");
+  if (rc) return rc;
+  return dist_halo(s, g, a, g.D, halo_depth);  // slab faces: full planes incl. the x/y ghosts just set
 }
 
 int bc_per(Sim& s, const GridD& g, float* a, const int* per, const int* active) {
   bool any = false;
   for (int k = 0; k < g.D; ++k) any |= per[k] != 0;
-  if (!any) return 0;  // perBC!(a,::Tuple{}) = nothing
-  const int64_t cnt = planes_count(g, 2);
-  k_per_bc<<<flat_grid(cnt, s.nsm * 8), 256, 0, s.stream>>>(g, a, per[0], g.D > 1 ? per[1] : 0, g.D > 2 ? per[2] : 0, cnt, active);
-  ++s.launches;
-  return wl_cuda_check(s, cudaGetLastError(), "k_per_bc");
+  if (any) {  // perBC!(a,::Tuple{}) = nothing
+    const int64_t cnt = planes_count(g, 2);
+    k_per_bc<<<flat_grid(cnt, s.nsm * 8), 256, 0, s.stream>>>(g, a, per[0], g.D > 1 ? per[1] : 0, g.D > 2 ? per[2] : 0, cnt, active);
+    ++s.launches;
+    const int rc = wl_cuda_check(s, cudaGetLastError(), "k_per_bc");
+    if (rc) return rc;
+  }
+  return dist_halo(s, g, a, 1, 1);
 }
 
 int bc_exit(Sim& s, const double* U, float dt) {
   const GridD& g = s.g;
   const int64_t cnt = (int64_t)(g.n[1] - 2) * (g.D > 2 ? g.n[2] - 2 : 1);
-  k_exit1<<<flat_grid(cnt, 256), 256, 0, s.stream>>>(g, s.u, s.u0, U[0] * (double)dt, U[0], s.ws, s.d_misc);
+  FinArgs fa = fin_misc(s);
+  fa.aux = U[0];
+  fa.count = (double)((int64_t)(g.n[1] - 2) * (g.D > 2 ? s.Nz_global : 1));  // length(exitR) of the whole domain
+  k_exit1<<<flat_grid(cnt, 256), 256, 0, s.stream>>>(g, s.u, s.u0, U[0] * (double)dt, s.ws, fa);
+  ++s.launches;
+  int rc = post_reduce(s, FIN_EXIT, fa);
+  if (rc) return rc;
   k_exit2<<<flat_grid(cnt, 256), 256, 0, s.stream>>>(g, s.u, s.d_misc);
-  s.launches += 2;
+  ++s.launches;
   return wl_cuda_check(s, cudaGetLastError(), "k_exit");
 }

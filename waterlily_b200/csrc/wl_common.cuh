@@ -17,12 +17,19 @@ struct GridD {
   int per[3];      // periodic flags
   int64_t s[3];    // strides in floats: 1, pitch, pitch*n[1]
   int64_t comp;    // floats per scalar field (allocation, incl. WL_OX and row padding)
-  int64_t interior;  // product of (n-2) over the D dims
+  int64_t interior;  // product of (n-2) over the D dims (this rank's slab)
+  int64_t interior_global;  // the same over the whole domain
+  // z-slab decomposition: a z-boundary flagged `halo` is served by a neighbour exchange instead of
+  // a boundary condition (interior slab faces, and the periodic wrap when there are several ranks)
+  int zlo_halo, zhi_halo;
+  int zoff;        // global z index of local plane 0 (global k = zoff + local k)
+  int64_t lead;    // floats between the start of an allocation and cell (0,0,0): WL_OX + one spare z-plane in 3-D
 };
 
 // device-resident solver scalars of one Poisson level (src/Poisson.jl:123-144 keeps these on the
 // host; here every data-dependent decision of pcg! is taken on the device)
 struct LevelScalars {
+  double raw[2];    // local reduction totals awaiting a cross-rank all-reduce (deferred finalisation)
   double ghost_dot; // Σ over the ghost shell of z·ϵ (level 1 only: z ≡ σ holds stale Φ)
   float rho;        // r⋅z
   float alpha;
@@ -40,6 +47,41 @@ struct Lvl {
   LevelScalars* sc;
 };
 
+// device scratch scalars shared by the momentum kernels
+struct MiscScalars {
+  double raw[2];
+  float exit_mean_minus_U;  // ∮u of exitBC!
+  float cfl_max;            // max over padded σ
+  float pad[2];
+};
+
+// What to do with a finished reduction.  On one GPU the last block of the producing kernel runs
+// `finalize` itself; with several ranks the totals are parked in raw[], all-reduced by NCCL, and a
+// one-thread kernel runs the same `finalize` on every rank (identical bits → identical decisions).
+enum FinStage {
+  FIN_RESIDUAL = 0,     // t0 = Σr, t1 = Σr²   → rsum, need_sub, r2
+  FIN_R2,               // t0 = Σr²            → r2
+  FIN_R2_IF_SUB,        // same, only if residual! subtracted the mean
+  FIN_PCG_INIT,         // t0 = r⋅z            → rho, active
+  FIN_GHOST_DOT,        // t0 = Σ_shell z·ϵ    → ghost_dot
+  FIN_PCG_MULT,         // t0 = z⋅ϵ (interior) → alpha, active
+  FIN_PCG_UPDATE,       // t0 = r⋅z, t1 = Σr²  → r2, beta, rho, active
+  FIN_PCG_UPDATE_LAST,  // same, last sweep    → r2, active = 0
+  FIN_EXIT,             // t0 = Σu on the exit plane → exit_mean_minus_U
+  FIN_CFL,              // t0 = max σ (interior)
+  FIN_CFL_SHELL,        // t0 = max σ (ghost shell), folded into cfl_max
+  FIN_DOT              // t0 → *out
+};
+struct FinArgs {
+  LevelScalars* sc;
+  MiscScalars* misc;
+  double* raw;      // where deferred totals are parked
+  double* out;
+  double count;     // global cell count the stage divides by
+  double aux;       // U[1] for FIN_EXIT
+  int defer;
+};
+
 // scratch for deterministic two-stage reductions: per-block partials + a ticket
 struct ReduceWS {
   double* partials;   // [maxBlocks * WL_MAXRED]
@@ -51,6 +93,66 @@ struct ReduceWS {
 #ifdef __CUDACC__
 
 #define WL_EPS32 1.1920929e-07f
+
+__device__ __forceinline__ bool fin_predicated_off(int stage, const FinArgs& fa) {
+  if (stage == FIN_R2_IF_SUB) return !fa.sc->need_sub;
+  return (stage == FIN_GHOST_DOT || stage == FIN_PCG_MULT || stage == FIN_PCG_UPDATE || stage == FIN_PCG_UPDATE_LAST) && !fa.sc->active;
+}
+__device__ __forceinline__ void finalize(int stage, const FinArgs& fa, double t0, double t1) {
+  LevelScalars* sc = fa.sc;
+  switch (stage) {
+    case FIN_RESIDUAL: {  // Poisson.jl:94-95
+      const float s = (float)t0 / (float)fa.count;
+      sc->rsum = s;
+      sc->need_sub = fabsf(s) > 2 * WL_EPS32 ? 1 : 0;
+      sc->r2 = (float)t1;
+    } break;
+    case FIN_R2:
+    case FIN_R2_IF_SUB: sc->r2 = (float)t0; break;
+    case FIN_PCG_INIT: {  // Poisson.jl:126-127
+      const float rho = (float)t0;
+      sc->rho = rho;
+      sc->active = fabsf(rho) < 10 * WL_EPS32 ? 0 : 1;
+    } break;
+    case FIN_GHOST_DOT: sc->ghost_dot = t0; break;
+    case FIN_PCG_MULT: {  // Poisson.jl:131-132
+      ++sc->cnt_mult;
+      const float ze = (float)(t0 + sc->ghost_dot);
+      const float alpha = sc->rho / ze;
+      sc->alpha = alpha;
+      const double aa = fabs((double)alpha);
+      if (aa < 1e-2 || aa > 1e2) sc->active = 0;
+    } break;
+    case FIN_PCG_UPDATE:
+    case FIN_PCG_UPDATE_LAST: {  // Poisson.jl:135-141
+      sc->r2 = (float)t1;
+      ++sc->cnt_update;
+      if (stage == FIN_PCG_UPDATE_LAST) {
+        sc->active = 0;
+      } else {
+        const float rho2 = (float)t0;
+        if (fabsf(rho2) < 10 * WL_EPS32) {
+          sc->active = 0;
+        } else {
+          sc->beta = rho2 / sc->rho;
+          sc->rho = rho2;
+        }
+      }
+    } break;
+    case FIN_EXIT: {  // util.jl:220
+      const float mean = (float)t0 / (float)fa.count;
+      fa.misc->exit_mean_minus_U = (float)((double)mean - fa.aux);
+    } break;
+    case FIN_CFL: fa.misc->cfl_max = (float)t0; break;
+    case FIN_CFL_SHELL: fa.misc->cfl_max = fmaxf(fa.misc->cfl_max, (float)t0); break;
+    case FIN_DOT: *fa.out = t0; break;
+  }
+}
+// called by the thread that holds the grid totals
+__device__ __forceinline__ void finish_reduction(int stage, const FinArgs& fa, double t0, double t1) {
+  if (fa.defer) { fa.raw[0] = t0; fa.raw[1] = t1; }
+  else finalize(stage, fa, t0, t1);
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -196,6 +298,12 @@ __device__ __forceinline__ bool shell_decode(const GridD& g, int64_t idx, int c[
     idx -= cnt;
   }
   return false;
+}
+// a cell of the local ghost shell is a ghost cell of the global domain owned by this rank unless it
+// lies in a z-plane that belongs to a neighbouring slab (there it is the neighbour's cell)
+__device__ __forceinline__ bool is_global_ghost(const GridD& g, const int c[3]) {
+  if (g.D > 2 && ((c[2] == 0 && g.zlo_halo) || (c[2] == g.n[2] - 1 && g.zhi_halo))) return false;
+  return true;
 }
 __host__ __device__ inline int64_t shell_count(const GridD& g, int t = 1) {
   int64_t all = 1, in = 1;

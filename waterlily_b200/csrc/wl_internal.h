@@ -37,11 +37,9 @@ struct ProfClass {
   int counter_base = 0;
 };
 
-// device scratch scalars shared by the momentum kernels
-struct MiscScalars {
-  float exit_mean_minus_U;  // ∮u of exitBC!
-  float cfl_max;            // max over padded σ
-  float pad[6];
+struct DistState {
+  int rank = 0, nranks = 1;
+  void* comm = nullptr;  // ncclComm_t
 };
 
 struct Sim {
@@ -65,6 +63,11 @@ struct Sim {
   float* h_pinned = nullptr;  // pinned readback buffer (64 floats)
   std::vector<int> n_log;
   int64_t launches = 0;
+  int64_t collectives = 0;
+  DistState dist;
+  std::vector<int> lvl_dist;   // 1: level is z-distributed, 0: replicated on every rank (coarse tail)
+  int Nz_global = 0;           // interior z-planes of the whole domain (3-D)
+  int per_z_global = 0;
   int sticky = 0;  // first CUDA error, sticky per handle
   bool profiling = false;
   ProfClass prof[WL_PROF_N];
@@ -82,8 +85,20 @@ int wl_grid_for(const Sim& s, int64_t ntiles);
 void wl_prof_begin(Sim& s, int cls);
 void wl_prof_end(Sim& s, int cls, double bytes);
 
+// ---- wl_dist.cu ----
+int dist_unique_id(char* out128);
+int dist_init(Sim& s, int rank, int nranks, const char* id128);
+void dist_destroy(Sim& s);
+int dist_halo(Sim& s, const GridD& g, float* base, int ncomp, int depth);
+int dist_allreduce(Sim& s, double* dptr, int count, bool is_max);
+int dist_allgather(Sim& s, float* base, size_t count);
+// runs finalize(stage) after the all-reduce of fa.raw when the producing kernel deferred it
+int post_reduce(Sim& s, int stage, const FinArgs& fa, bool is_max = false);
+FinArgs fin_level(const Sim& s, int level);
+FinArgs fin_misc(const Sim& s);
+
 // ---- wl_bc.cu ----
-int bc_vec(Sim& s, const GridD& g, float* a, const double* A, bool saveexit, const int* per);
+int bc_vec(Sim& s, const GridD& g, float* a, const double* A, bool saveexit, const int* per, int halo_depth = 1);
 int bc_per(Sim& s, const GridD& g, float* a, const int* per, const int* active = nullptr);
 int bc_exit(Sim& s, const double* U, float dt);
 

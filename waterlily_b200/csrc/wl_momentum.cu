@@ -73,6 +73,8 @@ __device__ __forceinline__ void convdiff_cell(const CDArgs& a, const int (&c)[3]
       if (cj == 1) {
         if (g.per[j]) {
           acc += phi_face(ui, uj, I, si, sj, (int64_t)(n - 4) * sj, a.nu);
+        } else if (j == 2 && g.zlo_halo) {  // slab face: a plain inner cell, I-2δ is in the depth-2 halo
+          acc += phi_face(ui, uj, I, si, sj, -2 * sj, a.nu);
         } else {  // ϕuL, accumulated in Float64
           const double uf = (double)(uj[I] + uj[I - si]) * 0.5;
           const double fl = uf > 0 ? uf * ((double)(ui[I] + ui[I - sj]) * 0.5) : uf * (double)quick(ui[I + sj], ui[I], ui[I - sj]);
@@ -85,6 +87,8 @@ __device__ __forceinline__ void convdiff_cell(const CDArgs& a, const int (&c)[3]
       if (cj == n - 2) {
         if (g.per[j]) {
           acc -= phi_face(ui, uj, I + (int64_t)(1 - cj) * sj, si, sj, (int64_t)(n - 4) * sj, a.nu);
+        } else if (j == 2 && g.zhi_halo) {
+          acc -= phi_face(ui, uj, I + sj, si, sj, -2 * sj, a.nu);
         } else {  // ϕuR
           const int64_t J = I + sj;
           const double uf = (double)(uj[J] + uj[J - si]) * 0.5;
@@ -107,6 +111,8 @@ __device__ __forceinline__ void convdiff_store_cell(const CDArgs& a, const int (
   bool lowghost = false, ghost = false;
 #pragma unroll
   for (int k = 0; k < D; ++k) { lowghost |= c[k] == 0; ghost |= c[k] == g.n[k] - 1; }
+  // a z-plane owned by the neighbouring slab: its f arrives by halo exchange, nothing to compute
+  if (D > 2 && c[2] == g.n[2] - 1 && g.zhi_halo) lowghost = true;
   if (lowghost) {
 #pragma unroll
     for (int i = 0; i < D; ++i) r[i] = 0.f;  // index-1 ghosts are never written (r .= 0)
@@ -115,11 +121,11 @@ __device__ __forceinline__ void convdiff_store_cell(const CDArgs& a, const int (
     if (ghost) {
       // stale Φ: last pass (i=D, largest j) that covers this upper-ghost cell
       for (int j = D - 1; j >= 0; --j) {
-        const int lo = g.per[j] ? 1 : 2;
+        const int lo = (g.per[j] || (j == 2 && g.zlo_halo)) ? 1 : 2;
         if (c[j] >= lo && c[j] <= g.n[j] - 2) {
           const int64_t sj = g.s[j];
           a.sigma[I] = phi_face(a.u + (D - 1) * g.comp, a.u + j * g.comp, I, g.s[D - 1], sj,
-                                c[j] == 1 ? (int64_t)(g.n[j] - 4) * sj : -2 * sj, a.nu);
+                                (c[j] == 1 && g.per[j]) ? (int64_t)(g.n[j] - 4) * sj : -2 * sj, a.nu);
           break;
         }
       }
@@ -148,7 +154,10 @@ template <int D>
 __global__ void __launch_bounds__(256) k_conv_diff_shell(CDArgs a, int64_t count) {
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < count; idx += (int64_t)gridDim.x * blockDim.x) {
     int c[3];
-    if (shell_decode(a.g, idx, c, 2)) convdiff_store_cell<D>(a, c, c[0] + c[1] * a.g.s[1] + c[2] * a.g.s[2]);
+    if (!shell_decode(a.g, idx, c, 2)) continue;
+    if (D > 2 && c[0] >= 2 && c[0] <= a.g.n[0] - 3 && c[1] >= 2 && c[1] <= a.g.n[1] - 3 &&
+        c[2] >= (a.g.zlo_halo ? 1 : 2) && c[2] <= (a.g.zhi_halo ? a.g.n[2] - 2 : a.g.n[2] - 3)) continue;  // core kernel's cell
+    convdiff_store_cell<D>(a, c, c[0] + c[1] * a.g.s[1] + c[2] * a.g.s[2]);
   }
 }
 
@@ -176,7 +185,8 @@ __global__ void __launch_bounds__(CD_TX * CD_TY, MINB) k_conv_diff3_march(CDArgs
   const int bt = blockIdx.x;
   const int tx = bt % ntx, ty = (bt / ntx) % nty, tz = bt / (ntx * nty);
   const int x = 2 + tx * CD_TX + tix, y = 2 + ty * CD_TY + tiy;
-  const int z0 = 2 + tz * zchunk, z1 = min(z0 + zchunk, nz - 2);
+  const int zlo = g.zlo_halo ? 1 : 2, zhi = g.zhi_halo ? nz - 2 : nz - 3;  // slab faces are plain inner cells
+  const int z0 = zlo + tz * zchunk, z1 = min(z0 + zchunk, zhi + 1);
   const bool valid = x <= nx - 3 && y <= ny - 3;
   const int xc = min(x, nx - 3), yc = min(y, ny - 3);  // clamped: out-of-range threads shadow the last cell
   const bool extra_x = (xc == nx - 3) || (tix == CD_TX - 1);
@@ -395,7 +405,7 @@ __global__ void __launch_bounds__(256) k_unscale(GridD g, float* __restrict__ x,
 
 // CFL: σ = flux_out (Flow.jl:173,176-182) + interior max
 template <int D, int V>
-__global__ void __launch_bounds__(256) k_cfl(GridD g, const float* __restrict__ u, float* __restrict__ sigma, ReduceWS ws, MiscScalars* misc) {
+__global__ void __launch_bounds__(256) k_cfl(GridD g, const float* __restrict__ u, float* __restrict__ sigma, ReduceWS ws, FinArgs fa) {
   double acc[1] = {0.0};
   for_rows<V>(g, [&](int, int, int, int64_t I) {
     double s[V];
@@ -416,18 +426,18 @@ __global__ void __launch_bounds__(256) k_cfl(GridD g, const float* __restrict__ 
     stp<V>(sigma + I, o);
   });
   double tot[1];
-  if (grid_reduce<1, true>(acc, ws, tot)) misc->cfl_max = (float)tot[0];
+  if (grid_reduce<1, true>(acc, ws, tot)) finish_reduction(FIN_CFL, fa, tot[0], 0.0);
 }
 // the reference takes maximum(σ) over the PADDED array (Flow.jl:174): fold in the ghost shell, which
 // holds the corrector's stale Φ.  Shell = cells with any coordinate on a boundary.
-__global__ void __launch_bounds__(256) k_shell_max(GridD g, const float* __restrict__ sigma, ReduceWS ws, MiscScalars* misc, int64_t count) {
+__global__ void __launch_bounds__(256) k_shell_max(GridD g, const float* __restrict__ sigma, ReduceWS ws, FinArgs fa, int64_t count) {
   double acc[1] = {-1e300};
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < count; idx += (int64_t)gridDim.x * blockDim.x) {
     int c[3];
-    if (shell_decode(g, idx, c)) acc[0] = fmax(acc[0], (double)sigma[c[0] + c[1] * g.s[1] + c[2] * g.s[2]]);
+    if (shell_decode(g, idx, c) && is_global_ghost(g, c)) acc[0] = fmax(acc[0], (double)sigma[c[0] + c[1] * g.s[1] + c[2] * g.s[2]]);
   }
   double tot[1];
-  if (grid_reduce<1, true>(acc, ws, tot)) misc->cfl_max = fmaxf(misc->cfl_max, (float)tot[0]);
+  if (grid_reduce<1, true>(acc, ws, tot)) finish_reduction(FIN_CFL_SHELL, fa, tot[0], 0.0);
 }
 // with exitBC the exit plane of u₁ survives from step to step (saveexit); after the u/u⁰ pointer swap
 // it has to be carried over explicitly
@@ -456,7 +466,8 @@ __global__ void __launch_bounds__(256) k_copy_exit_plane(GridD g, float* __restr
 template <int TX, int TY, int MINB>
 static void launch_march_cfg(Sim& s, const CDArgs& a, int zchunk, bool corr) {
   const GridD& g = s.g;
-  const int ntx = (g.n[0] - 4 + TX - 1) / TX, nty = (g.n[1] - 4 + TY - 1) / TY, ntz = (g.n[2] - 4 + zchunk - 1) / zchunk;
+  const int nzc = g.n[2] - 4 + (g.zlo_halo ? 1 : 0) + (g.zhi_halo ? 1 : 0);
+  const int ntx = (g.n[0] - 4 + TX - 1) / TX, nty = (g.n[1] - 4 + TY - 1) / TY, ntz = (nzc + zchunk - 1) / zchunk;
   const dim3 blk(TX, TY, 1);
   const int nblk = ntx * nty * ntz;
   if (a.has_g) {
@@ -505,7 +516,9 @@ int mom_conv_diff(Sim& s, const float* src, bool fuse_bdim1, const double* gacc)
   }
   // algorithmic words/cell: read u (D) [+ u⁰, V (2D)], write f (D)
   wl_prof_end(s, WL_PROF_CONVDIFF, 4.0 * (double)s.g.interior * (fuse_bdim1 ? (src == s.u0 ? 3 : 4) * s.D : 2 * s.D));
-  return wl_cuda_check(s, cudaGetLastError(), "k_conv_diff");
+  int rc = wl_cuda_check(s, cudaGetLastError(), "k_conv_diff");
+  if (rc) return rc;
+  return dist_halo(s, s.g, s.f, s.D, 1);  // BDIM! stage 2 reads f[I±δz] across slab faces
 }
 int mom_accelerate(Sim& s, const double* g) {
   if (!g) return 0;
@@ -549,14 +562,17 @@ int mom_project(Sim& s, double w, int* n) {
 }
 // CFL(a) (Flow.jl:172-175)
 int mom_cfl(Sim& s, double* dt) {
-  RLAUNCH(s, k_cfl, s.g, s.g, s.u, s.sigma, s.ws, s.d_misc);
+  const FinArgs fa = fin_misc(s);
+  RLAUNCH(s, k_cfl, s.g, s.g, s.u, s.sigma, s.ws, fa);
+  int rc = post_reduce(s, FIN_CFL, fa, true);
+  if (rc) return rc;
   {
     const int64_t cnt = shell_count(s.g);
-    k_shell_max<<<(int)std::min<int64_t>((cnt + 255) / 256, 256), 256, 0, s.stream>>>(s.g, s.sigma, s.ws, s.d_misc, cnt);
+    k_shell_max<<<(int)std::min<int64_t>((cnt + 255) / 256, 256), 256, 0, s.stream>>>(s.g, s.sigma, s.ws, fa, cnt);
     ++s.launches;
+    if ((rc = post_reduce(s, FIN_CFL_SHELL, fa, true))) return rc;
   }
-  int rc = wl_read_scalars(s, &s.d_misc->cfl_max, sizeof(float));
-  if (rc) return rc;
+  if ((rc = wl_read_scalars(s, &s.d_misc->cfl_max, sizeof(float)))) return rc;
   const float m = s.h_pinned[0] + 5 * s.nu;
   const float v = 1.f / m;
   *dt = (double)(v < 10.f ? v : 10.f);
@@ -576,16 +592,19 @@ int mom_step(Sim& s, const double* U, const double* gp, const double* gc, double
   // predictor u → u'
   if ((rc = mom_conv_diff(s, s.u0, true, gp))) return rc;
   if ((rc = mom_bdim2(s, false, 1.f))) return rc;
-  if ((rc = bc_vec(s, s.g, s.u, U, s.exitBC, s.g.per))) return rc;
-  if (s.exitBC && (rc = bc_exit(s, U, s.dt.back()))) return rc;
+  if ((rc = bc_vec(s, s.g, s.u, U, s.exitBC, s.g.per, 2))) return rc;
+  if (s.exitBC) {
+    if ((rc = bc_exit(s, U, s.dt.back()))) return rc;
+    if ((rc = dist_halo(s, s.g, s.u, 1, 2))) return rc;  // the exit plane changed after BC!'s exchange
+  }
   if ((rc = mom_project(s, 1.0, n_pred))) return rc;
-  if ((rc = bc_vec(s, s.g, s.u, U, s.exitBC, s.g.per))) return rc;
+  if ((rc = bc_vec(s, s.g, s.u, U, s.exitBC, s.g.per, 2))) return rc;
   // corrector u → u¹
   if ((rc = mom_conv_diff(s, s.u, true, gc))) return rc;
   if ((rc = mom_bdim2(s, true, 0.5f))) return rc;
-  if ((rc = bc_vec(s, s.g, s.u, U, s.exitBC, s.g.per))) return rc;
+  if ((rc = bc_vec(s, s.g, s.u, U, s.exitBC, s.g.per, 2))) return rc;
   if ((rc = mom_project(s, 0.5, n_corr))) return rc;
-  if ((rc = bc_vec(s, s.g, s.u, U, s.exitBC, s.g.per))) return rc;
+  if ((rc = bc_vec(s, s.g, s.u, U, s.exitBC, s.g.per, 2))) return rc;
   double dt;
   if ((rc = mom_cfl(s, &dt))) return rc;
   wl_prof_end(s, WL_PROF_STEP, 0.0);

@@ -68,14 +68,18 @@ __global__ void __launch_bounds__(256) k_set_diag(Lvl l) {
 
 // restrictL! interior part (MultiLevelPoisson.jl:26-30) with restrictL (:10-16), up(I,i) (:1)
 template <int D, int V>
-__global__ void __launch_bounds__(256) k_restrictL(Lvl c, Lvl f) {
+__global__ void __launch_bounds__(256) k_restrictL(Lvl c, Lvl f, int ck0, int ck1, int fshift) {
+  // ck0..ck1: coarse planes this rank computes; fshift: fine local k = fine global k + fshift
+  // (both trivial unless the fine level is z-distributed and the coarse one replicated)
   for_rows<1>(c.g, [&](int i0, int j0, int k0, int64_t I) {
+    if (D > 2 && (k0 < ck0 || k0 > ck1)) return;
     const int cc[3] = {i0, j0, k0};
 #pragma unroll
     for (int i = 0; i < D; ++i) {
       int lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
 #pragma unroll
       for (int k = 0; k < D; ++k) { lo[k] = 2 * cc[k] - 1; hi[k] = 2 * cc[k] - (k == i ? 1 : 0); }
+      if (D > 2) { lo[2] += fshift; hi[2] += fshift; }
       const float* Lf = f.L + i * f.g.comp;
       float s = 0.f;
       for (int z = lo[2]; z <= hi[2]; ++z)
@@ -88,7 +92,7 @@ __global__ void __launch_bounds__(256) k_restrictL(Lvl c, Lvl f) {
 
 // residual! first loop + sum (Poisson.jl:93-94)
 template <int D, int V>
-__global__ void __launch_bounds__(256) k_residual(Lvl l, ReduceWS ws) {
+__global__ void __launch_bounds__(256) k_residual(Lvl l, ReduceWS ws, FinArgs fa) {
   double acc[2] = {0.0, 0.0};
   for_rows<V>(l.g, [&](int, int, int, int64_t I) {
     const Pack<V> xc = ldp<V>(l.x + I), ax = mult_row<D, V>(l, I, l.x, xc), zc = ldp<V>(l.z + I), id = ldp<V>(l.iD + I);
@@ -102,16 +106,11 @@ __global__ void __launch_bounds__(256) k_residual(Lvl l, ReduceWS ws) {
     stp<V>(l.r + I, r);
   });
   double tot[2];
-  if (grid_reduce<2>(acc, ws, tot)) {
-    const float s = (float)tot[0] / (float)l.g.interior;
-    l.sc->rsum = s;
-    l.sc->need_sub = fabsf(s) > 2 * WL_EPS32 ? 1 : 0;
-    l.sc->r2 = (float)tot[1];
-  }
+  if (grid_reduce<2>(acc, ws, tot)) finish_reduction(FIN_RESIDUAL, fa, tot[0], tot[1]);
 }
 // residual! second loop (Poisson.jl:96), predicated on |s| > 2eps
 template <int D, int V>
-__global__ void __launch_bounds__(256) k_sub_mean(Lvl l, ReduceWS ws) {
+__global__ void __launch_bounds__(256) k_sub_mean(Lvl l, ReduceWS ws, FinArgs fa) {
   if (!l.sc->need_sub) return;
   const float s = l.sc->rsum;
   double acc[1] = {0.0};
@@ -122,7 +121,7 @@ __global__ void __launch_bounds__(256) k_sub_mean(Lvl l, ReduceWS ws) {
     stp<V>(l.r + I, r);
   });
   double tot[1];
-  if (grid_reduce<1>(acc, ws, tot)) l.sc->r2 = (float)tot[0];
+  if (grid_reduce<1>(acc, ws, tot)) finish_reduction(FIN_R2_IF_SUB, fa, tot[0], 0.0);
 }
 
 // mult! interior (Poisson.jl:66)
@@ -148,7 +147,7 @@ __global__ void __launch_bounds__(256) k_jacobi_eps(Lvl l) {
 
 // increment! (Poisson.jl:101-102) + L₂
 template <int D, int V>
-__global__ void __launch_bounds__(256) k_increment(Lvl l, ReduceWS ws) {
+__global__ void __launch_bounds__(256) k_increment(Lvl l, ReduceWS ws, FinArgs fa) {
   double acc[1] = {0.0};
   for_rows<V>(l.g, [&](int, int, int, int64_t I) {
     const Pack<V> ec = ldp<V>(l.eps + I), ae = mult_row<D, V>(l, I, l.eps, ec);
@@ -163,31 +162,34 @@ __global__ void __launch_bounds__(256) k_increment(Lvl l, ReduceWS ws) {
     stp<V>(l.x + I, x);
   });
   double tot[1];
-  if (grid_reduce<1>(acc, ws, tot)) l.sc->r2 = (float)tot[0];
+  if (grid_reduce<1>(acc, ws, tot)) finish_reduction(FIN_R2, fa, tot[0], 0.0);
 }
 
 // restrict! (MultiLevelPoisson.jl:33) + fill!(coarse.x,0) (:75)
 template <int D, int V>
-__global__ void __launch_bounds__(256) k_restrict(Lvl c, Lvl f) {
+__global__ void __launch_bounds__(256) k_restrict(Lvl c, Lvl f, int ck0, int ck1, int fshift) {
   for_rows<1>(c.g, [&](int i0, int j0, int k0, int64_t I) {
+    c.x[I] = 0.f;
+    if (D > 2 && (k0 < ck0 || k0 > ck1)) return;
     const int cc[3] = {i0, j0, k0};
     int lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
 #pragma unroll
     for (int k = 0; k < D; ++k) { lo[k] = 2 * cc[k] - 1; hi[k] = 2 * cc[k]; }
+    if (D > 2) { lo[2] += fshift; hi[2] += fshift; }
     float s = 0.f;
     for (int z = lo[2]; z <= hi[2]; ++z)
       for (int y = lo[1]; y <= hi[1]; ++y)
         for (int x = lo[0]; x <= hi[0]; ++x) s += f.r[x + y * f.g.s[1] + z * f.g.s[2]];
     c.r[I] = s;
-    c.x[I] = 0.f;
   });
 }
 
 // prolongate! (MultiLevelPoisson.jl:34) with down(I) (:2)
 template <int D, int V>
-__global__ void __launch_bounds__(256) k_prolongate(Lvl f, Lvl c) {
+__global__ void __launch_bounds__(256) k_prolongate(Lvl f, Lvl c, int fzadd) {
+  // fzadd: fine global k = fine local k + fzadd when the coarse level is replicated (else 0)
   for_rows<V>(f.g, [&](int i0, int j0, int k0, int64_t I) {
-    const int64_t J = (D > 1 ? ((j0 + 1) >> 1) * c.g.s[1] : 0) + (D > 2 ? ((k0 + 1) >> 1) * c.g.s[2] : 0);
+    const int64_t J = (D > 1 ? ((j0 + 1) >> 1) * c.g.s[1] : 0) + (D > 2 ? ((k0 + fzadd + 1) >> 1) * c.g.s[2] : 0);
     Pack<V> e;
 #pragma unroll
     for (int q = 0; q < V; ++q) e.v[q] = c.x[J + ((i0 + q + 1) >> 1)];
@@ -199,7 +201,7 @@ __global__ void __launch_bounds__(256) k_prolongate(Lvl f, Lvl c) {
 // :125-127  z = ϵ = r·iD ; ρ = r⋅z ; |ρ|<10eps → return      (z is rewritten by k_pcg_mult before
 // any read, so only ϵ is stored)
 template <int D, int V>
-__global__ void __launch_bounds__(256) k_pcg_init(Lvl l, ReduceWS ws) {
+__global__ void __launch_bounds__(256) k_pcg_init(Lvl l, ReduceWS ws, FinArgs fa) {
   double acc[1] = {0.0};
   for_rows<V>(l.g, [&](int, int, int, int64_t I) {
     const Pack<V> r = ldp<V>(l.r + I), id = ldp<V>(l.iD + I);
@@ -209,16 +211,12 @@ __global__ void __launch_bounds__(256) k_pcg_init(Lvl l, ReduceWS ws) {
     stp<V>(l.eps + I, e);
   });
   double tot[1];
-  if (grid_reduce<1>(acc, ws, tot)) {
-    const float rho = (float)tot[0];
-    l.sc->rho = rho;
-    l.sc->active = fabsf(rho) < 10 * WL_EPS32 ? 0 : 1;
-  }
+  if (grid_reduce<1>(acc, ws, tot)) finish_reduction(FIN_PCG_INIT, fa, tot[0], 0.0);
 }
 // :130-132  z = Aϵ ; α = ρ/(z⋅ϵ) ; |α|∉[1e-2,1e2] → return.  The dot runs over the padded arrays
 // in the reference; the ghost-shell part (non-zero only at level 1) is in sc->ghost_dot.
 template <int D, int V>
-__global__ void __launch_bounds__(256) k_pcg_mult(Lvl l, ReduceWS ws) {
+__global__ void __launch_bounds__(256) k_pcg_mult(Lvl l, ReduceWS ws, FinArgs fa) {
   if (!l.sc->active) return;
   double acc[1] = {0.0};
   for_rows<V>(l.g, [&](int, int, int, int64_t I) {
@@ -228,19 +226,12 @@ __global__ void __launch_bounds__(256) k_pcg_mult(Lvl l, ReduceWS ws) {
     stp<V>(l.z + I, z);
   });
   double tot[1];
-  if (grid_reduce<1>(acc, ws, tot)) {
-    ++l.sc->cnt_mult;
-    const float ze = (float)(tot[0] + l.sc->ghost_dot);
-    const float alpha = l.sc->rho / ze;
-    l.sc->alpha = alpha;
-    const double aa = fabs((double)alpha);
-    if (aa < 1e-2 || aa > 1e2) l.sc->active = 0;
-  }
+  if (grid_reduce<1>(acc, ws, tot)) finish_reduction(FIN_PCG_MULT, fa, tot[0], 0.0);
 }
 // :133-139  x += αϵ ; r -= αz ; [last sweep → return] ; z = r·iD ; ρ₂ = r⋅z ; |ρ₂|<10eps → return ;
 // β = ρ₂/ρ ; ρ = ρ₂
 template <int D, int V>
-__global__ void __launch_bounds__(256) k_pcg_update(Lvl l, ReduceWS ws, int last) {
+__global__ void __launch_bounds__(256) k_pcg_update(Lvl l, ReduceWS ws, FinArgs fa, int last) {
   if (!l.sc->active) return;
   const float alpha = l.sc->alpha;
   double acc[2] = {0.0, 0.0};
@@ -258,21 +249,7 @@ __global__ void __launch_bounds__(256) k_pcg_update(Lvl l, ReduceWS ws, int last
     stp<V>(l.r + I, r);
   });
   double tot[2];
-  if (grid_reduce<2>(acc, ws, tot)) {
-    l.sc->r2 = (float)tot[1];
-    ++l.sc->cnt_update;
-    if (last) {
-      l.sc->active = 0;
-    } else {
-      const float rho2 = (float)tot[0];
-      if (fabsf(rho2) < 10 * WL_EPS32) {
-        l.sc->active = 0;
-      } else {
-        l.sc->beta = rho2 / l.sc->rho;
-        l.sc->rho = rho2;
-      }
-    }
-  }
+  if (grid_reduce<2>(acc, ws, tot)) finish_reduction(last ? FIN_PCG_UPDATE_LAST : FIN_PCG_UPDATE, fa, tot[0], tot[1]);
 }
 // :140  ϵ = βϵ + z  with z = r·iD recomputed
 template <int D, int V>
@@ -291,22 +268,22 @@ __global__ void __launch_bounds__(256) k_pcg_dir(Lvl l) {
 
 // Σ_shell z·ϵ  → sc->ghost_dot  (level 1: z ≡ σ keeps the stale Φ of conv_diff! on its upper ghost
 // layer, and ϵ's ghosts are non-zero after perBC! — reference quirk Q2, must be reproduced)
-__global__ void __launch_bounds__(256) k_shell_dot(Lvl l, ReduceWS ws, int64_t count) {
+__global__ void __launch_bounds__(256) k_shell_dot(Lvl l, ReduceWS ws, FinArgs fa, int64_t count) {
   if (!l.sc->active) return;
   double acc[1] = {0.0};
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < count; idx += (int64_t)gridDim.x * blockDim.x) {
     int c[3];
-    if (shell_decode(l.g, idx, c)) {
+    if (shell_decode(l.g, idx, c) && is_global_ghost(l.g, c)) {
       const int64_t I = c[0] + c[1] * l.g.s[1] + c[2] * l.g.s[2];
       acc[0] += (double)l.z[I] * (double)l.eps[I];
     }
   }
   double tot[1];
-  if (grid_reduce<1>(acc, ws, tot)) l.sc->ghost_dot = tot[0];
+  if (grid_reduce<1>(acc, ws, tot)) finish_reduction(FIN_GHOST_DOT, fa, tot[0], 0.0);
 }
 
 template <int D, int V>
-__global__ void __launch_bounds__(256) k_dot_rr(Lvl l, ReduceWS ws, double* out) {
+__global__ void __launch_bounds__(256) k_dot_rr(Lvl l, ReduceWS ws, FinArgs fa) {
   double acc[1] = {0.0};
   for_rows<V>(l.g, [&](int, int, int, int64_t I) {
     const Pack<V> r = ldp<V>(l.r + I);
@@ -314,21 +291,70 @@ __global__ void __launch_bounds__(256) k_dot_rr(Lvl l, ReduceWS ws, double* out)
     for (int q = 0; q < V; ++q) acc[0] += (double)r.v[q] * (double)r.v[q];
   });
   double tot[1];
-  if (grid_reduce<1>(acc, ws, tot)) *out = tot[0];
+  if (grid_reduce<1>(acc, ws, tot)) finish_reduction(FIN_DOT, fa, tot[0], 0.0);
+}
+
+__global__ void k_finalize(int stage, FinArgs fa) {
+  if (fin_predicated_off(stage, fa)) return;
+  finalize(stage, fa, fa.raw[0], fa.raw[1]);
 }
 
 }  // namespace
 
 static inline double cellsB(const Lvl& l, int words) { return 4.0 * words * (double)l.g.interior; }
 
+FinArgs fin_level(const Sim& s, int level) {
+  FinArgs fa{};
+  const Lvl& l = s.levels[level];
+  fa.sc = l.sc;
+  fa.misc = s.d_misc;
+  fa.raw = &l.sc->raw[0];
+  fa.out = s.ws.partials + (size_t)WL_MAXBLOCKS * WL_MAXRED;  // spare slot behind the partials
+  fa.count = (double)l.g.interior_global;
+  fa.defer = (s.dist.nranks > 1 && s.lvl_dist[level]) ? 1 : 0;
+  return fa;
+}
+FinArgs fin_misc(const Sim& s) {
+  FinArgs fa = fin_level(s, 0);
+  fa.raw = &s.d_misc->raw[0];
+  return fa;
+}
+// deferred finalisation: all-reduce the parked totals, then run finalize on every rank
+int post_reduce(Sim& s, int stage, const FinArgs& fa, bool is_max) {
+  if (!fa.defer) return 0;
+  int rc = dist_allreduce(s, fa.raw, 2, is_max);
+  if (rc) return rc;
+  k_finalize<<<1, 1, 0, s.stream>>>(stage, fa);
+  ++s.launches;
+  return wl_cuda_check(s, cudaGetLastError(), "k_finalize");
+}
+
+static int level_of(const Sim& s, const Lvl& l) { return (int)(&l - &s.levels[0]); }
+
 int pois_set_diag(Sim& s, Lvl& l) {
   RLAUNCH(s, k_set_diag, l.g, l);
   return wl_cuda_check(s, cudaGetLastError(), "k_set_diag");
 }
+// restrictL! (MultiLevelPoisson.jl:26-32).  When the fine level is z-distributed and the coarse one
+// replicated, every rank restricts its own planes and the planes are all-gathered.
 int pois_restrictL(Sim& s, Lvl& c, const Lvl& f) {
-  RLAUNCH(s, k_restrictL, c.g, c, f);
+  const int lc = level_of(s, c);
+  const bool gather = s.dist.nranks > 1 && s.lvl_dist[lc - 1] && !s.lvl_dist[lc];
+  int ck0 = 1, ck1 = c.g.n[2] - 2, fshift = 0;
+  if (gather) {
+    const int cp = (c.g.n[2] - 2) / s.dist.nranks;  // coarse planes per rank
+    ck0 = 1 + s.dist.rank * cp; ck1 = ck0 + cp - 1; fshift = -f.g.zoff;
+  }
+  RLAUNCH(s, k_restrictL, c.g, c, f, ck0, ck1, fshift);
+  if (gather) {
+    const size_t cnt = (size_t)((c.g.n[2] - 2) / s.dist.nranks) * c.g.s[2];
+    for (int i = 0; i < s.D; ++i) {
+      const int rc = dist_allgather(s, c.L + i * c.g.comp + c.g.s[2], cnt);
+      if (rc) return rc;
+    }
+  }
   const double zero[3] = {0, 0, 0};
-  return bc_vec(s, c.g, c.L, zero, false, f.g.per);  // BC!(a,0,false,perdir) (MultiLevelPoisson.jl:31)
+  return bc_vec(s, c.g, c.L, zero, false, c.g.per, 1);  // BC!(a,0,false,perdir) (MultiLevelPoisson.jl:31)
 }
 // update!(ml) (MultiLevelPoisson.jl:62-68)
 int pois_update(Sim& s) {
@@ -344,7 +370,7 @@ int pois_mult(Sim& s) {
   Lvl& l = s.levels[0];
   int rc = bc_per(s, l.g, l.x, l.g.per);
   if (rc) return rc;
-  if ((rc = wl_fill(s, l.z - WL_OX, 0.f, l.g.comp))) return rc;
+  if ((rc = wl_fill(s, l.z - l.g.lead, 0.f, l.g.comp))) return rc;
   RLAUNCH(s, k_mult, l.g, l);
   return wl_cuda_check(s, cudaGetLastError(), "k_mult");
 }
@@ -352,10 +378,14 @@ int pois_mult(Sim& s) {
 int pois_residual(Sim& s, Lvl& l) {
   int rc = bc_per(s, l.g, l.x, l.g.per);
   if (rc) return rc;
-  const bool fine = &l == &s.levels[0];
+  const int lv = level_of(s, l);
+  const bool fine = lv == 0;
+  const FinArgs fa = fin_level(s, lv);
   if (fine) wl_prof_begin(s, WL_PROF_RESIDUAL);
-  RLAUNCH(s, k_residual, l.g, l, s.ws);
-  RLAUNCH(s, k_sub_mean, l.g, l, s.ws);
+  RLAUNCH(s, k_residual, l.g, l, s.ws, fa);
+  if ((rc = post_reduce(s, FIN_RESIDUAL, fa))) return rc;
+  RLAUNCH(s, k_sub_mean, l.g, l, s.ws, fa);
+  if ((rc = post_reduce(s, FIN_R2_IF_SUB, fa))) return rc;
   if (fine) wl_prof_end(s, WL_PROF_RESIDUAL, cellsB(l, 8));
   return wl_cuda_check(s, cudaGetLastError(), "k_residual");
 }
@@ -363,9 +393,12 @@ int pois_residual(Sim& s, Lvl& l) {
 static int pois_increment(Sim& s, Lvl& l) {
   int rc = bc_per(s, l.g, l.eps, l.g.per);
   if (rc) return rc;
-  const bool fine = &l == &s.levels[0];
+  const int lv = level_of(s, l);
+  const bool fine = lv == 0;
+  const FinArgs fa = fin_level(s, lv);
   if (fine) wl_prof_begin(s, WL_PROF_INCREMENT);
-  RLAUNCH(s, k_increment, l.g, l, s.ws);
+  RLAUNCH(s, k_increment, l.g, l, s.ws, fa);
+  if ((rc = post_reduce(s, FIN_R2, fa))) return rc;
   if (fine) wl_prof_end(s, WL_PROF_INCREMENT, cellsB(l, 9));
   return wl_cuda_check(s, cudaGetLastError(), "k_increment");
 }
@@ -382,25 +415,30 @@ int pois_jacobi(Sim& s, Lvl& l, int it) {
 int pois_pcg(Sim& s, int level, int it) {
   Lvl& l = s.levels[level];
   const bool fine = level == 0;
-  bool anyper = false;
-  for (int k = 0; k < s.D; ++k) anyper |= l.g.per[k] != 0;
+  const FinArgs fa = fin_level(s, level);
+  int rc;
+  bool ghosts = l.g.zlo_halo || l.g.zhi_halo;  // ϵ ghosts need refreshing: periodic copies or slab halos
+  for (int k = 0; k < s.D; ++k) ghosts |= l.g.per[k] != 0;
   if (fine) wl_prof_begin(s, WL_PROF_PCG_INIT);
-  RLAUNCH(s, k_pcg_init, l.g, l, s.ws);
+  RLAUNCH(s, k_pcg_init, l.g, l, s.ws, fa);
+  if ((rc = post_reduce(s, FIN_PCG_INIT, fa))) return rc;
   if (fine) wl_prof_end(s, WL_PROF_PCG_INIT, cellsB(l, 3));
   for (int i = 1; i <= it; ++i) {
-    if (anyper) {
-      const int rc = bc_per(s, l.g, l.eps, l.g.per, &l.sc->active);
-      if (rc) return rc;
+    if (ghosts) {
+      if ((rc = bc_per(s, l.g, l.eps, l.g.per, &l.sc->active))) return rc;
       if (fine) {  // only level 1 has non-zero z ghosts (z ≡ σ)
         const int64_t cnt = shell_count(l.g);
-        k_shell_dot<<<(int)std::min<int64_t>((cnt + 255) / 256, 256), 256, 0, s.stream>>>(l, s.ws, cnt);
+        k_shell_dot<<<(int)std::min<int64_t>((cnt + 255) / 256, 256), 256, 0, s.stream>>>(l, s.ws, fa, cnt);
         ++s.launches;
+        if ((rc = post_reduce(s, FIN_GHOST_DOT, fa))) return rc;
       }
     }
     if (fine) wl_prof_begin(s, WL_PROF_PCG_MULT);
-    RLAUNCH(s, k_pcg_mult, l.g, l, s.ws);
+    RLAUNCH(s, k_pcg_mult, l.g, l, s.ws, fa);
+    if ((rc = post_reduce(s, FIN_PCG_MULT, fa))) return rc;
     if (fine) { wl_prof_end(s, WL_PROF_PCG_MULT, 0); wl_prof_begin(s, WL_PROF_PCG_UPDATE); }
-    RLAUNCH(s, k_pcg_update, l.g, l, s.ws, i == it ? 1 : 0);
+    RLAUNCH(s, k_pcg_update, l.g, l, s.ws, fa, i == it ? 1 : 0);
+    if ((rc = post_reduce(s, i == it ? FIN_PCG_UPDATE_LAST : FIN_PCG_UPDATE, fa))) return rc;
     if (fine) wl_prof_end(s, WL_PROF_PCG_UPDATE, 0);
     if (i == it) break;
     if (fine) wl_prof_begin(s, WL_PROF_PCG_DIR);
@@ -415,10 +453,18 @@ int pois_vcycle(Sim& s, int level) {
   Lvl& coarse = s.levels[level + 1];
   int rc = pois_jacobi(s, fine, 1);
   if (rc) return rc;
-  RLAUNCH(s, k_restrict, coarse.g, coarse, fine);
+  // restrict! + fill!(coarse.x,0); a distributed→replicated transition gathers the planes
+  const bool gather = s.dist.nranks > 1 && s.lvl_dist[level] && !s.lvl_dist[level + 1];
+  int ck0 = 1, ck1 = coarse.g.n[2] - 2, fshift = 0;
+  if (gather) {
+    const int cp = (coarse.g.n[2] - 2) / s.dist.nranks;
+    ck0 = 1 + s.dist.rank * cp; ck1 = ck0 + cp - 1; fshift = -fine.g.zoff;
+  }
+  RLAUNCH(s, k_restrict, coarse.g, coarse, fine, ck0, ck1, fshift);
+  if (gather && (rc = dist_allgather(s, coarse.r + coarse.g.s[2], (size_t)((coarse.g.n[2] - 2) / s.dist.nranks) * coarse.g.s[2]))) return rc;
   if (level + 2 < (int)s.levels.size() && (rc = pois_vcycle(s, level + 1))) return rc;
   if ((rc = pois_pcg(s, level + 1, 6))) return rc;
-  RLAUNCH(s, k_prolongate, fine.g, fine, coarse);
+  RLAUNCH(s, k_prolongate, fine.g, fine, coarse, gather ? fine.g.zoff : 0);
   return pois_increment(s, fine);
 }
 // solver!(ml;tol,itmx) (MultiLevelPoisson.jl:87-99) / solver!(p::Poisson;tol,itmx) (Poisson.jl:162-172)
@@ -432,7 +478,8 @@ int pois_solve(Sim& s, double tol, int itmx, int* n_out) {
     if (s.pois_kind == WL_POIS_MULTILEVEL && (rc = pois_vcycle(s, 0))) return rc;
     if ((rc = pois_pcg(s, 0, 6))) return rc;
     ++n;
-    // r₂ = L₂(p): one host read per solver iteration (the reference needs ~100)
+    // r₂ = L₂(p): one host read per solver iteration (the reference needs ~100); every rank reads
+    // the same all-reduced value and therefore leaves the loop together
     if ((rc = wl_read_scalars(s, &p.sc->r2, sizeof(float)))) return rc;
     if ((double)s.h_pinned[0] < tol) break;
   }
@@ -443,10 +490,11 @@ int pois_solve(Sim& s, double tol, int itmx, int* n_out) {
   return rc;
 }
 int pois_dot_rr(Sim& s, Lvl& l, double* out) {
-  double* d = s.ws.partials + (size_t)WL_MAXBLOCKS * WL_MAXRED;  // spare slot behind the partials
-  RLAUNCH(s, k_dot_rr, l.g, l, s.ws, d);
-  int rc = wl_read_scalars(s, d, sizeof(double));
+  FinArgs fa = fin_level(s, level_of(s, l));
+  RLAUNCH(s, k_dot_rr, l.g, l, s.ws, fa);
+  int rc = post_reduce(s, FIN_DOT, fa);
   if (rc) return rc;
+  if ((rc = wl_read_scalars(s, fa.out, sizeof(double)))) return rc;
   double v;
   memcpy(&v, s.h_pinned, sizeof(double));
   *out = v;

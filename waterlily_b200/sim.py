@@ -152,7 +152,7 @@ class _SimulationBase:
     _cabi_lib = None  # set by subclasses
 
     def __init__(self, dims, u_BC, L, *, dt=0.25, nu=0.0, g=None, U=None, eps=1, perdir=(), ulam=None, exitBC=False,
-                 body: AbstractBody | None = None, T=np.float32, device=0):
+                 body: AbstractBody | None = None, T=np.float32, device=0, dist=None):
         N = len(dims)
         # the reference's constructor assertions (src/WaterLily.jl:70-72)
         if callable(u_BC) and callable(ulam):
@@ -168,7 +168,7 @@ class _SimulationBase:
             U = math.sqrt(sum(float(v) ** 2 for v in u_BC))
         self.U, self.L, self.eps = U, L, eps
         self.body = body if body is not None else NoBody()
-        self._eng = Engine(self._lib(), dims, nu=nu, dt0=dt, perdir=perdir, exitBC=exitBC, device=device)
+        self._eng = Engine(self._lib(), dims, nu=nu, dt0=dt, perdir=perdir, exitBC=exitBC, device=device, dist=dist)
         self.flow = Flow(self._eng, dims, u_BC, dt=dt, nu=nu, g=g, ulam=ulam, perdir=perdir, exitBC=exitBC, T=T)
         self.pois = MultiLevelPoisson(self._eng)
         measure_flow(self.flow, self.body, t=0.0, eps=eps)
