@@ -145,14 +145,43 @@ def run_ours(args):
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if world > 1 or args.gpus > 1:
-        raise SystemExit("bench.py: the z-slab multi-GPU path is not in this build yet; run with --gpus 1")
+    local = int(os.environ.get("LOCAL_RANK", "0"))
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
-    torch.cuda.set_device(0)
+    if args.gpus > 1 and world == 1:
+        raise SystemExit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local)
     N, K, W = args.size, args.steps, args.warmup
+    dd = None
+    if world > 1:
+        import torch.distributed as dist
+        from waterlily_b200 import lib
+        dist.init_process_group("gloo")   # host-side plumbing only: id broadcast, barriers, max over ranks
+        ident = [_cabi.nccl_unique_id(lib.load()) if rank == 0 else None]
+        dist.broadcast_object_list(ident, src=0)
+        dd = (rank, world, ident[0])
 
-    sim = make_tgv(Simulation, N)
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    sim = make_tgv(Simulation, N, device=local, dist=dd)
     eng = sim._eng
+    info = eng.dist_info()
     stream = torch.cuda.Stream()
     eng.set_stream(stream.cuda_stream)
     # pinned host copies of the initial state for the e2e arm
@@ -165,21 +194,23 @@ def run_ours(args):
     for _ in range(W):
         eng.mom_step(U)
     eng.profile(True)          # reset the per-kernel statistics; events are reused
-    sampler = ClockSampler(0)
+    sampler = ClockSampler(local)
     sampler.start()
     l0 = eng.launch_count()
+    c0 = eng.dist_info()["collectives"]
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
+    barrier()
     ev0.record(stream)
     ns = []
     for _ in range(K):
         _, n1, n2 = eng.mom_step(U)
         ns += [n1, n2]
     ev1.record(stream)
-    torch.cuda.synchronize()
+    barrier()
     clocks = sampler.stop()
-    ms = ev0.elapsed_time(ev1)
-    launches = eng.launch_count() - l0
+    ms = max_over_ranks(ev0.elapsed_time(ev1))
+    launches = sum_over_ranks(eng.launch_count() - l0)
+    collectives = eng.dist_info()["collectives"] - c0
     value = N ** 3 * K / (ms * 1e-3) / 1e6
     names = eng.profile_classes()
     prof = {}
@@ -203,7 +234,7 @@ def run_ours(args):
     p_np = p_host.numpy().reshape(Ng, order="F")
     out_u = torch.empty_like(u_host)
     out_p = torch.empty_like(p_host)
-    torch.cuda.synchronize()
+    barrier()
     t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -214,16 +245,17 @@ def run_ours(args):
     eng.set_dt(0.25)
     for _ in range(K):
         sim_step(sim)                      # default remeasure=True: measure! (NoBody → no-op) + update!(pois) + mom_step!
-    h2d = (2 * u_host.numel() + p_host.numel()) * 4
+    frac = (info["nz_local"] + 2) / Ng[2]   # a slab handle copies only its own planes of the global host array
+    h2d = sum_over_ranks((2 * u_host.numel() + p_host.numel()) * 4 * frac)
     # results back into pinned host memory
     import ctypes
     eng.cabi.check(eng.cabi.download(eng.h, _cabi.U, ctypes.cast(out_u.data_ptr(), _cabi.c_flt_p), out_u.numel()))
     eng.cabi.check(eng.cabi.download(eng.h, _cabi.P, ctypes.cast(out_p.data_ptr(), _cabi.c_flt_p), out_p.numel()))
     e1.record(stream)
-    torch.cuda.synchronize()
+    barrier()
     wall = time.perf_counter() - t0
-    e2e_ms = max(e0.elapsed_time(e1), wall * 1e3)
-    d2h = (out_u.numel() + out_p.numel()) * 4
+    e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), wall * 1e3))
+    d2h = sum_over_ranks((out_u.numel() + out_p.numel()) * 4 * frac)
     e2e = {"value": N ** 3 * K / (e2e_ms * 1e-3) / 1e6, "unit": "Mcell-updates/s",
            "h2d_bytes_per_step": h2d / K + 24, "d2h_bytes_per_step": d2h / K + 16,
            "what": "pinned-host upload of u,u0,p + K x sim_step(sim) (Python API -> C ABI, dt/n read back every step) + download of u,p; max(CUDA events, wall clock)",
@@ -231,20 +263,28 @@ def run_ours(args):
 
     # ---- CPU baseline on a bounded sample --------------------------------------------------------
     cpu = None
-    if not args.no_cpu:
+    if world > 1:
+        dist.barrier()
+        if rank != 0:
+            dist.destroy_process_group()
+            return
+    if not args.no_cpu and world == 1:
         cv, cms, cores, cns = cpu_oracle_run(args.cpu_size, args.cpu_steps, 1)
         cpu = {"value": cv, "unit": "Mcell-updates/s", "cores": cores, "kind": "port",
                "sample": f"TGV {args.cpu_size}^3 periodic Re=1600, {args.cpu_steps} mom_step! after 1 warm-up ({cms:.0f} ms/step, V-cycles {cns}); C++/OpenMP oracle — the Julia reference cannot run in this image"}
 
     line = {
-        "metric": METRIC, "value": value, "unit": "Mcell-updates/s", "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": ms / K,
+        "metric": METRIC, "value": value, "unit": "Mcell-updates/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"3D Taylor-Green vortex {N}^3 periodic, Re=1600, Float32, MultiLevelPoisson {eng.nlevels()} levels",
                    "vcycles_per_solve": ns, "l2": "working set (~17 GB at 512^3) far exceeds the 126 MB L2; no flush needed",
-                   "parallelism": "1 GPU"},
+                   "parallelism": "1 GPU" if world == 1 else f"z-slab x{world}: {info['nz_local']} planes/rank, NCCL halo exchange + all-reduce, coarse levels replicated",
+                   "nccl_calls_per_step": collectives / K if world > 1 else 0},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
     }
     print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def main():

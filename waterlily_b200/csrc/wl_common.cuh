@@ -80,6 +80,7 @@ struct FinArgs {
   double count;     // global cell count the stage divides by
   double aux;       // U[1] for FIN_EXIT
   int defer;
+  int has_ghost;    // this level's z⋅ϵ has a ghost-shell part (level 1 only)
 };
 
 // scratch for deterministic two-stage reductions: per-block partials + a ticket
@@ -114,10 +115,11 @@ __device__ __forceinline__ void finalize(int stage, const FinArgs& fa, double t0
       sc->rho = rho;
       sc->active = fabsf(rho) < 10 * WL_EPS32 ? 0 : 1;
     } break;
-    case FIN_GHOST_DOT: sc->ghost_dot = t0; break;
+    case FIN_GHOST_DOT: sc->ghost_dot = t0; break;  // single GPU only; deferred mode adds it in FIN_PCG_MULT
     case FIN_PCG_MULT: {  // Poisson.jl:131-132
       ++sc->cnt_mult;
-      const float ze = (float)(t0 + sc->ghost_dot);
+      // deferred (multi-rank): t1 is the all-reduced ghost-shell part, parked by k_shell_dot in raw[1]
+      const float ze = (float)(t0 + (fa.defer ? (fa.has_ghost ? t1 : 0.0) : sc->ghost_dot));
       const float alpha = sc->rho / ze;
       sc->alpha = alpha;
       const double aa = fabs((double)alpha);
@@ -150,8 +152,10 @@ __device__ __forceinline__ void finalize(int stage, const FinArgs& fa, double t0
 }
 // called by the thread that holds the grid totals
 __device__ __forceinline__ void finish_reduction(int stage, const FinArgs& fa, double t0, double t1) {
-  if (fa.defer) { fa.raw[0] = t0; fa.raw[1] = t1; }
-  else finalize(stage, fa, t0, t1);
+  if (!fa.defer) { finalize(stage, fa, t0, t1); return; }
+  if (stage == FIN_GHOST_DOT) { fa.raw[1] = t0; return; }        // rides along with the z⋅ϵ all-reduce
+  fa.raw[0] = t0;
+  if (stage != FIN_PCG_MULT) fa.raw[1] = t1;                      // keep the parked ghost part
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -62,6 +62,8 @@ struct Sim {
   ReduceWS ws{};
   float* h_pinned = nullptr;  // pinned readback buffer (64 floats)
   std::vector<int> n_log;
+  std::vector<int> pcg_cnt;    // host mirror of LevelScalars::cnt_mult at the last check
+  std::vector<int> pcg_guess;  // sweeps the last pcg! needed, per level (speculative enqueue)
   int64_t launches = 0;
   int64_t collectives = 0;
   DistState dist;
@@ -107,7 +109,7 @@ int pois_set_diag(Sim& s, Lvl& l);
 int pois_restrictL(Sim& s, Lvl& coarse, const Lvl& fine);
 int pois_update(Sim& s);
 int pois_mult(Sim& s);
-int pois_residual(Sim& s, Lvl& l);
+int pois_residual(Sim& s, Lvl& l, bool need_r2 = true);
 int pois_jacobi(Sim& s, Lvl& l, int it);
 int pois_pcg(Sim& s, int level, int it);
 int pois_vcycle(Sim& s, int level);

@@ -375,7 +375,7 @@ int pois_mult(Sim& s) {
   return wl_cuda_check(s, cudaGetLastError(), "k_mult");
 }
 // residual!(p) (Poisson.jl:91-97)
-int pois_residual(Sim& s, Lvl& l) {
+int pois_residual(Sim& s, Lvl& l, bool need_r2) {
   int rc = bc_per(s, l.g, l.x, l.g.per);
   if (rc) return rc;
   const int lv = level_of(s, l);
@@ -385,7 +385,8 @@ int pois_residual(Sim& s, Lvl& l) {
   RLAUNCH(s, k_residual, l.g, l, s.ws, fa);
   if ((rc = post_reduce(s, FIN_RESIDUAL, fa))) return rc;
   RLAUNCH(s, k_sub_mean, l.g, l, s.ws, fa);
-  if ((rc = post_reduce(s, FIN_R2_IF_SUB, fa))) return rc;
+  // r⋅r after the mean subtraction is only reported, never used for control: solver! skips its all-reduce
+  if (need_r2 && (rc = post_reduce(s, FIN_R2_IF_SUB, fa))) return rc;
   if (fine) wl_prof_end(s, WL_PROF_RESIDUAL, cellsB(l, 8));
   return wl_cuda_check(s, cudaGetLastError(), "k_residual");
 }
@@ -398,7 +399,7 @@ static int pois_increment(Sim& s, Lvl& l) {
   const FinArgs fa = fin_level(s, lv);
   if (fine) wl_prof_begin(s, WL_PROF_INCREMENT);
   RLAUNCH(s, k_increment, l.g, l, s.ws, fa);
-  if ((rc = post_reduce(s, FIN_R2, fa))) return rc;
+  if (fine && (rc = post_reduce(s, FIN_R2, fa))) return rc;  // L₂ is only ever read on the finest level
   if (fine) wl_prof_end(s, WL_PROF_INCREMENT, cellsB(l, 9));
   return wl_cuda_check(s, cudaGetLastError(), "k_increment");
 }
@@ -415,35 +416,53 @@ int pois_jacobi(Sim& s, Lvl& l, int it) {
 int pois_pcg(Sim& s, int level, int it) {
   Lvl& l = s.levels[level];
   const bool fine = level == 0;
-  const FinArgs fa = fin_level(s, level);
+  FinArgs fa = fin_level(s, level);
   int rc;
   bool ghosts = l.g.zlo_halo || l.g.zhi_halo;  // ϵ ghosts need refreshing: periodic copies or slab halos
   for (int k = 0; k < s.D; ++k) ghosts |= l.g.per[k] != 0;
+  fa.has_ghost = (fine && ghosts) ? 1 : 0;
   if (fine) wl_prof_begin(s, WL_PROF_PCG_INIT);
   RLAUNCH(s, k_pcg_init, l.g, l, s.ws, fa);
   if ((rc = post_reduce(s, FIN_PCG_INIT, fa))) return rc;
   if (fine) wl_prof_end(s, WL_PROF_PCG_INIT, cellsB(l, 3));
-  for (int i = 1; i <= it; ++i) {
-    if (ghosts) {
-      if ((rc = bc_per(s, l.g, l.eps, l.g.per, &l.sc->active))) return rc;
-      if (fine) {  // only level 1 has non-zero z ghosts (z ≡ σ)
-        const int64_t cnt = shell_count(l.g);
-        k_shell_dot<<<(int)std::min<int64_t>((cnt + 255) / 256, 256), 256, 0, s.stream>>>(l, s.ws, fa, cnt);
-        ++s.launches;
-        if ((rc = post_reduce(s, FIN_GHOST_DOT, fa))) return rc;
+  // Sweeps are enqueued speculatively: as many as the previous pcg! on this level needed, then ONE
+  // host read of {active, sweep counter} decides whether more are launched.  Exited sweeps would be
+  // predicated off on the device anyway; this only avoids enqueueing (and, across ranks,
+  // all-reducing) work that is known to be dead.  Every rank reads the same bits.
+  if ((int)s.pcg_guess.size() < (int)s.levels.size()) { s.pcg_guess.assign(s.levels.size(), std::min(it, 2)); s.pcg_cnt.assign(s.levels.size(), 0); }
+  int& guess = s.pcg_guess[level];
+  int i = 1;
+  while (i <= it) {
+    const int upto = std::min(it, std::max(guess, i));
+    for (; i <= upto; ++i) {
+      if (ghosts) {
+        if ((rc = bc_per(s, l.g, l.eps, l.g.per, &l.sc->active))) return rc;
+        if (fine) {  // only level 1 has non-zero z ghosts (z ≡ σ)
+          const int64_t cnt = shell_count(l.g);
+          k_shell_dot<<<(int)std::min<int64_t>((cnt + 255) / 256, 256), 256, 0, s.stream>>>(l, s.ws, fa, cnt);
+          ++s.launches;  // multi-rank: its partial is parked next to the z⋅ϵ partial and shares that all-reduce
+        }
       }
+      if (fine) wl_prof_begin(s, WL_PROF_PCG_MULT);
+      RLAUNCH(s, k_pcg_mult, l.g, l, s.ws, fa);
+      if ((rc = post_reduce(s, FIN_PCG_MULT, fa))) return rc;
+      if (fine) { wl_prof_end(s, WL_PROF_PCG_MULT, 0); wl_prof_begin(s, WL_PROF_PCG_UPDATE); }
+      RLAUNCH(s, k_pcg_update, l.g, l, s.ws, fa, i == it ? 1 : 0);
+      if ((rc = post_reduce(s, i == it ? FIN_PCG_UPDATE_LAST : FIN_PCG_UPDATE, fa))) return rc;
+      if (fine) wl_prof_end(s, WL_PROF_PCG_UPDATE, 0);
+      if (i == it) { i = it + 1; break; }
+      if (fine) wl_prof_begin(s, WL_PROF_PCG_DIR);
+      RLAUNCH(s, k_pcg_dir, l.g, l);
+      if (fine) wl_prof_end(s, WL_PROF_PCG_DIR, 0);
     }
-    if (fine) wl_prof_begin(s, WL_PROF_PCG_MULT);
-    RLAUNCH(s, k_pcg_mult, l.g, l, s.ws, fa);
-    if ((rc = post_reduce(s, FIN_PCG_MULT, fa))) return rc;
-    if (fine) { wl_prof_end(s, WL_PROF_PCG_MULT, 0); wl_prof_begin(s, WL_PROF_PCG_UPDATE); }
-    RLAUNCH(s, k_pcg_update, l.g, l, s.ws, fa, i == it ? 1 : 0);
-    if ((rc = post_reduce(s, i == it ? FIN_PCG_UPDATE_LAST : FIN_PCG_UPDATE, fa))) return rc;
-    if (fine) wl_prof_end(s, WL_PROF_PCG_UPDATE, 0);
-    if (i == it) break;
-    if (fine) wl_prof_begin(s, WL_PROF_PCG_DIR);
-    RLAUNCH(s, k_pcg_dir, l.g, l);
-    if (fine) wl_prof_end(s, WL_PROF_PCG_DIR, 0);
+    if (i > it) break;  // all sweeps enqueued
+    if ((rc = wl_read_scalars(s, l.sc, sizeof(LevelScalars)))) return rc;
+    LevelScalars h;
+    memcpy(&h, s.h_pinned, sizeof(h));
+    const int ran = h.cnt_mult - s.pcg_cnt[level];  // sweeps that really ran since the last check
+    s.pcg_cnt[level] = h.cnt_mult;
+    if (!h.active) { guess = std::max(1, std::min(it, ran)); break; }
+    guess = i;  // still iterating: one more sweep per check from here on
   }
   return wl_cuda_check(s, cudaGetLastError(), "pcg");
 }
@@ -471,7 +490,7 @@ int pois_vcycle(Sim& s, int level) {
 int pois_solve(Sim& s, double tol, int itmx, int* n_out) {
   Lvl& p = s.levels[0];
   wl_prof_begin(s, WL_PROF_SOLVER);
-  int rc = pois_residual(s, p);
+  int rc = pois_residual(s, p, false);
   if (rc) return rc;
   int n = 0;
   while (n < itmx) {
