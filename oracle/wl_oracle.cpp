@@ -627,6 +627,9 @@ int wlo_dist_info(wl_sim* s, int* rank, int* nranks, int* zoff, int* nz_local, i
   if (collectives) *collectives = 0;
   return WL_OK;
 }
+int wlo_dist_plan(int, const int*, const int*, int, int, int, int, int*, int*, int*, int*, int*, int*) {
+  return fail(WL_ERR_STATE, "the oracle is not distributed");
+}
 int wlo_destroy(wl_sim* s) { delete S; return WL_OK; }
 const char* wlo_last_error(void) { return g_err.c_str(); }
 int wlo_set_stream(wl_sim*, void*) { return WL_OK; }

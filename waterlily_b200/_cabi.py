@@ -23,6 +23,7 @@ SIGNATURES = {
     "create_dist": (C.c_int, [C.POINTER(H), C.c_int, c_int_p, C.c_double, C.c_double, c_int_p, C.c_int, C.c_int, C.c_int,
                               C.c_int, C.c_int, C.c_char_p]),
     "dist_info": (C.c_int, [H, c_int_p, c_int_p, c_int_p, c_int_p, c_i64_p]),
+    "dist_plan": (C.c_int, [C.c_int, c_int_p, c_int_p, C.c_int, C.c_int, C.c_int, C.c_int, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p]),
     "destroy": (C.c_int, [H]),
     "last_error": (C.c_char_p, []),
     "set_stream": (C.c_int, [H, C.c_void_p]),
@@ -96,6 +97,17 @@ def nccl_unique_id(cabi: CABI) -> bytes:
     buf = C.create_string_buffer(128)
     cabi.check(cabi.dist_unique_id(buf))
     return buf.raw
+
+
+def dist_plan(cabi: CABI, dims, perdir, rank, nranks, pois_kind=0):
+    """Slab plan of one rank (host-only, wl_dist_plan): list of per-level dicts."""
+    D = len(dims)
+    per = [1 if (j + 1) in tuple(perdir) else 0 for j in range(D)]
+    nl = C.c_int(0)
+    arrs = [(C.c_int * 16)() for _ in range(5)]
+    cabi.check(cabi.dist_plan(D, _ints(dims), _ints(per), pois_kind, rank, nranks, 16, C.byref(nl), *arrs))
+    keys = ("distributed", "nz_local", "zoff", "zlo_halo", "zhi_halo")
+    return [{k: int(a[l]) for k, a in zip(keys, arrs)} for l in range(nl.value)]
 
 
 def _ints(vals):

@@ -166,16 +166,31 @@ int wl_read_scalars(Sim& s, const void* dptr, size_t bytes) {
 
 extern "C" {
 
-static int create_impl(wl_sim** out, int D, const int* N, double nu, double dt0, const int* perdir, int exitBC, int pois_kind, int device,
-                       int rank, int nranks, const char* nccl_id) {
-  if (!out || !N || (D != 2 && D != 3)) return wl_fail(WL_ERR_ARG, "wl_create: D must be 2 or 3");
-  for (int k = 0; k < D; ++k) if (N[k] < 1) return wl_fail(WL_ERR_ARG, "wl_create: N must be positive");
-  if (nranks < 1 || rank < 0 || rank >= nranks) return wl_fail(WL_ERR_ARG, "wl_create_dist: bad rank/nranks");
-  // the MultiLevelPoisson size assertion comes first, as in the reference constructor
-  int Ng[3] = {1, 1, 1};
-  for (int k = 0; k < D; ++k) Ng[k] = N[k] + 2;
-  std::vector<std::vector<int>> dims;  // GLOBAL padded sizes per level
-  dims.push_back({Ng[0], Ng[1], Ng[2]});
+// Which multigrid levels are z-distributed (1) and which are replicated on every rank (0).
+static int plan_levels(int D, const int* N, int nranks, const std::vector<std::vector<int>>& dims, std::vector<int>& lvl_dist) {
+  lvl_dist.assign(dims.size(), 0);
+  if (nranks <= 1) return 0;
+  if (D != 3) return wl_fail(WL_ERR_ARG, "wl_create_dist: the z-slab decomposition needs D = 3");
+  if (N[2] % nranks != 0 || (N[2] / nranks) % 2 != 0)
+    return wl_fail(WL_ERR_ARG, "wl_create_dist: N[3] must split into an even number of z-planes per rank");
+  const char* e = getenv("WL_DIST_MIN_NZ");
+  const int min_nz = e ? atoi(e) : 8;  // coarser levels are agglomerated: replicated on every rank
+  lvl_dist[0] = 1;
+  for (size_t l = 1; l < dims.size(); ++l) {
+    const int nz = dims[l][2] - 2;
+    const int nzf_loc = (dims[l - 1][2] - 2) / nranks;
+    lvl_dist[l] = lvl_dist[l - 1] && nz % nranks == 0 && nz / nranks >= min_nz && nzf_loc % 2 == 0;
+  }
+  for (size_t l = 1; l < dims.size(); ++l)
+    if (lvl_dist[l - 1] && !lvl_dist[l] && (((dims[l - 1][2] - 2) / nranks) % 2 != 0 || (dims[l][2] - 2) % nranks != 0))
+      return wl_fail(WL_ERR_ARG, "wl_create_dist: cannot agglomerate — odd number of z-planes per rank on the last distributed level");
+  return 0;
+}
+static std::vector<std::vector<int>> level_dims(int D, const int* N, int pois_kind) {
+  std::vector<std::vector<int>> dims;
+  std::vector<int> g0(3, 1);
+  for (int k = 0; k < D; ++k) g0[k] = N[k] + 2;
+  dims.push_back(g0);
   if (pois_kind == WL_POIS_MULTILEVEL) {
     auto div_ok = [&](const std::vector<int>& n) { for (int k = 0; k < D; ++k) if (!divisible(n[k])) return false; return true; };
     while (div_ok(dims.back()) && (int)dims.size() <= 10) {  // MultiLevelPoisson.jl:53
@@ -183,25 +198,23 @@ static int create_impl(wl_sim** out, int D, const int* N, double nu, double dt0,
       for (int k = 0; k < D; ++k) c[k] = 1 + dims.back()[k] / 2;  // restrictML :20
       dims.push_back(c);
     }
-    if (dims.size() <= 2) return wl_fail(WL_ERR_ARG, "MultiLevelPoisson requires size=a2ⁿ, where n>2");
   }
+  return dims;
+}
+
+static int create_impl(wl_sim** out, int D, const int* N, double nu, double dt0, const int* perdir, int exitBC, int pois_kind, int device,
+                       int rank, int nranks, const char* nccl_id) {
+  if (!out || !N || (D != 2 && D != 3)) return wl_fail(WL_ERR_ARG, "wl_create: D must be 2 or 3");
+  for (int k = 0; k < D; ++k) if (N[k] < 1) return wl_fail(WL_ERR_ARG, "wl_create: N must be positive");
+  if (nranks < 1 || rank < 0 || rank >= nranks) return wl_fail(WL_ERR_ARG, "wl_create_dist: bad rank/nranks");
+  // the MultiLevelPoisson size assertion comes first, as in the reference constructor
+  const std::vector<std::vector<int>> dims = level_dims(D, N, pois_kind);  // GLOBAL padded sizes per level
+  if (pois_kind == WL_POIS_MULTILEVEL && dims.size() <= 2) return wl_fail(WL_ERR_ARG, "MultiLevelPoisson requires size=a2ⁿ, where n>2");
   // z-slab decomposition: which levels are distributed, which replicated (coarse tail)
   std::vector<int> lvl_dist(dims.size(), 0);
-  if (nranks > 1) {
-    if (D != 3) return wl_fail(WL_ERR_ARG, "wl_create_dist: the z-slab decomposition needs D = 3");
-    if (N[2] % nranks != 0 || (N[2] / nranks) % 2 != 0)
-      return wl_fail(WL_ERR_ARG, "wl_create_dist: N[3] must split into an even number of z-planes per rank");
-    const char* e = getenv("WL_DIST_MIN_NZ");
-    const int min_nz = e ? atoi(e) : 8;  // coarser levels are agglomerated: replicated on every rank
-    lvl_dist[0] = 1;
-    for (size_t l = 1; l < dims.size(); ++l) {
-      const int nz = dims[l][2] - 2;
-      const int nzf_loc = (dims[l - 1][2] - 2) / nranks;
-      lvl_dist[l] = lvl_dist[l - 1] && nz % nranks == 0 && nz / nranks >= min_nz && nzf_loc % 2 == 0;
-    }
-    for (size_t l = 1; l < dims.size(); ++l)
-      if (lvl_dist[l - 1] && !lvl_dist[l] && (((dims[l - 1][2] - 2) / nranks) % 2 != 0 || (dims[l][2] - 2) % nranks != 0))
-        return wl_fail(WL_ERR_ARG, "wl_create_dist: cannot agglomerate — odd number of z-planes per rank on the last distributed level");
+  {
+    const int rc0 = plan_levels(D, N, nranks, dims, lvl_dist);
+    if (rc0) return rc0;
   }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -285,6 +298,30 @@ int wl_create_dist(wl_sim** out, int D, const int* N, double nu, double dt0, con
                    int rank, int nranks, const char* nccl_id128) {
   if (nranks > 1 && !nccl_id128) return wl_fail(WL_ERR_ARG, "wl_create_dist: NCCL id required");
   return create_impl(out, D, N, nu, dt0, perdir, exitBC, pois_kind, device, rank, nranks, nccl_id128);
+}
+// Host-only: the slab plan of rank `rank` — per level: distributed flag, local interior planes, global
+// offset of local plane 0, halo flags of the lower/upper z face.  No GPU is touched (CPU-testable).
+int wl_dist_plan(int D, const int* N, const int* perdir, int pois_kind, int rank, int nranks, int max_levels, int* nlevels,
+                 int* distributed, int* nz_local, int* zoff, int* zlo_halo, int* zhi_halo) {
+  if (!N || (D != 2 && D != 3)) return wl_fail(WL_ERR_ARG, "wl_dist_plan: D must be 2 or 3");
+  const auto dims = level_dims(D, N, pois_kind);
+  if (pois_kind == WL_POIS_MULTILEVEL && dims.size() <= 2) return wl_fail(WL_ERR_ARG, "MultiLevelPoisson requires size=a2ⁿ, where n>2");
+  std::vector<int> ld;
+  const int rc = plan_levels(D, N, nranks, dims, ld);
+  if (rc) return rc;
+  const int perz = (D == 3 && perdir && perdir[2]) ? 1 : 0;
+  if (nlevels) *nlevels = (int)dims.size();
+  for (int l = 0; l < (int)dims.size() && l < max_levels; ++l) {
+    const bool d = nranks > 1 && ld[l];
+    const int nzg = D == 3 ? dims[l][2] - 2 : 1;
+    const int nzl = d ? nzg / nranks : nzg;
+    if (distributed) distributed[l] = d ? 1 : 0;
+    if (nz_local) nz_local[l] = nzl;
+    if (zoff) zoff[l] = d ? rank * nzl : 0;
+    if (zlo_halo) zlo_halo[l] = d && (rank > 0 || perz) ? 1 : 0;
+    if (zhi_halo) zhi_halo[l] = d && (rank < nranks - 1 || perz) ? 1 : 0;
+  }
+  return WL_OK;
 }
 int wl_dist_info(wl_sim* s, int* rank, int* nranks, int* zoff, int* nz_local, int64_t* collectives) {
   if (!s) return wl_fail(WL_ERR_ARG, "null handle");
