@@ -259,6 +259,11 @@ static int create_impl(wl_sim** out, int D, const int* N, double nu, double dt0,
   a.u = dev_alloc(a, a.g, D, &rc); a.u0 = dev_alloc(a, a.g, D, &rc); a.f = dev_alloc(a, a.g, D, &rc);
   a.p = dev_alloc(a, a.g, 1, &rc); a.sigma = dev_alloc(a, a.g, 1, &rc); a.V = dev_alloc(a, a.g, D, &rc);
   a.mu0 = dev_alloc(a, a.g, D, &rc); a.mu1 = dev_alloc(a, a.g, D * D, &rc);
+  {
+    void* m = nullptr;
+    if (!rc && cudaMalloc(&m, (size_t)a.g.comp) == cudaSuccess) { a.allocs.push_back(m); a.body_mask = (unsigned char*)m + a.g.lead; cudaMemsetAsync(m, 1, (size_t)a.g.comp, a.stream); }
+    else if (!rc) rc = wl_fail(WL_ERR_CUDA, "cudaMalloc mask");
+  }
   // solver scalars, reduction workspace, pinned readback
   void* tmp = nullptr;
   if (!rc && cudaMalloc(&tmp, sizeof(LevelScalars) * dims.size()) == cudaSuccess) { a.allocs.push_back(tmp); a.d_scalars = (LevelScalars*)tmp; cudaMemsetAsync(tmp, 0, sizeof(LevelScalars) * dims.size(), a.stream); } else if (!rc) rc = wl_fail(WL_ERR_CUDA, "cudaMalloc scalars");
@@ -369,6 +374,7 @@ int wl_upload(wl_sim* s, int field, const float* host, int64_t count) {
   int nc; float* d = field_ptr(S, field, &nc);
   const int nzg = nz_padded_global(S, 0);
   if (!d || count != (int64_t)S.g.n[0] * S.g.n[1] * nzg * nc) return wl_fail(WL_ERR_ARG, "wl_upload: bad field or size");
+  if (field == WL_V || field == WL_MU0 || field == WL_MU1) S.mask_dirty = true;
   int rc = copy_field(S, S.g, d, const_cast<float*>(host), nc, true, nzg);
   // slab faces: refresh the halo planes from the neighbours (collective: every rank uploads the field)
   if (!rc) rc = dist_halo(S, S.g, d, nc, (field == WL_U || field == WL_U0) ? 2 : 1);
@@ -396,6 +402,7 @@ int wl_level_upload(wl_sim* s, int level, int lf, const float* host, int64_t cou
   const GridD& g = S.levels[level].g;
   const int nzg = nz_padded_global(S, level);
   if (count != (int64_t)g.n[0] * g.n[1] * nzg * nc) return wl_fail(WL_ERR_ARG, "wl_level_upload: bad size");
+  if (level == 0 && lf == WL_LVL_L) S.mask_dirty = true;  // levels[1].L ≡ μ₀
   int rc = copy_field(S, g, d, const_cast<float*>(host), nc, true, nzg);
   if (!rc) rc = dist_halo(S, g, d, nc, 1);
   return rc ? rc : wl_sync(s);
@@ -418,7 +425,8 @@ int wl_bc(wl_sim* s, int field, const double* A, int saveexit, const int* perdir
   int nc; float* d = field_ptr(S, field, &nc);
   if (!d || nc != S.D) return wl_fail(WL_ERR_ARG, "wl_bc: not a vector field");
   int per[3]; per_flags(S, perdir, per);
-  int rc = bc_vec(S, S.g, d, A, saveexit != 0, per);
+  if (field == WL_V || field == WL_MU0) S.mask_dirty = true;
+  int rc = bc_vec(S, S.g, d, A, saveexit != 0, per, (field == WL_U || field == WL_U0) ? 2 : 1);
   return rc ? rc : wl_sync(s);
 }
 int wl_exit_bc(wl_sim* s, const double* U, double dt) {

@@ -52,6 +52,8 @@ struct Sim {
   // flow fields (pointers already offset by WL_OX); u/u0 are swapped by mom_step
   float *u = nullptr, *u0 = nullptr, *f = nullptr, *p = nullptr, *sigma = nullptr, *V = nullptr, *mu0 = nullptr, *mu1 = nullptr;
   std::vector<void*> allocs;
+  unsigned char* body_mask = nullptr;  // 1 byte per cell, same indexing as a scalar field (see k_body_mask)
+  bool mask_dirty = true;              // V, μ₀ or μ₁ changed since the mask was built
   float nu = 0.f;
   std::vector<float> dt;
   bool exitBC = false;

@@ -302,12 +302,59 @@ __global__ void __launch_bounds__(256) k_bdim1(GridD g, float* f, const float* u
   });
 }
 
+// "Body band" mask: 0 where BDIM! stage 2 degenerates to u += f (μ₁ = 0, V = 0, μ₀ = 1 for every
+// component — everywhere except within 2+ϵ cells of a body and on the domain-boundary faces), 1
+// elsewhere.  One byte per cell replaces 15 words of μ₁/V/μ₀ reads; rebuilt whenever one of the three
+// fields changes (upload, BC!).  The result is bit-identical: with those values the general
+// expression reduces to (Float64)u + (Float64)f exactly.
+template <int D, int V>
+__global__ void __launch_bounds__(256) k_body_mask(GridD g, const float* __restrict__ Vb, const float* __restrict__ mu0,
+                                                   const float* __restrict__ mu1, unsigned char* __restrict__ mask) {
+  for_rows<V>(g, [&](int, int, int, int64_t I) {
+    unsigned char m[V];
+#pragma unroll
+    for (int q = 0; q < V; ++q) m[q] = 0;
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      const Pack<V> vb = ldp<V>(Vb + I + i * g.comp), m0 = ldp<V>(mu0 + I + i * g.comp);
+#pragma unroll
+      for (int q = 0; q < V; ++q) m[q] |= (vb.v[q] != 0.f) | (m0.v[q] != 1.f);
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        const Pack<V> m1 = ldp<V>(mu1 + I + (int64_t)(i + D * j) * g.comp);
+#pragma unroll
+        for (int q = 0; q < V; ++q) m[q] |= (m1.v[q] != 0.f);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < V; ++q) mask[I + q] = m[q];
+  });
+}
+
 // BDIM! stage 2 (Flow.jl:134) with μddn (:18-24); `accumulate`=0 folds the predictor's
 // scale_u!(a,0), `scale` folds the corrector's scale_u!(a,0.5)
 template <int D, int V>
 __global__ void __launch_bounds__(256) k_bdim2(GridD g, float* __restrict__ u, const float* __restrict__ f, const float* __restrict__ Vb,
-                                               const float* __restrict__ mu0, const float* __restrict__ mu1, int accumulate, float scale) {
+                                               const float* __restrict__ mu0, const float* __restrict__ mu1,
+                                               const unsigned char* __restrict__ mask, int accumulate, float scale) {
   for_rows<V>(g, [&](int, int, int, int64_t I) {
+    // one 32-bit load covers the 4 cells of a pack (mask + I is 4-byte aligned like the fields are 16-byte aligned)
+    const bool plain = V == 4 ? (*reinterpret_cast<const unsigned int*>(mask + I) == 0u) : (mask[I] == 0);
+    if (plain) {  // away from any body and boundary face: u = (u + f)·scale
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        const int64_t Ii = I + i * g.comp;
+        const Pack<V> fc = ldp<V>(f + Ii);
+        Pack<V> un;
+#pragma unroll
+        for (int q = 0; q < V; ++q) un.v[q] = 0.f;
+        if (accumulate) un = ldp<V>(u + Ii);
+#pragma unroll
+        for (int q = 0; q < V; ++q) un.v[q] = (float)((accumulate ? (double)un.v[q] : 0.0) + (double)fc.v[q]) * scale;
+        stp<V>(u + Ii, un);
+      }
+      return;
+    }
 #pragma unroll
     for (int i = 0; i < D; ++i) {
       const int64_t Ii = I + i * g.comp;
@@ -532,10 +579,15 @@ int mom_bdim1(Sim& s) {
   return wl_cuda_check(s, cudaGetLastError(), "k_bdim1");
 }
 int mom_bdim2(Sim& s, bool accumulate, float scale) {
+  if (s.mask_dirty) {
+    RLAUNCH(s, k_body_mask, s.g, s.g, s.V, s.mu0, s.mu1, s.body_mask);
+    s.mask_dirty = false;
+  }
   wl_prof_begin(s, WL_PROF_BDIM2);
-  RLAUNCH(s, k_bdim2, s.g, s.g, s.u, s.f, s.V, s.mu0, s.mu1, accumulate ? 1 : 0, scale);
+  RLAUNCH(s, k_bdim2, s.g, s.g, s.u, s.f, s.V, s.mu0, s.mu1, s.body_mask, accumulate ? 1 : 0, scale);
   // read f, V, μ₀ (3D), μ₁ (D²) [+ u (D)], write u (D)
-  wl_prof_end(s, WL_PROF_BDIM2, 4.0 * (double)s.g.interior * ((accumulate ? 5 : 4) * s.D + s.D * s.D));
+  // algorithmic traffic away from a body: read f (D) [+ u (D)] + mask (¼), write u (D)
+  wl_prof_end(s, WL_PROF_BDIM2, 4.0 * (double)s.g.interior * ((accumulate ? 3 : 2) * s.D + 0.25));
   return wl_cuda_check(s, cudaGetLastError(), "k_bdim2");
 }
 int mom_scale_u(Sim& s, double scale) {
