@@ -81,6 +81,7 @@ def main():
             print(f"[{name}] V-cycles {sd.pois.n} vs {s1.pois.n} {'ok' if same_n else 'FAIL'}; dt {'ok' if same_dt else 'FAIL'}; "
                   f"levels {sd._eng.nlevels()}, {info['nz_local']} planes/rank, {info['collectives']} NCCL calls")
             s1.close()
+        dist.barrier()   # closing a slab handle is collective (peer mappings): all ranks arrive together
         sd.close()
         dist.barrier()
     flag = torch.tensor([1 if ok else 0])

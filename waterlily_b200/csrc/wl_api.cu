@@ -78,14 +78,20 @@ void grid_set(GridD& g, int D, const int* Ng, const int* per) {
   g.zoff = 0;
 }
 
+// Fields are bump-allocated from ONE arena per handle (a single cudaMalloc): the arena is what the
+// z-slab ranks export to each other over CUDA IPC, and since every rank runs the same allocation
+// sequence, a field sits at the same offset in every rank's arena (wl_p2p.cuh).  A first, dry pass
+// of the allocation sequence (s.arena == nullptr) only measures.
+void* arena_take(Sim& s, size_t bytes, int* rc) {
+  const size_t off = (s.arena_used + 255) / 256 * 256;
+  s.arena_used = off + bytes;
+  if (!s.arena) return nullptr;  // dry pass
+  if (s.arena_used > s.arena_bytes) { if (!*rc) *rc = wl_fail(WL_ERR_ARG, "internal: arena overflow"); return nullptr; }
+  return s.arena + off;
+}
 float* dev_alloc(Sim& s, const GridD& g, int ncomp, int* rc) {
-  void* p = nullptr;
-  const size_t bytes = sizeof(float) * (size_t)g.comp * ncomp;
-  cudaError_t e = cudaMalloc(&p, bytes);
-  if (e == cudaSuccess) e = cudaMemsetAsync(p, 0, bytes, s.stream);
-  if (e != cudaSuccess) { *rc = wl_cuda_check(s, e, "cudaMalloc"); return nullptr; }
-  s.allocs.push_back(p);
-  return (float*)p + g.lead;
+  float* p = (float*)arena_take(s, sizeof(float) * (size_t)g.comp * ncomp, rc);
+  return p ? p + g.lead : nullptr;
 }
 
 float* field_ptr(Sim& s, int field, int* ncomp) {
@@ -256,15 +262,30 @@ static int create_impl(wl_sim** out, int D, const int* N, double nu, double dt0,
     }
   };
   make_grid(a.g, dims[0], nranks > 1);
-  a.u = dev_alloc(a, a.g, D, &rc); a.u0 = dev_alloc(a, a.g, D, &rc); a.f = dev_alloc(a, a.g, D, &rc);
-  a.p = dev_alloc(a, a.g, 1, &rc); a.sigma = dev_alloc(a, a.g, 1, &rc); a.V = dev_alloc(a, a.g, D, &rc);
-  a.mu0 = dev_alloc(a, a.g, D, &rc); a.mu1 = dev_alloc(a, a.g, D * D, &rc);
-  {
-    void* m = nullptr;
-    if (!rc && cudaMalloc(&m, (size_t)a.g.comp) == cudaSuccess) { a.allocs.push_back(m); a.body_mask = (unsigned char*)m + a.g.lead; cudaMemsetAsync(m, 1, (size_t)a.g.comp, a.stream); }
-    else if (!rc) rc = wl_fail(WL_ERR_CUDA, "cudaMalloc mask");
-  }
-  // solver scalars, reduction workspace, pinned readback
+  // every field of the handle, in a fixed order (identical on every rank: the arenas are symmetric).
+  // levels[1] aliases the flow arrays (WaterLily.jl:77); r, ϵ, D, iD are its own (Poisson.jl:33-34)
+  auto alloc_fields = [&](int* prc) {
+    a.arena_used = WL_P2P_FLAG_BYTES;  // the peer-communication flag block leads the arena
+    a.u = dev_alloc(a, a.g, D, prc); a.u0 = dev_alloc(a, a.g, D, prc); a.f = dev_alloc(a, a.g, D, prc);
+    a.p = dev_alloc(a, a.g, 1, prc); a.sigma = dev_alloc(a, a.g, 1, prc); a.V = dev_alloc(a, a.g, D, prc);
+    a.mu0 = dev_alloc(a, a.g, D, prc); a.mu1 = dev_alloc(a, a.g, D * D, prc);
+    {
+      unsigned char* m = (unsigned char*)arena_take(a, (size_t)a.g.comp, prc);
+      a.body_mask = m ? m + a.g.lead : nullptr;
+    }
+    a.levels.clear();
+    for (size_t l = 0; l < dims.size(); ++l) {
+      Lvl lv{};
+      make_grid(lv.g, dims[l], nranks > 1 && lvl_dist[l]);
+      lv.sc = a.d_scalars + l;
+      if (l == 0) { lv.x = a.p; lv.L = a.mu0; lv.z = a.sigma; }
+      else { lv.L = dev_alloc(a, lv.g, D, prc); lv.x = dev_alloc(a, lv.g, 1, prc); lv.z = dev_alloc(a, lv.g, 1, prc); }
+      lv.r = dev_alloc(a, lv.g, 1, prc); lv.eps = dev_alloc(a, lv.g, 1, prc);
+      lv.Dg = dev_alloc(a, lv.g, 1, prc); lv.iD = dev_alloc(a, lv.g, 1, prc);
+      a.levels.push_back(lv);
+    }
+  };
+  // solver scalars, reduction workspace, pinned readback (rank-local, outside the arena)
   void* tmp = nullptr;
   if (!rc && cudaMalloc(&tmp, sizeof(LevelScalars) * dims.size()) == cudaSuccess) { a.allocs.push_back(tmp); a.d_scalars = (LevelScalars*)tmp; cudaMemsetAsync(tmp, 0, sizeof(LevelScalars) * dims.size(), a.stream); } else if (!rc) rc = wl_fail(WL_ERR_CUDA, "cudaMalloc scalars");
   if (!rc && cudaMalloc(&tmp, sizeof(MiscScalars)) == cudaSuccess) { a.allocs.push_back(tmp); a.d_misc = (MiscScalars*)tmp; cudaMemsetAsync(tmp, 0, sizeof(MiscScalars), a.stream); } else if (!rc) rc = wl_fail(WL_ERR_CUDA, "cudaMalloc misc");
@@ -272,17 +293,19 @@ static int create_impl(wl_sim** out, int D, const int* N, double nu, double dt0,
   if (!rc && cudaMalloc(&tmp, 64) == cudaSuccess) { a.allocs.push_back(tmp); a.ws.ticket = (unsigned int*)tmp; cudaMemsetAsync(tmp, 0, 64, a.stream); } else if (!rc) rc = wl_fail(WL_ERR_CUDA, "cudaMalloc ticket");
   if (!rc && cudaMallocHost((void**)&a.h_pinned, 64 * sizeof(float)) != cudaSuccess) rc = wl_fail(WL_ERR_CUDA, "cudaMallocHost");
   if (rc) { wl_destroy((wl_sim*)sp); return rc; }
-  // levels[1] aliases the flow arrays (WaterLily.jl:77); r, ϵ, D, iD are its own (Poisson.jl:33-34)
-  for (size_t l = 0; l < dims.size() && !rc; ++l) {
-    Lvl lv{};
-    make_grid(lv.g, dims[l], nranks > 1 && lvl_dist[l]);
-    lv.sc = a.d_scalars + l;
-    if (l == 0) { lv.x = a.p; lv.L = a.mu0; lv.z = a.sigma; }
-    else { lv.L = dev_alloc(a, lv.g, D, &rc); lv.x = dev_alloc(a, lv.g, 1, &rc); lv.z = dev_alloc(a, lv.g, 1, &rc); }
-    lv.r = dev_alloc(a, lv.g, 1, &rc); lv.eps = dev_alloc(a, lv.g, 1, &rc);
-    lv.Dg = dev_alloc(a, lv.g, 1, &rc); lv.iD = dev_alloc(a, lv.g, 1, &rc);
-    a.levels.push_back(lv);
+  alloc_fields(&rc);  // dry pass: measures
+  a.arena_bytes = (a.arena_used + 255) / 256 * 256;
+  {
+    void* m = nullptr;
+    cudaError_t e = cudaMalloc(&m, a.arena_bytes);
+    if (e == cudaSuccess) e = cudaMemsetAsync(m, 0, a.arena_bytes, a.stream);
+    if (e != cudaSuccess) { rc = wl_cuda_check(a, e, "cudaMalloc (field arena)"); wl_destroy((wl_sim*)sp); return rc; }
+    a.arena = (char*)m;
   }
+  alloc_fields(&rc);
+  if (!rc) rc = wl_cuda_check(a, cudaMemsetAsync(a.body_mask - a.g.lead, 1, (size_t)a.g.comp, a.stream), "mask init");
+  // peer mapping of the arenas (slab ranks): halos and reductions then bypass NCCL
+  if (!rc) rc = dist_p2p_setup(a);
   if (rc) { wl_destroy((wl_sim*)sp); return rc; }
   // μ₀ = 1, BC!(μ₀,0) (Flow.jl:118-119); then the Poisson constructors' set_diag!/restrictL!
   const double zero[3] = {0, 0, 0};
@@ -345,6 +368,7 @@ int wl_destroy(wl_sim* s) {
   cudaSetDevice(a.device);
   if (a.stream) cudaStreamSynchronize(a.stream);
   dist_destroy(a);
+  if (a.arena) cudaFree(a.arena);
   for (void* p : a.allocs) cudaFree(p);
   if (a.h_pinned) cudaFreeHost(a.h_pinned);
   for (auto& pc : a.prof) for (cudaEvent_t e : pc.ev) cudaEventDestroy(e);

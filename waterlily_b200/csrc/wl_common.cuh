@@ -9,6 +9,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "wl_p2p.cuh"
+
 #define WL_OX 3  // row offset: interior cell i=1 lands on a 16-byte boundary
 
 struct GridD {
@@ -79,7 +81,9 @@ struct FinArgs {
   double* out;
   double count;     // global cell count the stage divides by
   double aux;       // U[1] for FIN_EXIT
-  int defer;
+  const P2PDev* p2p; // peer-memory context (defer == 2)
+  int defer;        // 0: finalise locally; 1: park the totals for an NCCL all-reduce + k_finalize;
+                    // 2: the finishing thread all-reduces over peer memory and finalises in place
   int has_ghost;    // this level's z⋅ϵ has a ghost-shell part (level 1 only)
 };
 
@@ -154,6 +158,12 @@ __device__ __forceinline__ void finalize(int stage, const FinArgs& fa, double t0
 __device__ __forceinline__ void finish_reduction(int stage, const FinArgs& fa, double t0, double t1) {
   if (!fa.defer) { finalize(stage, fa, t0, t1); return; }
   if (stage == FIN_GHOST_DOT) { fa.raw[1] = t0; return; }        // rides along with the z⋅ϵ all-reduce
+  if (fa.defer == 2) {
+    double v0 = t0, v1 = stage == FIN_PCG_MULT ? fa.raw[1] : t1;
+    p2p_allreduce2(*fa.p2p, v0, v1, stage == FIN_CFL || stage == FIN_CFL_SHELL);
+    finalize(stage, fa, v0, v1);
+    return;
+  }
   fa.raw[0] = t0;
   if (stage != FIN_PCG_MULT) fa.raw[1] = t1;                      // keep the parked ghost part
 }

@@ -9,6 +9,7 @@
 
 #include "../../include/waterlily_b200.h"
 #include "wl_common.cuh"
+#include "wl_p2p.cuh"
 
 // profiled kernel classes (wl_profile_read `which`)
 enum {
@@ -39,7 +40,13 @@ struct ProfClass {
 
 struct DistState {
   int rank = 0, nranks = 1;
-  void* comm = nullptr;  // ncclComm_t
+  void* comm = nullptr;  // ncclComm_t (bootstrap, and the data path when peer mapping is off)
+  // peer-memory path (wl_p2p.cuh): arenas of all ranks mapped over CUDA IPC
+  bool p2p = false;
+  P2PDev host{};                 // host copy of the device context
+  P2PDev* dev = nullptr;         // the same in device memory (kernels take the pointer)
+  unsigned long long epoch = 0;  // push epochs issued so far (same sequence on every rank)
+  int64_t pushes = 0;            // peer-push kernels launched
 };
 
 struct Sim {
@@ -52,6 +59,8 @@ struct Sim {
   // flow fields (pointers already offset by WL_OX); u/u0 are swapped by mom_step
   float *u = nullptr, *u0 = nullptr, *f = nullptr, *p = nullptr, *sigma = nullptr, *V = nullptr, *mu0 = nullptr, *mu1 = nullptr;
   std::vector<void*> allocs;
+  char* arena = nullptr;       // all fields live in one allocation (symmetric across ranks, wl_p2p.cuh)
+  size_t arena_bytes = 0, arena_used = 0;
   unsigned char* body_mask = nullptr;  // 1 byte per cell, same indexing as a scalar field (see k_body_mask)
   bool mask_dirty = true;              // V, μ₀ or μ₁ changed since the mask was built
   float nu = 0.f;
@@ -92,6 +101,8 @@ void wl_prof_end(Sim& s, int cls, double bytes);
 // ---- wl_dist.cu ----
 int dist_unique_id(char* out128);
 int dist_init(Sim& s, int rank, int nranks, const char* id128);
+int dist_p2p_setup(Sim& s);   // after the arena exists: exchange IPC handles, map the peers
+int dist_check_p2p_error(Sim& s);  // a peer wait timed out → sticky failure
 void dist_destroy(Sim& s);
 int dist_halo(Sim& s, const GridD& g, float* base, int ncomp, int depth);
 int dist_allreduce(Sim& s, double* dptr, int count, bool is_max);

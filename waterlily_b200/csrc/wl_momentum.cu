@@ -660,6 +660,7 @@ int mom_step(Sim& s, const double* U, const double* gp, const double* gc, double
   double dt;
   if ((rc = mom_cfl(s, &dt))) return rc;
   wl_prof_end(s, WL_PROF_STEP, 0.0);
+  if ((rc = dist_check_p2p_error(s))) return rc;
   s.dt.push_back((float)dt);
   if (dt_next) *dt_next = dt;
   return 0;

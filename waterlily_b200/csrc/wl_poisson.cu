@@ -311,7 +311,8 @@ FinArgs fin_level(const Sim& s, int level) {
   fa.raw = &l.sc->raw[0];
   fa.out = s.ws.partials + (size_t)WL_MAXBLOCKS * WL_MAXRED;  // spare slot behind the partials
   fa.count = (double)l.g.interior_global;
-  fa.defer = (s.dist.nranks > 1 && s.lvl_dist[level]) ? 1 : 0;
+  fa.defer = (s.dist.nranks > 1 && s.lvl_dist[level]) ? (s.dist.p2p ? 2 : 1) : 0;
+  fa.p2p = s.dist.dev;
   return fa;
 }
 FinArgs fin_misc(const Sim& s) {
@@ -321,7 +322,7 @@ FinArgs fin_misc(const Sim& s) {
 }
 // deferred finalisation: all-reduce the parked totals, then run finalize on every rank
 int post_reduce(Sim& s, int stage, const FinArgs& fa, bool is_max) {
-  if (!fa.defer) return 0;
+  if (fa.defer != 1) return 0;  // local, or all-reduced over peer memory by the producing kernel itself
   int rc = dist_allreduce(s, fa.raw, 2, is_max);
   if (rc) return rc;
   k_finalize<<<1, 1, 0, s.stream>>>(stage, fa);
@@ -384,7 +385,11 @@ int pois_residual(Sim& s, Lvl& l, bool need_r2) {
   if (fine) wl_prof_begin(s, WL_PROF_RESIDUAL);
   RLAUNCH(s, k_residual, l.g, l, s.ws, fa);
   if ((rc = post_reduce(s, FIN_RESIDUAL, fa))) return rc;
-  RLAUNCH(s, k_sub_mean, l.g, l, s.ws, fa);
+  {
+    FinArgs fb = fa;
+    if (!need_r2 && fb.defer == 2) fb.defer = 0;  // not needed across ranks: keep the partial local
+    RLAUNCH(s, k_sub_mean, l.g, l, s.ws, fb);
+  }
   // r⋅r after the mean subtraction is only reported, never used for control: solver! skips its all-reduce
   if (need_r2 && (rc = post_reduce(s, FIN_R2_IF_SUB, fa))) return rc;
   if (fine) wl_prof_end(s, WL_PROF_RESIDUAL, cellsB(l, 8));
@@ -396,7 +401,8 @@ static int pois_increment(Sim& s, Lvl& l) {
   if (rc) return rc;
   const int lv = level_of(s, l);
   const bool fine = lv == 0;
-  const FinArgs fa = fin_level(s, lv);
+  FinArgs fa = fin_level(s, lv);
+  if (!fine && fa.defer == 2) fa.defer = 0;  // L₂ is only ever read on the finest level
   if (fine) wl_prof_begin(s, WL_PROF_INCREMENT);
   RLAUNCH(s, k_increment, l.g, l, s.ws, fa);
   if (fine && (rc = post_reduce(s, FIN_R2, fa))) return rc;  // L₂ is only ever read on the finest level
