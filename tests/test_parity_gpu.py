@@ -272,3 +272,21 @@ def test_full_size_properties_tgv128():
     assert 0.115 < ke < 0.126              # TGV kinetic energy 1/8 at t=0, decaying slowly
     assert all(1 <= n <= 32 for n in sim.pois.n)
     assert 0.5 < float(sim.flow.dt[-1]) < 1.1
+
+
+@pytest.mark.parametrize("make,steps", [(lambda cls: tgv3d(cls, 64), 3), (lambda cls: sphere3d(cls, exitBC=True), 4), (circle2d, 10)])
+def test_fused_vcycle_matches_per_level_kernels(make, steps, monkeypatch):
+    # wl_vcycle.cu (one persistent kernel for the coarse levels) against the per-function kernels of
+    # wl_poisson.cu: same arithmetic, different reduction tree → agreement to reduction-order noise
+    monkeypatch.setenv("WL_FUSED_VCYCLE", "0")
+    s0 = make(Simulation)
+    monkeypatch.setenv("WL_FUSED_VCYCLE", "1")
+    s1 = make(Simulation)
+    l0, l1 = s0._eng.launch_count(), s1._eng.launch_count()
+    for _ in range(steps):
+        sim_step(s0, remeasure=False)
+        sim_step(s1, remeasure=False)
+    assert s0.pois.n == s1.pois.n
+    for f in ("u", "p"):
+        assert rel_l2(getattr(s1.flow, f).numpy(), getattr(s0.flow, f).numpy()) < 2e-6, f
+    assert s1._eng.launch_count() - l1 < s0._eng.launch_count() - l0   # the fused path really ran

@@ -199,7 +199,7 @@ static std::vector<std::vector<int>> level_dims(int D, const int* N, int pois_ki
   dims.push_back(g0);
   if (pois_kind == WL_POIS_MULTILEVEL) {
     auto div_ok = [&](const std::vector<int>& n) { for (int k = 0; k < D; ++k) if (!divisible(n[k])) return false; return true; };
-    while (div_ok(dims.back()) && (int)dims.size() <= 10) {  // MultiLevelPoisson.jl:53
+    while (div_ok(dims.back()) && (int)dims.size() < WL_MAXLEVELS) {  // MultiLevelPoisson.jl:53
       std::vector<int> c(3, 1);
       for (int k = 0; k < D; ++k) c[k] = 1 + dims.back()[k] / 2;  // restrictML :20
       dims.push_back(c);
@@ -306,6 +306,7 @@ static int create_impl(wl_sim** out, int D, const int* N, double nu, double dt0,
   if (!rc) rc = wl_cuda_check(a, cudaMemsetAsync(a.body_mask - a.g.lead, 1, (size_t)a.g.comp, a.stream), "mask init");
   // peer mapping of the arenas (slab ranks): halos and reductions then bypass NCCL
   if (!rc) rc = dist_p2p_setup(a);
+  if (!rc) rc = vcycle_fused_setup(a);
   if (rc) { wl_destroy((wl_sim*)sp); return rc; }
   // μ₀ = 1, BC!(μ₀,0) (Flow.jl:118-119); then the Poisson constructors' set_diag!/restrictL!
   const double zero[3] = {0, 0, 0};
@@ -368,6 +369,7 @@ int wl_destroy(wl_sim* s) {
   cudaSetDevice(a.device);
   if (a.stream) cudaStreamSynchronize(a.stream);
   dist_destroy(a);
+  vcycle_fused_destroy(a);
   if (a.arena) cudaFree(a.arena);
   for (void* p : a.allocs) cudaFree(p);
   if (a.h_pinned) cudaFreeHost(a.h_pinned);

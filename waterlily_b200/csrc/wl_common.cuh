@@ -92,6 +92,7 @@ struct ReduceWS {
   double* partials;   // [maxBlocks * WL_MAXRED]
   unsigned int* ticket;
 };
+#define WL_MAXLEVELS 12
 #define WL_MAXRED 4
 #define WL_MAXBLOCKS 4096
 

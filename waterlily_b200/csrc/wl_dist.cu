@@ -114,12 +114,15 @@ struct PushPlan {
 };
 #define WL_PUSH_CHUNK 2048  // float4 per block-chunk (32 KiB)
 
-__global__ void __launch_bounds__(256) k_p2p_push(const P2PDev* __restrict__ ctxp, PushPlan plan, unsigned long long epoch) {
+__global__ void __launch_bounds__(256) k_p2p_push(const P2PDev* __restrict__ ctxp, PushPlan plan) {
   __shared__ P2PDev c;
   __shared__ bool last;
   if (threadIdx.x == 0) c = *ctxp;
   __syncthreads();
   P2PFlags* mine = p2p_flags(c, c.rank);
+  // the epoch counter lives on the device (the fused V-cycle kernel pushes without the host); every
+  // block samples it before taking its ticket, the last block advances it
+  const unsigned long long epoch = *((const volatile unsigned long long*)&mine->push_epoch) + 1;
   const int t = threadIdx.x;
   if (t < plan.npeers) {
     const int pr = plan.peers[t];
@@ -156,14 +159,13 @@ __global__ void __launch_bounds__(256) k_p2p_push(const P2PDev* __restrict__ ctx
     p2p_st_release(&p2p_flags(c, pr)->done[c.rank], epoch);
     p2p_wait<false>(c, &mine->done[pr], epoch);
   }
-  if (t == 0) mine->ticket = 0u;
+  if (t == 0) { mine->ticket = 0u; mine->push_epoch = epoch; }
 }
 
 int push(Sim& s, PushPlan& plan, int64_t total4) {
-  const unsigned long long e = ++s.dist.epoch;
   int64_t nchunk = (total4 + WL_PUSH_CHUNK - 1) / WL_PUSH_CHUNK + plan.nseg;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(nchunk, 2 * s.nsm));
-  k_p2p_push<<<grid, 256, 0, s.stream>>>(s.dist.dev, plan, e);
+  k_p2p_push<<<grid, 256, 0, s.stream>>>(s.dist.dev, plan);
   ++s.launches;
   ++s.dist.pushes;
   return wl_cuda_check(s, cudaGetLastError(), "k_p2p_push");

@@ -45,7 +45,6 @@ struct DistState {
   bool p2p = false;
   P2PDev host{};                 // host copy of the device context
   P2PDev* dev = nullptr;         // the same in device memory (kernels take the pointer)
-  unsigned long long epoch = 0;  // push epochs issued so far (same sequence on every rank)
   int64_t pushes = 0;            // peer-push kernels launched
 };
 
@@ -81,6 +80,8 @@ struct Sim {
   std::vector<int> lvl_dist;   // 1: level is z-distributed, 0: replicated on every rank (coarse tail)
   int Nz_global = 0;           // interior z-planes of the whole domain (3-D)
   int per_z_global = 0;
+  void* vc_fused = nullptr;    // fused coarse V-cycle (wl_vcycle.cu), or null
+  int vc_first = -1;           // first level the fused kernel covers (-1: off)
   int sticky = 0;  // first CUDA error, sticky per handle
   bool profiling = false;
   ProfClass prof[WL_PROF_N];
@@ -111,6 +112,11 @@ int dist_allgather(Sim& s, float* base, size_t count);
 int post_reduce(Sim& s, int stage, const FinArgs& fa, bool is_max = false);
 FinArgs fin_level(const Sim& s, int level);
 FinArgs fin_misc(const Sim& s);
+
+// ---- wl_vcycle.cu ----
+int vcycle_fused_setup(Sim& s);
+void vcycle_fused_destroy(Sim& s);
+int vcycle_fused_run(Sim& s);
 
 // ---- wl_bc.cu ----
 int bc_vec(Sim& s, const GridD& g, float* a, const double* A, bool saveexit, const int* per, int halo_depth = 1);

@@ -24,9 +24,10 @@ struct P2PFlags {
   unsigned long long done[WL_MAXRANKS];   // done[src]:  src's stores of push epoch e into this arena are visible
   P2PMail mbox[2][WL_MAXRANKS];           // all-reduce mailboxes, double-buffered by epoch parity
   unsigned long long ar_epoch;            // local: all-reduces performed so far (device-side counter)
+  unsigned long long push_epoch;          // local: pushes performed so far (device-side: the fused V-cycle pushes on its own)
   unsigned int ticket;                    // local: block counter of the push kernel
   int err;                                // local: a wait timed out (the handle becomes sticky-failed)
-  unsigned long long pad[4];
+  unsigned long long pad[3];
 };
 #define WL_P2P_FLAG_BYTES 1024  // sizeof(P2PFlags) rounded up; the first field starts behind it
 

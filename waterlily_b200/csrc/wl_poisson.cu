@@ -487,8 +487,13 @@ int pois_vcycle(Sim& s, int level) {
   }
   RLAUNCH(s, k_restrict, coarse.g, coarse, fine, ck0, ck1, fshift);
   if (gather && (rc = dist_allgather(s, coarse.r + coarse.g.s[2], (size_t)((coarse.g.n[2] - 2) / s.dist.nranks) * coarse.g.s[2]))) return rc;
-  if (level + 2 < (int)s.levels.size() && (rc = pois_vcycle(s, level + 1))) return rc;
-  if ((rc = pois_pcg(s, level + 1, 6))) return rc;
+  if (s.vc_first == level + 1) {
+    // the rest of the cycle below this level is one persistent kernel (wl_vcycle.cu)
+    if ((rc = vcycle_fused_run(s))) return rc;
+  } else {
+    if (level + 2 < (int)s.levels.size() && (rc = pois_vcycle(s, level + 1))) return rc;
+    if ((rc = pois_pcg(s, level + 1, 6))) return rc;
+  }
   RLAUNCH(s, k_prolongate, fine.g, fine, coarse, gather ? fine.g.zoff : 0);
   return pois_increment(s, fine);
 }

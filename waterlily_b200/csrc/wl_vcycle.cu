@@ -1,0 +1,588 @@
+// wl_vcycle.cu — the coarse part of Vcycle! (reference src/MultiLevelPoisson.jl:70-82) as ONE
+// persistent cooperative kernel.
+//
+// Below the finest levels a V-cycle is pure latency: ~30 launches per level, each a few
+// microseconds of work, plus (across slab ranks) a halo exchange or an all-reduce between most of
+// them.  k_vcycle_tail runs, for the levels lf … nl-1,
+//
+//     down:  Jacobi!(l) ; restrict!(l → l+1) ; fill!(x_{l+1},0)          l = lf … nl-2
+//            pcg!(nl-1)
+//     up:    prolongate!(l+1 → l) ; increment!(l) ; pcg!(l)               l = nl-2 … lf
+//
+// in a single launch: phases are separated by a grid barrier (~1 µs) instead of a kernel boundary,
+// every scalar decision of pcg! (|ρ|<10eps, |α|∉[1e-2,1e2]) is taken redundantly and identically
+// by all blocks from the same reduced bits, the smallest levels (≤ 16³) are run by one block with
+// __syncthreads as the barrier, and on z-distributed levels the halo planes and reduction partials
+// go to the neighbours' memory directly from inside the kernel (wl_p2p.cuh).
+//
+// Arithmetic is that of the per-function kernels in wl_poisson.cu (same expressions, -fmad=false,
+// Float64 dot accumulation); periodic ghosts of ϵ are not materialised — the stencil wraps its
+// index instead, which reads the same value (nothing else reads ϵ's ghosts below level 1).
+#include <algorithm>
+#include <cstdlib>
+
+#include "wl_internal.h"
+#include "wl_vec.cuh"
+
+namespace {
+
+#define VC_THREADS 256
+
+struct FusedParams {
+  int D, nl, lf, lb;          // dims, levels, first fused level, first single-block level
+  Lvl lv[WL_MAXLEVELS];
+  int dist[WL_MAXLEVELS];     // level is z-distributed (halo exchange + all-reduce)
+  int bxlog[WL_MAXLEVELS];    // log2 of the threads along x used for this level
+  int nranks, rank;
+  unsigned int* bar;          // grid barrier: {count, generation}
+  double* partials;           // [gridDim.x][2]
+  const P2PDev* p2p;          // null on one rank
+};
+
+struct Shared {
+  double red[2][VC_THREADS / 32];
+  double tot[2];
+  double mail[WL_MAXRANKS][2];
+  P2PDev c;
+};
+
+// state every thread carries (uniform across the grid)
+struct Run {
+  Shared* sh;
+  unsigned long long push_epoch, ar_epoch;
+  unsigned int bar_gen;
+};
+
+// ---- barriers -----------------------------------------------------------------------------
+__device__ __forceinline__ void grid_barrier(const FusedParams& p, Run& run) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int gen = run.bar_gen;
+    __threadfence();
+    if (atomicAdd(&p.bar[0], 1u) == gridDim.x - 1) {
+      p.bar[0] = 0u;
+      __threadfence();
+      atomicAdd(&p.bar[1], 1u);
+    } else {
+      while (*((volatile unsigned int*)&p.bar[1]) == gen) __nanosleep(40);
+    }
+    __threadfence();
+  }
+  ++run.bar_gen;
+  __syncthreads();
+}
+template <bool GRID>
+__device__ __forceinline__ void phase_sync(const FusedParams& p, Run& run) {
+  if (GRID) grid_barrier(p, run);
+  else __syncthreads();
+}
+
+// ---- iteration ----------------------------------------------------------------------------
+// interior rows of level l, V cells per thread; f(i, j, k, I)
+template <int V, bool GRID, class F>
+__device__ __forceinline__ void rows(const FusedParams& p, int l, F&& f) {
+  const GridD& g = p.lv[l].g;
+  const int bxl = p.bxlog[l], bx = 1 << bxl, by = VC_THREADS >> bxl;
+  const int tx = threadIdx.x & (bx - 1), ty = threadIdx.x >> bxl;
+  const int nj = g.D > 1 ? g.n[1] - 2 : 1, nk = g.D > 2 ? g.n[2] - 2 : 1;
+  const int njt = (nj + by - 1) / by;
+  const int nunits = njt * nk;
+  const int nxi = g.n[0] - 2;
+  const int bid = GRID ? blockIdx.x : 0, nb = GRID ? gridDim.x : 1;
+  for (int unit = bid; unit < nunits; unit += nb) {
+    const int kk = unit / njt, jt = unit - kk * njt;
+    const int j = 1 + jt * by + ty;
+    if (j > nj) continue;
+    const int k = g.D > 2 ? 1 + kk : 0;
+    const int64_t row = j * g.s[1] + k * g.s[2];
+    for (int i = 1 + V * tx; i <= nxi; i += V * bx) f(i, j, k, row + i);
+  }
+}
+
+// ---- reductions ---------------------------------------------------------------------------
+// Sum of NR per-thread Float64 accumulators over the whole level (all blocks, all ranks); every
+// thread of every block returns the same totals.  Contains the phase barrier.
+template <int NR, bool GRID>
+__device__ __forceinline__ void reduce(const FusedParams& p, Run& run, bool distributed, double (&v)[NR]) {
+  Shared& sh = *run.sh;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    const double w = warp_sum(v[r]);
+    if (lane == 0) sh.red[r][warp] = w;
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      double a = lane < VC_THREADS / 32 ? sh.red[r][lane] : 0.0;
+      a = warp_sum(a);
+      if (lane == 0) {
+        if (GRID) p.partials[(size_t)blockIdx.x * 2 + r] = a;
+        else sh.tot[r] = a;
+      }
+    }
+  }
+  if (!GRID) {
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < NR; ++r) v[r] = sh.tot[r];
+    __syncthreads();
+    return;
+  }
+  grid_barrier(p, run);
+  if (warp == 0) {
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      double a = 0.0;
+      for (unsigned int b = lane; b < gridDim.x; b += 32) a += ((volatile double*)p.partials)[(size_t)b * 2 + r];
+      a = warp_sum(a);
+      if (lane == 0) sh.tot[r] = a;
+    }
+  }
+  __syncthreads();
+  if (distributed) {
+    // block 0 mails this rank's totals to every rank; every block adds the R mails in rank order
+    const P2PDev& c = sh.c;
+    const unsigned long long e = ++run.ar_epoch;
+    const int slot = (int)(e & 1ull);
+    if (tid < c.nranks) {
+      if (blockIdx.x == 0) {
+        P2PMail* m = &p2p_flags(c, tid)->mbox[slot][c.rank];
+        ((volatile double*)m->v)[0] = sh.tot[0];
+        ((volatile double*)m->v)[1] = NR > 1 ? sh.tot[1] : 0.0;
+        __threadfence_system();
+        p2p_st_release(&m->epoch, e);
+      }
+      const P2PMail* in = &p2p_flags(c, c.rank)->mbox[slot][tid];
+      p2p_wait<true>(c, &in->epoch, e);
+      sh.mail[tid][0] = ((const volatile double*)in->v)[0];
+      sh.mail[tid][1] = ((const volatile double*)in->v)[1];
+    }
+    __syncthreads();
+    if (tid == 0) {
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        double a = 0.0;
+        for (int q = 0; q < c.nranks; ++q) a += sh.mail[q][r];
+        sh.tot[r] = a;
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int r = 0; r < NR; ++r) v[r] = sh.tot[r];
+  __syncthreads();
+}
+
+// ---- peer pushes from inside the kernel ------------------------------------------------------
+__device__ __forceinline__ void post_ready(const FusedParams& p, Run& run) {
+  // "all my reads of ghost data delivered by pushes ≤ push_epoch are complete" — to every peer
+  if (!p.p2p || blockIdx.x != 0) return;
+  const P2PDev& c = run.sh->c;
+  if (threadIdx.x < c.nranks && threadIdx.x != c.rank) p2p_st_release(&p2p_flags(c, threadIdx.x)->ready[c.rank], run.push_epoch + 1);
+}
+struct Seg { int peer; int64_t src_off, dst_off, n4; };  // float offsets are converted to byte offsets by the caller
+#define VC_CHUNK 1024  // float4 per chunk
+// the caller has passed a grid barrier since the data was produced
+__device__ __forceinline__ void push_segments(const FusedParams& p, Run& run, const Seg* seg, int nseg, unsigned int peer_mask) {
+  const P2PDev& c = run.sh->c;
+  P2PFlags* mine = p2p_flags(c, c.rank);
+  const unsigned long long e = ++run.push_epoch;
+  const int t = threadIdx.x;
+  const bool mypeer = t < c.nranks && ((peer_mask >> t) & 1u);
+  if (mypeer) p2p_wait<false>(c, &mine->ready[t], e);
+  __syncthreads();
+  int64_t nchunk = 0;
+  for (int s = 0; s < nseg; ++s) nchunk += (seg[s].n4 + VC_CHUNK - 1) / VC_CHUNK;
+  const int npart = (int)min((int64_t)gridDim.x, nchunk);
+  if ((int)blockIdx.x < npart) {
+    int64_t first = 0;
+    for (int s = 0; s < nseg; ++s) {
+      const int64_t nc = (seg[s].n4 + VC_CHUNK - 1) / VC_CHUNK;
+      const float4* src = reinterpret_cast<const float4*>(c.base[c.rank] + seg[s].src_off);
+      float4* dst = reinterpret_cast<float4*>(c.base[seg[s].peer] + seg[s].dst_off);
+      int64_t k = ((int64_t)blockIdx.x - first % npart + npart) % npart;
+      for (; k < nc; k += npart) {
+        const int64_t lo = k * VC_CHUNK, hi = min(lo + (int64_t)VC_CHUNK, seg[s].n4);
+        for (int64_t i = lo + t; i < hi; i += VC_THREADS) dst[i] = src[i];
+      }
+      first += nc;
+    }
+    __threadfence_system();
+    __syncthreads();
+    __shared__ bool lastb;
+    if (t == 0) lastb = (atomicAdd(&mine->ticket, 1u) == (unsigned int)npart - 1);
+    __syncthreads();
+    if (lastb) {
+      __threadfence_system();
+      if (mypeer) p2p_st_release(&p2p_flags(c, t)->done[c.rank], e);
+      if (t == 0) mine->ticket = 0u;
+    }
+  }
+  if (mypeer) p2p_wait<false>(c, &mine->done[t], e);
+  __syncthreads();
+}
+// halo of a scalar field of distributed level l (one plane each way)
+__device__ __forceinline__ void halo_push(const FusedParams& p, Run& run, int l, float* a) {
+  const GridD& g = p.lv[l].g;
+  const P2PDev& c = run.sh->c;
+  const int R = c.nranks, me = c.rank, up = (me + 1) % R, dn = (me + R - 1) % R, n = g.n[2];
+  Seg seg[2];
+  int ns = 0;
+  unsigned int mask = 0;
+  const char* base = c.base[me];
+  if (g.zhi_halo) {
+    seg[ns++] = Seg{up, (int64_t)((const char*)(a + (int64_t)(n - 2) * g.s[2] - WL_OX) - base), (int64_t)((const char*)(a - WL_OX) - base), g.s[2] / 4};
+    mask |= 1u << up;
+  }
+  if (g.zlo_halo) {
+    seg[ns++] = Seg{dn, (int64_t)((const char*)(a + g.s[2] - WL_OX) - base), (int64_t)((const char*)(a + (int64_t)(n - 1) * g.s[2] - WL_OX) - base), g.s[2] / 4};
+    mask |= 1u << dn;
+  }
+  push_segments(p, run, seg, ns, mask);
+}
+
+// ---- stencil ---------------------------------------------------------------------------------
+// mult (Poisson.jl:69-75) for V cells at (i..i+V-1, j, k); periodic neighbours are read through a
+// wrapped index instead of a ghost copy
+template <int D, int V>
+__device__ __forceinline__ Pack<V> mult_w(const Lvl& l, const float* x, int i, int j, int k, int64_t I, const Pack<V>& xc) {
+  const GridD& g = l.g;
+  const Pack<V> Dc = ldp<V>(l.Dg + I);
+  Pack<V> s;
+#pragma unroll
+  for (int q = 0; q < V; ++q) s.v[q] = xc.v[q] * Dc.v[q];
+  {
+    const Pack<V> Lc = ldp<V>(l.L + I), Lp = ld_xp<V>(l.L + I, Lc);
+    Pack<V> xm, xp;
+    xm.v[0] = x[(g.per[0] && i == 1) ? I + (g.n[0] - 3) : I - 1];
+#pragma unroll
+    for (int q = 1; q < V; ++q) xm.v[q] = xc.v[q - 1];
+#pragma unroll
+    for (int q = 0; q < V - 1; ++q) xp.v[q] = xc.v[q + 1];
+    xp.v[V - 1] = x[(g.per[0] && i + V - 1 == g.n[0] - 2) ? I + (V - 1) - (g.n[0] - 3) : I + V];
+#pragma unroll
+    for (int q = 0; q < V; ++q) s.v[q] += (xm.v[q] * Lc.v[q] + xp.v[q] * Lp.v[q]);
+  }
+#pragma unroll
+  for (int d = 1; d < D; ++d) {
+    const int64_t st = g.s[d];
+    const int cd = d == 1 ? j : k, n = g.n[d];
+    const int64_t om = (g.per[d] && cd == 1) ? (int64_t)(n - 3) * st : -st;
+    const int64_t op = (g.per[d] && cd == n - 2) ? -(int64_t)(n - 3) * st : st;
+    const float* Li = l.L + d * g.comp;
+    const Pack<V> Lc = ldp<V>(Li + I), Lp = ldp<V>(Li + I + st), xm = ldp<V>(x + I + om), xp = ldp<V>(x + I + op);
+#pragma unroll
+    for (int q = 0; q < V; ++q) s.v[q] += (xm.v[q] * Lc.v[q] + xp.v[q] * Lp.v[q]);
+  }
+  return s;
+}
+
+// ---- phases ----------------------------------------------------------------------------------
+// increment! (Poisson.jl:99-103) of level l, ϵ already stored; on a distributed level ϵ's halo first
+template <int D, int V, bool GRID>
+__device__ __forceinline__ void increment(const FusedParams& p, Run& run, int l) {
+  const Lvl& L = p.lv[l];
+  if (GRID && p.dist[l]) halo_push(p, run, l, L.eps);
+  rows<V, GRID>(p, l, [&](int i, int j, int k, int64_t I) {
+    const Pack<V> ec = ldp<V>(L.eps + I), ae = mult_w<D, V>(L, L.eps, i, j, k, I, ec);
+    Pack<V> r = ldp<V>(L.r + I), x = ldp<V>(L.x + I);
+#pragma unroll
+    for (int q = 0; q < V; ++q) { r.v[q] = r.v[q] - ae.v[q]; x.v[q] = x.v[q] + ec.v[q]; }
+    stp<V>(L.r + I, r);
+    stp<V>(L.x + I, x);
+  });
+  phase_sync<GRID>(p, run);
+  if (GRID && p.dist[l]) post_ready(p, run);
+}
+// Jacobi!(l; it=1) (Poisson.jl:110-113)
+template <int D, int V, bool GRID>
+__device__ __forceinline__ void jacobi(const FusedParams& p, Run& run, int l) {
+  const Lvl& L = p.lv[l];
+  rows<V, GRID>(p, l, [&](int, int, int, int64_t I) {
+    const Pack<V> r = ldp<V>(L.r + I), id = ldp<V>(L.iD + I);
+    Pack<V> e;
+#pragma unroll
+    for (int q = 0; q < V; ++q) e.v[q] = r.v[q] * id.v[q];
+    stp<V>(L.eps + I, e);
+  });
+  phase_sync<GRID>(p, run);
+  increment<D, V, GRID>(p, run, l);
+}
+// pcg!(l; it=6) (Poisson.jl:123-144)
+template <int D, int V, bool GRID>
+__device__ __forceinline__ void pcg(const FusedParams& p, Run& run, int l, int it) {
+  const Lvl& L = p.lv[l];
+  const bool dist = GRID && p.dist[l];
+  float rho;
+  {
+    double acc[1] = {0.0};
+    rows<V, GRID>(p, l, [&](int, int, int, int64_t I) {
+      const Pack<V> r = ldp<V>(L.r + I), id = ldp<V>(L.iD + I);
+      Pack<V> e;
+#pragma unroll
+      for (int q = 0; q < V; ++q) { e.v[q] = r.v[q] * id.v[q]; acc[0] += (double)r.v[q] * (double)e.v[q]; }
+      stp<V>(L.eps + I, e);
+    });
+    reduce<1, GRID>(p, run, dist, acc);
+    rho = (float)acc[0];
+  }
+  if (fabsf(rho) < 10 * WL_EPS32) return;
+  for (int i = 1; i <= it; ++i) {
+    if (dist) halo_push(p, run, l, L.eps);
+    float alpha;
+    {
+      double acc[1] = {0.0};
+      rows<V, GRID>(p, l, [&](int ii, int j, int k, int64_t I) {
+        const Pack<V> ec = ldp<V>(L.eps + I), z = mult_w<D, V>(L, L.eps, ii, j, k, I, ec);
+#pragma unroll
+        for (int q = 0; q < V; ++q) acc[0] += (double)z.v[q] * (double)ec.v[q];
+        stp<V>(L.z + I, z);
+      });
+      reduce<1, GRID>(p, run, dist, acc);
+      if (dist) post_ready(p, run);
+      alpha = rho / (float)acc[0];
+    }
+    const double aa = fabs((double)alpha);
+    if (aa < 1e-2 || aa > 1e2) return;
+    float rho2;
+    {
+      double acc[2] = {0.0, 0.0};
+      rows<V, GRID>(p, l, [&](int, int, int, int64_t I) {
+        const Pack<V> e = ldp<V>(L.eps + I), z = ldp<V>(L.z + I), id = ldp<V>(L.iD + I);
+        Pack<V> x = ldp<V>(L.x + I), r = ldp<V>(L.r + I);
+#pragma unroll
+        for (int q = 0; q < V; ++q) {
+          x.v[q] += alpha * e.v[q];
+          r.v[q] -= alpha * z.v[q];
+          acc[0] += (double)r.v[q] * (double)(r.v[q] * id.v[q]);
+          acc[1] += (double)r.v[q] * (double)r.v[q];
+        }
+        stp<V>(L.x + I, x);
+        stp<V>(L.r + I, r);
+      });
+      if (i == it) { phase_sync<GRID>(p, run); return; }  // the dots of the last sweep are never used below level 1
+      reduce<2, GRID>(p, run, dist, acc);
+      rho2 = (float)acc[0];
+    }
+    if (fabsf(rho2) < 10 * WL_EPS32) return;
+    const float beta = rho2 / rho;
+    rho = rho2;
+    rows<V, GRID>(p, l, [&](int, int, int, int64_t I) {
+      const Pack<V> r = ldp<V>(L.r + I), id = ldp<V>(L.iD + I);
+      Pack<V> e = ldp<V>(L.eps + I);
+#pragma unroll
+      for (int q = 0; q < V; ++q) e.v[q] = beta * e.v[q] + r.v[q] * id.v[q];
+      stp<V>(L.eps + I, e);
+    });
+    phase_sync<GRID>(p, run);
+  }
+}
+// restrict!(l → l+1) (MultiLevelPoisson.jl:33) + fill!(x_{l+1},0) (:75); a distributed → replicated
+// transition computes this rank's coarse planes and pushes them to every peer
+template <int D, bool GRID>
+__device__ __forceinline__ void restrict_to(const FusedParams& p, Run& run, int l) {
+  const Lvl& f = p.lv[l];
+  const Lvl& c = p.lv[l + 1];
+  const bool gather = GRID && p.dist[l] && !p.dist[l + 1];
+  int ck0 = 1, ck1 = c.g.n[2] - 2, fshift = 0;
+  if (gather) {
+    const int cp = (c.g.n[2] - 2) / p.nranks;
+    ck0 = 1 + p.rank * cp; ck1 = ck0 + cp - 1; fshift = -f.g.zoff;
+  }
+  rows<1, GRID>(p, l + 1, [&](int i0, int j0, int k0, int64_t I) {
+    c.x[I] = 0.f;
+    if (D > 2 && (k0 < ck0 || k0 > ck1)) return;
+    const int cc[3] = {i0, j0, k0};
+    int lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+#pragma unroll
+    for (int d = 0; d < D; ++d) { lo[d] = 2 * cc[d] - 1; hi[d] = 2 * cc[d]; }
+    if (D > 2) { lo[2] += fshift; hi[2] += fshift; }
+    float s = 0.f;
+    for (int z = lo[2]; z <= hi[2]; ++z)
+      for (int y = lo[1]; y <= hi[1]; ++y)
+        for (int x = lo[0]; x <= hi[0]; ++x) s += f.r[x + y * f.g.s[1] + z * f.g.s[2]];
+    c.r[I] = s;
+  });
+  phase_sync<GRID>(p, run);
+  if (gather) {
+    const P2PDev& pc = run.sh->c;
+    const int64_t count = (int64_t)((c.g.n[2] - 2) / p.nranks) * c.g.s[2];
+    const char* base = pc.base[pc.rank];
+    const float* mine = c.r + c.g.s[2] + (int64_t)p.rank * count - WL_OX;
+    Seg seg[WL_MAXRANKS];
+    int ns = 0;
+    unsigned int mask = 0;
+    for (int r = 0; r < p.nranks; ++r) {
+      if (r == p.rank) continue;
+      const int64_t off = (int64_t)((const char*)mine - base);
+      seg[ns++] = Seg{r, off, off, count / 4};
+      mask |= 1u << r;
+    }
+    push_segments(p, run, seg, ns, mask);
+  }
+}
+// prolongate!(l+1 → l) (MultiLevelPoisson.jl:34)
+template <int D, int V, bool GRID>
+__device__ __forceinline__ void prolongate_to(const FusedParams& p, Run& run, int l) {
+  const Lvl& f = p.lv[l];
+  const Lvl& c = p.lv[l + 1];
+  const int fzadd = (GRID && p.dist[l] && !p.dist[l + 1]) ? f.g.zoff : 0;
+  rows<V, GRID>(p, l, [&](int i0, int j0, int k0, int64_t I) {
+    const int64_t J = (D > 1 ? ((j0 + 1) >> 1) * c.g.s[1] : 0) + (D > 2 ? ((k0 + fzadd + 1) >> 1) * c.g.s[2] : 0);
+    Pack<V> e;
+#pragma unroll
+    for (int q = 0; q < V; ++q) e.v[q] = c.x[J + ((i0 + q + 1) >> 1)];
+    stp<V>(f.eps + I, e);
+  });
+  phase_sync<GRID>(p, run);
+}
+
+template <int D, bool GRID>
+__device__ __forceinline__ void down_level(const FusedParams& p, Run& run, int l) {
+  if ((p.lv[l].g.n[0] - 2) % 4 == 0 && GRID) jacobi<D, 4, GRID>(p, run, l);
+  else jacobi<D, 1, GRID>(p, run, l);
+  restrict_to<D, GRID>(p, run, l);
+}
+template <int D, bool GRID>
+__device__ __forceinline__ void pcg_level(const FusedParams& p, Run& run, int l) {
+  if ((p.lv[l].g.n[0] - 2) % 4 == 0 && GRID) pcg<D, 4, GRID>(p, run, l, 6);
+  else pcg<D, 1, GRID>(p, run, l, 6);
+}
+template <int D, bool GRID>
+__device__ __forceinline__ void up_level(const FusedParams& p, Run& run, int l) {
+  if ((p.lv[l].g.n[0] - 2) % 4 == 0 && GRID) { prolongate_to<D, 4, GRID>(p, run, l); increment<D, 4, GRID>(p, run, l); }
+  else { prolongate_to<D, 1, GRID>(p, run, l); increment<D, 1, GRID>(p, run, l); }
+  pcg_level<D, GRID>(p, run, l);
+}
+
+template <int D>
+__global__ void __launch_bounds__(VC_THREADS) k_vcycle_tail(FusedParams p) {
+  __shared__ Shared sh;
+  Run run;
+  run.sh = &sh;
+  run.push_epoch = run.ar_epoch = 0;
+  if (p.p2p) {
+    if (threadIdx.x == 0) sh.c = *p.p2p;
+    __syncthreads();
+    const P2PFlags* mine = p2p_flags(sh.c, sh.c.rank);
+    run.push_epoch = *((const volatile unsigned long long*)&mine->push_epoch);
+    run.ar_epoch = *((const volatile unsigned long long*)&mine->ar_epoch);
+    post_ready(p, run);  // every earlier kernel of this rank has retired
+  }
+  run.bar_gen = *((volatile unsigned int*)&p.bar[1]);
+  // every block must have sampled the generation / epochs before anyone moves them
+  grid_barrier(p, run);
+  const int last = p.nl - 1;
+  const int lb = max(p.lb, p.lf);  // levels ≥ lb: block 0 alone
+  // down-leg on the grid
+  for (int l = p.lf; l < min(lb, last); ++l) down_level<D, true>(p, run, l);
+  if (lb <= last) {
+    // whole sub-cycle of the smallest levels in one block
+    if (blockIdx.x == 0) {
+      for (int l = lb; l < last; ++l) down_level<D, false>(p, run, l);
+      pcg_level<D, false>(p, run, last);
+      for (int l = last - 1; l >= lb; --l) up_level<D, false>(p, run, l);
+    }
+    grid_barrier(p, run);
+  } else {
+    pcg_level<D, true>(p, run, last);
+  }
+  for (int l = min(lb, last) - 1; l >= p.lf; --l) {
+    // the replicated tail is finished: its gathered residual may be overwritten by the next V-cycle
+    if (p.p2p && p.dist[l] && !p.dist[l + 1]) post_ready(p, run);
+    up_level<D, true>(p, run, l);
+  }
+  if (p.p2p && blockIdx.x == 0 && threadIdx.x == 0) {
+    P2PFlags* mine = p2p_flags(sh.c, sh.c.rank);
+    mine->push_epoch = run.push_epoch;
+    mine->ar_epoch = run.ar_epoch;
+  }
+}
+
+}  // namespace
+
+// Host side: the fused coarse tail replaces pois_vcycle(level ≥ lf-1)'s recursion.
+struct VcycleFused {
+  FusedParams p;
+  int grid = 0;
+  bool ok = false;
+};
+
+static int ilog2(int v) { int l = 0; while ((1 << (l + 1)) <= v) ++l; return l; }
+
+int vcycle_fused_setup(Sim& s) {
+  s.vc_first = -1;
+  const char* env = getenv("WL_FUSED_VCYCLE");
+  if (env && atoi(env) == 0) return 0;
+  if (s.pois_kind != WL_POIS_MULTILEVEL || s.levels.size() < 2 || s.levels.size() > WL_MAXLEVELS) return 0;
+  if (s.dist.nranks > 1 && !s.dist.p2p) return 0;  // distributed levels need the peer-memory path
+  int coop = 0;
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, s.device);
+  if (!coop) return 0;
+  VcycleFused* vf = new VcycleFused;
+  FusedParams& p = vf->p;
+  p.D = s.D;
+  p.nl = (int)s.levels.size();
+  p.nranks = s.dist.nranks;
+  p.rank = s.dist.rank;
+  p.p2p = s.dist.nranks > 1 ? s.dist.dev : nullptr;
+  // fuse from the first level below the finest whose kernels are launch-latency bound
+  const char* e1 = getenv("WL_FUSED_MAX_CELLS");
+  const int64_t max_cells = e1 ? atoll(e1) : (int64_t)1 << 22;
+  int lf = 1;
+  while (lf < p.nl - 1 && s.levels[lf].g.interior > max_cells) ++lf;
+  p.lf = lf;
+  const char* e2 = getenv("WL_FUSED_BLOCK_CELLS");
+  const int64_t blk_cells = e2 ? atoll(e2) : 4096;
+  int lb = p.nl;
+  for (int l = p.nl - 1; l >= lf; --l) {
+    const bool dist = s.dist.nranks > 1 && s.lvl_dist[l];
+    if (dist || s.levels[l].g.interior > blk_cells) break;
+    lb = l;
+  }
+  p.lb = lb;
+  for (int l = 0; l < p.nl; ++l) {
+    p.lv[l] = s.levels[l];
+    p.dist[l] = (s.dist.nranks > 1 && s.lvl_dist[l]) ? 1 : 0;
+    const int nxi = s.levels[l].g.n[0] - 2;
+    const bool grid_mode = l < lb;
+    const int V = (grid_mode && nxi % 4 == 0) ? 4 : 1;
+    int bx = 8;
+    while (bx < nxi / V && bx < 128) bx <<= 1;
+    p.bxlog[l] = ilog2(bx);
+  }
+  int per_sm = 0;
+  cudaError_t e = s.D == 2 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_vcycle_tail<2>, VC_THREADS, 0)
+                           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_vcycle_tail<3>, VC_THREADS, 0);
+  if (e != cudaSuccess || per_sm < 1) { cudaGetLastError(); delete vf; return 0; }
+  const char* e3 = getenv("WL_FUSED_BLOCKS_PER_SM");
+  const int want = e3 ? atoi(e3) : 4;
+  vf->grid = s.nsm * std::max(1, std::min(per_sm, want));
+  void* tmp = nullptr;
+  if (cudaMalloc(&tmp, 64) != cudaSuccess) { delete vf; return wl_fail(WL_ERR_CUDA, "cudaMalloc barrier"); }
+  s.allocs.push_back(tmp);
+  cudaMemsetAsync(tmp, 0, 64, s.stream);
+  p.bar = (unsigned int*)tmp;
+  if (cudaMalloc(&tmp, sizeof(double) * 2 * vf->grid) != cudaSuccess) { delete vf; return wl_fail(WL_ERR_CUDA, "cudaMalloc partials"); }
+  s.allocs.push_back(tmp);
+  p.partials = (double*)tmp;
+  vf->ok = true;
+  s.vc_fused = vf;
+  s.vc_first = lf;
+  return 0;
+}
+void vcycle_fused_destroy(Sim& s) {
+  delete (VcycleFused*)s.vc_fused;
+  s.vc_fused = nullptr;
+}
+// runs levels lf … nl-1 of the V-cycle (the residual of level lf has just been restricted)
+int vcycle_fused_run(Sim& s) {
+  VcycleFused* vf = (VcycleFused*)s.vc_fused;
+  void* args[] = {&vf->p};
+  cudaError_t e = s.D == 2 ? cudaLaunchCooperativeKernel((void*)k_vcycle_tail<2>, dim3(vf->grid), dim3(VC_THREADS), args, 0, s.stream)
+                           : cudaLaunchCooperativeKernel((void*)k_vcycle_tail<3>, dim3(vf->grid), dim3(VC_THREADS), args, 0, s.stream);
+  ++s.launches;
+  return wl_cuda_check(s, e, "k_vcycle_tail");
+}
