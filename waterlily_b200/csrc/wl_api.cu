@@ -307,6 +307,7 @@ static int create_impl(wl_sim** out, int D, const int* N, double nu, double dt0,
   // peer mapping of the arenas (slab ranks): halos and reductions then bypass NCCL
   if (!rc) rc = dist_p2p_setup(a);
   if (!rc) rc = vcycle_fused_setup(a);
+  if (!rc) rc = convdiff_tma_setup(a);
   if (rc) { wl_destroy((wl_sim*)sp); return rc; }
   // μ₀ = 1, BC!(μ₀,0) (Flow.jl:118-119); then the Poisson constructors' set_diag!/restrictL!
   const double zero[3] = {0, 0, 0};
@@ -370,6 +371,7 @@ int wl_destroy(wl_sim* s) {
   if (a.stream) cudaStreamSynchronize(a.stream);
   dist_destroy(a);
   vcycle_fused_destroy(a);
+  convdiff_tma_destroy(a);
   if (a.arena) cudaFree(a.arena);
   for (void* p : a.allocs) cudaFree(p);
   if (a.h_pinned) cudaFreeHost(a.h_pinned);
@@ -571,7 +573,7 @@ int wl_profile_read(wl_sim* s, int which, double* ms, int64_t* launches, double*
 int wl_profile_count(void) { return WL_PROF_N; }
 const char* wl_profile_name(int which) {
   static const char* names[WL_PROF_N] = {"conv_diff+bdim1", "bdim2", "pcg_mult", "pcg_update", "pcg_dir", "pcg_init",
-                                         "increment", "residual", "project_misc", "solver", "mom_step"};
+                                         "increment", "residual", "project_misc", "vcycle_tail", "solver", "mom_step"};
   return (which >= 0 && which < WL_PROF_N) ? names[which] : "";
 }
 

@@ -1,0 +1,327 @@
+// wl_convdiff_tma.cu — conv_diff! (+ accelerate! + BDIM! stage 1) for the 3-D core, TMA-staged.
+// Reference: src/Flow.jl:36-60 (conv_diff!), :68-73 (accelerate!), :133 (BDIM! stage 1).
+//
+// The kernel is bound by instruction issue on the ALU pipe (min/max/select and integer adds run
+// there at half rate), not by HBM: the first marching kernel (wl_momentum.cu) spent ~40 % of its
+// ALU slots on 64-bit address arithmetic for its ~45 neighbour loads per cell.  Here a block owns a
+// TX×TY (x,y) tile and marches along z, and the three velocity components of every plane it needs
+// arrive — with their 2-cell halo — through ONE TMA tensor copy per plane (cp.async.bulk.tensor on
+// a 4-D map x,y,z,component) into a 4-stage shared-memory ring.  All neighbour reads are then LDS
+// with compile-time offsets, there is no halo logic in the threads, and the copy of plane z+4 is in
+// flight while plane z is being differenced.
+//
+//  * each thread keeps its own column's z-window (4 samples × 3 components) in registers;
+//  * every face flux is evaluated once: the z-flux of the upper face is carried to the next step,
+//    x-fluxes travel between lanes by shuffle (between warps through shared memory), y-fluxes
+//    between warps through shared memory (double-buffered, one barrier per step);
+//  * the z-loop is unrolled by the ring depth so that every shared-memory offset is an immediate.
+#include <cuda.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+
+#include "wl_internal.h"
+#include "wl_flux.cuh"
+
+namespace {
+
+__device__ __forceinline__ unsigned int smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned int bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned int parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WL_MBAR_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WL_MBAR_DONE;\n"
+      "bra WL_MBAR_WAIT;\n"
+      "WL_MBAR_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// one plane (box PX × PY × 1 × 3) of the velocity field → shared memory
+__device__ __forceinline__ void tma_load_plane(void* dst, const CUtensorMap* map, unsigned long long* bar, int x, int y, int z) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(x), "r"(y), "r"(z), "r"(0), "r"(smem_u32(bar))
+      : "memory");
+}
+
+template <int TX, int TY>
+struct Tile {
+  // a TMA box must start on a 16-byte boundary in x (measured on B200: any other innermost coordinate
+  // faults with "illegal instruction"): the box starts WL_OX cells left of the 2-cell halo, where the
+  // rows of the padded layout are aligned, and is TX+8 wide
+  static constexpr int PX = TX + 8, PY = TY + 4, PP = PX * PY, STAGE = 3 * PP;  // floats
+  static constexpr unsigned int BYTES = STAGE * sizeof(float);
+};
+
+template <int TX, int TY, int MINB, bool HASG, bool CORR>
+__global__ void __launch_bounds__(TX * TY, MINB)
+    k_conv_diff3_tma(const __grid_constant__ CUtensorMap tmU, CDArgs a, int zchunk, int ntx, int nty) {
+  using T = Tile<TX, TY>;
+  constexpr int PX = T::PX, PP = T::PP;
+  __shared__ __align__(128) float tile[4][T::STAGE];
+  __shared__ float Fx[2][3][TY][TX / 32];
+  __shared__ float Fy[2][3][TY][TX];
+  __shared__ __align__(8) unsigned long long full[4];
+  const GridD& g = a.g;
+  const int nx = g.n[0], ny = g.n[1], nz = g.n[2];
+  const int64_t s1 = g.s[1], s2 = g.s[2];
+  const int tix = threadIdx.x, tiy = threadIdx.y, lane = tix & 31, wx = tix >> 5;
+  const bool leader = (tix | tiy) == 0;
+  const int bt = blockIdx.x;
+  const int tx = bt % ntx, ty = (bt / ntx) % nty, tz = bt / (ntx * nty);
+  const int xb = tx * TX, yb = ty * TY;  // tile origin (cell index of the first halo cell)
+  const int x = 2 + xb + tix, y = 2 + yb + tiy;
+  const int zlo = g.zlo_halo ? 1 : 2, zhi = g.zhi_halo ? nz - 2 : nz - 3;  // slab faces are plain inner cells
+  const int z0 = zlo + tz * zchunk, z1 = min(z0 + zchunk, zhi + 1);
+  const bool valid = x <= nx - 3 && y <= ny - 3;
+  const int xc = min(x, nx - 3), yc = min(y, ny - 3);  // out-of-range threads shadow the last cell
+  const bool extra_x = (xc == nx - 3) || (tix == TX - 1);
+  const bool extra_y = (yc == ny - 3) || (tiy == TY - 1);
+  const float nu = a.nu;
+  const int toff = (yc - yb) * PX + (xc - xb) + WL_OX;  // this thread's cell inside a staged plane
+  const int zb = z0 - 2;                        // plane held by ring stage 0 first
+  // tensor coordinates of cell (i,j,k): (i + WL_OX, j, k + 1) — the map starts at the allocation.
+  // Box origin: cell (xb - WL_OX, yb) ↔ tensor x = xb, a multiple of 4 floats.
+  const int cx = xb, cy = yb;
+  if (leader) {
+#pragma unroll
+    for (int s = 0; s < 4; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  if (leader) {
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      mbar_expect_tx(&full[s], T::BYTES);
+      tma_load_plane(tile[s], &tmU, &full[s], cx, cy, zb + s + 1);
+    }
+  }
+  // global pointers of this thread's cell for f, V, u⁰ (plain coalesced accesses)
+  int64_t I = xc + yc * s1 + (int64_t)z0 * s2;
+  float w[3][5];  // w[c][k] = u_c at z-2+k of the current step (k = 1..4 used)
+  float fz_lo[3];
+  float cxp, cyp;  // u_x(x+1) and u_y(y+1) of the previous plane (upper-edge fluxes only)
+  // ---- pre-step at z0-1: the z-flux through the lower face of the first cell ----
+#pragma unroll
+  for (int s = 0; s < 4; ++s) mbar_wait(&full[s], 0);
+  {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      w[c][0] = 0.f;
+#pragma unroll
+      for (int k = 1; k <= 4; ++k) w[c][k] = tile[k - 1][c * PP + toff];
+    }
+    const float* C = tile[1] + toff;  // plane z0-1
+    const float* N = tile[2] + toff;  // plane z0
+    cxp = C[1];
+    cyp = C[PP + PX];
+    const float uz = w[2][3];
+    const float ufx = (uz + N[2 * PP - 1]) * 0.5f, ufy = (uz + N[2 * PP - PX]) * 0.5f, ufz = (uz + w[2][2]) * 0.5f;
+    fz_lo[0] = flux1(ufx, w[0][1], w[0][2], w[0][3], w[0][4], nu);
+    fz_lo[1] = flux1(ufy, w[1][1], w[1][2], w[1][3], w[1][4], nu);
+    fz_lo[2] = flux1(ufz, w[2][1], w[2][2], w[2][3], w[2][4], nu);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { w[c][1] = w[c][2]; w[c][2] = w[c][3]; w[c][3] = w[c][4]; }
+  }
+  __syncthreads();
+  if (leader) {  // planes z0-2 and z0-1 are spent: refill their stages with z0+2 and z0+3
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      if (zb + s + 4 <= z1 + 1) {
+        mbar_expect_tx(&full[s], T::BYTES);
+        tma_load_plane(tile[s], &tmU, &full[s], cx, cy, zb + s + 4 + 1);
+      }
+    }
+  }
+  int buf = 0;
+  // one step of the march: cell plane z lives in ring stage S, z+1 in S+1, z+2 in S+2
+  auto step = [&](auto stage_tag, int z) {
+    constexpr int S = decltype(stage_tag)::value;
+    const float* C = tile[S] + toff;
+    const float* N = tile[(S + 1) & 3] + toff;
+    const float* NN = tile[(S + 2) & 3] + toff;
+    float xm2[3], xm1[3], xp1[3], ym2[3], ym1[3], yp1[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      xm2[c] = C[c * PP - 2]; xm1[c] = C[c * PP - 1]; xp1[c] = C[c * PP + 1];
+      ym2[c] = C[c * PP - 2 * PX]; ym1[c] = C[c * PP - PX]; yp1[c] = C[c * PP + PX];
+    }
+    float fx_lo[3], fy_lo[3], fx_hi[3], fy_hi[3];
+    {
+      const float ux = w[0][2];
+      fx_lo[0] = flux1((ux + xm1[0]) * 0.5f, xm2[0], xm1[0], w[0][2], xp1[0], nu);
+      fx_lo[1] = flux1((ux + ym1[0]) * 0.5f, xm2[1], xm1[1], w[1][2], xp1[1], nu);
+      fx_lo[2] = flux1((ux + w[0][1]) * 0.5f, xm2[2], xm1[2], w[2][2], xp1[2], nu);
+      const float uy = w[1][2];
+      fy_lo[0] = flux1((uy + xm1[1]) * 0.5f, ym2[0], ym1[0], w[0][2], yp1[0], nu);
+      fy_lo[1] = flux1((uy + ym1[1]) * 0.5f, ym2[1], ym1[1], w[1][2], yp1[1], nu);
+      fy_lo[2] = flux1((uy + w[1][1]) * 0.5f, ym2[2], ym1[2], w[2][2], yp1[2], nu);
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      if (lane == 0) Fx[buf][i][tiy][wx] = fx_lo[i];
+      Fy[buf][i][tiy][tix] = fy_lo[i];
+    }
+    // lower faces of the cells x+1 / y+1 that no thread of the block owns
+    float ex[3] = {0.f, 0.f, 0.f}, ey[3] = {0.f, 0.f, 0.f};
+    if (extra_x) {
+      const float ux = xp1[0];
+      ex[0] = flux1((ux + w[0][2]) * 0.5f, xm1[0], w[0][2], xp1[0], C[2], nu);
+      ex[1] = flux1((ux + C[1 - PX]) * 0.5f, xm1[1], w[1][2], xp1[1], C[PP + 2], nu);
+      ex[2] = flux1((ux + cxp) * 0.5f, xm1[2], w[2][2], xp1[2], C[2 * PP + 2], nu);
+    }
+    if (extra_y) {
+      const float uy = yp1[1];
+      ey[0] = flux1((uy + C[PP + PX - 1]) * 0.5f, ym1[0], w[0][2], yp1[0], C[2 * PX], nu);
+      ey[1] = flux1((uy + w[1][2]) * 0.5f, ym1[1], w[1][2], yp1[1], C[PP + 2 * PX], nu);
+      ey[2] = flux1((uy + cyp) * 0.5f, ym1[2], w[2][2], yp1[2], C[2 * PP + 2 * PX], nu);
+    }
+    cxp = xp1[0];
+    cyp = yp1[1];
+    __syncthreads();
+    // every read of plane z is done: its stage takes plane z+4
+    if (leader && z + 4 <= z1 + 1) {
+      mbar_expect_tx(&full[S], T::BYTES);
+      tma_load_plane(tile[S], &tmU, &full[S], cx, cy, z + 4 + 1);
+    }
+    // upper z-face = lower z-face of cell z+1: uf = (u_z[J] + u_z[J-δi])/2, J = I+δz
+    mbar_wait(&full[(S + 2) & 3], ((unsigned int)(z + 2 - zb) >> 2) & 1u);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) w[c][4] = NN[c * PP];
+    float fz_hi[3];
+    {
+      const float uz = w[2][3];
+      const float ufx = (uz + N[2 * PP - 1]) * 0.5f, ufy = (uz + N[2 * PP - PX]) * 0.5f, ufz = (uz + w[2][2]) * 0.5f;
+      fz_hi[0] = flux1(ufx, w[0][1], w[0][2], w[0][3], w[0][4], nu);
+      fz_hi[1] = flux1(ufy, w[1][1], w[1][2], w[1][3], w[1][4], nu);
+      fz_hi[2] = flux1(ufz, w[2][1], w[2][2], w[2][3], w[2][4], nu);
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      fx_hi[i] = __shfl_down_sync(0xffffffffu, fx_lo[i], 1);
+      if (lane == 31 && wx < TX / 32 - 1) fx_hi[i] = Fx[buf][i][tiy][wx + 1];
+      fy_hi[i] = tiy < TY - 1 ? Fy[buf][i][tiy + 1][tix] : 0.f;
+      if (extra_x) fx_hi[i] = ex[i];
+      if (extra_y) fy_hi[i] = ey[i];
+    }
+    if (valid) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        float v = 0.f;
+        v += fx_lo[i]; v -= fx_hi[i];
+        v += fy_lo[i]; v -= fy_hi[i];
+        v += fz_lo[i]; v -= fz_hi[i];
+        if (HASG) v = (float)((double)v + a.gacc[i]);
+        if (a.fuse_bdim1) {
+          const float u0v = CORR ? a.u0[I + i * g.comp] : w[i][2];
+          v = u0v + a.dt * v - a.V[I + i * g.comp];
+        }
+        a.f[I + i * g.comp] = v;
+      }
+    }
+    buf ^= 1;
+    I += s2;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { w[c][1] = w[c][2]; w[c][2] = w[c][3]; w[c][3] = w[c][4]; }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) fz_lo[i] = fz_hi[i];
+  };
+  // plane z0 sits in stage 2
+  for (int z = z0;;) {
+    step(std::integral_constant<int, 2>{}, z); if (++z >= z1) break;
+    step(std::integral_constant<int, 3>{}, z); if (++z >= z1) break;
+    step(std::integral_constant<int, 0>{}, z); if (++z >= z1) break;
+    step(std::integral_constant<int, 1>{}, z); if (++z >= z1) break;
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+constexpr int kTX = 64, kTY = 4, kMINB = 4;
+
+}  // namespace
+
+struct ConvDiffTma {
+  CUtensorMap map_u, map_u0;  // the two velocity buffers (mom_step swaps the pointers, not the data)
+  const float* ptr_u;
+  const float* ptr_u0;
+};
+
+// Builds the tensor maps of the two velocity buffers.  Leaves s.cd_tma null (the first marching
+// kernel stays in use) if the driver entry point is missing or the grid is too small.
+int convdiff_tma_setup(Sim& s) {
+  s.cd_tma = nullptr;
+  const char* env = getenv("WL_CD_TMA");
+  if (env && atoi(env) == 0) return 0;
+  const GridD& g = s.g;
+  if (s.D != 3 || g.n[0] < 8 || g.n[1] < 8 || g.n[2] < 8) return 0;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn || qres != cudaDriverEntryPointSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  EncodeTiledFn encode = (EncodeTiledFn)fn;
+  ConvDiffTma* t = new ConvDiffTma;
+  using T = Tile<kTX, kTY>;
+  auto make = [&](CUtensorMap* m, const float* field) -> bool {
+    void* base = (void*)(field - g.lead);  // start of the allocation: 256-byte aligned
+    const cuuint64_t dims[4] = {(cuuint64_t)g.s[1], (cuuint64_t)g.n[1], (cuuint64_t)g.n[2] + 2, 3};
+    const cuuint64_t strides[3] = {(cuuint64_t)g.s[1] * 4, (cuuint64_t)g.s[2] * 4, (cuuint64_t)g.comp * 4};
+    const cuuint32_t box[4] = {(cuuint32_t)T::PX, (cuuint32_t)T::PY, 1, 3};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    return encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  };
+  if (!make(&t->map_u, s.u) || !make(&t->map_u0, s.u0)) {
+    if (getenv("WL_VERBOSE")) fprintf(stderr, "[waterlily_b200] cuTensorMapEncodeTiled failed: conv_diff! uses the untiled kernel\n");
+    delete t;
+    return 0;
+  }
+  if (getenv("WL_VERBOSE")) fprintf(stderr, "[waterlily_b200] conv_diff!: TMA-staged kernel\n");
+  t->ptr_u = s.u;
+  t->ptr_u0 = s.u0;
+  s.cd_tma = t;
+  return 0;
+}
+void convdiff_tma_destroy(Sim& s) {
+  delete (ConvDiffTma*)s.cd_tma;
+  s.cd_tma = nullptr;
+}
+
+template <bool HASG, bool CORR>
+static void launch_tma(Sim& s, const CUtensorMap& m, const CDArgs& a, int zchunk) {
+  const GridD& g = s.g;
+  const int nzc = g.n[2] - 4 + (g.zlo_halo ? 1 : 0) + (g.zhi_halo ? 1 : 0);
+  const int ntx = (g.n[0] - 4 + kTX - 1) / kTX, nty = (g.n[1] - 4 + kTY - 1) / kTY, ntz = (nzc + zchunk - 1) / zchunk;
+  k_conv_diff3_tma<kTX, kTY, kMINB, HASG, CORR><<<ntx * nty * ntz, dim3(kTX, kTY, 1), 0, s.stream>>>(m, a, zchunk, ntx, nty);
+}
+// the 3-D core [2,n-3]³ (slab faces included); false if this source buffer has no tensor map
+bool convdiff_tma_launch(Sim& s, const CDArgs& a, int zchunk, bool corr) {
+  ConvDiffTma* t = (ConvDiffTma*)s.cd_tma;
+  if (!t) return false;
+  const CUtensorMap* m = a.u == t->ptr_u ? &t->map_u : (a.u == t->ptr_u0 ? &t->map_u0 : nullptr);
+  if (!m) return false;
+  if (a.has_g) {
+    if (corr) launch_tma<true, true>(s, *m, a, zchunk);
+    else launch_tma<true, false>(s, *m, a, zchunk);
+  } else {
+    if (corr) launch_tma<false, true>(s, *m, a, zchunk);
+    else launch_tma<false, false>(s, *m, a, zchunk);
+  }
+  ++s.launches;
+  return true;
+}

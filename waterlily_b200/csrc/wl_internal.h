@@ -22,6 +22,7 @@ enum {
   WL_PROF_INCREMENT,      // fine level: increment! (r -= Aϵ, x += ϵ)
   WL_PROF_RESIDUAL,       // fine level: residual!
   WL_PROF_PROJECT,        // div, x scaling, pressure correction
+  WL_PROF_VCTAIL,         // fused coarse V-cycle kernel (wl_vcycle.cu)
   WL_PROF_SOLVER,         // whole solver! call (all levels)
   WL_PROF_STEP,           // whole mom_step!
   WL_PROF_N
@@ -80,6 +81,7 @@ struct Sim {
   std::vector<int> lvl_dist;   // 1: level is z-distributed, 0: replicated on every rank (coarse tail)
   int Nz_global = 0;           // interior z-planes of the whole domain (3-D)
   int per_z_global = 0;
+  void* cd_tma = nullptr;      // TMA tensor maps of u/u⁰ for the staged conv_diff! kernel (wl_convdiff_tma.cu), or null
   void* vc_fused = nullptr;    // fused coarse V-cycle (wl_vcycle.cu), or null
   int vc_first = -1;           // first level the fused kernel covers (-1: off)
   int sticky = 0;  // first CUDA error, sticky per handle
@@ -112,6 +114,12 @@ int dist_allgather(Sim& s, float* base, size_t count);
 int post_reduce(Sim& s, int stage, const FinArgs& fa, bool is_max = false);
 FinArgs fin_level(const Sim& s, int level);
 FinArgs fin_misc(const Sim& s);
+
+// ---- wl_convdiff_tma.cu ----
+struct CDArgs;
+int convdiff_tma_setup(Sim& s);
+void convdiff_tma_destroy(Sim& s);
+bool convdiff_tma_launch(Sim& s, const CDArgs& a, int zchunk, bool corr);
 
 // ---- wl_vcycle.cu ----
 int vcycle_fused_setup(Sim& s);

@@ -15,35 +15,9 @@
 
 #include "wl_internal.h"
 #include "wl_vec.cuh"
+#include "wl_flux.cuh"
 
 namespace {
-
-// median (Flow.jl:25-34), branch-free: max(min(a,b), min(max(a,b),c)) is the same value for every
-// ordering and tie of finite inputs (only the sign of a zero can differ)
-__device__ __forceinline__ float median3(float a, float b, float c) { return fmaxf(fminf(a, b), fminf(fmaxf(a, b), c)); }
-// x/6 correctly rounded without the IEEE-division subroutine: one Newton step on q = x·RN(1/6).
-// Checked exhaustively against x/6.0f over all 2³² bit patterns: identical for 1e-30 < |x| < 1e30
-// and for ±0 (tools/check_div6.c); below 1e-30 it may differ in the last place of a number that small.
-__device__ __forceinline__ float div6(float x) {
-  const float y = 1.0f / 6.0f;
-  const float q = x * y;
-  return fmaf(fmaf(-6.0f, q, x), y, q);
-}
-// quick (Flow.jl:4)
-__device__ __forceinline__ float quick(float u, float c, float d) { return median3(div6(5 * c + 2 * d - u), c, median3(10 * c - 9 * u, c, d)); }
-
-struct CDArgs {
-  GridD g;
-  const float* u;    // field being differenced (u⁰ in the predictor, u in the corrector)
-  const float* u0;   // BDIM stage 1 operands
-  const float* V;
-  float* f;
-  float* sigma;      // Φ scratch ≡ flow.σ: only its ghost layer is materialised
-  float nu, dt;
-  double gacc[3];
-  int has_g;
-  int fuse_bdim1;
-};
 
 // Φ[I] of the inner loop (Flow.jl:45) / periodic lower boundary (:58-59); `upup` is the offset of the
 // upwind-upwind sample (−2sj, or the periodic wrap to N[j]-2).
@@ -170,10 +144,6 @@ __global__ void __launch_bounds__(256) k_conv_diff_shell(CDArgs a, int64_t count
 //    a register, x-fluxes travel between lanes by shuffle (between warps through shared memory),
 //    y-fluxes between warps through shared memory (double-buffered: one barrier per step);
 //  * Φ = uf·λ − ν∂ is one fmaf: the reference rounds the Float64 expression once (Appendix A).
-__device__ __forceinline__ float flux1(float uf, float um2, float um1, float uc, float up1, float nu) {
-  const float q = uf > 0 ? quick(um2, um1, uc) : quick(up1, uc, um1);
-  return fmaf(uf, q, -(nu * (uc - um1)));
-}
 template <int CD_TX, int CD_TY, int MINB, bool HASG, bool CORR>
 __global__ void __launch_bounds__(CD_TX * CD_TY, MINB) k_conv_diff3_march(CDArgs a, int zchunk, int ntx, int nty) {
   __shared__ float Fx[2][3][CD_TY][CD_TX / 32];
@@ -553,7 +523,9 @@ int mom_conv_diff(Sim& s, const float* src, bool fuse_bdim1, const double* gacc)
     if (variant < 0) { const char* e = getenv("WL_CD_VARIANT"); variant = e ? atoi(e) : 4; }
     static int zchunk = 0;
     if (!zchunk) { const char* e = getenv("WL_CD_ZCHUNK"); zchunk = e ? atoi(e) : 32; }
-    launch_march(s, a, variant, zchunk, corr);
+    static int zchunk_tma = 0;
+    if (!zchunk_tma) { const char* e = getenv("WL_CD_TMA_ZCHUNK"); zchunk_tma = e ? atoi(e) : 64; }
+    if (!convdiff_tma_launch(s, a, zchunk_tma, corr)) launch_march(s, a, variant, zchunk, corr);
     const int64_t cnt = shell_count(g, 2);
     k_conv_diff_shell<3><<<(int)std::min<int64_t>((cnt + 255) / 256, s.nsm * 16), 256, 0, s.stream>>>(a, cnt);
     ++s.launches;

@@ -64,7 +64,7 @@ __device__ __forceinline__ void grid_barrier(const FusedParams& p, Run& run) {
       __threadfence();
       atomicAdd(&p.bar[1], 1u);
     } else {
-      while (*((volatile unsigned int*)&p.bar[1]) == gen) __nanosleep(40);
+      while (*((volatile unsigned int*)&p.bar[1]) == gen) {}
     }
     __threadfence();
   }
@@ -581,8 +581,10 @@ void vcycle_fused_destroy(Sim& s) {
 int vcycle_fused_run(Sim& s) {
   VcycleFused* vf = (VcycleFused*)s.vc_fused;
   void* args[] = {&vf->p};
+  wl_prof_begin(s, WL_PROF_VCTAIL);
   cudaError_t e = s.D == 2 ? cudaLaunchCooperativeKernel((void*)k_vcycle_tail<2>, dim3(vf->grid), dim3(VC_THREADS), args, 0, s.stream)
                            : cudaLaunchCooperativeKernel((void*)k_vcycle_tail<3>, dim3(vf->grid), dim3(VC_THREADS), args, 0, s.stream);
   ++s.launches;
+  wl_prof_end(s, WL_PROF_VCTAIL, 0.0);
   return wl_cuda_check(s, e, "k_vcycle_tail");
 }
