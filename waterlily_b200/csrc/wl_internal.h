@@ -61,6 +61,8 @@ struct Sim {
   std::vector<void*> allocs;
   char* arena = nullptr;       // all fields live in one allocation (symmetric across ranks, wl_p2p.cuh)
   size_t arena_bytes = 0, arena_used = 0;
+  void* stage = nullptr;       // device staging buffer of the host <-> device field copies
+  size_t stage_bytes = 0;
   unsigned char* body_mask = nullptr;  // 1 byte per cell, same indexing as a scalar field (see k_body_mask)
   bool mask_dirty = true;              // V, μ₀ or μ₁ changed since the mask was built
   float nu = 0.f;
