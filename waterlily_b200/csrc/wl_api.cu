@@ -535,18 +535,21 @@ int wl_pois_jacobi(wl_sim* s, int level, int it) {
   GUARD(s);
   if (level < 0 || level >= (int)S.levels.size()) return wl_fail(WL_ERR_ARG, "bad level");
   int rc = pois_jacobi(S, S.levels[level], it);
+  if (!rc) rc = bc_per(S, S.levels[level].g, S.levels[level].eps, S.levels[level].g.per);  // perBC!(ϵ) made visible
   return rc ? rc : wl_sync(s);
 }
 int wl_pois_pcg(wl_sim* s, int level, int it) {
   GUARD(s);
   if (level < 0 || level >= (int)S.levels.size()) return wl_fail(WL_ERR_ARG, "bad level");
   int rc = pois_pcg(S, level, it);
+  if (!rc) rc = bc_per(S, S.levels[level].g, S.levels[level].eps, S.levels[level].g.per);
   return rc ? rc : wl_sync(s);
 }
 int wl_pois_vcycle(wl_sim* s, int level) {
   GUARD(s);
   if (level < 0 || level + 1 >= (int)S.levels.size()) return wl_fail(WL_ERR_ARG, "bad level");
   int rc = pois_vcycle(S, level);
+  if (!rc) rc = pois_materialize_eps(S, level);
   return rc ? rc : wl_sync(s);
 }
 int wl_pois_solve(wl_sim* s, double tol, int itmx, int* n) {

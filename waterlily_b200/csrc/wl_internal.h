@@ -84,6 +84,7 @@ struct Sim {
   int Nz_global = 0;           // interior z-planes of the whole domain (3-D)
   int per_z_global = 0;
   void* cd_tma = nullptr;      // TMA tensor maps of u/u⁰ for the staged conv_diff! kernel (wl_convdiff_tma.cu), or null
+  bool eps_is_jacobi = false;  // levels[1].ϵ already holds r·iD of the current residual (written by k_residual)
   void* vc_fused = nullptr;    // fused coarse V-cycle (wl_vcycle.cu), or null
   int vc_first = -1;           // first level the fused kernel covers (-1: off)
   int sticky = 0;  // first CUDA error, sticky per handle
@@ -138,11 +139,12 @@ int pois_set_diag(Sim& s, Lvl& l);
 int pois_restrictL(Sim& s, Lvl& coarse, const Lvl& fine);
 int pois_update(Sim& s);
 int pois_mult(Sim& s);
-int pois_residual(Sim& s, Lvl& l, bool need_r2 = true);
+int pois_residual(Sim& s, Lvl& l, bool need_r2 = true, bool ghosts_valid = false, bool jacobi_eps = false);
 int pois_jacobi(Sim& s, Lvl& l, int it);
 int pois_pcg(Sim& s, int level, int it);
 int pois_vcycle(Sim& s, int level);
-int pois_solve(Sim& s, double tol, int itmx, int* n);
+int pois_solve(Sim& s, double tol, int itmx, int* n, bool ghosts_valid = false);
+int pois_materialize_eps(Sim& s, int level);
 int pois_dot_rr(Sim& s, Lvl& l, double* out);
 
 // ---- wl_momentum.cu ----

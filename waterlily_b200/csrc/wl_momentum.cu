@@ -368,11 +368,9 @@ __global__ void __launch_bounds__(256) k_scale_u(GridD g, float* u, double scale
   });
 }
 
-// project!: z = div(u) (Flow.jl:139, :11-17) fused with x .*= dt on the interior (the periodic
-// ghosts of x are refreshed by residual!'s perBC!, all other ghosts of x are never written)
+// project!: z = div(u) (Flow.jl:139, :11-17)
 template <int D, int V>
-__global__ void __launch_bounds__(256) k_project_pre(GridD g, const float* __restrict__ u, float* __restrict__ z, float* __restrict__ x,
-                                                     float f32v, double f64v, int f32) {
+__global__ void __launch_bounds__(256) k_project_pre(GridD g, const float* __restrict__ u, float* __restrict__ z) {
   for_rows<V>(g, [&](int, int, int, int64_t I) {
     Pack<V> s;
     {
@@ -387,11 +385,23 @@ __global__ void __launch_bounds__(256) k_project_pre(GridD g, const float* __res
       for (int q = 0; q < V; ++q) s.v[q] += up.v[q] - uc.v[q];
     }
     stp<V>(z + I, s);
-    Pack<V> xv = ldp<V>(x + I);
-#pragma unroll
-    for (int q = 0; q < V; ++q) xv.v[q] = f32 ? xv.v[q] * f32v : (float)((double)xv.v[q] * f64v);
-    stp<V>(x + I, xv);
   });
+}
+// project!: x .*= dt (Flow.jl:139) / x ./= dt (:144) over the WHOLE allocation of x — interior, ghost
+// cells and slab halo planes alike.  A ghost cell holds a copy of an interior value, and scaling a
+// copy gives the bits of the scaled original, so the ghosts stay consistent and neither the perBC!
+// of residual! (Poisson.jl:92) nor a halo exchange is needed afterwards.
+__global__ void __launch_bounds__(256) k_scale_alloc(float4* __restrict__ x, int64_t n4, float f32v, double f64v, int f32, int divide) {
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n4; t += (int64_t)gridDim.x * blockDim.x) {
+    float4 v = x[t];
+    float* p = reinterpret_cast<float*>(&v);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (divide) p[q] = f32 ? p[q] / f32v : (float)((double)p[q] / f64v);
+      else p[q] = f32 ? p[q] * f32v : (float)((double)p[q] * f64v);
+    }
+    x[t] = v;
+  }
 }
 // project!: u[I,i] -= L[I,i]*∂(i,I,x) (Flow.jl:141-143)
 template <int D, int V>
@@ -409,17 +419,6 @@ __global__ void __launch_bounds__(256) k_project_correct(GridD g, float* __restr
     }
   });
 }
-// project!: x ./= dt (Flow.jl:144) on the interior; perBC! afterwards restores the periodic ghosts
-template <int D, int V>
-__global__ void __launch_bounds__(256) k_unscale(GridD g, float* __restrict__ x, float f32v, double f64v, int f32) {
-  for_rows<V>(g, [&](int, int, int, int64_t I) {
-    Pack<V> xv = ldp<V>(x + I);
-#pragma unroll
-    for (int q = 0; q < V; ++q) xv.v[q] = f32 ? xv.v[q] / f32v : (float)((double)xv.v[q] / f64v);
-    stp<V>(x + I, xv);
-  });
-}
-
 // CFL: σ = flux_out (Flow.jl:173,176-182) + interior max
 template <int D, int V>
 __global__ void __launch_bounds__(256) k_cfl(GridD g, const float* __restrict__ u, float* __restrict__ sigma, ReduceWS ws, FinArgs fa) {
@@ -572,17 +571,22 @@ int mom_project(Sim& s, double w, int* n) {
   const bool f32 = (w == 1.0);                 // dt = w*Δt: Float32 for the Int w=1, Float64 for w=0.5
   const double dtw = f32 ? (double)dt32 : w * (double)dt32;
   Lvl& b = s.levels[0];
+  float4* xall = reinterpret_cast<float4*>(b.x - s.g.lead);
+  const int64_t n4 = s.g.comp / 4;
+  const int sgrid = (int)std::min<int64_t>((n4 + 255) / 256, (int64_t)s.nsm * 8);
   wl_prof_begin(s, WL_PROF_PROJECT);
-  RLAUNCH(s, k_project_pre, s.g, s.g, s.u, b.z, b.x, (float)dtw, dtw, f32 ? 1 : 0);
+  RLAUNCH(s, k_project_pre, s.g, s.g, s.u, b.z);
+  k_scale_alloc<<<sgrid, 256, 0, s.stream>>>(xall, n4, (float)dtw, dtw, f32 ? 1 : 0, 0);
+  ++s.launches;
   wl_prof_end(s, WL_PROF_PROJECT, 4.0 * (double)s.g.interior * (s.D + 1 + 2));
-  int rc = pois_solve(s, 1e-4, s.pois_kind == WL_POIS_MULTILEVEL ? 32 : 1000, n);
+  int rc = pois_solve(s, 1e-4, s.pois_kind == WL_POIS_MULTILEVEL ? 32 : 1000, n, true);
   if (rc) return rc;
   wl_prof_begin(s, WL_PROF_PROJECT);
   RLAUNCH(s, k_project_correct, s.g, s.g, s.u, b.L, b.x);
-  RLAUNCH(s, k_unscale, s.g, s.g, b.x, (float)dtw, dtw, f32 ? 1 : 0);
-  rc = bc_per(s, s.g, b.x, s.g.per);
+  k_scale_alloc<<<sgrid, 256, 0, s.stream>>>(xall, n4, (float)dtw, dtw, f32 ? 1 : 0, 1);
+  ++s.launches;
   wl_prof_end(s, WL_PROF_PROJECT, 4.0 * (double)s.g.interior * (3 * s.D + 1 + 2));
-  return rc;
+  return wl_cuda_check(s, cudaGetLastError(), "project");
 }
 // CFL(a) (Flow.jl:172-175)
 int mom_cfl(Sim& s, double* dt) {

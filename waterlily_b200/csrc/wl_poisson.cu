@@ -92,10 +92,10 @@ __global__ void __launch_bounds__(256) k_restrictL(Lvl c, Lvl f, int ck0, int ck
 
 // residual! first loop + sum (Poisson.jl:93-94)
 template <int D, int V>
-__global__ void __launch_bounds__(256) k_residual(Lvl l, ReduceWS ws, FinArgs fa) {
+__global__ void __launch_bounds__(256) k_residual(Lvl l, ReduceWS ws, FinArgs fa, int write_eps) {
   double acc[2] = {0.0, 0.0};
-  for_rows<V>(l.g, [&](int, int, int, int64_t I) {
-    const Pack<V> xc = ldp<V>(l.x + I), ax = mult_row<D, V>(l, I, l.x, xc), zc = ldp<V>(l.z + I), id = ldp<V>(l.iD + I);
+  for_rows<V>(l.g, [&](int i, int j, int k, int64_t I) {
+    const Pack<V> xc = ldp<V>(l.x + I), ax = mult_w<D, V>(l, l.x, i, j, k, I, xc), zc = ldp<V>(l.z + I), id = ldp<V>(l.iD + I);
     Pack<V> r;
 #pragma unroll
     for (int q = 0; q < V; ++q) {
@@ -104,13 +104,19 @@ __global__ void __launch_bounds__(256) k_residual(Lvl l, ReduceWS ws, FinArgs fa
       acc[1] += (double)r.v[q] * (double)r.v[q];
     }
     stp<V>(l.r + I, r);
+    if (write_eps) {  // ϵ = r·iD of the Jacobi! that opens the V-cycle (Poisson.jl:111): saves its own pass over r, iD
+      Pack<V> e;
+#pragma unroll
+      for (int q = 0; q < V; ++q) e.v[q] = r.v[q] * id.v[q];
+      stp<V>(l.eps + I, e);
+    }
   });
   double tot[2];
   if (grid_reduce<2>(acc, ws, tot)) finish_reduction(FIN_RESIDUAL, fa, tot[0], tot[1]);
 }
 // residual! second loop (Poisson.jl:96), predicated on |s| > 2eps
 template <int D, int V>
-__global__ void __launch_bounds__(256) k_sub_mean(Lvl l, ReduceWS ws, FinArgs fa) {
+__global__ void __launch_bounds__(256) k_sub_mean(Lvl l, ReduceWS ws, FinArgs fa, int write_eps) {
   if (!l.sc->need_sub) return;
   const float s = l.sc->rsum;
   double acc[1] = {0.0};
@@ -119,6 +125,13 @@ __global__ void __launch_bounds__(256) k_sub_mean(Lvl l, ReduceWS ws, FinArgs fa
 #pragma unroll
     for (int q = 0; q < V; ++q) { r.v[q] = r.v[q] - s; acc[0] += (double)r.v[q] * (double)r.v[q]; }
     stp<V>(l.r + I, r);
+    if (write_eps) {
+      const Pack<V> id = ldp<V>(l.iD + I);
+      Pack<V> e;
+#pragma unroll
+      for (int q = 0; q < V; ++q) e.v[q] = r.v[q] * id.v[q];
+      stp<V>(l.eps + I, e);
+    }
   });
   double tot[1];
   if (grid_reduce<1>(acc, ws, tot)) finish_reduction(FIN_R2_IF_SUB, fa, tot[0], 0.0);
@@ -149,8 +162,8 @@ __global__ void __launch_bounds__(256) k_jacobi_eps(Lvl l) {
 template <int D, int V>
 __global__ void __launch_bounds__(256) k_increment(Lvl l, ReduceWS ws, FinArgs fa) {
   double acc[1] = {0.0};
-  for_rows<V>(l.g, [&](int, int, int, int64_t I) {
-    const Pack<V> ec = ldp<V>(l.eps + I), ae = mult_row<D, V>(l, I, l.eps, ec);
+  for_rows<V>(l.g, [&](int i, int j, int k, int64_t I) {
+    const Pack<V> ec = ldp<V>(l.eps + I), ae = mult_w<D, V>(l, l.eps, i, j, k, I, ec);
     Pack<V> r = ldp<V>(l.r + I), x = ldp<V>(l.x + I);
 #pragma unroll
     for (int q = 0; q < V; ++q) {
@@ -219,8 +232,8 @@ template <int D, int V>
 __global__ void __launch_bounds__(256) k_pcg_mult(Lvl l, ReduceWS ws, FinArgs fa) {
   if (!l.sc->active) return;
   double acc[1] = {0.0};
-  for_rows<V>(l.g, [&](int, int, int, int64_t I) {
-    const Pack<V> ec = ldp<V>(l.eps + I), z = mult_row<D, V>(l, I, l.eps, ec);
+  for_rows<V>(l.g, [&](int i, int j, int k, int64_t I) {
+    const Pack<V> ec = ldp<V>(l.eps + I), z = mult_w<D, V>(l, l.eps, i, j, k, I, ec);
 #pragma unroll
     for (int q = 0; q < V; ++q) acc[0] += (double)z.v[q] * (double)ec.v[q];
     stp<V>(l.z + I, z);
@@ -275,7 +288,11 @@ __global__ void __launch_bounds__(256) k_shell_dot(Lvl l, ReduceWS ws, FinArgs f
     int c[3];
     if (shell_decode(l.g, idx, c) && is_global_ghost(l.g, c)) {
       const int64_t I = c[0] + c[1] * l.g.s[1] + c[2] * l.g.s[2];
-      acc[0] += (double)l.z[I] * (double)l.eps[I];
+      // ϵ's periodic ghosts are not materialised (the stencils wrap their index): read the image perBC! would copy
+      int w[3] = {c[0], c[1], c[2]};
+      for (int d = 0; d < l.g.D; ++d)
+        if (l.g.per[d]) w[d] = c[d] == 0 ? l.g.n[d] - 2 : (c[d] == l.g.n[d] - 1 ? 1 : c[d]);
+      acc[0] += (double)l.z[I] * (double)l.eps[w[0] + w[1] * l.g.s[1] + w[2] * l.g.s[2]];
     }
   }
   double tot[1];
@@ -376,20 +393,23 @@ int pois_mult(Sim& s) {
   return wl_cuda_check(s, cudaGetLastError(), "k_mult");
 }
 // residual!(p) (Poisson.jl:91-97)
-int pois_residual(Sim& s, Lvl& l, bool need_r2) {
-  int rc = bc_per(s, l.g, l.x, l.g.per);
+int pois_residual(Sim& s, Lvl& l, bool need_r2, bool ghosts_valid, bool jacobi_eps) {
+  // perBC!(x) (Poisson.jl:92).  project! hands over an x whose ghost cells and halo planes were scaled
+  // together with the interior, i.e. are already consistent: nothing to refresh then.
+  int rc = ghosts_valid ? 0 : bc_per(s, l.g, l.x, l.g.per);
   if (rc) return rc;
   const int lv = level_of(s, l);
   const bool fine = lv == 0;
   const FinArgs fa = fin_level(s, lv);
   if (fine) wl_prof_begin(s, WL_PROF_RESIDUAL);
-  RLAUNCH(s, k_residual, l.g, l, s.ws, fa);
+  RLAUNCH(s, k_residual, l.g, l, s.ws, fa, jacobi_eps ? 1 : 0);
   if ((rc = post_reduce(s, FIN_RESIDUAL, fa))) return rc;
   {
     FinArgs fb = fa;
     if (!need_r2 && fb.defer == 2) fb.defer = 0;  // not needed across ranks: keep the partial local
-    RLAUNCH(s, k_sub_mean, l.g, l, s.ws, fb);
+    RLAUNCH(s, k_sub_mean, l.g, l, s.ws, fb, jacobi_eps ? 1 : 0);
   }
+  s.eps_is_jacobi = jacobi_eps;
   // r⋅r after the mean subtraction is only reported, never used for control: solver! skips its all-reduce
   if (need_r2 && (rc = post_reduce(s, FIN_R2_IF_SUB, fa))) return rc;
   if (fine) wl_prof_end(s, WL_PROF_RESIDUAL, cellsB(l, 8));
@@ -397,7 +417,9 @@ int pois_residual(Sim& s, Lvl& l, bool need_r2) {
 }
 // increment!(p) (Poisson.jl:99-103)
 static int pois_increment(Sim& s, Lvl& l) {
-  int rc = bc_per(s, l.g, l.eps, l.g.per);
+  // perBC!(ϵ) (Poisson.jl:100): the stencil reads periodic neighbours through a wrapped index, so only
+  // the slab faces need data (the periodic ghost copies are materialised on demand, see wl_api.cu)
+  int rc = dist_halo(s, l.g, l.eps, 1, 1);
   if (rc) return rc;
   const int lv = level_of(s, l);
   const bool fine = lv == 0;
@@ -412,7 +434,9 @@ static int pois_increment(Sim& s, Lvl& l) {
 // Jacobi!(p;it) (Poisson.jl:110-113)
 int pois_jacobi(Sim& s, Lvl& l, int it) {
   for (int t = 0; t < it; ++t) {
-    RLAUNCH(s, k_jacobi_eps, l.g, l);
+    const bool ready = t == 0 && &l == &s.levels[0] && s.eps_is_jacobi;  // residual! already stored ϵ = r·iD
+    s.eps_is_jacobi = false;
+    if (!ready) RLAUNCH(s, k_jacobi_eps, l.g, l);
     const int rc = pois_increment(s, l);
     if (rc) return rc;
   }
@@ -442,7 +466,7 @@ int pois_pcg(Sim& s, int level, int it) {
     const int upto = std::min(it, std::max(guess, i));
     for (; i <= upto; ++i) {
       if (ghosts) {
-        if ((rc = bc_per(s, l.g, l.eps, l.g.per, &l.sc->active))) return rc;
+        if ((rc = dist_halo(s, l.g, l.eps, 1, 1))) return rc;  // perBC!(ϵ) (:129), see pois_increment
         if (fine) {  // only level 1 has non-zero z ghosts (z ≡ σ)
           const int64_t cnt = shell_count(l.g);
           k_shell_dot<<<(int)std::min<int64_t>((cnt + 255) / 256, 256), 256, 0, s.stream>>>(l, s.ws, fa, cnt);
@@ -498,10 +522,10 @@ int pois_vcycle(Sim& s, int level) {
   return pois_increment(s, fine);
 }
 // solver!(ml;tol,itmx) (MultiLevelPoisson.jl:87-99) / solver!(p::Poisson;tol,itmx) (Poisson.jl:162-172)
-int pois_solve(Sim& s, double tol, int itmx, int* n_out) {
+int pois_solve(Sim& s, double tol, int itmx, int* n_out, bool ghosts_valid) {
   Lvl& p = s.levels[0];
   wl_prof_begin(s, WL_PROF_SOLVER);
-  int rc = pois_residual(s, p, false);
+  int rc = pois_residual(s, p, false, ghosts_valid, s.pois_kind == WL_POIS_MULTILEVEL && itmx > 0);
   if (rc) return rc;
   int n = 0;
   while (n < itmx) {
@@ -518,6 +542,14 @@ int pois_solve(Sim& s, double tol, int itmx, int* n_out) {
   s.n_log.push_back(n);
   if (n_out) *n_out = n;
   return rc;
+}
+// perBC!(ϵ) made visible: the periodic ghost cells of ϵ on levels ≥ `level` (API inspection only)
+int pois_materialize_eps(Sim& s, int level) {
+  for (size_t l = (size_t)level; l < s.levels.size(); ++l) {
+    const int rc = bc_per(s, s.levels[l].g, s.levels[l].eps, s.levels[l].g.per);
+    if (rc) return rc;
+  }
+  return 0;
 }
 int pois_dot_rr(Sim& s, Lvl& l, double* out) {
   FinArgs fa = fin_level(s, level_of(s, l));

@@ -40,6 +40,41 @@ template <int V> __device__ __forceinline__ Pack<V> ld_xp(const float* __restric
   return r;
 }
 
+// mult (Poisson.jl:69-75) for V cells at (i..i+V-1, j, k); periodic neighbours are read through a
+// wrapped index instead of a ghost copy
+template <int D, int V>
+__device__ __forceinline__ Pack<V> mult_w(const Lvl& l, const float* x, int i, int j, int k, int64_t I, const Pack<V>& xc) {
+  const GridD& g = l.g;
+  const Pack<V> Dc = ldp<V>(l.Dg + I);
+  Pack<V> s;
+#pragma unroll
+  for (int q = 0; q < V; ++q) s.v[q] = xc.v[q] * Dc.v[q];
+  {
+    const Pack<V> Lc = ldp<V>(l.L + I), Lp = ld_xp<V>(l.L + I, Lc);
+    Pack<V> xm, xp;
+    xm.v[0] = x[(g.per[0] && i == 1) ? I + (g.n[0] - 3) : I - 1];
+#pragma unroll
+    for (int q = 1; q < V; ++q) xm.v[q] = xc.v[q - 1];
+#pragma unroll
+    for (int q = 0; q < V - 1; ++q) xp.v[q] = xc.v[q + 1];
+    xp.v[V - 1] = x[(g.per[0] && i + V - 1 == g.n[0] - 2) ? I + (V - 1) - (g.n[0] - 3) : I + V];
+#pragma unroll
+    for (int q = 0; q < V; ++q) s.v[q] += (xm.v[q] * Lc.v[q] + xp.v[q] * Lp.v[q]);
+  }
+#pragma unroll
+  for (int d = 1; d < D; ++d) {
+    const int64_t st = g.s[d];
+    const int cd = d == 1 ? j : k, n = g.n[d];
+    const int64_t om = (g.per[d] && cd == 1) ? (int64_t)(n - 3) * st : -st;
+    const int64_t op = (g.per[d] && cd == n - 2) ? -(int64_t)(n - 3) * st : st;
+    const float* Li = l.L + d * g.comp;
+    const Pack<V> Lc = ldp<V>(Li + I), Lp = ldp<V>(Li + I + st), xm = ldp<V>(x + I + om), xp = ldp<V>(x + I + op);
+#pragma unroll
+    for (int q = 0; q < V; ++q) s.v[q] += (xm.v[q] * Lc.v[q] + xp.v[q] * Lp.v[q]);
+  }
+  return s;
+}
+
 // interior rows; f(i, j, k, I) is called for the first cell of each V-group
 template <int V, class F>
 __device__ __forceinline__ void for_rows(const GridD& g, F&& f) {
