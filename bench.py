@@ -223,8 +223,13 @@ def run_ours(args):
     dom = max(kern, key=lambda k: kern[k]["ms"])
     d = kern[dom]
     achieved = d["bytes"] / (d["ms"] * 1e-3) / 1e9
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu capture of this command at 512^3
+    # (profiles/r01_launches_tgv512_1gpu_v2.txt): predictor 5.01 GB, corrector 6.65 GB; algorithmic 4.83 / 6.44 GB
+    traffic = 0.5 * (5.013e9 + 6.651e9) if (dom == "conv_diff+bdim1" and N == 512 and world == 1) else None
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "launches": d["launches"], "avg_ms": d["ms"] / d["launches"],
+                "traffic": traffic, "peak_source": peak_src,
+                "note": "conv_diff! (k_conv_diff3_tma) is bound by instruction issue, not HBM: 459 warp instructions per 32 cells at 84 % issue-slot "
+                        "utilisation (profiles/r01_ncu_full_conv_diff3_tma_384.txt); the HBM-bound solver kernels run at 74-92 % of the measured peak (kernels{})", "launches": d["launches"], "avg_ms": d["ms"] / d["launches"],
                 "share_of_step": d["ms"] / prof["mom_step"]["ms"] if prof["mom_step"]["ms"] else None,
                 "kernels": {k: {"GB/s": (v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] else None, "ms_total": v["ms"], "launches": v["launches"]} for k, v in prof.items()}}
 

@@ -84,10 +84,12 @@ int wl_sync(wl_sim* s);
 /* ---- z-slab domain decomposition over the GPUs of one box (new; the reference is single-device,
  *      README.md:157).  One process per GPU: rank 0 makes an id with wl_dist_unique_id, the launcher
  *      broadcasts its 128 bytes (torch.distributed, MPI, a file …), every rank calls wl_create_dist
- *      with the GLOBAL N.  N[2] is split into N[2]/nranks planes per rank (must be even); halo
- *      planes travel by NCCL send/recv at the reference's BC!/perBC! sites, scalar reductions by
- *      NCCL all-reduce, and multigrid levels with fewer than 8 planes per rank are replicated on
- *      every rank (agglomeration).  All other entry points then act on the rank's slab and are
+ *      with the GLOBAL N.  N[2] is split into N[2]/nranks planes per rank (must be even).  The id
+ *      bootstraps a NCCL communicator that exchanges CUDA IPC handles: afterwards halo planes (at the
+ *      reference's BC!/perBC! sites) and scalar reductions travel as direct stores into the peers'
+ *      memory over NVLink from inside the kernels (WL_P2P=0 keeps NCCL send/recv + all-reduce);
+ *      multigrid levels with fewer than 8 planes per rank are replicated on every rank
+ *      (agglomeration).  wl_destroy of such a handle is collective too.  All other entry points then act on the rank's slab and are
  *      collective: every rank must make the same calls in the same order.  Host arrays passed to
  *      upload/download always have the GLOBAL shape; upload reads the rank's planes from it,
  *      download fills only the planes the rank owns. ------------------------------------------- */

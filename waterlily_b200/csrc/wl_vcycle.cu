@@ -421,8 +421,8 @@ __device__ __forceinline__ void up_level(const FusedParams& p, Run& run, int l) 
   pcg_level<D, GRID>(p, run, l);
 }
 
-template <int D>
-__global__ void __launch_bounds__(VC_THREADS) k_vcycle_tail(FusedParams p) {
+template <int D, int MINB>
+__global__ void __launch_bounds__(VC_THREADS, MINB) k_vcycle_tail(FusedParams p) {
   __shared__ Shared sh;
   Run run;
   run.sh = &sh;
@@ -471,8 +471,13 @@ __global__ void __launch_bounds__(VC_THREADS) k_vcycle_tail(FusedParams p) {
 struct VcycleFused {
   FusedParams p;
   int grid = 0;
+  int minb = 2;
   bool ok = false;
 };
+static const void* tail_kernel(int D, int minb) {
+  if (D == 2) return minb >= 3 ? (const void*)k_vcycle_tail<2, 3> : (const void*)k_vcycle_tail<2, 2>;
+  return minb >= 3 ? (const void*)k_vcycle_tail<3, 3> : (const void*)k_vcycle_tail<3, 2>;
+}
 
 static int ilog2(int v) { int l = 0; while ((1 << (l + 1)) <= v) ++l; return l; }
 
@@ -517,9 +522,10 @@ int vcycle_fused_setup(Sim& s) {
     while (bx < nxi / V && bx < 128) bx <<= 1;
     p.bxlog[l] = ilog2(bx);
   }
+  const char* e4 = getenv("WL_FUSED_MINB");
+  vf->minb = e4 ? atoi(e4) : 2;
   int per_sm = 0;
-  cudaError_t e = s.D == 2 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_vcycle_tail<2>, VC_THREADS, 0)
-                           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_vcycle_tail<3>, VC_THREADS, 0);
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tail_kernel(s.D, vf->minb), VC_THREADS, 0);
   if (e != cudaSuccess || per_sm < 1) { cudaGetLastError(); delete vf; return 0; }
   const char* e3 = getenv("WL_FUSED_BLOCKS_PER_SM");
   const int want = e3 ? atoi(e3) : 4;
@@ -546,8 +552,7 @@ int vcycle_fused_run(Sim& s) {
   VcycleFused* vf = (VcycleFused*)s.vc_fused;
   void* args[] = {&vf->p};
   wl_prof_begin(s, WL_PROF_VCTAIL);
-  cudaError_t e = s.D == 2 ? cudaLaunchCooperativeKernel((void*)k_vcycle_tail<2>, dim3(vf->grid), dim3(VC_THREADS), args, 0, s.stream)
-                           : cudaLaunchCooperativeKernel((void*)k_vcycle_tail<3>, dim3(vf->grid), dim3(VC_THREADS), args, 0, s.stream);
+  cudaError_t e = cudaLaunchCooperativeKernel(tail_kernel(s.D, vf->minb), dim3(vf->grid), dim3(VC_THREADS), args, 0, s.stream);
   ++s.launches;
   wl_prof_end(s, WL_PROF_VCTAIL, 0.0);
   return wl_cuda_check(s, e, "k_vcycle_tail");
