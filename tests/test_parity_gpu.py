@@ -274,13 +274,16 @@ def test_full_size_properties_tgv128():
     assert 0.5 < float(sim.flow.dt[-1]) < 1.1
 
 
+@pytest.mark.parametrize("solve_cells", ["0", "1000000000"])   # coarse tail only / the whole solver! in one kernel
 @pytest.mark.parametrize("make,steps", [(lambda cls: tgv3d(cls, 64), 3), (lambda cls: sphere3d(cls, exitBC=True), 4), (circle2d, 10)])
-def test_fused_vcycle_matches_per_level_kernels(make, steps, monkeypatch):
-    # wl_vcycle.cu (one persistent kernel for the coarse levels) against the per-function kernels of
-    # wl_poisson.cu: same arithmetic, different reduction tree → agreement to reduction-order noise
+def test_fused_vcycle_matches_per_level_kernels(make, steps, solve_cells, monkeypatch):
+    # wl_vcycle.cu (one persistent kernel for the coarse levels, or for the whole solver!) against the
+    # per-function kernels of wl_poisson.cu: same arithmetic, different reduction tree → agreement to
+    # reduction-order noise
     monkeypatch.setenv("WL_FUSED_VCYCLE", "0")
     s0 = make(Simulation)
     monkeypatch.setenv("WL_FUSED_VCYCLE", "1")
+    monkeypatch.setenv("WL_FUSED_SOLVE_CELLS", solve_cells)
     s1 = make(Simulation)
     l0, l1 = s0._eng.launch_count(), s1._eng.launch_count()
     for _ in range(steps):

@@ -17,39 +17,6 @@ struct BCArgs {
   int saveexit;
 };
 
-// threads enumerate, for every direction j, the planes c[j] ∈ {0,1,n-1} in full (edge cells are
-// visited more than once and receive the same value each time)
-__device__ __forceinline__ bool planes_decode(const GridD& g, int64_t idx, int nplanes, int c[3]) {
-  c[0] = c[1] = c[2] = 0;
-  for (int j = 0; j < g.D; ++j) {
-    int64_t other = 1;
-    for (int k = 0; k < g.D; ++k) if (k != j) other *= g.n[k];
-    const int64_t cnt = nplanes * other;
-    if (idx < cnt) {
-      const int pl = (int)(idx / other);
-      int64_t q = idx % other;
-      for (int k = 0; k < g.D; ++k) {
-        if (k == j) continue;
-        c[k] = (int)(q % g.n[k]);
-        q /= g.n[k];
-      }
-      c[j] = nplanes == 3 ? (pl == 0 ? 0 : (pl == 1 ? 1 : g.n[j] - 1)) : (pl == 0 ? 0 : g.n[j] - 1);
-      return true;
-    }
-    idx -= cnt;
-  }
-  return false;
-}
-__host__ int64_t planes_count(const GridD& g, int nplanes) {
-  int64_t tot = 0;
-  for (int j = 0; j < g.D; ++j) {
-    int64_t other = 1;
-    for (int k = 0; k < g.D; ++k) if (k != j) other *= g.n[k];
-    tot += nplanes * other;
-  }
-  return tot;
-}
-
 // BC!(a,A,saveexit,perdir) (util.jl:192-210)
 __global__ void __launch_bounds__(256) k_bc_vec(GridD g, float* __restrict__ a, BCArgs args, int64_t count) {
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < count; idx += (int64_t)gridDim.x * blockDim.x) {

@@ -54,7 +54,7 @@ struct MiscScalars {
   double raw[2];
   float exit_mean_minus_U;  // ∮u of exitBC!
   float cfl_max;            // max over padded σ
-  float pad[2];
+  int solve_n[2];           // V-cycle counts of the predictor / corrector solver! (whole-solver kernel)
 };
 
 // What to do with a finished reduction.  On one GPU the last block of the producing kernel runs
@@ -325,4 +325,37 @@ __host__ __device__ inline int64_t shell_count(const GridD& g, int t = 1) {
   for (int k = 0; k < g.D; ++k) { all *= g.n[k]; in *= g.n[k] - 2 * t; }
   return all - in;
 }
+// threads enumerate, for every direction j, the planes c[j] ∈ {0,1,n-1} in full (edge cells are
+// visited more than once and receive the same value each time)
+__device__ __forceinline__ bool planes_decode(const GridD& g, int64_t idx, int nplanes, int c[3]) {
+  c[0] = c[1] = c[2] = 0;
+  for (int j = 0; j < g.D; ++j) {
+    int64_t other = 1;
+    for (int k = 0; k < g.D; ++k) if (k != j) other *= g.n[k];
+    const int64_t cnt = nplanes * other;
+    if (idx < cnt) {
+      const int pl = (int)(idx / other);
+      int64_t q = idx % other;
+      for (int k = 0; k < g.D; ++k) {
+        if (k == j) continue;
+        c[k] = (int)(q % g.n[k]);
+        q /= g.n[k];
+      }
+      c[j] = nplanes == 3 ? (pl == 0 ? 0 : (pl == 1 ? 1 : g.n[j] - 1)) : (pl == 0 ? 0 : g.n[j] - 1);
+      return true;
+    }
+    idx -= cnt;
+  }
+  return false;
+}
+__host__ __device__ inline int64_t planes_count(const GridD& g, int nplanes) {
+  int64_t tot = 0;
+  for (int j = 0; j < g.D; ++j) {
+    int64_t other = 1;
+    for (int k = 0; k < g.D; ++k) if (k != j) other *= g.n[k];
+    tot += nplanes * other;
+  }
+  return tot;
+}
+
 #endif

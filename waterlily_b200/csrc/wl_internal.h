@@ -87,6 +87,8 @@ struct Sim {
   bool eps_is_jacobi = false;  // levels[1].ϵ already holds r·iD of the current residual (written by k_residual)
   void* vc_fused = nullptr;    // fused coarse V-cycle (wl_vcycle.cu), or null
   int vc_first = -1;           // first level the fused kernel covers (-1: off)
+  int last_solve_n[2] = {0, 0};
+  bool vc_solve = false;       // the fused kernel runs the whole solver! (one launch, no host read)
   int sticky = 0;  // first CUDA error, sticky per handle
   bool profiling = false;
   ProfClass prof[WL_PROF_N];
@@ -128,6 +130,7 @@ bool convdiff_tma_launch(Sim& s, const CDArgs& a, int zchunk, bool corr);
 int vcycle_fused_setup(Sim& s);
 void vcycle_fused_destroy(Sim& s);
 int vcycle_fused_run(Sim& s);
+int vcycle_fused_solve(Sim& s, double tol, int itmx, bool ghosts_valid, int slot);
 
 // ---- wl_bc.cu ----
 int bc_vec(Sim& s, const GridD& g, float* a, const double* A, bool saveexit, const int* per, int halo_depth = 1);
@@ -143,7 +146,7 @@ int pois_residual(Sim& s, Lvl& l, bool need_r2 = true, bool ghosts_valid = false
 int pois_jacobi(Sim& s, Lvl& l, int it);
 int pois_pcg(Sim& s, int level, int it);
 int pois_vcycle(Sim& s, int level);
-int pois_solve(Sim& s, double tol, int itmx, int* n, bool ghosts_valid = false);
+int pois_solve(Sim& s, double tol, int itmx, int* n, bool ghosts_valid = false, int slot = 0, bool defer_count = false);
 int pois_materialize_eps(Sim& s, int level);
 int pois_dot_rr(Sim& s, Lvl& l, double* out);
 
@@ -153,7 +156,7 @@ int mom_accelerate(Sim& s, const double* g);
 int mom_bdim1(Sim& s);
 int mom_bdim2(Sim& s, bool accumulate, float scale);
 int mom_scale_u(Sim& s, double scale);
-int mom_project(Sim& s, double w, int* n);
+int mom_project(Sim& s, double w, int* n, int slot = 0, bool defer_count = false);
 int mom_cfl(Sim& s, double* dt);
 int mom_step(Sim& s, const double* U, const double* gp, const double* gc, double* dt_next, int* n_pred, int* n_corr);
 

@@ -12,6 +12,7 @@
 // Float64 sub-expressions follow Julia's promotion rules.
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 
 #include "wl_internal.h"
 #include "wl_vec.cuh"
@@ -593,7 +594,7 @@ int mom_scale_u(Sim& s, double scale) {
   return wl_cuda_check(s, cudaGetLastError(), "k_scale_u");
 }
 // project!(a,b,w) (Flow.jl:137-145)
-int mom_project(Sim& s, double w, int* n) {
+int mom_project(Sim& s, double w, int* n, int slot, bool defer_count) {
   const float dt32 = s.dt.back();
   const bool f32 = (w == 1.0);                 // dt = w*Δt: Float32 for the Int w=1, Float64 for w=0.5
   const double dtw = f32 ? (double)dt32 : w * (double)dt32;
@@ -606,7 +607,7 @@ int mom_project(Sim& s, double w, int* n) {
   k_scale_alloc<<<sgrid, 256, 0, s.stream>>>(xall, n4, (float)dtw, dtw, f32 ? 1 : 0, 0);
   ++s.launches;
   wl_prof_end(s, WL_PROF_PROJECT, 4.0 * (double)s.g.interior * (s.D + 1 + 2));
-  int rc = pois_solve(s, 1e-4, s.pois_kind == WL_POIS_MULTILEVEL ? 32 : 1000, n, true);
+  int rc = pois_solve(s, 1e-4, s.pois_kind == WL_POIS_MULTILEVEL ? 32 : 1000, n, true, slot, defer_count);
   if (rc) return rc;
   wl_prof_begin(s, WL_PROF_PROJECT);
   RLAUNCH(s, k_project_correct, s.g, s.g, s.u, b.L, b.x);
@@ -627,8 +628,13 @@ int mom_cfl(Sim& s, double* dt) {
     ++s.launches;
     if ((rc = post_reduce(s, FIN_CFL_SHELL, fa, true))) return rc;
   }
-  if ((rc = wl_read_scalars(s, &s.d_misc->cfl_max, sizeof(float)))) return rc;
-  const float m = s.h_pinned[0] + 5 * s.nu;
+  // one readback for the step: CFL's maximum and the V-cycle counts of the two solver! kernels
+  if ((rc = wl_read_scalars(s, s.d_misc, sizeof(MiscScalars)))) return rc;
+  MiscScalars hm;
+  memcpy(&hm, s.h_pinned, sizeof(hm));
+  s.last_solve_n[0] = hm.solve_n[0];
+  s.last_solve_n[1] = hm.solve_n[1];
+  const float m = hm.cfl_max + 5 * s.nu;
   const float v = 1.f / m;
   *dt = (double)(v < 10.f ? v : 10.f);
   return 0;
@@ -652,16 +658,22 @@ int mom_step(Sim& s, const double* U, const double* gp, const double* gc, double
     if ((rc = bc_exit(s, U, s.dt.back()))) return rc;
     if ((rc = dist_halo(s, s.g, s.u, 1, 2))) return rc;  // the exit plane changed after BC!'s exchange
   }
-  if ((rc = mom_project(s, 1.0, n_pred))) return rc;
+  const bool defer = s.vc_solve && s.pois_kind == WL_POIS_MULTILEVEL;
+  if ((rc = mom_project(s, 1.0, n_pred, 0, defer))) return rc;
   if ((rc = bc_vec(s, s.g, s.u, U, s.exitBC, s.g.per, 2))) return rc;
   // corrector u → u¹
   if ((rc = mom_conv_diff(s, s.u, true, gc))) return rc;
   if ((rc = mom_bdim2(s, true, 0.5f))) return rc;
   if ((rc = bc_vec(s, s.g, s.u, U, s.exitBC, s.g.per, 2))) return rc;
-  if ((rc = mom_project(s, 0.5, n_corr))) return rc;
+  if ((rc = mom_project(s, 0.5, n_corr, 1, defer))) return rc;
   if ((rc = bc_vec(s, s.g, s.u, U, s.exitBC, s.g.per, 2))) return rc;
   double dt;
   if ((rc = mom_cfl(s, &dt))) return rc;
+  if (defer) {
+    for (int k = 0; k < 2; ++k) s.n_log.push_back(s.last_solve_n[k]);
+    if (n_pred) *n_pred = s.last_solve_n[0];
+    if (n_corr) *n_corr = s.last_solve_n[1];
+  }
   wl_prof_end(s, WL_PROF_STEP, 0.0);
   if ((rc = dist_check_p2p_error(s))) return rc;
   s.dt.push_back((float)dt);

@@ -522,9 +522,22 @@ int pois_vcycle(Sim& s, int level) {
   return pois_increment(s, fine);
 }
 // solver!(ml;tol,itmx) (MultiLevelPoisson.jl:87-99) / solver!(p::Poisson;tol,itmx) (Poisson.jl:162-172)
-int pois_solve(Sim& s, double tol, int itmx, int* n_out, bool ghosts_valid) {
+int pois_solve(Sim& s, double tol, int itmx, int* n_out, bool ghosts_valid, int slot, bool defer_count) {
   Lvl& p = s.levels[0];
   wl_prof_begin(s, WL_PROF_SOLVER);
+  if (s.vc_solve && s.pois_kind == WL_POIS_MULTILEVEL) {
+    // the whole solver! is one persistent kernel (wl_vcycle.cu); its V-cycle count stays on the device
+    // until the caller reads it (mom_step! reads both counts together with CFL's maximum)
+    int rc = vcycle_fused_solve(s, tol, itmx, ghosts_valid, slot);
+    wl_prof_end(s, WL_PROF_SOLVER, 0.0);
+    if (rc || defer_count) return rc;
+    if ((rc = wl_read_scalars(s, &s.d_misc->solve_n[slot], sizeof(int)))) return rc;
+    int n;
+    memcpy(&n, s.h_pinned, sizeof(int));
+    s.n_log.push_back(n);
+    if (n_out) *n_out = n;
+    return 0;
+  }
   int rc = pois_residual(s, p, false, ghosts_valid, s.pois_kind == WL_POIS_MULTILEVEL && itmx > 0);
   if (rc) return rc;
   int n = 0;

@@ -37,6 +37,16 @@ struct FusedParams {
   unsigned int* bar;          // grid barrier: {count, generation}
   double* partials;           // [gridDim.x][2]
   const P2PDev* p2p;          // null on one rank
+  MiscScalars* misc;          // solve mode: V-cycle count out
+};
+// per-launch arguments of the whole-solver mode (solver!(ml), MultiLevelPoisson.jl:87-99)
+struct SolveArgs {
+  int solve;         // 0: coarse tail only (levels lf…), 1: the whole solver! including level 1 of the reference
+  float tol;
+  int itmx;
+  int ghosts_valid;  // x's ghost cells / halo planes are consistent (project! scaled them with the interior)
+  int has_ghost;     // z⋅ϵ has a ghost-shell part (z ≡ σ keeps conv_diff!'s stale Φ)
+  int slot;          // which entry of MiscScalars::solve_n receives the count
 };
 
 struct Shared {
@@ -246,24 +256,35 @@ __device__ __forceinline__ void halo_push(const FusedParams& p, Run& run, int l,
 // ---- phases ----------------------------------------------------------------------------------
 // increment! (Poisson.jl:99-103) of level l, ϵ already stored; on a distributed level ϵ's halo first
 template <int D, int V, bool GRID>
-__device__ __forceinline__ void increment(const FusedParams& p, Run& run, int l) {
+__device__ __forceinline__ void increment(const FusedParams& p, Run& run, int l, float* r2 = nullptr) {
   const Lvl& L = p.lv[l];
   if (GRID && p.dist[l]) halo_push(p, run, l, L.eps);
+  double acc[1] = {0.0};
   rows<V, GRID>(p, l, [&](int i, int j, int k, int64_t I) {
     const Pack<V> ec = ldp<V>(L.eps + I), ae = mult_w<D, V>(L, L.eps, i, j, k, I, ec);
     Pack<V> r = ldp<V>(L.r + I), x = ldp<V>(L.x + I);
 #pragma unroll
-    for (int q = 0; q < V; ++q) { r.v[q] = r.v[q] - ae.v[q]; x.v[q] = x.v[q] + ec.v[q]; }
+    for (int q = 0; q < V; ++q) {
+      r.v[q] = r.v[q] - ae.v[q];
+      x.v[q] = x.v[q] + ec.v[q];
+      acc[0] += (double)r.v[q] * (double)r.v[q];
+    }
     stp<V>(L.r + I, r);
     stp<V>(L.x + I, x);
   });
-  phase_sync<GRID>(p, run);
+  if (r2) {  // L₂ (Poisson.jl:146) is only ever read on the finest level
+    reduce<1, GRID>(p, run, GRID && p.dist[l], acc);
+    *r2 = (float)acc[0];
+  } else {
+    phase_sync<GRID>(p, run);
+  }
   if (GRID && p.dist[l]) post_ready(p, run);
 }
 // Jacobi!(l; it=1) (Poisson.jl:110-113)
 template <int D, int V, bool GRID>
-__device__ __forceinline__ void jacobi(const FusedParams& p, Run& run, int l) {
+__device__ __forceinline__ void jacobi(const FusedParams& p, Run& run, int l, bool eps_ready = false) {
   const Lvl& L = p.lv[l];
+  if (eps_ready) { increment<D, V, GRID>(p, run, l); return; }  // residual! already stored ϵ = r·iD
   rows<V, GRID>(p, l, [&](int, int, int, int64_t I) {
     const Pack<V> r = ldp<V>(L.r + I), id = ldp<V>(L.iD + I);
     Pack<V> e;
@@ -275,8 +296,10 @@ __device__ __forceinline__ void jacobi(const FusedParams& p, Run& run, int l) {
   increment<D, V, GRID>(p, run, l);
 }
 // pcg!(l; it=6) (Poisson.jl:123-144)
+// `shell`: add Σ over the global ghost shell of z·ϵ to z⋅ϵ (level 1 of the reference only);
+// `r2`: keep L₂ = r⋅r up to date (finest level only)
 template <int D, int V, bool GRID>
-__device__ __forceinline__ void pcg(const FusedParams& p, Run& run, int l, int it) {
+__device__ __forceinline__ void pcg(const FusedParams& p, Run& run, int l, int it, bool shell = false, float* r2 = nullptr) {
   const Lvl& L = p.lv[l];
   const bool dist = GRID && p.dist[l];
   float rho;
@@ -304,6 +327,19 @@ __device__ __forceinline__ void pcg(const FusedParams& p, Run& run, int l, int i
         for (int q = 0; q < V; ++q) acc[0] += (double)z.v[q] * (double)ec.v[q];
         stp<V>(L.z + I, z);
       });
+      if (shell) {
+        const GridD& g = L.g;
+        const int64_t cnt = shell_count(g);
+        for (int64_t idx = blockIdx.x * (int64_t)VC_THREADS + threadIdx.x; idx < cnt; idx += (int64_t)gridDim.x * VC_THREADS) {
+          int c[3];
+          if (shell_decode(g, idx, c) && is_global_ghost(g, c)) {
+            int w[3] = {c[0], c[1], c[2]};
+            for (int d = 0; d < g.D; ++d)
+              if (g.per[d]) w[d] = c[d] == 0 ? g.n[d] - 2 : (c[d] == g.n[d] - 1 ? 1 : c[d]);
+            acc[0] += (double)L.z[c[0] + c[1] * g.s[1] + c[2] * g.s[2]] * (double)L.eps[w[0] + w[1] * g.s[1] + w[2] * g.s[2]];
+          }
+        }
+      }
       reduce<1, GRID>(p, run, dist, acc);
       if (dist) post_ready(p, run);
       alpha = rho / (float)acc[0];
@@ -326,8 +362,10 @@ __device__ __forceinline__ void pcg(const FusedParams& p, Run& run, int l, int i
         stp<V>(L.x + I, x);
         stp<V>(L.r + I, r);
       });
-      if (i == it) { phase_sync<GRID>(p, run); return; }  // the dots of the last sweep are never used below level 1
+      if (i == it && !r2) { phase_sync<GRID>(p, run); return; }  // the dots of the last sweep are never used below level 1
       reduce<2, GRID>(p, run, dist, acc);
+      if (r2) *r2 = (float)acc[1];
+      if (i == it) return;
       rho2 = (float)acc[0];
     }
     if (fabsf(rho2) < 10 * WL_EPS32) return;
@@ -421,8 +459,106 @@ __device__ __forceinline__ void up_level(const FusedParams& p, Run& run, int l) 
   pcg_level<D, GRID>(p, run, l);
 }
 
+// levels lf … nl-1 of one V-cycle (the residual of level lf has just been restricted)
+template <int D>
+__device__ __forceinline__ void vcycle_tail(const FusedParams& p, Run& run, int lf) {
+  const int last = p.nl - 1;
+  const int lb = max(p.lb, lf);  // levels ≥ lb: block 0 alone
+  // down-leg on the grid
+  for (int l = lf; l < min(lb, last); ++l) down_level<D, true>(p, run, l);
+  if (lb <= last) {
+    // whole sub-cycle of the smallest levels in one block
+    if (blockIdx.x == 0) {
+      for (int l = lb; l < last; ++l) down_level<D, false>(p, run, l);
+      pcg_level<D, false>(p, run, last);
+      for (int l = last - 1; l >= lb; --l) up_level<D, false>(p, run, l);
+    }
+    grid_barrier(p, run);
+  } else {
+    pcg_level<D, true>(p, run, last);
+  }
+  for (int l = min(lb, last) - 1; l >= lf; --l) {
+    // the replicated tail is finished: its gathered residual may be overwritten by the next V-cycle
+    if (p.p2p && p.dist[l] && !p.dist[l + 1]) post_ready(p, run);
+    up_level<D, true>(p, run, l);
+  }
+}
+
+// ---- finest level (whole-solver mode) -------------------------------------------------------
+// residual! (Poisson.jl:91-97) + the ϵ = r·iD of the Jacobi! that opens the first V-cycle
+template <int D, int V>
+__device__ __forceinline__ void residual0(const FusedParams& p, Run& run, const SolveArgs& sa, float& r2) {
+  const Lvl& L = p.lv[0];
+  const bool dist = p.dist[0] != 0;
+  // x's periodic neighbours are read through wrapped indices; slab faces need the neighbours' planes
+  if (dist && !sa.ghosts_valid) halo_push(p, run, 0, L.x);
+  double acc[2] = {0.0, 0.0};
+  rows<V, true>(p, 0, [&](int i, int j, int k, int64_t I) {
+    const Pack<V> xc = ldp<V>(L.x + I), ax = mult_w<D, V>(L, L.x, i, j, k, I, xc), zc = ldp<V>(L.z + I), id = ldp<V>(L.iD + I);
+    Pack<V> r, e;
+#pragma unroll
+    for (int q = 0; q < V; ++q) {
+      r.v[q] = id.v[q] == 0.f ? 0.f : zc.v[q] - ax.v[q];
+      acc[0] += (double)r.v[q];
+      acc[1] += (double)r.v[q] * (double)r.v[q];
+      e.v[q] = r.v[q] * id.v[q];
+    }
+    stp<V>(L.r + I, r);
+    stp<V>(L.eps + I, e);
+  });
+  reduce<2, true>(p, run, dist, acc);
+  if (dist && !sa.ghosts_valid) post_ready(p, run);
+  const float rmean = (float)acc[0] / (float)L.g.interior_global;
+  r2 = (float)acc[1];
+  if (fabsf(rmean) > 2 * WL_EPS32) {
+    rows<V, true>(p, 0, [&](int, int, int, int64_t I) {
+      Pack<V> r = ldp<V>(L.r + I);
+      const Pack<V> id = ldp<V>(L.iD + I);
+      Pack<V> e;
+#pragma unroll
+      for (int q = 0; q < V; ++q) { r.v[q] = r.v[q] - rmean; e.v[q] = r.v[q] * id.v[q]; }
+      stp<V>(L.r + I, r);
+      stp<V>(L.eps + I, e);
+    });
+    grid_barrier(p, run);
+  }
+}
+// perBC!(x) (MultiLevelPoisson.jl:97): periodic ghost cells, then the slab halo planes
+template <int D>
+__device__ __forceinline__ void per_bc_x0(const FusedParams& p, Run& run) {
+  const Lvl& L = p.lv[0];
+  const GridD& g = L.g;
+  bool any_per = false;
+  for (int d = 0; d < D; ++d) any_per |= g.per[d] != 0;
+  if (any_per) {
+    const int64_t cnt = planes_count(g, 2);
+    for (int64_t idx = blockIdx.x * (int64_t)VC_THREADS + threadIdx.x; idx < cnt; idx += (int64_t)gridDim.x * VC_THREADS) {
+      int c0[3];
+      if (!planes_decode(g, idx, 2, c0)) continue;
+      if (D > 2 && ((c0[2] == 0 && g.zlo_halo) || (c0[2] == g.n[2] - 1 && g.zhi_halo))) continue;
+      int c[3] = {c0[0], c0[1], c0[2]};
+      bool written = false;
+      for (int j = D - 1; j >= 0; --j) {
+        if (!g.per[j]) continue;
+        if (c[j] == 0) { c[j] = g.n[j] - 2; written = true; }
+        else if (c[j] == g.n[j] - 1) { c[j] = 1; written = true; }
+      }
+      if (written) L.x[c0[0] + c0[1] * g.s[1] + c0[2] * g.s[2]] = L.x[c[0] + c[1] * g.s[1] + c[2] * g.s[2]];
+    }
+  }
+  if (p.dist[0]) {
+    grid_barrier(p, run);
+    halo_push(p, run, 0, L.x);
+  }
+}
+
+// Two modes, one flow (so that the coarse tail is instantiated once):
+//  tail mode  — levels lf … nl-1 of one V-cycle (the finer levels run as separate kernels);
+//  solve mode — solver!(ml; tol, itmx) (MultiLevelPoisson.jl:87-99) entirely on the device: residual!,
+//               then {Vcycle!, pcg!(finest), L₂ test} until converged, then perBC!(x); the V-cycle count
+//               and L₂ go to device memory, the host reads them when it needs them.
 template <int D, int MINB>
-__global__ void __launch_bounds__(VC_THREADS, MINB) k_vcycle_tail(FusedParams p) {
+__global__ void __launch_bounds__(VC_THREADS, MINB) k_vcycle_tail(FusedParams p, SolveArgs sa) {
   __shared__ Shared sh;
   Run run;
   run.sh = &sh;
@@ -438,25 +574,42 @@ __global__ void __launch_bounds__(VC_THREADS, MINB) k_vcycle_tail(FusedParams p)
   run.bar_gen = *((volatile unsigned int*)&p.bar[1]);
   // every block must have sampled the generation / epochs before anyone moves them
   grid_barrier(p, run);
-  const int last = p.nl - 1;
-  const int lb = max(p.lb, p.lf);  // levels ≥ lb: block 0 alone
-  // down-leg on the grid
-  for (int l = p.lf; l < min(lb, last); ++l) down_level<D, true>(p, run, l);
-  if (lb <= last) {
-    // whole sub-cycle of the smallest levels in one block
-    if (blockIdx.x == 0) {
-      for (int l = lb; l < last; ++l) down_level<D, false>(p, run, l);
-      pcg_level<D, false>(p, run, last);
-      for (int l = last - 1; l >= lb; --l) up_level<D, false>(p, run, l);
-    }
-    grid_barrier(p, run);
-  } else {
-    pcg_level<D, true>(p, run, last);
+  const bool solve = sa.solve != 0;
+  const bool v4 = (p.lv[0].g.n[0] - 2) % 4 == 0;
+  const int lf = solve ? 1 : p.lf;
+  float r2 = 0.f;
+  int n = 0;
+  if (solve) {
+    if (v4) residual0<D, 4>(p, run, sa, r2);
+    else residual0<D, 1>(p, run, sa, r2);
   }
-  for (int l = min(lb, last) - 1; l >= p.lf; --l) {
-    // the replicated tail is finished: its gathered residual may be overwritten by the next V-cycle
-    if (p.p2p && p.dist[l] && !p.dist[l + 1]) post_ready(p, run);
-    up_level<D, true>(p, run, l);
+  for (;;) {
+    if (solve) {  // Vcycle!(ml) on the finest level: Jacobi!, restrict!
+      if (v4) jacobi<D, 4, true>(p, run, 0, n == 0);
+      else jacobi<D, 1, true>(p, run, 0, n == 0);
+      restrict_to<D, true>(p, run, 0);
+    }
+    vcycle_tail<D>(p, run, lf);
+    if (!solve) break;
+    if (p.p2p && p.dist[0] && !p.dist[1]) post_ready(p, run);
+    if (v4) {
+      prolongate_to<D, 4, true>(p, run, 0);
+      increment<D, 4, true>(p, run, 0, &r2);
+      pcg<D, 4, true>(p, run, 0, 6, sa.has_ghost != 0, &r2);
+    } else {
+      prolongate_to<D, 1, true>(p, run, 0);
+      increment<D, 1, true>(p, run, 0, &r2);
+      pcg<D, 1, true>(p, run, 0, 6, sa.has_ghost != 0, &r2);
+    }
+    ++n;
+    if (r2 < sa.tol || n >= sa.itmx) break;
+  }
+  if (solve) {
+    per_bc_x0<D>(p, run);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      p.lv[0].sc->r2 = r2;
+      p.misc->solve_n[sa.slot] = n;
+    }
   }
   if (p.p2p && blockIdx.x == 0 && threadIdx.x == 0) {
     P2PFlags* mine = p2p_flags(sh.c, sh.c.rank);
@@ -473,10 +626,10 @@ struct VcycleFused {
   int grid = 0;
   int minb = 2;
   bool ok = false;
+  bool solve = false;  // the whole solver! runs in the kernel (level 1 of the reference included)
 };
-static const void* tail_kernel(int D, int minb) {
-  if (D == 2) return minb >= 3 ? (const void*)k_vcycle_tail<2, 3> : (const void*)k_vcycle_tail<2, 2>;
-  return minb >= 3 ? (const void*)k_vcycle_tail<3, 3> : (const void*)k_vcycle_tail<3, 2>;
+static const void* tail_kernel(int D, int) {
+  return D == 2 ? (const void*)k_vcycle_tail<2, 2> : (const void*)k_vcycle_tail<3, 2>;
 }
 
 static int ilog2(int v) { int l = 0; while ((1 << (l + 1)) <= v) ++l; return l; }
@@ -497,6 +650,7 @@ int vcycle_fused_setup(Sim& s) {
   p.nranks = s.dist.nranks;
   p.rank = s.dist.rank;
   p.p2p = s.dist.nranks > 1 ? s.dist.dev : nullptr;
+  p.misc = s.d_misc;
   // fuse from the first level below the finest whose kernels are launch-latency bound
   const char* e1 = getenv("WL_FUSED_MAX_CELLS");
   const int64_t max_cells = e1 ? atoll(e1) : (int64_t)1 << 22;
@@ -539,8 +693,14 @@ int vcycle_fused_setup(Sim& s) {
   s.allocs.push_back(tmp);
   p.partials = (double*)tmp;
   vf->ok = true;
+  // whole-solver mode: one launch and no host read per solver! when the finest level is small enough
+  // per rank for a 2-blocks-per-SM persistent grid to stream it at full bandwidth
+  const char* e5 = getenv("WL_FUSED_SOLVE_CELLS");
+  const int64_t solve_cells = e5 ? atoll(e5) : (int64_t)40 << 20;
+  vf->solve = s.levels[0].g.interior <= solve_cells;
   s.vc_fused = vf;
   s.vc_first = lf;
+  s.vc_solve = vf->solve;
   return 0;
 }
 void vcycle_fused_destroy(Sim& s) {
@@ -550,10 +710,30 @@ void vcycle_fused_destroy(Sim& s) {
 // runs levels lf … nl-1 of the V-cycle (the residual of level lf has just been restricted)
 int vcycle_fused_run(Sim& s) {
   VcycleFused* vf = (VcycleFused*)s.vc_fused;
-  void* args[] = {&vf->p};
+  SolveArgs sa{};
+  void* args[] = {&vf->p, &sa};
   wl_prof_begin(s, WL_PROF_VCTAIL);
   cudaError_t e = cudaLaunchCooperativeKernel(tail_kernel(s.D, vf->minb), dim3(vf->grid), dim3(VC_THREADS), args, 0, s.stream);
   ++s.launches;
   wl_prof_end(s, WL_PROF_VCTAIL, 0.0);
   return wl_cuda_check(s, e, "k_vcycle_tail");
+}
+
+// solver!(ml; tol, itmx) as ONE launch; the V-cycle count lands in MiscScalars::solve_n[slot]
+int vcycle_fused_solve(Sim& s, double tol, int itmx, bool ghosts_valid, int slot) {
+  VcycleFused* vf = (VcycleFused*)s.vc_fused;
+  const Lvl& l = s.levels[0];
+  bool ghosts = l.g.zlo_halo || l.g.zhi_halo;
+  for (int k = 0; k < s.D; ++k) ghosts |= l.g.per[k] != 0;
+  SolveArgs sa{};
+  sa.solve = 1;
+  sa.tol = (float)tol;
+  sa.itmx = itmx;
+  sa.ghosts_valid = ghosts_valid ? 1 : 0;
+  sa.has_ghost = ghosts ? 1 : 0;
+  sa.slot = slot;
+  void* args[] = {&vf->p, &sa};
+  cudaError_t e = cudaLaunchCooperativeKernel(tail_kernel(s.D, vf->minb), dim3(vf->grid), dim3(VC_THREADS), args, 0, s.stream);
+  ++s.launches;
+  return wl_cuda_check(s, e, "k_vcycle_tail (solver!)");
 }
