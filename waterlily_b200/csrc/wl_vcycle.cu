@@ -696,7 +696,7 @@ int vcycle_fused_setup(Sim& s) {
   // whole-solver mode: one launch and no host read per solver! when the finest level is small enough
   // per rank for a 2-blocks-per-SM persistent grid to stream it at full bandwidth
   const char* e5 = getenv("WL_FUSED_SOLVE_CELLS");
-  const int64_t solve_cells = e5 ? atoll(e5) : (int64_t)40 << 20;
+  const int64_t solve_cells = e5 ? atoll(e5) : (int64_t)96 << 20;  // measured: 67 M cells per rank gains 0.4 ms/step, 134 M loses 2.4 ms (2 blocks/SM stream the finest level at lower bandwidth)
   vf->solve = s.levels[0].g.interior <= solve_cells;
   s.vc_fused = vf;
   s.vc_first = lf;
