@@ -107,32 +107,35 @@ __global__ void __launch_bounds__(TX * TY, MINB)
       tma_load_plane(tile[s], &tmU, &full[s], cx, cy, zb + s + 1);
     }
   }
-  // global pointers of this thread's cell for f, V, u⁰ (plain coalesced accesses)
-  int64_t I = xc + yc * s1 + (int64_t)z0 * s2;
-  float w[3][5];  // w[c][k] = u_c at z-2+k of the current step (k = 1..4 used)
-  float fz_lo[3];
+  // byte offset of this thread's cell in f, V, u⁰ (plain coalesced accesses; the per-component bases are uniform)
+  int64_t off = (xc + yc * s1 + (int64_t)z0 * s2) * (int64_t)sizeof(float);
+  const int64_t doff = s2 * (int64_t)sizeof(float);
+  const char* const fb[3] = {(const char*)a.f, (const char*)(a.f + g.comp), (const char*)(a.f + 2 * g.comp)};
+  const char* const vb[3] = {(const char*)a.V, (const char*)(a.V + g.comp), (const char*)(a.V + 2 * g.comp)};
+  const char* const ub[3] = {(const char*)a.u0, (const char*)(a.u0 + g.comp), (const char*)(a.u0 + 2 * g.comp)};
+  // z-window of the own column: plane P sits in slot (P - zb) & 3, the slot number of its smem stage, so
+  // the window never has to be shifted (the loop is unrolled by 4 and every slot index is static)
+  float R[3][4];
+  float Fz[2][3];  // z-flux carried from one step to the next, double-buffered by step parity
   float cxp, cyp;  // u_x(x+1) and u_y(y+1) of the previous plane (upper-edge fluxes only)
-  // ---- pre-step at z0-1: the z-flux through the lower face of the first cell ----
+  // ---- pre-step at z0-1 (stage 1): the z-flux through the lower face of the first cell ----
 #pragma unroll
   for (int s = 0; s < 4; ++s) mbar_wait(&full[s], 0);
   {
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      w[c][0] = 0.f;
 #pragma unroll
-      for (int k = 1; k <= 4; ++k) w[c][k] = tile[k - 1][c * PP + toff];
+      for (int k = 0; k < 4; ++k) R[c][k] = tile[k][c * PP + toff];
     }
     const float* C = tile[1] + toff;  // plane z0-1
     const float* N = tile[2] + toff;  // plane z0
     cxp = C[1];
     cyp = C[PP + PX];
-    const float uz = w[2][3];
-    const float ufx = (uz + N[2 * PP - 1]) * 0.5f, ufy = (uz + N[2 * PP - PX]) * 0.5f, ufz = (uz + w[2][2]) * 0.5f;
-    fz_lo[0] = flux1(ufx, w[0][1], w[0][2], w[0][3], w[0][4], nu);
-    fz_lo[1] = flux1(ufy, w[1][1], w[1][2], w[1][3], w[1][4], nu);
-    fz_lo[2] = flux1(ufz, w[2][1], w[2][2], w[2][3], w[2][4], nu);
-#pragma unroll
-    for (int c = 0; c < 3; ++c) { w[c][1] = w[c][2]; w[c][2] = w[c][3]; w[c][3] = w[c][4]; }
+    const float uz = R[2][2];
+    const float ufx = (uz + N[2 * PP - 1]) * 0.5f, ufy = (uz + N[2 * PP - PX]) * 0.5f, ufz = (uz + R[2][1]) * 0.5f;
+    Fz[0][0] = flux1(ufx, R[0][0], R[0][1], R[0][2], R[0][3], nu);
+    Fz[0][1] = flux1(ufy, R[1][0], R[1][1], R[1][2], R[1][3], nu);
+    Fz[0][2] = flux1(ufz, R[2][0], R[2][1], R[2][2], R[2][3], nu);
   }
   __syncthreads();
   if (leader) {  // planes z0-2 and z0-1 are spent: refill their stages with z0+2 and z0+3
@@ -148,9 +151,10 @@ __global__ void __launch_bounds__(TX * TY, MINB)
   // one step of the march: cell plane z lives in ring stage S, z+1 in S+1, z+2 in S+2
   auto step = [&](auto stage_tag, int z) {
     constexpr int S = decltype(stage_tag)::value;
+    constexpr int SM1 = (S + 3) & 3, SP1 = (S + 1) & 3, SP2 = (S + 2) & 3;  // window slots of z-1, z+1, z+2
     const float* C = tile[S] + toff;
-    const float* N = tile[(S + 1) & 3] + toff;
-    const float* NN = tile[(S + 2) & 3] + toff;
+    const float* N = tile[SP1] + toff;
+    const float* NN = tile[SP2] + toff;
     float xm2[3], xm1[3], xp1[3], ym2[3], ym1[3], yp1[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -159,14 +163,14 @@ __global__ void __launch_bounds__(TX * TY, MINB)
     }
     float fx_lo[3], fy_lo[3], fx_hi[3], fy_hi[3];
     {
-      const float ux = w[0][2];
-      fx_lo[0] = flux1((ux + xm1[0]) * 0.5f, xm2[0], xm1[0], w[0][2], xp1[0], nu);
-      fx_lo[1] = flux1((ux + ym1[0]) * 0.5f, xm2[1], xm1[1], w[1][2], xp1[1], nu);
-      fx_lo[2] = flux1((ux + w[0][1]) * 0.5f, xm2[2], xm1[2], w[2][2], xp1[2], nu);
-      const float uy = w[1][2];
-      fy_lo[0] = flux1((uy + xm1[1]) * 0.5f, ym2[0], ym1[0], w[0][2], yp1[0], nu);
-      fy_lo[1] = flux1((uy + ym1[1]) * 0.5f, ym2[1], ym1[1], w[1][2], yp1[1], nu);
-      fy_lo[2] = flux1((uy + w[1][1]) * 0.5f, ym2[2], ym1[2], w[2][2], yp1[2], nu);
+      const float ux = R[0][S];
+      fx_lo[0] = flux1((ux + xm1[0]) * 0.5f, xm2[0], xm1[0], R[0][S], xp1[0], nu);
+      fx_lo[1] = flux1((ux + ym1[0]) * 0.5f, xm2[1], xm1[1], R[1][S], xp1[1], nu);
+      fx_lo[2] = flux1((ux + R[0][SM1]) * 0.5f, xm2[2], xm1[2], R[2][S], xp1[2], nu);
+      const float uy = R[1][S];
+      fy_lo[0] = flux1((uy + xm1[1]) * 0.5f, ym2[0], ym1[0], R[0][S], yp1[0], nu);
+      fy_lo[1] = flux1((uy + ym1[1]) * 0.5f, ym2[1], ym1[1], R[1][S], yp1[1], nu);
+      fy_lo[2] = flux1((uy + R[1][SM1]) * 0.5f, ym2[2], ym1[2], R[2][S], yp1[2], nu);
     }
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
@@ -177,15 +181,15 @@ __global__ void __launch_bounds__(TX * TY, MINB)
     float ex[3] = {0.f, 0.f, 0.f}, ey[3] = {0.f, 0.f, 0.f};
     if (extra_x) {
       const float ux = xp1[0];
-      ex[0] = flux1((ux + w[0][2]) * 0.5f, xm1[0], w[0][2], xp1[0], C[2], nu);
-      ex[1] = flux1((ux + C[1 - PX]) * 0.5f, xm1[1], w[1][2], xp1[1], C[PP + 2], nu);
-      ex[2] = flux1((ux + cxp) * 0.5f, xm1[2], w[2][2], xp1[2], C[2 * PP + 2], nu);
+      ex[0] = flux1((ux + R[0][S]) * 0.5f, xm1[0], R[0][S], xp1[0], C[2], nu);
+      ex[1] = flux1((ux + C[1 - PX]) * 0.5f, xm1[1], R[1][S], xp1[1], C[PP + 2], nu);
+      ex[2] = flux1((ux + cxp) * 0.5f, xm1[2], R[2][S], xp1[2], C[2 * PP + 2], nu);
     }
     if (extra_y) {
       const float uy = yp1[1];
-      ey[0] = flux1((uy + C[PP + PX - 1]) * 0.5f, ym1[0], w[0][2], yp1[0], C[2 * PX], nu);
-      ey[1] = flux1((uy + w[1][2]) * 0.5f, ym1[1], w[1][2], yp1[1], C[PP + 2 * PX], nu);
-      ey[2] = flux1((uy + cyp) * 0.5f, ym1[2], w[2][2], yp1[2], C[2 * PP + 2 * PX], nu);
+      ey[0] = flux1((uy + C[PP + PX - 1]) * 0.5f, ym1[0], R[0][S], yp1[0], C[2 * PX], nu);
+      ey[1] = flux1((uy + R[1][S]) * 0.5f, ym1[1], R[1][S], yp1[1], C[PP + 2 * PX], nu);
+      ey[2] = flux1((uy + cyp) * 0.5f, ym1[2], R[2][S], yp1[2], C[2 * PP + 2 * PX], nu);
     }
     cxp = xp1[0];
     cyp = yp1[1];
@@ -196,16 +200,15 @@ __global__ void __launch_bounds__(TX * TY, MINB)
       tma_load_plane(tile[S], &tmU, &full[S], cx, cy, z + 4 + 1);
     }
     // upper z-face = lower z-face of cell z+1: uf = (u_z[J] + u_z[J-δi])/2, J = I+δz
-    mbar_wait(&full[(S + 2) & 3], ((unsigned int)(z + 2 - zb) >> 2) & 1u);
+    mbar_wait(&full[SP2], ((unsigned int)(z + 2 - zb) >> 2) & 1u);
 #pragma unroll
-    for (int c = 0; c < 3; ++c) w[c][4] = NN[c * PP];
-    float fz_hi[3];
+    for (int c = 0; c < 3; ++c) R[c][SP2] = NN[c * PP];
     {
-      const float uz = w[2][3];
-      const float ufx = (uz + N[2 * PP - 1]) * 0.5f, ufy = (uz + N[2 * PP - PX]) * 0.5f, ufz = (uz + w[2][2]) * 0.5f;
-      fz_hi[0] = flux1(ufx, w[0][1], w[0][2], w[0][3], w[0][4], nu);
-      fz_hi[1] = flux1(ufy, w[1][1], w[1][2], w[1][3], w[1][4], nu);
-      fz_hi[2] = flux1(ufz, w[2][1], w[2][2], w[2][3], w[2][4], nu);
+      const float uz = R[2][SP1];
+      const float ufx = (uz + N[2 * PP - 1]) * 0.5f, ufy = (uz + N[2 * PP - PX]) * 0.5f, ufz = (uz + R[2][S]) * 0.5f;
+      Fz[(S + 1) & 1][0] = flux1(ufx, R[0][SM1], R[0][S], R[0][SP1], R[0][SP2], nu);
+      Fz[(S + 1) & 1][1] = flux1(ufy, R[1][SM1], R[1][S], R[1][SP1], R[1][SP2], nu);
+      Fz[(S + 1) & 1][2] = flux1(ufz, R[2][SM1], R[2][S], R[2][SP1], R[2][SP2], nu);
     }
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
@@ -221,21 +224,17 @@ __global__ void __launch_bounds__(TX * TY, MINB)
         float v = 0.f;
         v += fx_lo[i]; v -= fx_hi[i];
         v += fy_lo[i]; v -= fy_hi[i];
-        v += fz_lo[i]; v -= fz_hi[i];
+        v += Fz[S & 1][i]; v -= Fz[(S + 1) & 1][i];
         if (HASG) v = (float)((double)v + a.gacc[i]);
         if (a.fuse_bdim1) {
-          const float u0v = CORR ? a.u0[I + i * g.comp] : w[i][2];
-          v = u0v + a.dt * v - a.V[I + i * g.comp];
+          const float u0v = CORR ? *reinterpret_cast<const float*>(ub[i] + off) : R[i][S];
+          v = u0v + a.dt * v - *reinterpret_cast<const float*>(vb[i] + off);
         }
-        a.f[I + i * g.comp] = v;
+        *reinterpret_cast<float*>(const_cast<char*>(fb[i]) + off) = v;
       }
     }
     buf ^= 1;
-    I += s2;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) { w[c][1] = w[c][2]; w[c][2] = w[c][3]; w[c][3] = w[c][4]; }
-#pragma unroll
-    for (int i = 0; i < 3; ++i) fz_lo[i] = fz_hi[i];
+    off += doff;
   };
   // plane z0 sits in stage 2
   for (int z = z0;;) {
