@@ -88,7 +88,7 @@ int wl_sync(wl_sim* s);
  *      bootstraps a NCCL communicator that exchanges CUDA IPC handles: afterwards halo planes (at the
  *      reference's BC!/perBC! sites) and scalar reductions travel as direct stores into the peers'
  *      memory over NVLink from inside the kernels (WL_P2P=0 keeps NCCL send/recv + all-reduce);
- *      multigrid levels with fewer than 8 planes per rank are replicated on every rank
+ *      multigrid levels with fewer than 16 planes per rank are replicated on every rank
  *      (agglomeration).  wl_destroy of such a handle is collective too.  All other entry points then act on the rank's slab and are
  *      collective: every rank must make the same calls in the same order.  Host arrays passed to
  *      upload/download always have the GLOBAL shape; upload reads the rank's planes from it,

@@ -293,3 +293,13 @@ def test_fused_vcycle_matches_per_level_kernels(make, steps, solve_cells, monkey
     for f in ("u", "p"):
         assert rel_l2(getattr(s1.flow, f).numpy(), getattr(s0.flow, f).numpy()) < 2e-6, f
     assert s1._eng.launch_count() - l1 < s0._eng.launch_count() - l0   # the fused path really ran
+
+
+def test_mom_step_tgv_128_full_config():
+    # BASELINE.json configs[1] at its full size: 3-D TGV 128³ periodic, two steps
+    run_pair(lambda cls: tgv3d(cls, 128), 2)
+
+
+def test_mom_step_sphere_full_config():
+    # BASELINE.json configs[2] at its full size: sphere 2^8 x 2^7 x 2^7, Re=3700, exitBC
+    run_pair(lambda cls: sphere3d(cls, n=256, m=128, exitBC=True), 2)

@@ -214,7 +214,7 @@ static int plan_levels(int D, const int* N, int nranks, const std::vector<std::v
   if (N[2] % nranks != 0 || (N[2] / nranks) % 2 != 0)
     return wl_fail(WL_ERR_ARG, "wl_create_dist: N[3] must split into an even number of z-planes per rank");
   const char* e = getenv("WL_DIST_MIN_NZ");
-  const int min_nz = e ? atoi(e) : 8;  // coarser levels are agglomerated: replicated on every rank
+  const int min_nz = e ? atoi(e) : 16;  // coarser levels are agglomerated: replicated on every rank
   lvl_dist[0] = 1;
   for (size_t l = 1; l < dims.size(); ++l) {
     const int nz = dims[l][2] - 2;
