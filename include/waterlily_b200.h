@@ -152,6 +152,20 @@ int wl_pois_vcycle(wl_sim* s, int level);
  * pass tol<0 / itmx<0 for the reference defaults.  n = iterations, also appended to the log. */
 int wl_pois_solve(wl_sim* s, double tol, int itmx, int* n);
 
+/* ---- Metrics: surface-integrated loads (src/Metrics.jl:84-141) ---------------------------------
+ * nds is the BDIM-masked surface normal nds(body, loc(0,I,Float64), t) (src/Metrics.jl:84-87) at every
+ * cell of the padded grid, a Float64 array (Ng...,D) evaluated by the host — the geometry stays in
+ * Julia, as for measure!.  NULL reuses the array of the previous call (static body).  The per-cell
+ * products, the Float32 store into flow.f (the reference's df scratch, overwritten here too) and the
+ * Float64 sums run on the device.  Collective on slab handles; every rank receives the global value. */
+/* pressure_force(p,df,body,t): sum over inside(p) of p[I]*nds (src/Metrics.jl:94-100); force has D entries */
+int wl_pressure_force(wl_sim* s, const double* nds, int64_t count, double* force);
+/* viscous_force(u,ν,df,body,t): sum of -ν*∇²u(I,u)*nds (src/Metrics.jl:102-118) */
+int wl_viscous_force(wl_sim* s, const double* nds, int64_t count, double* force);
+/* pressure_moment(x₀,p,df,body,t): sum of p[I]*cross(loc(0,I)-x₀, nds) (src/Metrics.jl:129-141);
+ * D entries (in 2-D the scalar cross product is broadcast into both, as in the reference) */
+int wl_pressure_moment(wl_sim* s, const double* x0, const double* nds, int64_t count, double* moment);
+
 /* ---- the hot path --------------------------------------------------------------------- */
 /* mom_step!(a,b) (src/Flow.jl:153-169).
  * U       : BCTuple(a.U,a.Δt,N) evaluated by the host at t+Δt (D entries)

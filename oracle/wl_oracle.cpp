@@ -407,6 +407,7 @@ struct Sim {
   std::vector<Pois> levels;
   std::vector<int> n_log;
   int64_t launches = 0;
+  std::vector<double> nds;  // Metrics: nds(body, loc(0,I,Float64), t), (Ng...,D)
 };
 
 void make_level1(Sim& s) {
@@ -582,6 +583,78 @@ void per_flags(const Sim& s, const int* perdir, bool* out) {
   for (int k = 0; k < 3; ++k) out[k] = perdir ? (k < s.D && perdir[k] != 0) : s.per[k];
 }
 
+// ------------------------------------------------------------------------------------------
+// Metrics: surface-integrated loads (src/Metrics.jl:23-31,94-141).  T = promote_type(Float64,
+// Float32) = Float64: nds and loc are Float64, the per-cell product is rounded to Float32 when it
+// is stored into df (≡ flow.f), and `sum(T, df)` accumulates those Float32 values in Float64.
+// ------------------------------------------------------------------------------------------
+int set_nds(Sim& s, const double* nds, int64_t count) {
+  if (!nds) return s.nds.empty() ? fail(WL_ERR_STATE, "no nds array has been passed yet") : WL_OK;
+  if (count != s.g.cells * s.D) return fail(WL_ERR_ARG, "nds: bad size");
+  s.nds.assign(nds, nds + count);
+  return WL_OK;
+}
+void sum_df(const Sim& s, double* out) {
+  for (int i = 0; i < s.D; ++i) {
+    const float* d = s.f.data() + i * s.g.cells;
+    double acc = 0.0;
+#pragma omp parallel for reduction(+ : acc) schedule(static)
+    for (int64_t I = 0; I < s.g.cells; ++I) acc += (double)d[I];
+    out[i] = acc;
+  }
+}
+// pressure_force (Metrics.jl:96-100)
+void pressure_force(Sim& s, double* out) {
+  std::fill(s.f.begin(), s.f.end(), 0.f);
+  loop(s.g, r_inside(s.g), [&](int64_t I, int, int, int) {
+    for (int i = 0; i < s.D; ++i) s.f[I + i * s.g.cells] = (float)((double)s.p[I] * s.nds[I + i * s.g.cells]);
+  });
+  sum_df(s, out);
+}
+// ∂(i,j,I,u) (Metrics.jl:27-31): ∂uᵢ/∂xⱼ at the centre of cell I
+inline float dudx(const Sim& s, int i, int j, int64_t I) {
+  const float* u = s.u.data() + i * s.g.cells;
+  const int64_t si = s.g.s[i], sj = s.g.s[j];
+  if (i == j) return u[I + si] - u[I];
+  return (u[I + sj] + u[I + sj + si] - u[I - sj] - u[I - sj + si]) / 4;
+}
+// viscous_force (Metrics.jl:114-118): df[I,:] = -ν*∇²u(I,u)*nds, ∇²u[i,j] = ∂(i,j)+∂(j,i) (:107-108)
+void viscous_force(Sim& s, double* out) {
+  std::fill(s.f.begin(), s.f.end(), 0.f);
+  const float mnu = -s.nu;
+  loop(s.g, r_inside(s.g), [&](int64_t I, int, int, int) {
+    for (int i = 0; i < s.D; ++i) {
+      double acc = 0.0;
+      for (int j = 0; j < s.D; ++j) {
+        const float m = mnu * (dudx(s, i, j, I) + dudx(s, j, i, I));
+        const double term = (double)m * s.nds[I + j * s.g.cells];
+        acc = j == 0 ? term : acc + term;
+      }
+      s.f[I + i * s.g.cells] = (float)acc;
+    }
+  });
+  sum_df(s, out);
+}
+// pressure_moment (Metrics.jl:137-141): df[I,:] = p[I]*cross(loc(0,I)-x₀, nds)
+void pressure_moment(Sim& s, const double* x0, double* out) {
+  std::fill(s.f.begin(), s.f.end(), 0.f);
+  loop(s.g, r_inside(s.g), [&](int64_t I, int i1, int j1, int k1) {
+    const double r[3] = {(i1 - 1.5) - x0[0], (j1 - 1.5) - x0[1], s.D > 2 ? (k1 - 1.5) - x0[2] : 0.0};
+    double n[3] = {0, 0, 0};
+    for (int i = 0; i < s.D; ++i) n[i] = s.nds[I + i * s.g.cells];
+    const double p = (double)s.p[I];
+    if (s.D == 2) {
+      const float v = (float)(p * (r[0] * n[1] - r[1] * n[0]));
+      s.f[I] = v; s.f[I + s.g.cells] = v;
+    } else {
+      s.f[I] = (float)(p * (r[1] * n[2] - r[2] * n[1]));
+      s.f[I + s.g.cells] = (float)(p * (r[2] * n[0] - r[0] * n[2]));
+      s.f[I + 2 * s.g.cells] = (float)(p * (r[0] * n[1] - r[1] * n[0]));
+    }
+  });
+  sum_df(s, out);
+}
+
 }  // namespace
 
 #define S ((Sim*)s)
@@ -708,6 +781,18 @@ int wlo_pois_solve(wl_sim* s, double tol, int itmx, int* n) {
   if (tol < 0) tol = 1e-4;
   if (itmx < 0) itmx = S->pois_kind == WL_POIS_MULTILEVEL ? 32 : 1000;
   const int k = solver(*S, tol, itmx); if (n) *n = k; return WL_OK;
+}
+int wlo_pressure_force(wl_sim* s, const double* nds, int64_t count, double* force) {
+  const int rc = set_nds(*S, nds, count); if (rc) return rc;
+  pressure_force(*S, force); return WL_OK;
+}
+int wlo_viscous_force(wl_sim* s, const double* nds, int64_t count, double* force) {
+  const int rc = set_nds(*S, nds, count); if (rc) return rc;
+  viscous_force(*S, force); return WL_OK;
+}
+int wlo_pressure_moment(wl_sim* s, const double* x0, const double* nds, int64_t count, double* moment) {
+  const int rc = set_nds(*S, nds, count); if (rc) return rc;
+  pressure_moment(*S, x0, moment); return WL_OK;
 }
 int wlo_mom_step(wl_sim* s, const double* U, const double* gp, const double* gc, double* dt_next, int* n_pred, int* n_corr) {
   int a = 0, b = 0; mom_step(*S, U, gp, gc, &a, &b);

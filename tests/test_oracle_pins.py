@@ -193,3 +193,53 @@ def test_sim_time_stopping():
     assert sim_time(sim) == 0
     sim_step(sim, 0.1, remeasure=False)
     assert sim_time(sim) >= 0.1 > float(np.sum(sim.flow.dt[:-2])) * sim.U / sim.L
+
+
+def _hydro_setup(make_engine, N, D):
+    """The force-routine fixtures of maintests.jl:341-345,365-366: a body `√Σ(x-N/2)² - N÷4` on an N^D padded
+    grid and a hydrostatic pressure."""
+    from waterlily_b200.body import nds_field, loc_grid
+    Ng = (N,) * D
+    e = make_engine(tuple(n - 2 for n in Ng), pois_kind=_cabi.POIS_SINGLE)
+    body = AutoBody(lambda x, t: torch.sqrt(((x - N / 2) ** 2).sum(-1)) - N // 4, lambda x, t: x)
+    nds = nds_field(body, Ng, t=0.0)
+    y = loc_grid(0, Ng, np.float32)[..., 1]
+    return e, nds, np.asfortranarray(y), Ng
+
+
+def check_force_routines(make_engine):
+    N = 32
+    # pressure_force on p[I] = loc(0,I)[2] over inside(p): buoyancy of the disc (maintests.jl:343-346)
+    e, nds, y, Ng = _hydro_setup(make_engine, N, 2)
+    p = np.zeros(Ng, dtype=np.float32, order="F")
+    p[1:-1, 1:-1] = y[1:-1, 1:-1]
+    e.upload("p", p)
+    force = e.pressure_force(nds)
+    assert np.abs(force / (np.pi * (N / 4) ** 2) - np.array([0.0, 1.0])).sum() < 2e-3          # :346
+    df = e.download("f")
+    assert np.allclose(df.astype(np.float64).sum(axis=(0, 1)), force, rtol=0, atol=1e-9)      # df is left in flow.f
+    # viscous_force of a fluid at rest (:361-363)
+    assert (e.viscous_force() == 0).all()
+    # no moment in hydrostatic pressure about the centre (:365-368); p = x[2] on the WHOLE array (apply!)
+    e.upload("p", y)
+    assert abs(e.pressure_moment((N / 2, N / 2))[0]) < 1e-9
+    e3, nds3, y3, _ = _hydro_setup(make_engine, N, 3)
+    e3.upload("p", y3)
+    assert np.abs(e3.pressure_moment((N / 2, N / 2, N / 2), nds3)).max() < 1e-8
+    assert (e3.viscous_force() == 0).all()
+    # a uniform shear u_x = y gives ∇²u = [[0,1],[1,0]] (:357-359) → viscous force -ν ∮ (n_y, n_x) ds = 0 by symmetry,
+    # and a non-zero df field whose entries are -ν·nds swapped
+    e4, nds4, y4, Ng4 = _hydro_setup(lambda dims, **kw: make_engine(dims, nu=0.5, **kw), N, 2)
+    u = np.zeros(Ng4 + (2,), dtype=np.float32, order="F")
+    u[..., 0] = y4
+    e4.upload("u", u)
+    fv = e4.viscous_force(nds4)
+    df = e4.download("f")[1:-1, 1:-1]
+    assert np.allclose(df[..., 0], -0.5 * nds4[1:-1, 1:-1, 1], atol=1e-6) and np.allclose(df[..., 1], -0.5 * nds4[1:-1, 1:-1, 0], atol=1e-6)
+    assert np.abs(fv).max() < 1e-5
+    return force
+
+
+def test_metrics_force_routines():
+    # maintests.jl:341-368 (force routines of the Metrics.jl testset)
+    check_force_routines(oracle.engine)

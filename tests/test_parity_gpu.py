@@ -303,3 +303,27 @@ def test_mom_step_tgv_128_full_config():
 def test_mom_step_sphere_full_config():
     # BASELINE.json configs[2] at its full size: sphere 2^8 x 2^7 x 2^7, Re=3700, exitBC
     run_pair(lambda cls: sphere3d(cls, n=256, m=128, exitBC=True), 2)
+
+
+def test_metrics_reference_pins_on_cuda():
+    # maintests.jl:341-368 through the CUDA library, and the same numbers as the oracle
+    from test_oracle_pins import check_force_routines
+    fc = check_force_routines(cuda_engine)
+    fo = check_force_routines(oracle.engine)
+    assert np.allclose(fc, fo, rtol=1e-12, atol=1e-9)
+
+
+@pytest.mark.parametrize("make", [lambda cls: sphere3d(cls, exitBC=True), circle2d])
+def test_metrics_on_a_running_flow(make):
+    # pressure_force / viscous_force / pressure_moment (src/Metrics.jl:94-141) of a developing wake
+    from waterlily_b200 import pressure_force, viscous_force, total_force, pressure_moment
+    so, sc = make(OracleSimulation), make(Simulation)
+    for _ in range(5):
+        sim_step(so, remeasure=False)
+        sim_step(sc, remeasure=False)
+    x0 = tuple(float(n) / 2 for n in sc._eng.N)
+    for fn in (pressure_force, viscous_force, total_force, lambda s: pressure_moment(x0, s)):
+        a, b = fn(sc), fn(so)
+        scale = max(np.abs(b).max(), 1e-12)
+        assert np.abs(a - b).max() <= 2e-4 * scale, (a, b)
+    assert np.abs(pressure_force(so)).max() > 1e-3   # the comparison is not vacuous

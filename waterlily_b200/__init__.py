@@ -10,7 +10,7 @@ from . import _cabi
 from ._cabi import Engine, WLError
 from .body import AbstractBody, AutoBody, NoBody
 from .sim import (BCTuple, DeviceField, Flow, MultiLevelPoisson, _SimulationBase, measure, measure_flow, mom_step,
-                  sim_step, sim_time, time)
+                  pressure_force, pressure_moment, sim_step, sim_time, time, total_force, viscous_force)
 
 
 class Simulation(_SimulationBase):
@@ -23,4 +23,5 @@ class Simulation(_SimulationBase):
 
 
 __all__ = ["Simulation", "sim_step", "sim_time", "time", "measure", "mom_step", "Flow", "MultiLevelPoisson",
-           "AbstractBody", "AutoBody", "NoBody", "BCTuple", "Engine", "WLError", "DeviceField"]
+           "AbstractBody", "AutoBody", "NoBody", "BCTuple", "Engine", "WLError", "DeviceField",
+           "pressure_force", "viscous_force", "total_force", "pressure_moment"]

@@ -51,6 +51,9 @@ SIGNATURES = {
     "pois_pcg": (C.c_int, [H, C.c_int, C.c_int]),
     "pois_vcycle": (C.c_int, [H, C.c_int]),
     "pois_solve": (C.c_int, [H, C.c_double, C.c_int, c_int_p]),
+    "pressure_force": (C.c_int, [H, c_dbl_p, C.c_int64, c_dbl_p]),
+    "viscous_force": (C.c_int, [H, c_dbl_p, C.c_int64, c_dbl_p]),
+    "pressure_moment": (C.c_int, [H, c_dbl_p, c_dbl_p, C.c_int64, c_dbl_p]),
     "mom_step": (C.c_int, [H, c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p, c_int_p, c_int_p]),
     "get_dt": (C.c_int, [H, c_dbl_p]),
     "set_dt": (C.c_int, [H, C.c_double]),
@@ -245,6 +248,34 @@ class Engine:
         dt = C.c_double(0)
         self.cabi.check(self.cabi.cfl(self.h, C.byref(dt)))
         return dt.value
+
+    # -- Metrics (src/Metrics.jl:94-141); nds: Float64 (Ng...,D) from the host geometry, None = reuse
+    def _nds_args(self, nds):
+        if nds is None:
+            return None, 0
+        a = np.asfortranarray(nds, dtype=np.float64)
+        if a.shape != tuple(self.Ng) + (self.D,):
+            raise ValueError(f"nds: expected shape {tuple(self.Ng) + (self.D,)}, got {a.shape}")
+        self._nds_keep = a
+        return a.ctypes.data_as(c_dbl_p), a.size
+
+    def pressure_force(self, nds=None):
+        ptr, cnt = self._nds_args(nds)
+        out = (C.c_double * self.D)()
+        self.cabi.check(self.cabi.pressure_force(self.h, ptr, cnt, out))
+        return np.array(out[:], dtype=np.float64)
+
+    def viscous_force(self, nds=None):
+        ptr, cnt = self._nds_args(nds)
+        out = (C.c_double * self.D)()
+        self.cabi.check(self.cabi.viscous_force(self.h, ptr, cnt, out))
+        return np.array(out[:], dtype=np.float64)
+
+    def pressure_moment(self, x0, nds=None):
+        ptr, cnt = self._nds_args(nds)
+        out = (C.c_double * self.D)()
+        self.cabi.check(self.cabi.pressure_moment(self.h, _dbls(x0), ptr, cnt, out))
+        return np.array(out[:], dtype=np.float64)
 
     # -- Poisson
     def pois_update(self):

@@ -203,3 +203,24 @@ def measure_fields(body, Ng, t=0.0, eps=1.0, dtype=np.float32):
                 mu1[inside + (i - 1, j - 1)] = mc
         mu0[inside + (i - 1,)] = m0
     return mu0, mu1, V, dfield
+
+
+def kern(d):
+    """``kern(d) = 0.5+0.5cos(πd)`` — reference src/Body.jl:56."""
+    return 0.5 + 0.5 * np.cos(np.pi * d)
+
+
+def nds_field(body, Ng, t=0.0):
+    """``nds(body, loc(0,I,Float64), t)`` for every cell of the padded grid — reference
+    src/Metrics.jl:84-87: ``d,n,_ = measure(body,x,t,fastd²=1); n*kern(clamp(d,-1,1))``.
+    Returns a Float64 Fortran-ordered array ``(Ng..., D)`` (zero for ``NoBody``)."""
+    D = len(Ng)
+    out = np.zeros(tuple(Ng) + (D,), dtype=np.float64, order="F")
+    if body is None or type(body) is NoBody:
+        return out
+    x = torch.from_numpy(np.ascontiguousarray(loc_grid(0, Ng, np.float64)))
+    d, n, _ = body.measure(x, t, fastd2=1.0)
+    d = d.detach().numpy().astype(np.float64)
+    n = n.detach().numpy().astype(np.float64)
+    out[...] = n * kern(np.clip(d, -1, 1))[..., None]
+    return out

@@ -124,7 +124,8 @@ float* level_ptr(Sim& s, int level, int lf, int* ncomp) {
   return nullptr;
 }
 // dense rows (n0 floats) <-> re-pitched rows (pitch s1) for `rows` consecutive rows of one component
-__global__ void k_repitch(float* __restrict__ dev, float* __restrict__ dense, int n0, int64_t s1, int64_t rows, int to_device) {
+template <class T>
+__global__ void k_repitch(T* __restrict__ dev, T* __restrict__ dense, int n0, int64_t s1, int64_t rows, int to_device) {
   const int64_t total = rows * n0;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = t / n0;
@@ -139,7 +140,8 @@ __global__ void k_repitch(float* __restrict__ dev, float* __restrict__ dense, in
 // Download writes only the planes this rank owns (its interior planes and global ghost planes).
 // The PCIe copies are CONTIGUOUS chunks of whole planes through a device staging buffer and a
 // re-pitch kernel: a strided cudaMemcpy2D of ~2 KB rows is descriptor-bound (measured 2.4 GB/s at 514³).
-int copy_field(Sim& s, const GridD& g, float* dev, float* host, int ncomp, bool to_device, int nz_global_padded) {
+template <class T>
+int copy_field(Sim& s, const GridD& g, T* dev, T* host, int ncomp, bool to_device, int nz_global_padded) {
   const int64_t dense = (int64_t)g.n[0] * g.n[1] * nz_global_padded;
   int k0 = 0, k1 = g.n[2] - 1;
   if (!to_device) {  // planes of a neighbouring slab are not ours to report; the global ghost planes are
@@ -152,23 +154,23 @@ int copy_field(Sim& s, const GridD& g, float* dev, float* host, int ncomp, bool 
     if (cudaMalloc(&s.stage, want) != cudaSuccess) return wl_cuda_check(s, cudaGetLastError(), "cudaMalloc (staging)");
     s.stage_bytes = want;
   }
-  const int64_t cap = (int64_t)(s.stage_bytes / sizeof(float));
+  const int64_t cap = (int64_t)(s.stage_bytes / sizeof(T));
   const int pchunk = (int)std::max<int64_t>(1, std::min<int64_t>(cap / plane, k1 - k0 + 1));
   if (plane > cap) return wl_fail(WL_ERR_ARG, "field plane larger than the staging buffer");
   for (int c = 0; c < ncomp; ++c) {
     for (int k = k0; k <= k1; k += pchunk) {
       const int np = std::min(pchunk, k1 - k + 1);
-      float* d = dev + c * g.comp + (int64_t)k * g.s[2];
-      float* h = host + c * dense + (int64_t)(g.zoff + k) * plane;
-      const size_t bytes = sizeof(float) * (size_t)plane * np;
+      T* d = dev + c * g.comp + (int64_t)k * g.s[2];
+      T* h = host + c * dense + (int64_t)(g.zoff + k) * plane;
+      const size_t bytes = sizeof(T) * (size_t)plane * np;
       const int64_t rows = (int64_t)g.n[1] * np;
       const int grid = (int)std::min<int64_t>((rows * g.n[0] + 255) / 256, (int64_t)s.nsm * 16);
       cudaError_t e = cudaSuccess;
       if (to_device) {
         e = cudaMemcpyAsync(s.stage, h, bytes, cudaMemcpyHostToDevice, s.stream);
-        if (e == cudaSuccess) k_repitch<<<grid, 256, 0, s.stream>>>(d, (float*)s.stage, g.n[0], g.s[1], rows, 1);
+        if (e == cudaSuccess) k_repitch<T><<<grid, 256, 0, s.stream>>>(d, (T*)s.stage, g.n[0], g.s[1], rows, 1);
       } else {
-        k_repitch<<<grid, 256, 0, s.stream>>>(d, (float*)s.stage, g.n[0], g.s[1], rows, 0);
+        k_repitch<T><<<grid, 256, 0, s.stream>>>(d, (T*)s.stage, g.n[0], g.s[1], rows, 0);
         e = cudaMemcpyAsync(h, s.stage, bytes, cudaMemcpyDeviceToHost, s.stream);
       }
       ++s.launches;
@@ -558,6 +560,40 @@ int wl_pois_solve(wl_sim* s, double tol, int itmx, int* n) {
   if (itmx < 0) itmx = S.pois_kind == WL_POIS_MULTILEVEL ? 32 : 1000;
   int rc = pois_solve(S, tol, itmx, n);
   return rc ? rc : wl_sync(s);
+}
+// nds(body, loc(0,I,Float64), t) from the host → device (same re-pitched indexing as the fields, Float64)
+static int metrics_nds(Sim& a, const double* nds, int64_t count) {
+  if (!nds) return a.nds ? 0 : wl_fail(WL_ERR_STATE, "no nds array has been passed yet");
+  const int nzg = nz_padded_global(a, 0);
+  if (count != (int64_t)a.g.n[0] * a.g.n[1] * nzg * a.D) return wl_fail(WL_ERR_ARG, "nds: bad size");
+  if (!a.nds) {
+    void* p = nullptr;
+    const size_t bytes = sizeof(double) * (size_t)a.g.comp * a.D;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) e = cudaMemsetAsync(p, 0, bytes, a.stream);
+    if (e != cudaSuccess) return wl_cuda_check(a, e, "cudaMalloc (nds)");
+    a.allocs.push_back(p);
+    a.nds = (double*)p + a.g.lead;
+  }
+  return copy_field<double>(a, a.g, a.nds, const_cast<double*>(nds), a.D, true, nzg);
+}
+int wl_pressure_force(wl_sim* s, const double* nds, int64_t count, double* force) {
+  GUARD(s);
+  if (!force) return wl_fail(WL_ERR_ARG, "null output");
+  int rc = metrics_nds(S, nds, count);
+  return rc ? rc : metrics_run(S, 0, nullptr, force);
+}
+int wl_viscous_force(wl_sim* s, const double* nds, int64_t count, double* force) {
+  GUARD(s);
+  if (!force) return wl_fail(WL_ERR_ARG, "null output");
+  int rc = metrics_nds(S, nds, count);
+  return rc ? rc : metrics_run(S, 1, nullptr, force);
+}
+int wl_pressure_moment(wl_sim* s, const double* x0, const double* nds, int64_t count, double* moment) {
+  GUARD(s);
+  if (!moment || !x0) return wl_fail(WL_ERR_ARG, "null argument");
+  int rc = metrics_nds(S, nds, count);
+  return rc ? rc : metrics_run(S, 2, x0, moment);
 }
 int wl_mom_step(wl_sim* s, const double* U, const double* gp, const double* gc, double* dt_next, int* n_pred, int* n_corr) {
   GUARD(s);

@@ -61,6 +61,7 @@ struct Sim {
   std::vector<void*> allocs;
   char* arena = nullptr;       // all fields live in one allocation (symmetric across ranks, wl_p2p.cuh)
   size_t arena_bytes = 0, arena_used = 0;
+  double* nds = nullptr;       // Metrics: nds(body, loc(0,I), t) in Float64, D components, field indexing
   void* stage = nullptr;       // device staging buffer of the host <-> device field copies
   size_t stage_bytes = 0;
   unsigned char* body_mask = nullptr;  // 1 byte per cell, same indexing as a scalar field (see k_body_mask)
@@ -125,6 +126,10 @@ struct CDArgs;
 int convdiff_tma_setup(Sim& s);
 void convdiff_tma_destroy(Sim& s);
 bool convdiff_tma_launch(Sim& s, const CDArgs& a, int zchunk, bool corr);
+
+// ---- wl_metrics.cu ----
+// which: 0 pressure_force, 1 viscous_force, 2 pressure_moment (x0 required); out has D entries
+int metrics_run(Sim& s, int which, const double* x0, double* out);
 
 // ---- wl_vcycle.cu ----
 int vcycle_fused_setup(Sim& s);

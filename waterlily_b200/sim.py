@@ -252,3 +252,31 @@ def sim_step(sim, t_end=None, *, remeasure=True, max_steps=None, verbose=False):
         sim_step(sim, remeasure=remeasure)
         if verbose:
             print(f"tU/L={sim_time(sim):.4f}, Δt={float(sim.flow.dt[-1]):.3f}")
+
+
+# ---- Metrics: surface-integrated loads (reference src/Metrics.jl:94-141) -------------------------
+def _nds(sim, t=None):
+    from .body import nds_field
+    t = sim.flow.time() if t is None else t
+    return nds_field(sim.body, sim._eng.Ng, t=t)
+
+
+def pressure_force(sim):
+    """``pressure_force(sim)`` — reference src/Metrics.jl:94-100 (flow.f is overwritten, as there)."""
+    return sim._eng.pressure_force(_nds(sim))
+
+
+def viscous_force(sim):
+    """``viscous_force(sim)`` — reference src/Metrics.jl:112-118."""
+    return sim._eng.viscous_force(_nds(sim))
+
+
+def total_force(sim):
+    """``total_force(sim)`` — reference src/Metrics.jl:125."""
+    nds = _nds(sim)
+    return sim._eng.pressure_force(nds) + sim._eng.viscous_force(None)
+
+
+def pressure_moment(x0, sim):
+    """``pressure_moment(x₀,sim)`` — reference src/Metrics.jl:133-141."""
+    return sim._eng.pressure_moment(x0, _nds(sim))
