@@ -107,4 +107,25 @@ function measure!(a::Flow{D,T,<:B200Array}, body::WaterLily.AbstractBody; t=zero
 end
 measure!(::Flow{D,T,<:B200Array}, ::WaterLily.NoBody; t=0, ϵ=1) where {D,T} = nothing
 
+# Metrics — src/Metrics.jl:94-141.  nds(body, loc(0,I,Float64), t) is evaluated here, on the host, for every cell
+# of the padded grid (the geometry stays in Julia); products and Float64 sums run on the device; df is flow.f.
+function nds_field(p::B200Array{T,D}, body, t) where {T,D}
+    a = zeros(Float64, size(p)..., D)
+    for I in CartesianIndices(size(p)); a[I, :] .= WaterLily.nds(body, loc(0, I, Float64), t); end
+    a
+end
+function pressure_force(p::B200Array{T,D}, df::B200Array, body, t=0, _=Float64) where {T,D}
+    nds = nds_field(p, body, t); out = zeros(Cdouble, D)
+    check(ccall((:wl_pressure_force, lib), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Int64, Ptr{Cdouble}), p.h.ptr, nds, length(nds), out)); out
+end
+function viscous_force(u::B200Array{T}, ν, df::B200Array, body, t=0, _=Float64) where T
+    D = ndims(u) - 1; nds = nds_field(df, body, t)[ntuple(_ -> :, D)..., 1, :]; out = zeros(Cdouble, D)   # ν is the handle's own
+    check(ccall((:wl_viscous_force, lib), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Int64, Ptr{Cdouble}), u.h.ptr, nds, length(nds), out)); out
+end
+function pressure_moment(x₀, p::B200Array{T,D}, df::B200Array, body, t=0, _=Float64) where {T,D}
+    nds = nds_field(p, body, t); out = zeros(Cdouble, D)
+    check(ccall((:wl_pressure_moment, lib), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Int64, Ptr{Cdouble}),
+                p.h.ptr, collect(Float64, x₀), nds, length(nds), out)); out
+end
+
 end # module
