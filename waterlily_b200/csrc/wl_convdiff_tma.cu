@@ -71,6 +71,8 @@ __global__ void __launch_bounds__(TX * TY, MINB)
   __shared__ __align__(128) float tile[4][T::STAGE];
   __shared__ float Fx[2][3][TY][TX / 32];
   __shared__ float Fy[2][3][TY][TX];
+  __shared__ float FxE[2][3][TY];   // fluxes through the x-face beyond the tile's last column (see below)
+  __shared__ float UxE[2][TY];      // u_x at that face on the previous plane
   __shared__ __align__(8) unsigned long long full[4];
   const GridD& g = a.g;
   const int nx = g.n[0], ny = g.n[1], nz = g.n[2];
@@ -90,6 +92,13 @@ __global__ void __launch_bounds__(TX * TY, MINB)
   const float nu = a.nu;
   const int toff = (yc - yb) * PX + (xc - xb) + WL_OX;  // this thread's cell inside a staged plane
   const int zb = z0 - 2;                        // plane held by ring stage 0 first
+  // The x-face beyond the tile's last column belongs to a cell no thread of the block owns.  Its 3·TY
+  // fluxes per plane are evaluated together by ONE warp (lane = 3·row + component) instead of three
+  // serial evaluations in every warp that holds a last-column thread.
+  const bool edge_warp = tiy == 0 && wx == 0;
+  const int erow = min(lane / 3, TY - 1), ecmp = lane - 3 * (lane / 3);
+  const int xe = min(2 + xb + TX, nx - 2);                                         // cell whose lower x-face it is
+  const int eoff = (min(2 + yb + erow, ny - 3) - yb) * PX + (xe - xb) + WL_OX;   // that cell in a staged plane (component 0)
   // tensor coordinates of cell (i,j,k): (i + WL_OX, j, k + 1) — the map starts at the allocation.
   // Box origin: cell (xb - WL_OX, yb) ↔ tensor x = xb, a multiple of 4 floats.
   const int cx = xb, cy = yb;
@@ -117,7 +126,7 @@ __global__ void __launch_bounds__(TX * TY, MINB)
   // the window never has to be shifted (the loop is unrolled by 4 and every slot index is static)
   float R[3][4];
   float Fz[2][3];  // z-flux carried from one step to the next, double-buffered by step parity
-  float cxp, cyp;  // u_x(x+1) and u_y(y+1) of the previous plane (upper-edge fluxes only)
+  float cyp;  // u_y(y+1) of the previous plane (upper-edge fluxes only)
   // ---- pre-step at z0-1 (stage 1): the z-flux through the lower face of the first cell ----
 #pragma unroll
   for (int s = 0; s < 4; ++s) mbar_wait(&full[s], 0);
@@ -129,7 +138,7 @@ __global__ void __launch_bounds__(TX * TY, MINB)
     }
     const float* C = tile[1] + toff;  // plane z0-1
     const float* N = tile[2] + toff;  // plane z0
-    cxp = C[1];
+    if (edge_warp && lane < 3 * TY && ecmp == 2) UxE[0][erow] = tile[1][eoff];
     cyp = C[PP + PX];
     const float uz = R[2][2];
     const float ufx = (uz + N[2 * PP - 1]) * 0.5f, ufy = (uz + N[2 * PP - PX]) * 0.5f, ufz = (uz + R[2][1]) * 0.5f;
@@ -178,12 +187,17 @@ __global__ void __launch_bounds__(TX * TY, MINB)
       Fy[buf][i][tiy][tix] = fy_lo[i];
     }
     // lower faces of the cells x+1 / y+1 that no thread of the block owns
-    float ex[3] = {0.f, 0.f, 0.f}, ey[3] = {0.f, 0.f, 0.f};
-    if (extra_x) {
-      const float ux = xp1[0];
-      ex[0] = flux1((ux + R[0][S]) * 0.5f, xm1[0], R[0][S], xp1[0], C[2], nu);
-      ex[1] = flux1((ux + C[1 - PX]) * 0.5f, xm1[1], R[1][S], xp1[1], C[PP + 2], nu);
-      ex[2] = flux1((ux + cxp) * 0.5f, xm1[2], R[2][S], xp1[2], C[2 * PP + 2], nu);
+    float ey[3] = {0.f, 0.f, 0.f};
+    if (edge_warp) {
+      const float* E = tile[S] + eoff;   // u_x at the edge cell; component c of the same cell is E[c*PP]
+      const float* Ei = E + ecmp * PP;
+      const float ux = E[0];
+      const float other = ecmp == 0 ? E[-1] : (ecmp == 1 ? E[-PX] : UxE[buf][erow]);
+      const float fe = flux1((ux + other) * 0.5f, Ei[-2], Ei[-1], Ei[0], Ei[1], nu);
+      if (lane < 3 * TY) {
+        FxE[buf][ecmp][erow] = fe;
+        if (ecmp == 2) UxE[buf ^ 1][erow] = ux;
+      }
     }
     if (extra_y) {
       const float uy = yp1[1];
@@ -191,7 +205,6 @@ __global__ void __launch_bounds__(TX * TY, MINB)
       ey[1] = flux1((uy + R[1][S]) * 0.5f, ym1[1], R[1][S], yp1[1], C[PP + 2 * PX], nu);
       ey[2] = flux1((uy + cyp) * 0.5f, ym1[2], R[2][S], yp1[2], C[2 * PP + 2 * PX], nu);
     }
-    cxp = xp1[0];
     cyp = yp1[1];
     __syncthreads();
     // every read of plane z is done: its stage takes plane z+4
@@ -215,7 +228,7 @@ __global__ void __launch_bounds__(TX * TY, MINB)
       fx_hi[i] = __shfl_down_sync(0xffffffffu, fx_lo[i], 1);
       if (lane == 31 && wx < TX / 32 - 1) fx_hi[i] = Fx[buf][i][tiy][wx + 1];
       fy_hi[i] = tiy < TY - 1 ? Fy[buf][i][tiy + 1][tix] : 0.f;
-      if (extra_x) fx_hi[i] = ex[i];
+      if (extra_x) fx_hi[i] = FxE[buf][i][tiy];
       if (extra_y) fy_hi[i] = ey[i];
     }
     if (valid) {
