@@ -258,11 +258,259 @@ __global__ void __launch_bounds__(TX * TY, MINB)
   }
 }
 
+// ---- two cells per thread ------------------------------------------------------------------------
+// Same staging, but a lane owns the x-adjacent cells (x, x+1), x odd, so that the pair is 8-byte aligned in
+// the staged planes and in global memory: neighbour reads become LDS.64 (21 per two cells instead of 62),
+// the x-flux between the two cells never leaves the thread, a warp is one 64-cell row (the x-exchange is a
+// single shuffle), and the loop/addressing/control overhead is shared by two cells.  The core therefore
+// starts at x = 3; the column x = 2 goes to the boundary-shell kernel.
+__device__ __forceinline__ float2 ld2(const float* p) { return *reinterpret_cast<const float2*>(p); }
+// 8-byte asynchronous global → shared copy (LDGSTS): no destination registers while the miss is outstanding
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+
+template <int TY, int MINB, bool HASG, bool CORR>
+__global__ void __launch_bounds__(32 * TY, MINB)
+    k_conv_diff3_tma2(const __grid_constant__ CUtensorMap tmU, CDArgs a, int zchunk, int ntx, int nty) {
+  constexpr int TX = 64;
+  using T = Tile<TX, TY>;
+  constexpr int PX = T::PX, PP = T::PP, STAGE = T::STAGE;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* const tile0 = reinterpret_cast<float*>(smem_raw);                                  // [4][STAGE]
+  float* const Fy = tile0 + 4 * STAGE;                                                      // [2][3][TY][TX]
+  float* const FxE = Fy + 2 * 3 * TY * TX;                                                  // [2][3][TY]
+  float* const UxE = FxE + 2 * 3 * TY;                                                      // [2][TY]
+  unsigned long long* const full = reinterpret_cast<unsigned long long*>(UxE + 2 * TY);    // [4]
+  float* const VU = reinterpret_cast<float*>(full + 4);                                     // [2][6][TY][TX]: V, u⁰ of the own cells
+  const GridD& g = a.g;
+  const int nx = g.n[0], ny = g.n[1], nz = g.n[2];
+  const int64_t s1 = g.s[1], s2 = g.s[2];
+  const int lane = threadIdx.x, tiy = threadIdx.y;
+  const bool leader = (lane | tiy) == 0;
+  const int bt = blockIdx.x;
+  const int tx = bt % ntx, ty = (bt / ntx) % nty, tz = bt / (ntx * nty);
+  const int xb = tx * TX, yb = ty * TY;
+  const int x = 3 + xb + 2 * lane, y = 2 + yb + tiy;  // cell A; cell B = x+1
+  const int zlo = g.zlo_halo ? 1 : 2, zhi = g.zhi_halo ? nz - 2 : nz - 3;
+  const int z0 = zlo + tz * zchunk, z1 = min(z0 + zchunk, zhi + 1);
+  const int xlast = (nx - 3) - (((nx - 3) & 1) ^ 1);  // last odd cell index of the core
+  const int xc = min(x, xlast), yc = min(y, ny - 3);   // out-of-range threads shadow the last pair / row
+  const bool row_ok = y <= ny - 3;
+  const bool valid_a = row_ok && x <= xlast, valid_b = row_ok && x + 1 <= nx - 3;
+  const bool extra_y = (yc == ny - 3) || (tiy == TY - 1);
+  const float nu = a.nu;
+  const int toff = (yc - yb) * PX + (xc - xb) + WL_OX;  // cell A inside a staged plane (even: float2-aligned)
+  const int zb = z0 - 2;
+  const bool edge_warp = tiy == 0;
+  const int erow = min(lane / 3, TY - 1), ecmp = lane - 3 * (lane / 3);
+  const int xe = min(3 + xb + TX, nx - 2);  // cell whose lower x-face lies beyond the tile's last valid cell
+  const int eoff = (min(2 + yb + erow, ny - 3) - yb) * PX + (xe - xb) + WL_OX;
+  const bool a_edge = xc == xe - 1, b_edge = xc + 1 == xe - 1;
+  const int cx = xb, cy = yb;
+  if (leader) {
+#pragma unroll
+    for (int s = 0; s < 4; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  if (leader) {
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      mbar_expect_tx(&full[s], T::BYTES);
+      tma_load_plane(tile0 + s * STAGE, &tmU, &full[s], cx, cy, zb + s + 1);
+    }
+  }
+  int64_t off = (xc + yc * s1 + (int64_t)z0 * s2) * (int64_t)sizeof(float);
+  const int64_t doff = s2 * (int64_t)sizeof(float);
+  const char* const fb[3] = {(const char*)a.f, (const char*)(a.f + g.comp), (const char*)(a.f + 2 * g.comp)};
+  const char* const vb[3] = {(const char*)a.V, (const char*)(a.V + g.comp), (const char*)(a.V + 2 * g.comp)};
+  const char* const ub[3] = {(const char*)a.u0, (const char*)(a.u0 + g.comp), (const char*)(a.u0 + 2 * g.comp)};
+  float2 R[3][4];   // own two columns, plane P in slot (P - zb) & 3
+  float2 Fz[2][3];  // carried z-fluxes, double-buffered by step parity
+  float2 cyp;       // u_y(y+1) of the previous plane
+  const float* const tb = tile0 + toff;
+#pragma unroll
+  for (int s = 0; s < 4; ++s) mbar_wait(&full[s], 0);
+  {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) R[c][k] = ld2(tb + k * STAGE + c * PP);
+    }
+    const float* C = tb + 1 * STAGE;
+    const float* N = tb + 2 * STAGE;
+    if (edge_warp && lane < 3 * TY && ecmp == 2) UxE[erow] = tile0[1 * STAGE + eoff];
+    cyp = ld2(C + PP + PX);
+    const float2 uz = R[2][2];
+    const float2 nzy = ld2(N + 2 * PP - PX);
+    const float nzx = N[2 * PP - 1];
+    Fz[0][0].x = flux1((uz.x + nzx) * 0.5f, R[0][0].x, R[0][1].x, R[0][2].x, R[0][3].x, nu);
+    Fz[0][0].y = flux1((uz.y + uz.x) * 0.5f, R[0][0].y, R[0][1].y, R[0][2].y, R[0][3].y, nu);
+    Fz[0][1].x = flux1((uz.x + nzy.x) * 0.5f, R[1][0].x, R[1][1].x, R[1][2].x, R[1][3].x, nu);
+    Fz[0][1].y = flux1((uz.y + nzy.y) * 0.5f, R[1][0].y, R[1][1].y, R[1][2].y, R[1][3].y, nu);
+    Fz[0][2].x = flux1((uz.x + R[2][1].x) * 0.5f, R[2][0].x, R[2][1].x, R[2][2].x, R[2][3].x, nu);
+    Fz[0][2].y = flux1((uz.y + R[2][1].y) * 0.5f, R[2][0].y, R[2][1].y, R[2][2].y, R[2][3].y, nu);
+  }
+  __syncthreads();
+  if (leader) {
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      if (zb + s + 4 <= z1 + 1) {
+        mbar_expect_tx(&full[s], T::BYTES);
+        tma_load_plane(tile0 + s * STAGE, &tmU, &full[s], cx, cy, zb + s + 4 + 1);
+      }
+    }
+  }
+  int buf = 0;
+  // V and u⁰ are read once, at the very end of a step, with few warps per SM to hide the miss: each thread
+  // copies the values of its own two cells asynchronously into shared memory one plane ahead
+  // (cp.async, no registers held) and picks them up after cp.async.wait_group
+  float* const vu = VU + tiy * TX + 2 * lane;
+  auto fetch_plane = [&](int st, int64_t o) {
+    if (a.fuse_bdim1) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        cp_async8(vu + (st * 6 + i) * TY * TX, vb[i] + o);
+        if (CORR) cp_async8(vu + (st * 6 + 3 + i) * TY * TX, ub[i] + o);
+      }
+    }
+    cp_async_commit();
+  };
+  fetch_plane(0, off);
+  auto step = [&](auto stage_tag, int z) {
+    constexpr int S = decltype(stage_tag)::value;
+    constexpr int SM1 = (S + 3) & 3, SP1 = (S + 1) & 3, SP2 = (S + 2) & 3;
+    const float* C = tb + S * STAGE;
+    const float* N = tb + SP1 * STAGE;
+    const float* NN = tb + SP2 * STAGE;
+    fetch_plane(buf ^ 1, off + doff);
+    float2 fx[3], fxh[3], fy[3], fyh[3];
+    float2 ym1[3], yp1[3];
+    float2 xm[3];
+    {
+      float2 xq[3], ym2[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        xm[c] = ld2(C + c * PP - 2);
+        xq[c] = ld2(C + c * PP + 2);
+        ym2[c] = ld2(C + c * PP - 2 * PX);
+        ym1[c] = ld2(C + c * PP - PX);
+        yp1[c] = ld2(C + c * PP + PX);
+      }
+      const float2 ux = R[0][S], uy = R[1][S];
+      // lower x-faces of A and B
+      fx[0].x = flux1((ux.x + xm[0].y) * 0.5f, xm[0].x, xm[0].y, R[0][S].x, R[0][S].y, nu);
+      fx[0].y = flux1((ux.y + ux.x) * 0.5f, xm[0].y, R[0][S].x, R[0][S].y, xq[0].x, nu);
+      fx[1].x = flux1((ux.x + ym1[0].x) * 0.5f, xm[1].x, xm[1].y, R[1][S].x, R[1][S].y, nu);
+      fx[1].y = flux1((ux.y + ym1[0].y) * 0.5f, xm[1].y, R[1][S].x, R[1][S].y, xq[1].x, nu);
+      fx[2].x = flux1((ux.x + R[0][SM1].x) * 0.5f, xm[2].x, xm[2].y, R[2][S].x, R[2][S].y, nu);
+      fx[2].y = flux1((ux.y + R[0][SM1].y) * 0.5f, xm[2].y, R[2][S].x, R[2][S].y, xq[2].x, nu);
+      // lower y-faces
+      fy[0].x = flux1((uy.x + xm[1].y) * 0.5f, ym2[0].x, ym1[0].x, R[0][S].x, yp1[0].x, nu);
+      fy[0].y = flux1((uy.y + uy.x) * 0.5f, ym2[0].y, ym1[0].y, R[0][S].y, yp1[0].y, nu);
+      fy[1].x = flux1((uy.x + ym1[1].x) * 0.5f, ym2[1].x, ym1[1].x, R[1][S].x, yp1[1].x, nu);
+      fy[1].y = flux1((uy.y + ym1[1].y) * 0.5f, ym2[1].y, ym1[1].y, R[1][S].y, yp1[1].y, nu);
+      fy[2].x = flux1((uy.x + R[1][SM1].x) * 0.5f, ym2[2].x, ym1[2].x, R[2][S].x, yp1[2].x, nu);
+      fy[2].y = flux1((uy.y + R[1][SM1].y) * 0.5f, ym2[2].y, ym1[2].y, R[2][S].y, yp1[2].y, nu);
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) *reinterpret_cast<float2*>(Fy + ((buf * 3 + i) * TY + tiy) * TX + 2 * lane) = fy[i];
+    if (edge_warp) {  // the x-face beyond the tile: 3·TY fluxes in one evaluation
+      const float* E = tile0 + S * STAGE + eoff;
+      const float* Ei = E + ecmp * PP;
+      const float uxe = E[0];
+      const float other = ecmp == 0 ? E[-1] : (ecmp == 1 ? E[-PX] : UxE[buf * TY + erow]);
+      const float fe = flux1((uxe + other) * 0.5f, Ei[-2], Ei[-1], Ei[0], Ei[1], nu);
+      if (lane < 3 * TY) {
+        FxE[(buf * 3 + ecmp) * TY + erow] = fe;
+        if (ecmp == 2) UxE[(buf ^ 1) * TY + erow] = uxe;
+      }
+    }
+    if (extra_y) {  // lower y-faces of the cells y+1 that no thread of the block owns
+      const float uyxm = C[PP + PX - 1];  // u_y(x-1, y+1)
+      const float2 uyp = yp1[1];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float2 yp2 = ld2(C + c * PP + 2 * PX);
+        float2 uf;
+        if (c == 0) { uf.x = (uyp.x + uyxm) * 0.5f; uf.y = (uyp.y + uyp.x) * 0.5f; }
+        else if (c == 1) { uf.x = (uyp.x + R[1][S].x) * 0.5f; uf.y = (uyp.y + R[1][S].y) * 0.5f; }
+        else { uf.x = (uyp.x + cyp.x) * 0.5f; uf.y = (uyp.y + cyp.y) * 0.5f; }
+        fyh[c].x = flux1(uf.x, ym1[c].x, R[c][S].x, yp1[c].x, yp2.x, nu);
+        fyh[c].y = flux1(uf.y, ym1[c].y, R[c][S].y, yp1[c].y, yp2.y, nu);
+      }
+    }
+    cyp = yp1[1];
+    __syncthreads();
+    if (leader && z + 4 <= z1 + 1) {
+      mbar_expect_tx(&full[S], T::BYTES);
+      tma_load_plane(tile0 + S * STAGE, &tmU, &full[S], cx, cy, z + 4 + 1);
+    }
+    mbar_wait(&full[SP2], ((unsigned int)(z + 2 - zb) >> 2) & 1u);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) R[c][SP2] = ld2(NN + c * PP);
+    {
+      const float2 uz = R[2][SP1];
+      const float2 nzy = ld2(N + 2 * PP - PX);
+      const float nzx = N[2 * PP - 1];
+      constexpr int Q = (S + 1) & 1;
+      Fz[Q][0].x = flux1((uz.x + nzx) * 0.5f, R[0][SM1].x, R[0][S].x, R[0][SP1].x, R[0][SP2].x, nu);
+      Fz[Q][0].y = flux1((uz.y + uz.x) * 0.5f, R[0][SM1].y, R[0][S].y, R[0][SP1].y, R[0][SP2].y, nu);
+      Fz[Q][1].x = flux1((uz.x + nzy.x) * 0.5f, R[1][SM1].x, R[1][S].x, R[1][SP1].x, R[1][SP2].x, nu);
+      Fz[Q][1].y = flux1((uz.y + nzy.y) * 0.5f, R[1][SM1].y, R[1][S].y, R[1][SP1].y, R[1][SP2].y, nu);
+      Fz[Q][2].x = flux1((uz.x + R[2][S].x) * 0.5f, R[2][SM1].x, R[2][S].x, R[2][SP1].x, R[2][SP2].x, nu);
+      Fz[Q][2].y = flux1((uz.y + R[2][S].y) * 0.5f, R[2][SM1].y, R[2][S].y, R[2][SP1].y, R[2][SP2].y, nu);
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      fxh[i].x = fx[i].y;                                          // B's lower face is A's upper face
+      fxh[i].y = __shfl_down_sync(0xffffffffu, fx[i].x, 1);      // the next lane's A
+      const float fe = FxE[(buf * 3 + i) * TY + tiy];
+      if (a_edge) fxh[i].x = fe;
+      if (b_edge) fxh[i].y = fe;
+      if (!extra_y) fyh[i] = *reinterpret_cast<const float2*>(Fy + ((buf * 3 + i) * TY + tiy + 1) * TX + 2 * lane);
+    }
+    cp_async_wait1();  // this plane's V/u⁰ (the group committed one step ago) have landed
+    if (valid_a) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        float2 v;
+        v.x = 0.f; v.x += fx[i].x; v.x -= fxh[i].x; v.x += fy[i].x; v.x -= fyh[i].x; v.x += Fz[S & 1][i].x; v.x -= Fz[(S + 1) & 1][i].x;
+        v.y = 0.f; v.y += fx[i].y; v.y -= fxh[i].y; v.y += fy[i].y; v.y -= fyh[i].y; v.y += Fz[S & 1][i].y; v.y -= Fz[(S + 1) & 1][i].y;
+        if (HASG) { v.x = (float)((double)v.x + a.gacc[i]); v.y = (float)((double)v.y + a.gacc[i]); }
+        if (a.fuse_bdim1) {
+          const float2 u0v = CORR ? ld2(vu + (buf * 6 + 3 + i) * TY * TX) : R[i][S];
+          const float2 Vv = ld2(vu + (buf * 6 + i) * TY * TX);
+          v.x = u0v.x + a.dt * v.x - Vv.x;
+          v.y = u0v.y + a.dt * v.y - Vv.y;
+        }
+        float* dst = reinterpret_cast<float*>(const_cast<char*>(fb[i]) + off);
+        if (valid_b) *reinterpret_cast<float2*>(dst) = v;
+        else dst[0] = v.x;
+      }
+    }
+    buf ^= 1;
+    off += doff;
+  };
+  for (int z = z0;;) {
+    step(std::integral_constant<int, 2>{}, z); if (++z >= z1) break;
+    step(std::integral_constant<int, 3>{}, z); if (++z >= z1) break;
+    step(std::integral_constant<int, 0>{}, z); if (++z >= z1) break;
+    step(std::integral_constant<int, 1>{}, z); if (++z >= z1) break;
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 constexpr int kTX = 64, kTY = 4, kMINB = 4;
+constexpr int kTY2 = 8, kMINB2 = 2;  // two-cells-per-thread variant: 32 x 8 threads, 64 x 8 cells
+constexpr size_t kSmem2 = sizeof(float) * (4 * Tile<64, kTY2>::STAGE + 2 * 3 * kTY2 * 64 + 2 * 3 * kTY2 + 2 * kTY2 + 2 * 6 * kTY2 * 64) + 4 * sizeof(unsigned long long);
 
 }  // namespace
 
@@ -270,6 +518,7 @@ struct ConvDiffTma {
   CUtensorMap map_u, map_u0;  // the two velocity buffers (mom_step swaps the pointers, not the data)
   const float* ptr_u;
   const float* ptr_u0;
+  int cells_per_thread;       // 1: k_conv_diff3_tma (core from x = 2), 2: k_conv_diff3_tma2 (core from x = 3)
 };
 
 // Builds the tensor maps of the two velocity buffers.  Leaves s.cd_tma null (the first marching
@@ -289,11 +538,15 @@ int convdiff_tma_setup(Sim& s) {
   EncodeTiledFn encode = (EncodeTiledFn)fn;
   ConvDiffTma* t = new ConvDiffTma;
   using T = Tile<kTX, kTY>;
+  const char* e2 = getenv("WL_CD_CELLS");
+  t->cells_per_thread = e2 ? atoi(e2) : 2;
+  if (t->cells_per_thread != 1) t->cells_per_thread = 2;
+  const cuuint32_t box_y = t->cells_per_thread == 2 ? (cuuint32_t)Tile<64, kTY2>::PY : (cuuint32_t)T::PY;
   auto make = [&](CUtensorMap* m, const float* field) -> bool {
     void* base = (void*)(field - g.lead);  // start of the allocation: 256-byte aligned
     const cuuint64_t dims[4] = {(cuuint64_t)g.s[1], (cuuint64_t)g.n[1], (cuuint64_t)g.n[2] + 2, 3};
     const cuuint64_t strides[3] = {(cuuint64_t)g.s[1] * 4, (cuuint64_t)g.s[2] * 4, (cuuint64_t)g.comp * 4};
-    const cuuint32_t box[4] = {(cuuint32_t)T::PX, (cuuint32_t)T::PY, 1, 3};
+    const cuuint32_t box[4] = {(cuuint32_t)T::PX, box_y, 1, 3};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     return encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -303,7 +556,16 @@ int convdiff_tma_setup(Sim& s) {
     delete t;
     return 0;
   }
-  if (getenv("WL_VERBOSE")) fprintf(stderr, "[waterlily_b200] conv_diff!: TMA-staged kernel\n");
+  if (t->cells_per_thread == 2) {
+    cudaError_t e = cudaSuccess;
+    auto optin = [&](const void* k) { if (e == cudaSuccess) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem2); };
+    optin((const void*)k_conv_diff3_tma2<kTY2, kMINB2, false, false>);
+    optin((const void*)k_conv_diff3_tma2<kTY2, kMINB2, false, true>);
+    optin((const void*)k_conv_diff3_tma2<kTY2, kMINB2, true, false>);
+    optin((const void*)k_conv_diff3_tma2<kTY2, kMINB2, true, true>);
+    if (e != cudaSuccess) { cudaGetLastError(); delete t; return 0; }
+  }
+  if (getenv("WL_VERBOSE")) fprintf(stderr, "[waterlily_b200] conv_diff!: TMA-staged kernel, %d cell(s) per thread\n", t->cells_per_thread);
   t->ptr_u = s.u;
   t->ptr_u0 = s.u0;
   s.cd_tma = t;
@@ -314,6 +576,13 @@ void convdiff_tma_destroy(Sim& s) {
   s.cd_tma = nullptr;
 }
 
+template <bool HASG, bool CORR>
+static void launch_tma2(Sim& s, const CUtensorMap& m, const CDArgs& a, int zchunk) {
+  const GridD& g = s.g;
+  const int nzc = g.n[2] - 4 + (g.zlo_halo ? 1 : 0) + (g.zhi_halo ? 1 : 0);
+  const int ntx = (g.n[0] - 5 + 63) / 64, nty = (g.n[1] - 4 + kTY2 - 1) / kTY2, ntz = (nzc + zchunk - 1) / zchunk;
+  k_conv_diff3_tma2<kTY2, kMINB2, HASG, CORR><<<ntx * nty * ntz, dim3(32, kTY2, 1), kSmem2, s.stream>>>(m, a, zchunk, ntx, nty);
+}
 template <bool HASG, bool CORR>
 static void launch_tma(Sim& s, const CUtensorMap& m, const CDArgs& a, int zchunk) {
   const GridD& g = s.g;
@@ -327,7 +596,15 @@ bool convdiff_tma_launch(Sim& s, const CDArgs& a, int zchunk, bool corr) {
   if (!t) return false;
   const CUtensorMap* m = a.u == t->ptr_u ? &t->map_u : (a.u == t->ptr_u0 ? &t->map_u0 : nullptr);
   if (!m) return false;
-  if (a.has_g) {
+  if (t->cells_per_thread == 2) {
+    if (a.has_g) {
+      if (corr) launch_tma2<true, true>(s, *m, a, zchunk);
+      else launch_tma2<true, false>(s, *m, a, zchunk);
+    } else {
+      if (corr) launch_tma2<false, true>(s, *m, a, zchunk);
+      else launch_tma2<false, false>(s, *m, a, zchunk);
+    }
+  } else if (a.has_g) {
     if (corr) launch_tma<true, true>(s, *m, a, zchunk);
     else launch_tma<true, false>(s, *m, a, zchunk);
   } else {
@@ -336,4 +613,9 @@ bool convdiff_tma_launch(Sim& s, const CDArgs& a, int zchunk, bool corr) {
   }
   ++s.launches;
   return true;
+}
+// first x index of the core the TMA kernel covers (the boundary-shell kernel takes everything below it)
+int convdiff_tma_core_x0(const Sim& s) {
+  const ConvDiffTma* t = (const ConvDiffTma*)s.cd_tma;
+  return (t && t->cells_per_thread == 2) ? 3 : 2;
 }

@@ -126,6 +126,7 @@ struct CDArgs;
 int convdiff_tma_setup(Sim& s);
 void convdiff_tma_destroy(Sim& s);
 bool convdiff_tma_launch(Sim& s, const CDArgs& a, int zchunk, bool corr);
+int convdiff_tma_core_x0(const Sim& s);
 
 // ---- wl_metrics.cu ----
 // which: 0 pressure_force, 1 viscous_force, 2 pressure_moment (x0 required); out has D entries

@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(256) k_conv_diff(CDArgs a) {
 // an x extent: full z-planes outside the core's z-range, then the 4 outer y-rows of every core plane,
 // then the 4 outer x-cells of every remaining row.
 template <int D>
-__global__ void __launch_bounds__(256) k_conv_diff_shell(CDArgs a, unsigned int nZ, unsigned int nY, unsigned int nX) {
+__global__ void __launch_bounds__(256) k_conv_diff_shell(CDArgs a, unsigned int nZ, unsigned int nY, unsigned int nX, int xlow) {
   const GridD& g = a.g;
   const int n0 = g.n[0], n1 = g.n[1], n2 = g.n[2];
   const int zc0 = g.zlo_halo ? 1 : 2, zc1 = g.zhi_halo ? n2 - 2 : n2 - 3;  // core z-range
@@ -147,8 +147,9 @@ __global__ void __launch_bounds__(256) k_conv_diff_shell(CDArgs a, unsigned int 
       c[1] = jj < 2 ? (int)jj : n1 - 4 + (int)jj;
       c[2] = zc0 + (int)kk;
     } else {
-      const unsigned int t = idx - nZ - nY, ii = t & 3u, row = t >> 2, kk = row / (unsigned int)(n1 - 4);
-      c[0] = ii < 2 ? (int)ii : n0 - 4 + (int)ii;
+      // the xlow low columns (the core starts at x = xlow) and the 2 high ones of every remaining row
+      const unsigned int t = idx - nZ - nY, nxs = (unsigned int)xlow + 2u, row = t / nxs, ii = t - row * nxs, kk = row / (unsigned int)(n1 - 4);
+      c[0] = (int)ii < xlow ? (int)ii : n0 - 2 + ((int)ii - xlow);
       c[1] = 2 + (int)(row - kk * (n1 - 4));
       c[2] = zc0 + (int)kk;
     }
@@ -545,16 +546,18 @@ int mom_conv_diff(Sim& s, const float* src, bool fuse_bdim1, const double* gacc)
     if (!zchunk) { const char* e = getenv("WL_CD_ZCHUNK"); zchunk = e ? atoi(e) : 32; }
     static int zchunk_tma = 0;
     if (!zchunk_tma) { const char* e = getenv("WL_CD_TMA_ZCHUNK"); zchunk_tma = e ? atoi(e) : 64; }
-    if (!convdiff_tma_launch(s, a, zchunk_tma, corr)) launch_march(s, a, variant, zchunk, corr);
+    const bool used_tma = convdiff_tma_launch(s, a, zchunk_tma, corr);
+    if (!used_tma) launch_march(s, a, variant, zchunk, corr);
     // the profiled "dominant kernel" is the core march alone: algorithmic words/cell = read u (D) [+ u⁰, V (2D)], write f (D)
     wl_prof_end(s, WL_PROF_CONVDIFF, 4.0 * (double)s.g.interior * (fuse_bdim1 ? (src == s.u0 ? 3 : 4) * s.D : 2 * s.D));
     {
       const int zc0 = g.zlo_halo ? 1 : 2, zc1 = g.zhi_halo ? g.n[2] - 2 : g.n[2] - 3, nzc = zc1 - zc0 + 1;
       const unsigned int nZ = (unsigned int)g.n[0] * g.n[1] * (unsigned int)(g.n[2] - nzc);
       const unsigned int nY = (unsigned int)g.n[0] * 4u * (unsigned int)nzc;
-      const unsigned int nX = 4u * (unsigned int)(g.n[1] - 4) * (unsigned int)nzc;
+      const int xlow = used_tma ? convdiff_tma_core_x0(s) : 2;
+      const unsigned int nX = (unsigned int)(xlow + 2) * (unsigned int)(g.n[1] - 4) * (unsigned int)nzc;
       const int64_t cnt = (int64_t)nZ + nY + nX;
-      k_conv_diff_shell<3><<<(int)std::min<int64_t>((cnt + 255) / 256, s.nsm * 16), 256, 0, s.stream>>>(a, nZ, nY, nX);
+      k_conv_diff_shell<3><<<(int)std::min<int64_t>((cnt + 255) / 256, s.nsm * 16), 256, 0, s.stream>>>(a, nZ, nY, nX, xlow);
       ++s.launches;
     }
   } else {
