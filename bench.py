@@ -223,13 +223,16 @@ def run_ours(args):
     dom = max(kern, key=lambda k: kern[k]["ms"])
     d = kern[dom]
     achieved = d["bytes"] / (d["ms"] * 1e-3) / 1e9
-    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu capture of this command at 512^3
-    # (profiles/r01_launches_tgv512_1gpu_v2.txt): predictor 5.01 GB, corrector 6.65 GB; algorithmic 4.83 / 6.44 GB
-    traffic = 0.5 * (5.013e9 + 6.651e9) if (dom == "conv_diff+bdim1" and N == 512 and world == 1) else None
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch from ncu captures at 512^3 on one GPU
+    # (profiles/r01_launches_tgv512_1gpu_v3.txt, profiles/r01_ncu_full_increment_512.txt)
+    ncu_traffic = {"increment": 5.61e9, "conv_diff+bdim1": 0.5 * (5.05e9 + 6.73e9), "pcg_update": 3.78e9, "pcg_mult": 4.00e9,
+                   "residual": 5.65e9}
+    traffic = ncu_traffic.get(dom) if (N == 512 and world == 1) else None
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src,
-                "note": "conv_diff! (k_conv_diff3_tma) is bound by instruction issue, not HBM: 459 warp instructions per 32 cells at 84 % issue-slot "
-                        "utilisation (profiles/r01_ncu_full_conv_diff3_tma_384.txt); the HBM-bound solver kernels run at 74-92 % of the measured peak (kernels{})", "launches": d["launches"], "avg_ms": d["ms"] / d["launches"],
+                "note": "dominant kernel = the profiling class with the largest device time in the timed region; conv_diff! (k_conv_diff3_tma2) is "
+                        "bound by instruction issue, not HBM (300 warp instructions per 32 cells at 75 % issue-slot utilisation, "
+                        "profiles/r01_ncu_full_conv_diff3_tma2_384.txt); the solver kernels are HBM-bound (kernels{})", "launches": d["launches"], "avg_ms": d["ms"] / d["launches"],
                 "share_of_step": d["ms"] / prof["mom_step"]["ms"] if prof["mom_step"]["ms"] else None,
                 "kernels": {k: {"GB/s": (v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] else None, "ms_total": v["ms"], "launches": v["launches"]} for k, v in prof.items()}}
 
