@@ -65,6 +65,7 @@ enum FinStage {
   FIN_R2,               // t0 = Σr²            → r2
   FIN_R2_IF_SUB,        // same, only if residual! subtracted the mean
   FIN_PCG_INIT,         // t0 = r⋅z            → rho, active
+  FIN_INC_INIT,         // t0 = r⋅z, t1 = Σr²  → rho, active, r2   (increment! fused with the head of pcg!)
   FIN_GHOST_DOT,        // t0 = Σ_shell z·ϵ    → ghost_dot
   FIN_PCG_MULT,         // t0 = z⋅ϵ (interior) → alpha, active
   FIN_PCG_UPDATE,       // t0 = r⋅z, t1 = Σr²  → r2, beta, rho, active
@@ -117,6 +118,12 @@ __device__ __forceinline__ void finalize(int stage, const FinArgs& fa, double t0
     case FIN_R2_IF_SUB: sc->r2 = (float)t0; break;
     case FIN_PCG_INIT: {  // Poisson.jl:126-127
       const float rho = (float)t0;
+      sc->rho = rho;
+      sc->active = fabsf(rho) < 10 * WL_EPS32 ? 0 : 1;
+    } break;
+    case FIN_INC_INIT: {
+      const float rho = (float)t0;
+      sc->r2 = (float)t1;
       sc->rho = rho;
       sc->active = fabsf(rho) < 10 * WL_EPS32 ? 0 : 1;
     } break;

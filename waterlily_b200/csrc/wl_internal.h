@@ -85,6 +85,8 @@ struct Sim {
   int Nz_global = 0;           // interior z-planes of the whole domain (3-D)
   int per_z_global = 0;
   void* cd_tma = nullptr;      // TMA tensor maps of u/u⁰ for the staged conv_diff! kernel (wl_convdiff_tma.cu), or null
+  bool fuse_prolong = false;   // inside solver!: Vcycle! ends with the fused prolongate!/increment!/pcg!-init pass
+  int pcg_init_done = -1;      // level whose pcg! head (ϵ = r·iD, ρ) that pass already produced
   bool eps_is_jacobi = false;  // levels[1].ϵ already holds r·iD of the current residual (written by k_residual)
   void* vc_fused = nullptr;    // fused coarse V-cycle (wl_vcycle.cu), or null
   int vc_first = -1;           // first level the fused kernel covers (-1: off)

@@ -9,6 +9,7 @@
 //  * kernels of an exited pcg! are predicated off by `sc->active`;
 //  * L₂(p)=r⋅r is refreshed by whichever kernel last wrote r — no separate dot pass.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "wl_internal.h"
@@ -208,6 +209,15 @@ __global__ void __launch_bounds__(256) k_prolongate(Lvl f, Lvl c, int fzadd) {
     for (int q = 0; q < V; ++q) e.v[q] = c.x[J + ((i0 + q + 1) >> 1)];
     stp<V>(f.eps + I, e);
   });
+}
+
+// prolongate! + increment! + ϵ = r·iD, ρ = r⋅ϵ of the pcg! that follows (see wl_vec.cuh)
+template <int D, int V>
+__global__ void __launch_bounds__(256) k_prolong_increment_init(Lvl f, Lvl c, ProMap m, ReduceWS ws, FinArgs fa) {
+  double acc[2] = {0.0, 0.0};
+  for_rows<V>(f.g, [&](int i, int j, int k, int64_t I) { prolong_increment_init<D, V>(f, c, m, i, j, k, I, acc[0], acc[1]); });
+  double tot[2];
+  if (grid_reduce<2>(acc, ws, tot)) finish_reduction(FIN_INC_INIT, fa, tot[0], tot[1]);
 }
 
 // ---- pcg! (Poisson.jl:123-144) -----------------------------------------------------------
@@ -451,10 +461,15 @@ int pois_pcg(Sim& s, int level, int it) {
   bool ghosts = l.g.zlo_halo || l.g.zhi_halo;  // ϵ ghosts need refreshing: periodic copies or slab halos
   for (int k = 0; k < s.D; ++k) ghosts |= l.g.per[k] != 0;
   fa.has_ghost = (fine && ghosts) ? 1 : 0;
-  if (fine) wl_prof_begin(s, WL_PROF_PCG_INIT);
-  RLAUNCH(s, k_pcg_init, l.g, l, s.ws, fa);
-  if ((rc = post_reduce(s, FIN_PCG_INIT, fa))) return rc;
-  if (fine) wl_prof_end(s, WL_PROF_PCG_INIT, cellsB(l, 3));
+  if (s.pcg_init_done == level) {
+    rc = 0;  // ϵ = r·iD and ρ were produced by the fused prolongate!/increment! pass of the V-cycle
+  } else {
+    if (fine) wl_prof_begin(s, WL_PROF_PCG_INIT);
+    RLAUNCH(s, k_pcg_init, l.g, l, s.ws, fa);
+    if ((rc = post_reduce(s, FIN_PCG_INIT, fa))) return rc;
+    if (fine) wl_prof_end(s, WL_PROF_PCG_INIT, cellsB(l, 3));
+  }
+  s.pcg_init_done = -1;
   // Sweeps are enqueued speculatively: as many as the previous pcg! on this level needed, then ONE
   // host read of {active, sweep counter} decides whether more are launched.  Exited sweeps would be
   // predicated off on the device anyway; this only avoids enqueueing (and, across ranks,
@@ -518,6 +533,25 @@ int pois_vcycle(Sim& s, int level) {
     if (level + 2 < (int)s.levels.size() && (rc = pois_vcycle(s, level + 1))) return rc;
     if ((rc = pois_pcg(s, level + 1, 6))) return rc;
   }
+  if (s.fuse_prolong) {
+    // inside solver!: prolongate! + increment! + the head of the pcg! that always follows, in one pass
+    const bool fdist = s.dist.nranks > 1 && s.lvl_dist[level];
+    if (fdist && !gather && (rc = dist_halo(s, coarse.g, coarse.x, 1, 1))) return rc;  // ϵ across slab faces = the neighbour's coarse x
+    ProMap m{};
+    for (int d = 0; d < 3; ++d) { m.per[d] = fine.g.per[d]; m.n[d] = fine.g.n[d]; }
+    m.zmode = gather ? 1 : 0;
+    m.zoff = fine.g.zoff;
+    m.nzg = s.Nz_global >> level;
+    m.perz_global = s.per_z_global;
+    const FinArgs fa = fin_level(s, level);  // ρ steers the pcg! of this level: all-reduced on every distributed level
+    const bool top = level == 0;
+    if (top) wl_prof_begin(s, WL_PROF_INCREMENT);
+    RLAUNCH(s, k_prolong_increment_init, fine.g, fine, coarse, m, s.ws, fa);
+    if ((rc = post_reduce(s, FIN_INC_INIT, fa))) return rc;
+    if (top) wl_prof_end(s, WL_PROF_INCREMENT, 4.0 * 10.125 * (double)fine.g.interior);
+    s.pcg_init_done = level;
+    return wl_cuda_check(s, cudaGetLastError(), "k_prolong_increment_init");
+  }
   RLAUNCH(s, k_prolongate, fine.g, fine, coarse, gather ? fine.g.zoff : 0);
   return pois_increment(s, fine);
 }
@@ -541,15 +575,20 @@ int pois_solve(Sim& s, double tol, int itmx, int* n_out, bool ghosts_valid, int 
   int rc = pois_residual(s, p, false, ghosts_valid, s.pois_kind == WL_POIS_MULTILEVEL && itmx > 0);
   if (rc) return rc;
   int n = 0;
+  static int fuse_env = -1;
+  if (fuse_env < 0) { const char* e = getenv("WL_FUSE_PROLONG"); fuse_env = e ? atoi(e) : 1; }
+  s.fuse_prolong = fuse_env != 0;
+  s.pcg_init_done = -1;
   while (n < itmx) {
-    if (s.pois_kind == WL_POIS_MULTILEVEL && (rc = pois_vcycle(s, 0))) return rc;
-    if ((rc = pois_pcg(s, 0, 6))) return rc;
+    if (s.pois_kind == WL_POIS_MULTILEVEL && (rc = pois_vcycle(s, 0))) { s.fuse_prolong = false; return rc; }
+    if ((rc = pois_pcg(s, 0, 6))) { s.fuse_prolong = false; return rc; }
     ++n;
     // r₂ = L₂(p): one host read per solver iteration (the reference needs ~100); every rank reads
     // the same all-reduced value and therefore leaves the loop together
     if ((rc = wl_read_scalars(s, &p.sc->r2, sizeof(float)))) return rc;
     if ((double)s.h_pinned[0] < tol) break;
   }
+  s.fuse_prolong = false;
   rc = bc_per(s, p.g, p.x, p.g.per);
   wl_prof_end(s, WL_PROF_SOLVER, 0.0);
   s.n_log.push_back(n);

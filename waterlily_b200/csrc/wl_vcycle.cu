@@ -38,6 +38,7 @@ struct FusedParams {
   double* partials;           // [gridDim.x][2]
   const P2PDev* p2p;          // null on one rank
   MiscScalars* misc;          // solve mode: V-cycle count out
+  int nzg0, perz_global;      // interior z-planes of the whole finest level; the global domain is periodic in z
 };
 // per-launch arguments of the whole-solver mode (solver!(ml), MultiLevelPoisson.jl:87-99)
 struct SolveArgs {
@@ -299,11 +300,14 @@ __device__ __forceinline__ void jacobi(const FusedParams& p, Run& run, int l, bo
 // `shell`: add Σ over the global ghost shell of z·ϵ to z⋅ϵ (level 1 of the reference only);
 // `r2`: keep L₂ = r⋅r up to date (finest level only)
 template <int D, int V, bool GRID>
-__device__ __forceinline__ void pcg(const FusedParams& p, Run& run, int l, int it, bool shell = false, float* r2 = nullptr) {
+__device__ __forceinline__ void pcg(const FusedParams& p, Run& run, int l, int it, bool shell = false, float* r2 = nullptr,
+                                    const float* rho_in = nullptr) {
   const Lvl& L = p.lv[l];
   const bool dist = GRID && p.dist[l];
   float rho;
-  {
+  if (rho_in) {  // ϵ = r·iD and ρ = r⋅ϵ came out of the fused prolongate!/increment! pass
+    rho = *rho_in;
+  } else {
     double acc[1] = {0.0};
     rows<V, GRID>(p, l, [&](int, int, int, int64_t I) {
       const Pack<V> r = ldp<V>(L.r + I), id = ldp<V>(L.iD + I);
@@ -441,6 +445,29 @@ __device__ __forceinline__ void prolongate_to(const FusedParams& p, Run& run, in
   phase_sync<GRID>(p, run);
 }
 
+// prolongate!(l+1 → l) + increment!(l) + the head of pcg!(l) in one phase (wl_vec.cuh); across slab faces
+// ϵ is the neighbour's coarse x, so the halo that travels is the (4× smaller) coarse one
+template <int D, int V, bool GRID>
+__device__ __forceinline__ void prolong_inc_init(const FusedParams& p, Run& run, int l, float& rho, float* r2) {
+  const Lvl& f = p.lv[l];
+  const Lvl& c = p.lv[l + 1];
+  const bool fdist = GRID && p.dist[l], cdist = GRID && p.dist[l + 1];
+  if (fdist && cdist) halo_push(p, run, l + 1, c.x);
+  ProMap m;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) { m.per[d] = f.g.per[d]; m.n[d] = f.g.n[d]; }
+  m.zmode = (fdist && !cdist) ? 1 : 0;
+  m.zoff = f.g.zoff;
+  m.nzg = p.nzg0 >> l;
+  m.perz_global = p.perz_global;
+  double acc[2] = {0.0, 0.0};
+  rows<V, GRID>(p, l, [&](int i, int j, int k, int64_t I) { prolong_increment_init<D, V>(f, c, m, i, j, k, I, acc[0], acc[1]); });
+  reduce<2, GRID>(p, run, fdist, acc);
+  if (fdist && cdist) post_ready(p, run);
+  rho = (float)acc[0];
+  if (r2) *r2 = (float)acc[1];
+}
+
 template <int D, bool GRID>
 __device__ __forceinline__ void down_level(const FusedParams& p, Run& run, int l) {
   if ((p.lv[l].g.n[0] - 2) % 4 == 0 && GRID) jacobi<D, 4, GRID>(p, run, l);
@@ -454,9 +481,14 @@ __device__ __forceinline__ void pcg_level(const FusedParams& p, Run& run, int l)
 }
 template <int D, bool GRID>
 __device__ __forceinline__ void up_level(const FusedParams& p, Run& run, int l) {
-  if ((p.lv[l].g.n[0] - 2) % 4 == 0 && GRID) { prolongate_to<D, 4, GRID>(p, run, l); increment<D, 4, GRID>(p, run, l); }
-  else { prolongate_to<D, 1, GRID>(p, run, l); increment<D, 1, GRID>(p, run, l); }
-  pcg_level<D, GRID>(p, run, l);
+  float rho;
+  if ((p.lv[l].g.n[0] - 2) % 4 == 0 && GRID) {
+    prolong_inc_init<D, 4, GRID>(p, run, l, rho, nullptr);
+    pcg<D, 4, GRID>(p, run, l, 6, false, nullptr, &rho);
+  } else {
+    prolong_inc_init<D, 1, GRID>(p, run, l, rho, nullptr);
+    pcg<D, 1, GRID>(p, run, l, 6, false, nullptr, &rho);
+  }
 }
 
 // levels lf … nl-1 of one V-cycle (the residual of level lf has just been restricted)
@@ -592,14 +624,13 @@ __global__ void __launch_bounds__(VC_THREADS, MINB) k_vcycle_tail(FusedParams p,
     vcycle_tail<D>(p, run, lf);
     if (!solve) break;
     if (p.p2p && p.dist[0] && !p.dist[1]) post_ready(p, run);
+    float rho;
     if (v4) {
-      prolongate_to<D, 4, true>(p, run, 0);
-      increment<D, 4, true>(p, run, 0, &r2);
-      pcg<D, 4, true>(p, run, 0, 6, sa.has_ghost != 0, &r2);
+      prolong_inc_init<D, 4, true>(p, run, 0, rho, &r2);
+      pcg<D, 4, true>(p, run, 0, 6, sa.has_ghost != 0, &r2, &rho);
     } else {
-      prolongate_to<D, 1, true>(p, run, 0);
-      increment<D, 1, true>(p, run, 0, &r2);
-      pcg<D, 1, true>(p, run, 0, 6, sa.has_ghost != 0, &r2);
+      prolong_inc_init<D, 1, true>(p, run, 0, rho, &r2);
+      pcg<D, 1, true>(p, run, 0, 6, sa.has_ghost != 0, &r2, &rho);
     }
     ++n;
     if (r2 < sa.tol || n >= sa.itmx) break;
@@ -651,6 +682,8 @@ int vcycle_fused_setup(Sim& s) {
   p.rank = s.dist.rank;
   p.p2p = s.dist.nranks > 1 ? s.dist.dev : nullptr;
   p.misc = s.d_misc;
+  p.nzg0 = s.Nz_global;
+  p.perz_global = s.per_z_global;
   // fuse from the first level below the finest whose kernels are launch-latency bound
   const char* e1 = getenv("WL_FUSED_MAX_CELLS");
   const int64_t max_cells = e1 ? atoll(e1) : (int64_t)1 << 22;

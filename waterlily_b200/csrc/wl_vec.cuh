@@ -75,6 +75,83 @@ __device__ __forceinline__ Pack<V> mult_w(const Lvl& l, const float* x, int i, i
   return s;
 }
 
+// ---- prolongate! + increment! + the head of pcg! in one pass -------------------------------------
+// Vcycle! ends with  ϵ_f = x_c[down(I)] (prolongate!, MultiLevelPoisson.jl:34) ; perBC!(ϵ) ; r -= Aϵ ;
+// x += ϵ (increment!, Poisson.jl:99-103), and the pcg! that follows opens with ϵ = r·iD ; ρ = r⋅ϵ
+// (:125-126).  ϵ_f is a pure function of the coarse x, so it is evaluated on the fly at the cell and
+// its 2D neighbours (periodic wrap / slab halo handled in the index map) instead of being stored and
+// re-read: r, x and the NEW ϵ are written in place with no read-after-write hazard.  13.1 → 10.1 words.
+struct ProMap {
+  int per[3];       // wrap the fine index in this dimension (periodic and not z-distributed)
+  int n[3];         // fine padded sizes of this rank
+  int zmode;        // 1: the coarse level is replicated while the fine one is z-distributed
+  int zoff;         // global fine padded z index of local plane 0            (zmode 1)
+  int nzg;          // interior z-planes of the whole fine level             (zmode 1)
+  int perz_global;  // the global domain is periodic in z                     (zmode 1)
+};
+__device__ __forceinline__ int pro_cidx(const ProMap& m, int d, int v) {
+  if (d == 2 && m.zmode == 1) {
+    int kg = v + m.zoff;
+    if (m.perz_global) kg = kg == 0 ? m.nzg : (kg == m.nzg + 1 ? 1 : kg);
+    return (kg + 1) >> 1;
+  }
+  if (m.per[d]) v = v == 0 ? m.n[d] - 2 : (v == m.n[d] - 1 ? 1 : v);
+  return (v + 1) >> 1;
+}
+template <int D, int V>
+__device__ __forceinline__ void prolong_increment_init(const Lvl& f, const Lvl& c, const ProMap& m, int i, int j, int k, int64_t I,
+                                                       double& acc_rho, double& acc_r2) {
+  const float* __restrict__ xc = c.x;
+  const int64_t cs1 = c.g.s[1], cs2 = c.g.s[2];
+  int ci[V];
+#pragma unroll
+  for (int q = 0; q < V; ++q) ci[q] = (i + q + 1) >> 1;  // interior cells never wrap
+  const int64_t J = (D > 1 ? pro_cidx(m, 1, j) * cs1 : 0) + (D > 2 ? pro_cidx(m, 2, k) * cs2 : 0);
+  Pack<V> e, xm, xp;
+#pragma unroll
+  for (int q = 0; q < V; ++q) e.v[q] = xc[J + ci[q]];
+  xm.v[0] = xc[J + pro_cidx(m, 0, i - 1)];
+#pragma unroll
+  for (int q = 1; q < V; ++q) xm.v[q] = e.v[q - 1];
+#pragma unroll
+  for (int q = 0; q < V - 1; ++q) xp.v[q] = e.v[q + 1];
+  xp.v[V - 1] = xc[J + pro_cidx(m, 0, i + V)];
+  const Pack<V> Dc = ldp<V>(f.Dg + I);
+  Pack<V> s;
+#pragma unroll
+  for (int q = 0; q < V; ++q) s.v[q] = e.v[q] * Dc.v[q];
+  {
+    const Pack<V> Lc = ldp<V>(f.L + I), Lp = ld_xp<V>(f.L + I, Lc);
+#pragma unroll
+    for (int q = 0; q < V; ++q) s.v[q] += (xm.v[q] * Lc.v[q] + xp.v[q] * Lp.v[q]);
+  }
+#pragma unroll
+  for (int d = 1; d < D; ++d) {
+    const int cd = d == 1 ? j : k;
+    const int64_t cst = d == 1 ? cs1 : cs2;
+    const int64_t Jo = J - pro_cidx(m, d, cd) * cst;  // J without dimension d's term
+    const int64_t Jm = Jo + pro_cidx(m, d, cd - 1) * cst, Jp = Jo + pro_cidx(m, d, cd + 1) * cst;
+    const float* Li = f.L + d * f.g.comp;
+    const Pack<V> Lc = ldp<V>(Li + I), Lp = ldp<V>(Li + I + f.g.s[d]);
+#pragma unroll
+    for (int q = 0; q < V; ++q) s.v[q] += (xc[Jm + ci[q]] * Lc.v[q] + xc[Jp + ci[q]] * Lp.v[q]);
+  }
+  Pack<V> r = ldp<V>(f.r + I), x = ldp<V>(f.x + I);
+  const Pack<V> id = ldp<V>(f.iD + I);
+  Pack<V> en;
+#pragma unroll
+  for (int q = 0; q < V; ++q) {
+    r.v[q] = r.v[q] - s.v[q];
+    x.v[q] = x.v[q] + e.v[q];
+    en.v[q] = r.v[q] * id.v[q];
+    acc_rho += (double)r.v[q] * (double)en.v[q];
+    acc_r2 += (double)r.v[q] * (double)r.v[q];
+  }
+  stp<V>(f.r + I, r);
+  stp<V>(f.x + I, x);
+  stp<V>(f.eps + I, en);
+}
+
 // interior rows; f(i, j, k, I) is called for the first cell of each V-group
 template <int V, class F>
 __device__ __forceinline__ void for_rows(const GridD& g, F&& f) {
