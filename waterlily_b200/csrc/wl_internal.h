@@ -164,7 +164,7 @@ int mom_accelerate(Sim& s, const double* g);
 int mom_bdim1(Sim& s);
 int mom_bdim2(Sim& s, bool accumulate, float scale);
 int mom_scale_u(Sim& s, double scale);
-int mom_project(Sim& s, double w, int* n, int slot = 0, bool defer_count = false);
+int mom_project(Sim& s, double w, int* n, int slot = 0, bool defer_count = false, bool skip_unscale = false, float prediv = 0.f);
 int mom_cfl(Sim& s, double* dt);
 int mom_step(Sim& s, const double* U, const double* gp, const double* gc, double* dt_next, int* n_pred, int* n_corr);
 

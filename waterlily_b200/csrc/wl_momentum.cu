@@ -413,12 +413,15 @@ __global__ void __launch_bounds__(256) k_project_pre(GridD g, const float* __res
 // cells and slab halo planes alike.  A ghost cell holds a copy of an interior value, and scaling a
 // copy gives the bits of the scaled original, so the ghosts stay consistent and neither the perBC!
 // of residual! (Poisson.jl:92) nor a halo exchange is needed afterwards.
-__global__ void __launch_bounds__(256) k_scale_alloc(float4* __restrict__ x, int64_t n4, float f32v, double f64v, int f32, int divide) {
+// `prediv` > 0: first undo the PREVIOUS project!'s scaling (x ./= dt with its Float32 dt, w = 1) — mom_step!
+// merges the predictor's x ./= dt with the corrector's x .*= dt (two roundings in one pass, same bits)
+__global__ void __launch_bounds__(256) k_scale_alloc(float4* __restrict__ x, int64_t n4, float f32v, double f64v, int f32, int divide, float prediv) {
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n4; t += (int64_t)gridDim.x * blockDim.x) {
     float4 v = x[t];
     float* p = reinterpret_cast<float*>(&v);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
+      if (prediv > 0.f) p[q] = p[q] / prediv;
       if (divide) p[q] = f32 ? p[q] / f32v : (float)((double)p[q] / f64v);
       else p[q] = f32 ? p[q] * f32v : (float)((double)p[q] * f64v);
     }
@@ -597,7 +600,9 @@ int mom_scale_u(Sim& s, double scale) {
   return wl_cuda_check(s, cudaGetLastError(), "k_scale_u");
 }
 // project!(a,b,w) (Flow.jl:137-145)
-int mom_project(Sim& s, double w, int* n, int slot, bool defer_count) {
+// `skip_unscale`: leave x scaled by dt (the caller's next project! undoes it in its own first pass);
+// `prediv`: the Float32 dt such a previous project! left in x
+int mom_project(Sim& s, double w, int* n, int slot, bool defer_count, bool skip_unscale, float prediv) {
   const float dt32 = s.dt.back();
   const bool f32 = (w == 1.0);                 // dt = w*Δt: Float32 for the Int w=1, Float64 for w=0.5
   const double dtw = f32 ? (double)dt32 : w * (double)dt32;
@@ -607,16 +612,18 @@ int mom_project(Sim& s, double w, int* n, int slot, bool defer_count) {
   const int sgrid = (int)std::min<int64_t>((n4 + 255) / 256, (int64_t)s.nsm * 8);
   wl_prof_begin(s, WL_PROF_PROJECT);
   RLAUNCH(s, k_project_pre, s.g, s.g, s.u, b.z);
-  k_scale_alloc<<<sgrid, 256, 0, s.stream>>>(xall, n4, (float)dtw, dtw, f32 ? 1 : 0, 0);
+  k_scale_alloc<<<sgrid, 256, 0, s.stream>>>(xall, n4, (float)dtw, dtw, f32 ? 1 : 0, 0, prediv);
   ++s.launches;
   wl_prof_end(s, WL_PROF_PROJECT, 4.0 * (double)s.g.interior * (s.D + 1 + 2));
   int rc = pois_solve(s, 1e-4, s.pois_kind == WL_POIS_MULTILEVEL ? 32 : 1000, n, true, slot, defer_count);
   if (rc) return rc;
   wl_prof_begin(s, WL_PROF_PROJECT);
   RLAUNCH(s, k_project_correct, s.g, s.g, s.u, b.L, b.x);
-  k_scale_alloc<<<sgrid, 256, 0, s.stream>>>(xall, n4, (float)dtw, dtw, f32 ? 1 : 0, 1);
-  ++s.launches;
-  wl_prof_end(s, WL_PROF_PROJECT, 4.0 * (double)s.g.interior * (3 * s.D + 1 + 2));
+  if (!skip_unscale) {
+    k_scale_alloc<<<sgrid, 256, 0, s.stream>>>(xall, n4, (float)dtw, dtw, f32 ? 1 : 0, 1, 0.f);
+    ++s.launches;
+  }
+  wl_prof_end(s, WL_PROF_PROJECT, 4.0 * (double)s.g.interior * (3 * s.D + 1 + (skip_unscale ? 0 : 2)));
   return wl_cuda_check(s, cudaGetLastError(), "project");
 }
 // CFL(a) (Flow.jl:172-175)
@@ -662,13 +669,15 @@ int mom_step(Sim& s, const double* U, const double* gp, const double* gc, double
     if ((rc = dist_halo(s, s.g, s.u, 1, 2))) return rc;  // the exit plane changed after BC!'s exchange
   }
   const bool defer = s.vc_solve && s.pois_kind == WL_POIS_MULTILEVEL;
-  if ((rc = mom_project(s, 1.0, n_pred, 0, defer))) return rc;
+  // the pressure is not observable between the two project! calls of a step: the predictor leaves it scaled
+  // and the corrector's first pass does x = (x / Δt) * (Δt/2) with the reference's two roundings
+  if ((rc = mom_project(s, 1.0, n_pred, 0, defer, true, 0.f))) return rc;
   if ((rc = bc_vec(s, s.g, s.u, U, s.exitBC, s.g.per, 2))) return rc;
   // corrector u → u¹
   if ((rc = mom_conv_diff(s, s.u, true, gc))) return rc;
   if ((rc = mom_bdim2(s, true, 0.5f))) return rc;
   if ((rc = bc_vec(s, s.g, s.u, U, s.exitBC, s.g.per, 2))) return rc;
-  if ((rc = mom_project(s, 0.5, n_corr, 1, defer))) return rc;
+  if ((rc = mom_project(s, 0.5, n_corr, 1, defer, false, s.dt.back()))) return rc;
   if ((rc = bc_vec(s, s.g, s.u, U, s.exitBC, s.g.per, 2))) return rc;
   double dt;
   if ((rc = mom_cfl(s, &dt))) return rc;
