@@ -1,12 +1,17 @@
-// wl_dist.cu — z-slab domain decomposition: one process per GPU, NCCL over NVLink/NVSwitch.
+// wl_dist.cu — z-slab domain decomposition: one process per GPU of an NVLink/NVSwitch box.
 //
 // The reference has no multi-GPU path (README.md:157 lists it as a goal); this is new work
 // (SURVEY.md §8e).  Each rank owns Nz/R interior z-planes of every field plus one ghost plane per
 // side (two extra for u/u⁰: QUICK reaches I-2δ…I+2δ).  z is the slowest index, so a plane is one
-// contiguous run of floats and a halo exchange is 2 sends + 2 receives of contiguous memory,
-// issued at exactly the sites where the reference calls BC!/perBC!.  Global reductions are
-// ncclAllReduce on 1-2 Float64 partials that stay on the device; every rank then takes the same
-// data-dependent decision from the same bits.
+// contiguous run of floats and a halo exchange moves contiguous memory, at exactly the sites where
+// the reference calls BC!/perBC!.  Global reductions combine 1-2 Float64 partials that stay on the
+// device; every rank then takes the same data-dependent decision from the same bits.
+//
+// Two data paths.  Default: peer memory (wl_p2p.cuh) — the ranks map each other's field arena over
+// CUDA IPC and kernels store halo planes / reduction partials straight into the neighbours' memory
+// (k_p2p_push here, p2p_allreduce2 in the producing kernels, push_segments inside the persistent
+// solver kernel).  Fallback (WL_P2P=0 or a failed mapping): grouped ncclSend/ncclRecv and
+// ncclAllReduce + a finalise kernel.  NCCL also bootstraps the peer path (IPC handle exchange).
 //
 // NCCL is loaded with dlopen so that a single-GPU build has no link-time dependency, and so that
 // inside a torch process the library torch already loaded (same soname) is reused.

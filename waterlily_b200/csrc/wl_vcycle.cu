@@ -1,23 +1,29 @@
-// wl_vcycle.cu — the coarse part of Vcycle! (reference src/MultiLevelPoisson.jl:70-82) as ONE
-// persistent cooperative kernel.
+// wl_vcycle.cu — the multigrid solver as ONE persistent cooperative kernel
+// (reference src/MultiLevelPoisson.jl:70-99, src/Poisson.jl:91-144).
 //
 // Below the finest levels a V-cycle is pure latency: ~30 launches per level, each a few
 // microseconds of work, plus (across slab ranks) a halo exchange or an all-reduce between most of
-// them.  k_vcycle_tail runs, for the levels lf … nl-1,
+// them.  k_vcycle_tail runs in one launch either
 //
-//     down:  Jacobi!(l) ; restrict!(l → l+1) ; fill!(x_{l+1},0)          l = lf … nl-2
-//            pcg!(nl-1)
-//     up:    prolongate!(l+1 → l) ; increment!(l) ; pcg!(l)               l = nl-2 … lf
+//   tail mode  — levels lf … nl-1 of one V-cycle:
+//       down:  Jacobi!(l) ; restrict!(l → l+1) ; fill!(x_{l+1},0)               l = lf … nl-2
+//              pcg!(nl-1)
+//       up:    prolongate!(l+1 → l) ; increment!(l) ; pcg!(l)                    l = nl-2 … lf
+//   solve mode — the whole solver!(ml; tol, itmx): residual! (+ mean subtraction), then
+//       { Jacobi!(1) ; restrict! ; the tail ; prolongate! ; increment! ; pcg!(1) ; L₂ test } until
+//       converged, then perBC!(x); chosen when the finest level has ≤ 96 M cells per rank.
 //
-// in a single launch: phases are separated by a grid barrier (~1 µs) instead of a kernel boundary,
-// every scalar decision of pcg! (|ρ|<10eps, |α|∉[1e-2,1e2]) is taken redundantly and identically
-// by all blocks from the same reduced bits, the smallest levels (≤ 16³) are run by one block with
-// __syncthreads as the barrier, and on z-distributed levels the halo planes and reduction partials
-// go to the neighbours' memory directly from inside the kernel (wl_p2p.cuh).
+// Phases are separated by a grid barrier (~1-2 µs) instead of a kernel boundary, every scalar
+// decision of pcg! (|ρ|<10eps, |α|∉[1e-2,1e2]) and of solver! (L₂ < tol) is taken redundantly and
+// identically by all blocks from the same reduced bits, the smallest levels (≤ 16³) are run by one
+// block with __syncthreads as the barrier, and on z-distributed levels the halo planes and
+// reduction partials go to the neighbours' memory directly from inside the kernel (wl_p2p.cuh).
+// In solve mode the host reads nothing until the end of the time step.
 //
 // Arithmetic is that of the per-function kernels in wl_poisson.cu (same expressions, -fmad=false,
 // Float64 dot accumulation); periodic ghosts of ϵ are not materialised — the stencil wraps its
-// index instead, which reads the same value (nothing else reads ϵ's ghosts below level 1).
+// index instead, which reads the same value — and prolongate!/increment!/the head of pcg! run as
+// one phase with ϵ evaluated from the coarse x on the fly (wl_vec.cuh).
 #include <algorithm>
 #include <cstdlib>
 
