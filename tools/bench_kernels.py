@@ -47,7 +47,8 @@ def main():
         for _ in range(args.reps):
             e.conv_diff("u")
         ms, n, b = e.profile_read(names.index("conv_diff+bdim1"))
-        print(f"conv_diff N={N} variant={os.environ.get('WL_CD_VARIANT','0')} zchunk={os.environ.get('WL_CD_ZCHUNK','32')}: "
+        print(f"conv_diff N={N} tma={os.environ.get('WL_CD_TMA','1')} cells/thread={os.environ.get('WL_CD_CELLS','2')} "
+              f"zchunk={os.environ.get('WL_CD_TMA_ZCHUNK','64')}: "
               f"{ms / n:.3f} ms/launch, {b / n / (ms / n * 1e-3) / 1e9:.0f} GB/s algorithmic")
 
 

@@ -435,22 +435,6 @@ __device__ __forceinline__ void restrict_to(const FusedParams& p, Run& run, int 
     push_segments(p, run, seg, ns, mask);
   }
 }
-// prolongate!(l+1 → l) (MultiLevelPoisson.jl:34)
-template <int D, int V, bool GRID>
-__device__ __forceinline__ void prolongate_to(const FusedParams& p, Run& run, int l) {
-  const Lvl& f = p.lv[l];
-  const Lvl& c = p.lv[l + 1];
-  const int fzadd = (GRID && p.dist[l] && !p.dist[l + 1]) ? f.g.zoff : 0;
-  rows<V, GRID>(p, l, [&](int i0, int j0, int k0, int64_t I) {
-    const int64_t J = (D > 1 ? ((j0 + 1) >> 1) * c.g.s[1] : 0) + (D > 2 ? ((k0 + fzadd + 1) >> 1) * c.g.s[2] : 0);
-    Pack<V> e;
-#pragma unroll
-    for (int q = 0; q < V; ++q) e.v[q] = c.x[J + ((i0 + q + 1) >> 1)];
-    stp<V>(f.eps + I, e);
-  });
-  phase_sync<GRID>(p, run);
-}
-
 // prolongate!(l+1 → l) + increment!(l) + the head of pcg!(l) in one phase (wl_vec.cuh); across slab faces
 // ϵ is the neighbour's coarse x, so the halo that travels is the (4× smaller) coarse one
 template <int D, int V, bool GRID>
