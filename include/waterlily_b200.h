@@ -166,6 +166,17 @@ int wl_viscous_force(wl_sim* s, const double* nds, int64_t count, double* force)
  * D entries (in 2-D the scalar cross product is broadcast into both, as in the reference) */
 int wl_pressure_moment(wl_sim* s, const double* x0, const double* nds, int64_t count, double* moment);
 
+/* ---- Metrics: derived fields for output (src/Metrics.jl:14-77) --------------------------------
+ * `@inside flow.σ[I] = f(I, flow.u)` for the reference's per-cell diagnostics: the interior of σ
+ * is filled on the device (ghost cells untouched, as with @inside), the caller downloads WL_SIGMA.
+ *   WL_DF_KE          ke(I,u,U)           ½‖u−U‖² at the cell centre; U = NULL for U=0        (:20-22)
+ *   WL_DF_CURL        curl(comp,I,u)      component comp (1-based; 3 in 2-D) of ∇×u at the cell edge (:55)
+ *   WL_DF_OMEGA_MAG   ω_mag(I,u)          ‖∇×u‖ at the cell centre (3-D)                       (:61-67)
+ *   WL_DF_LAMBDA2     λ₂(I,u)             middle eigenvalue of S²+Ω² (3-D)                     (:40-44)
+ *   WL_DF_OMEGA_THETA ω_θ(I,z,center,u)   azimuthal vorticity about the axis `axis` through `center` (3-D) (:74-78) */
+enum wl_derived_kind { WL_DF_KE = 0, WL_DF_CURL = 1, WL_DF_OMEGA_MAG = 2, WL_DF_LAMBDA2 = 3, WL_DF_OMEGA_THETA = 4 };
+int wl_derived(wl_sim* s, int kind, int comp, const double* U, const double* axis, const double* center);
+
 /* ---- the hot path --------------------------------------------------------------------- */
 /* mom_step!(a,b) (src/Flow.jl:153-169).
  * U       : BCTuple(a.U,a.Δt,N) evaluated by the host at t+Δt (D entries)

@@ -128,4 +128,13 @@ function pressure_moment(x₀, p::B200Array{T,D}, df::B200Array, body, t=0, _=Fl
                 p.h.ptr, collect(Float64, x₀), nds, length(nds), out)); out
 end
 
+# derived output fields — `@inside flow.σ[I] = WaterLily.curl(3,I,flow.u)` and friends (src/Metrics.jl:14-77) on the device
+const DERIVED = Dict(:ke => 0, :curl => 1, :ω_mag => 2, :λ₂ => 3, :ω_θ => 4)
+function derived!(a::Flow{D,T,<:B200Array}, kind::Symbol; i=0, U=nothing, z=nothing, center=nothing) where {D,T}
+    dbl(v) = v === nothing ? C_NULL : collect(Float64, v)
+    check(ccall((:wl_derived, lib), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
+                a.σ.h.ptr, DERIVED[kind], i, dbl(U), dbl(z), dbl(center)))
+    a.σ
+end
+
 end # module

@@ -655,6 +655,84 @@ void pressure_moment(Sim& s, const double* x0, double* out) {
   sum_df(s, out);
 }
 
+// ------------------------------------------------------------------------------------------
+// Metrics: derived fields, `@inside σ[I] = f(I,u)` (src/Metrics.jl:14-77)
+// ------------------------------------------------------------------------------------------
+// eigvals(Hermitian(A))[2] of a symmetric 3×3 matrix (the reference calls LAPACK): trigonometric closed form
+double mid_eig_sym3(const double A[3][3]) {
+  const double p1 = A[0][1] * A[0][1] + A[0][2] * A[0][2] + A[1][2] * A[1][2];
+  const double q = (A[0][0] + A[1][1] + A[2][2]) / 3.0;
+  if (p1 == 0.0) {
+    double d[3] = {A[0][0], A[1][1], A[2][2]};
+    std::sort(d, d + 3);
+    return d[1];
+  }
+  double B[3][3];
+  double p2 = 2.0 * p1;
+  for (int i = 0; i < 3; ++i) { const double t = A[i][i] - q; p2 += t * t; }
+  const double pp = std::sqrt(p2 / 6.0);
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) B[i][j] = (A[i][j] - (i == j ? q : 0.0)) / pp;
+  const double det = B[0][0] * (B[1][1] * B[2][2] - B[1][2] * B[1][2]) - B[0][1] * (B[0][1] * B[2][2] - B[1][2] * B[0][2]) +
+                     B[0][2] * (B[0][1] * B[1][2] - B[1][1] * B[0][2]);
+  const double r = std::min(1.0, std::max(-1.0, det / 2.0));
+  const double phi = std::acos(r) / 3.0;
+  const double e1 = q + 2.0 * pp * std::cos(phi), e3 = q + 2.0 * pp * std::cos(phi + 2.0943951023931954923084289221863);
+  return 3.0 * q - e1 - e3;
+}
+int derived(Sim& s, int kind, int comp, const double* U, const double* axis, const double* center) {
+  const Grid& g = s.g;
+  const int D = s.D;
+  if (kind < WL_DF_KE || kind > WL_DF_OMEGA_THETA) return fail(WL_ERR_ARG, "wl_derived: bad kind");
+  if (kind == WL_DF_CURL && (comp < 1 || comp > 3 || (D == 2 && comp != 3))) return fail(WL_ERR_ARG, "wl_derived: curl component must be 1..3 (3 in 2-D)");
+  if (kind >= WL_DF_OMEGA_MAG && D != 3) return fail(WL_ERR_ARG, "wl_derived: this diagnostic needs a 3-D flow");
+  if (kind == WL_DF_OMEGA_THETA && (!axis || !center)) return fail(WL_ERR_ARG, "wl_derived: ω_θ needs an axis and a centre");
+  loop(g, r_inside(g), [&](int64_t I, int i1, int j1, int k1) {
+    float out = 0.f;
+    if (kind == WL_DF_KE) {  // ke(I,u,U) (:20-22)
+      if (U) {
+        double acc = 0.0;
+        for (int i = 0; i < D; ++i) { const double t = (double)(s.u[I + i * g.cells] + s.u[I + g.s[i] + i * g.cells]) - 2.0 * U[i]; acc += t * t; }
+        out = (float)(0.125 * acc);
+      } else {
+        float acc = 0.f;
+        for (int i = 0; i < D; ++i) { const float t = s.u[I + i * g.cells] + s.u[I + g.s[i] + i * g.cells]; acc += t * t; }
+        out = (float)(0.125 * (double)acc);
+      }
+    } else if (kind == WL_DF_CURL) {  // curl(i,I,u) (:55) with ∂(a,I,f) = f[I]-f[I-δa] (Flow.jl:1)
+      const int i = comp - 1, j = (i + 1) % 3, k = (i + 2) % 3;
+      const float fjk = s.u[I + k * g.cells] - s.u[I - g.s[j] + k * g.cells];
+      const float fkj = s.u[I + j * g.cells] - s.u[I - g.s[k] + j * g.cells];
+      out = fjk - fkj;
+    } else {
+      float J[3][3];
+      for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) J[i][j] = dudx(s, i, j, I);
+      const float w[3] = {J[2][1] - J[1][2], J[0][2] - J[2][0], J[1][0] - J[0][1]};  // ω(I,u) (:61)
+      if (kind == WL_DF_OMEGA_MAG) {
+        out = std::sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+      } else if (kind == WL_DF_LAMBDA2) {  // λ₂ (:40-44)
+        float Sm[3][3], Om[3][3];
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { Sm[i][j] = (J[i][j] + J[j][i]) / 2; Om[i][j] = (J[i][j] - J[j][i]) / 2; }
+        double M[3][3];
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
+          float s2 = 0.f, o2 = 0.f;
+          for (int k = 0; k < 3; ++k) { s2 += Sm[i][k] * Sm[k][j]; o2 += Om[i][k] * Om[k][j]; }
+          M[i][j] = (double)(s2 + o2);
+        }
+        out = (float)mid_eig_sym3(M);
+      } else {  // ω_θ (:74-78)
+        const int c1[3] = {i1, j1, k1};
+        double d[3], th[3];
+        for (int i = 0; i < 3; ++i) d[i] = (double)(float)(c1[i] - 1.5) - center[i];
+        th[0] = axis[1] * d[2] - axis[2] * d[1]; th[1] = axis[2] * d[0] - axis[0] * d[2]; th[2] = axis[0] * d[1] - axis[1] * d[0];
+        const double n = std::sqrt(th[0] * th[0] + th[1] * th[1] + th[2] * th[2]);
+        out = n == 0.0 ? 0.f : (float)((th[0] * (double)w[0] + th[1] * (double)w[1] + th[2] * (double)w[2]) / n);
+      }
+    }
+    s.sigma[I] = out;
+  });
+  return WL_OK;
+}
+
 }  // namespace
 
 #define S ((Sim*)s)
@@ -793,6 +871,9 @@ int wlo_viscous_force(wl_sim* s, const double* nds, int64_t count, double* force
 int wlo_pressure_moment(wl_sim* s, const double* x0, const double* nds, int64_t count, double* moment) {
   const int rc = set_nds(*S, nds, count); if (rc) return rc;
   pressure_moment(*S, x0, moment); return WL_OK;
+}
+int wlo_derived(wl_sim* s, int kind, int comp, const double* U, const double* axis, const double* center) {
+  return derived(*S, kind, comp, U, axis, center);
 }
 int wlo_mom_step(wl_sim* s, const double* U, const double* gp, const double* gc, double* dt_next, int* n_pred, int* n_corr) {
   int a = 0, b = 0; mom_step(*S, U, gp, gc, &a, &b);

@@ -243,3 +243,43 @@ def check_force_routines(make_engine):
 def test_metrics_force_routines():
     # maintests.jl:341-368 (force routines of the Metrics.jl testset)
     check_force_routines(oracle.engine)
+
+
+def check_derived_fields(make_engine):
+    """Metrics.jl testset, maintests.jl:320-337 (the reference runs it on Float64 arrays; the engine is
+    Float32, hence the tolerances)."""
+    from waterlily_b200.body import loc_grid
+    Ng = (3, 4, 5)
+    e = make_engine((1, 2, 3), pois_kind=_cabi.POIS_SINGLE)
+    u = np.zeros(Ng + (3,), dtype=np.float32, order="F")
+    for i in range(1, 4):                                   # apply!((i,x)->x[i]+prod(x),u)   :323
+        x = loc_grid(i, Ng, np.float64)
+        u[..., i - 1] = x[..., i - 1] + x.prod(axis=-1)
+    e.upload("u", u)
+    J = (1, 2, 3)                                           # CartesianIndex(2,3,4)            :321
+    x = np.array([0.5, 1.5, 2.5])
+    px = x.prod()
+    assert np.isclose(e.derived("ke")[J], 0.5 * ((x + px) ** 2).sum(), rtol=1e-6)                   # :325-326
+    assert np.isclose(e.derived("ke", U=x)[J], 1.5 * px ** 2, rtol=1e-6)                            # :327-328
+    assert np.isclose(e.derived("lambda2")[J], 1.0, rtol=1e-5)                                      # :329-330
+    om = np.cross(1 / x, np.repeat(px, 3))                                                          # :331
+    assert np.isclose(e.derived("curl", comp=2)[J], om[1], rtol=1e-6)                               # :332-333
+    assert np.isclose(e.derived("omega_mag")[J], np.sqrt((om ** 2).sum()), rtol=1e-6)               # :335-336
+    assert np.isclose(e.derived("omega_theta", axis=(0, 0, 1), center=x + (0, 1, 2))[J], om[0], rtol=1e-5)   # :337-338
+    return {k: e.derived(k, comp=3 if k == "curl" else 0, axis=(0.3, -0.2, 1.0), center=(0.7, 1.1, 0.2)) for k in
+            ("ke", "curl", "omega_mag", "lambda2", "omega_theta")}
+
+
+def test_metrics_derived_fields():
+    check_derived_fields(oracle.engine)
+    # 2-D: curl(3,I,u) of a solid-body rotation u = (-y, x) is 2 everywhere (README.md:95-97 pattern)
+    from waterlily_b200.body import loc_grid
+    Ng = (10, 12)
+    e = oracle.engine((8, 10), pois_kind=_cabi.POIS_SINGLE)
+    u = np.zeros(Ng + (2,), dtype=np.float32, order="F")
+    u[..., 0] = -loc_grid(1, Ng, np.float64)[..., 1]
+    u[..., 1] = loc_grid(2, Ng, np.float64)[..., 0]
+    e.upload("u", u)
+    assert np.allclose(e.derived("curl", comp=3)[1:-1, 1:-1], 2.0, atol=1e-6)
+    with pytest.raises(_cabi.WLError, match="3-D"):
+        e.derived("lambda2")

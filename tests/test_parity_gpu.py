@@ -327,3 +327,20 @@ def test_metrics_on_a_running_flow(make):
         scale = max(np.abs(b).max(), 1e-12)
         assert np.abs(a - b).max() <= 2e-4 * scale, (a, b)
     assert np.abs(pressure_force(so)).max() > 1e-3   # the comparison is not vacuous
+
+
+def test_derived_fields_on_cuda():
+    # Metrics.jl diagnostics (maintests.jl:320-337) through the CUDA library, and against the oracle on a developed flow
+    from test_oracle_pins import check_derived_fields
+    fc, fo = check_derived_fields(cuda_engine), check_derived_fields(oracle.engine)
+    for k in fc:
+        assert np.allclose(fc[k][1:-1, 1:-1, 1:-1], fo[k][1:-1, 1:-1, 1:-1], rtol=1e-5, atol=1e-5), k
+    so, sc = tgv3d(OracleSimulation, 32), tgv3d(Simulation, 32)
+    for _ in range(3):
+        sim_step(so, remeasure=False)
+        sim_step(sc, remeasure=False)
+    inside = (slice(1, -1),) * 3
+    for kind, kw in (("ke", {}), ("ke", {"U": (0.1, -0.2, 0.3)}), ("curl", {"comp": 1}), ("curl", {"comp": 3}), ("omega_mag", {}),
+                     ("lambda2", {}), ("omega_theta", {"axis": (0, 0, 1), "center": (16, 16, 16)})):
+        a, b = sc._eng.derived(kind, **kw)[inside], so._eng.derived(kind, **kw)[inside]
+        assert np.abs(a - b).max() <= 1e-4 * max(np.abs(b).max(), 1e-6), (kind, np.abs(a - b).max(), np.abs(b).max())

@@ -9,8 +9,9 @@ behind a C ABI, with a host-side mirror of the reference's user API.
 from . import _cabi
 from ._cabi import Engine, WLError
 from .body import AbstractBody, AutoBody, NoBody
-from .sim import (BCTuple, DeviceField, Flow, MultiLevelPoisson, _SimulationBase, measure, measure_flow, mom_step,
-                  pressure_force, pressure_moment, sim_step, sim_time, time, total_force, viscous_force)
+from .sim import (BCTuple, DeviceField, Flow, MultiLevelPoisson, _SimulationBase, curl_field, ke_field, lambda2_field, measure,
+                  measure_flow, mom_step, omega_mag_field, omega_theta_field, pressure_force, pressure_moment, sim_step, sim_time,
+                  time, total_force, viscous_force)
 
 
 class Simulation(_SimulationBase):
@@ -24,4 +25,5 @@ class Simulation(_SimulationBase):
 
 __all__ = ["Simulation", "sim_step", "sim_time", "time", "measure", "mom_step", "Flow", "MultiLevelPoisson",
            "AbstractBody", "AutoBody", "NoBody", "BCTuple", "Engine", "WLError", "DeviceField",
-           "pressure_force", "viscous_force", "total_force", "pressure_moment"]
+           "pressure_force", "viscous_force", "total_force", "pressure_moment",
+           "ke_field", "curl_field", "omega_mag_field", "lambda2_field", "omega_theta_field"]

@@ -54,6 +54,7 @@ SIGNATURES = {
     "pressure_force": (C.c_int, [H, c_dbl_p, C.c_int64, c_dbl_p]),
     "viscous_force": (C.c_int, [H, c_dbl_p, C.c_int64, c_dbl_p]),
     "pressure_moment": (C.c_int, [H, c_dbl_p, c_dbl_p, C.c_int64, c_dbl_p]),
+    "derived": (C.c_int, [H, C.c_int, C.c_int, c_dbl_p, c_dbl_p, c_dbl_p]),
     "mom_step": (C.c_int, [H, c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p, c_int_p, c_int_p]),
     "get_dt": (C.c_int, [H, c_dbl_p]),
     "set_dt": (C.c_int, [H, C.c_double]),
@@ -276,6 +277,14 @@ class Engine:
         out = (C.c_double * self.D)()
         self.cabi.check(self.cabi.pressure_moment(self.h, _dbls(x0), ptr, cnt, out))
         return np.array(out[:], dtype=np.float64)
+
+    def derived(self, kind, comp=0, U=None, axis=None, center=None):
+        """``@inside σ[I] = f(I,u)`` for a Metrics.jl diagnostic (wl_derived); returns σ."""
+        kinds = {"ke": 0, "curl": 1, "omega_mag": 2, "lambda2": 3, "omega_theta": 4}
+        k = kinds.get(kind, kind)
+        self.cabi.check(self.cabi.derived(self.h, int(k), int(comp), None if U is None else _dbls(U),
+                                          None if axis is None else _dbls(axis), None if center is None else _dbls(center)))
+        return self.download(SIGMA)
 
     # -- Poisson
     def pois_update(self):

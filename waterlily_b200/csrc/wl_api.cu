@@ -595,6 +595,11 @@ int wl_pressure_moment(wl_sim* s, const double* x0, const double* nds, int64_t c
   int rc = metrics_nds(S, nds, count);
   return rc ? rc : metrics_run(S, 2, x0, moment);
 }
+int wl_derived(wl_sim* s, int kind, int comp, const double* U, const double* axis, const double* center) {
+  GUARD(s);
+  int rc = derived_run(S, kind, comp, U, axis, center);
+  return rc ? rc : wl_sync(s);
+}
 int wl_mom_step(wl_sim* s, const double* U, const double* gp, const double* gc, double* dt_next, int* n_pred, int* n_corr) {
   GUARD(s);
   if (!U) return wl_fail(WL_ERR_ARG, "wl_mom_step: U is required");

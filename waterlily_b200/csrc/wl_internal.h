@@ -133,6 +133,7 @@ int convdiff_tma_core_x0(const Sim& s);
 // ---- wl_metrics.cu ----
 // which: 0 pressure_force, 1 viscous_force, 2 pressure_moment (x0 required); out has D entries
 int metrics_run(Sim& s, int which, const double* x0, double* out);
+int derived_run(Sim& s, int kind, int comp, const double* U, const double* axis, const double* center);
 
 // ---- wl_vcycle.cu ----
 int vcycle_fused_setup(Sim& s);

@@ -85,7 +85,118 @@ __global__ void __launch_bounds__(256) k_metric(MetricArgs a, ReduceWS ws) {
   }
 }
 
+// ---- derived fields: @inside σ[I] = f(I,u) (Metrics.jl:14-77) --------------------------------------
+struct DerivedArgs {
+  GridD g;
+  const float* u;
+  float* sigma;
+  int kind, comp, hasU;
+  double U[3], axis[3], center[3];
+};
+// middle eigenvalue of a symmetric 3×3 matrix (closed form; the reference calls LAPACK's eigvals)
+__device__ __forceinline__ double sym3_mid_eig(double a00, double a01, double a02, double a11, double a12, double a22) {
+  const double p1 = a01 * a01 + a02 * a02 + a12 * a12;
+  const double q = (a00 + a11 + a22) / 3.0;
+  if (p1 == 0.0) {  // diagonal: the median of the diagonal
+    const double lo = fmin(a00, a11), hi = fmax(a00, a11);
+    return fmax(lo, fmin(hi, a22));
+  }
+  const double b00 = a00 - q, b11 = a11 - q, b22 = a22 - q;
+  const double p2 = b00 * b00 + b11 * b11 + b22 * b22 + 2.0 * p1;
+  const double pp = sqrt(p2 / 6.0);
+  const double c00 = b00 / pp, c11 = b11 / pp, c22 = b22 / pp, c01 = a01 / pp, c02 = a02 / pp, c12 = a12 / pp;
+  const double det = c00 * (c11 * c22 - c12 * c12) - c01 * (c01 * c22 - c12 * c02) + c02 * (c01 * c12 - c11 * c02);
+  const double r = fmin(1.0, fmax(-1.0, det / 2.0));
+  const double phi = acos(r) / 3.0;
+  const double e1 = q + 2.0 * pp * cos(phi);                                   // largest
+  const double e3 = q + 2.0 * pp * cos(phi + 2.0943951023931954923084289221863);  // smallest
+  return 3.0 * q - e1 - e3;
+}
+template <int D>
+__global__ void __launch_bounds__(256) k_derived(DerivedArgs a) {
+  const GridD& g = a.g;
+  const Box b = box_interior(g);
+  for_cells(g, b, [&](int i0, int j0, int k0, int64_t I) {
+    float out = 0.f;
+    if (a.kind == WL_DF_KE) {  // Metrics.jl:20-22
+      if (a.hasU) {
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < D; ++i) { const double t = (double)(a.u[I + i * g.comp] + a.u[I + g.s[i] + i * g.comp]) - 2.0 * a.U[i]; s += t * t; }
+        out = (float)(0.125 * s);
+      } else {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < D; ++i) { const float t = a.u[I + i * g.comp] + a.u[I + g.s[i] + i * g.comp]; s += t * t; }
+        out = (float)(0.125 * (double)s);
+      }
+    } else if (a.kind == WL_DF_CURL) {  // Metrics.jl:55: permute((j,k)->∂(j,CI(I,k),u), i), ∂(a,I,f) = f[I]-f[I-δa] (Flow.jl:1)
+      const int i = a.comp - 1, j = (i + 1) % 3, k = (i + 2) % 3;
+      const float fjk = a.u[I + k * g.comp] - a.u[I - g.s[j] + k * g.comp];
+      const float fkj = a.u[I + j * g.comp] - a.u[I - g.s[k] + j * g.comp];
+      out = fjk - fkj;
+    } else if (D == 3) {
+      float J[3][3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) J[i][j] = dudx(g, a.u, i, j, I);
+      // ω(I,u) (Metrics.jl:61): ωᵢ = ∂(k,j) - ∂(j,k), (j,k) = (i%3+1, (i+1)%3+1)
+      const float w[3] = {J[2][1] - J[1][2], J[0][2] - J[2][0], J[1][0] - J[0][1]};
+      if (a.kind == WL_DF_OMEGA_MAG) {
+        out = sqrtf(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+      } else if (a.kind == WL_DF_LAMBDA2) {  // Metrics.jl:40-44
+        float S[3][3], O[3][3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) { S[i][j] = (J[i][j] + J[j][i]) / 2; O[i][j] = (J[i][j] - J[j][i]) / 2; }
+        float M[3][3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            float s2 = 0.f, o2 = 0.f;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { s2 += S[i][k] * S[k][j]; o2 += O[i][k] * O[k][j]; }
+            M[i][j] = s2 + o2;
+          }
+        out = (float)sym3_mid_eig(M[0][0], M[0][1], M[0][2], M[1][1], M[1][2], M[2][2]);
+      } else {  // ω_θ (Metrics.jl:74-78): θ = z × (loc(0,I) - center)
+        const int c[3] = {i0, j0, k0 + g.zoff};
+        double d[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) d[i] = (double)((float)c[i] - 0.5f) - a.center[i];
+        const double th[3] = {a.axis[1] * d[2] - a.axis[2] * d[1], a.axis[2] * d[0] - a.axis[0] * d[2], a.axis[0] * d[1] - a.axis[1] * d[0]};
+        const double n = sqrt(th[0] * th[0] + th[1] * th[1] + th[2] * th[2]);
+        out = n == 0.0 ? 0.f : (float)((th[0] * (double)w[0] + th[1] * (double)w[1] + th[2] * (double)w[2]) / n);
+      }
+    }
+    a.sigma[I] = out;
+  });
+}
+
 }  // namespace
+
+int derived_run(Sim& s, int kind, int comp, const double* U, const double* axis, const double* center) {
+  if (kind < WL_DF_KE || kind > WL_DF_OMEGA_THETA) return wl_fail(WL_ERR_ARG, "wl_derived: bad kind");
+  if (kind == WL_DF_CURL && (comp < 1 || comp > 3 || (s.D == 2 && comp != 3))) return wl_fail(WL_ERR_ARG, "wl_derived: curl component must be 1..3 (3 in 2-D)");
+  if (kind >= WL_DF_OMEGA_MAG && s.D != 3) return wl_fail(WL_ERR_ARG, "wl_derived: this diagnostic needs a 3-D flow");
+  if (kind == WL_DF_OMEGA_THETA && (!axis || !center)) return wl_fail(WL_ERR_ARG, "wl_derived: ω_θ needs an axis and a centre");
+  DerivedArgs a{};
+  a.g = s.g; a.u = s.u; a.sigma = s.sigma; a.kind = kind; a.comp = comp; a.hasU = U ? 1 : 0;
+  for (int k = 0; k < 3; ++k) {
+    a.U[k] = (U && k < s.D) ? U[k] : 0.0;
+    a.axis[k] = (axis && k < s.D) ? axis[k] : 0.0;
+    a.center[k] = (center && k < s.D) ? center[k] : 0.0;
+  }
+  const dim3 blk = wl_pick_block(s.g);
+  const int grid = wl_grid_for(s, box_tiles(box_interior(s.g), blk));
+  if (s.D == 2) k_derived<2><<<grid, blk, 0, s.stream>>>(a);
+  else k_derived<3><<<grid, blk, 0, s.stream>>>(a);
+  ++s.launches;
+  return wl_cuda_check(s, cudaGetLastError(), "k_derived");
+}
 
 int metrics_run(Sim& s, int which, const double* x0, double* out) {
   MetricArgs a{};

@@ -280,3 +280,29 @@ def total_force(sim):
 def pressure_moment(x0, sim):
     """``pressure_moment(x₀,sim)`` — reference src/Metrics.jl:133-141."""
     return sim._eng.pressure_moment(x0, _nds(sim))
+
+
+# ---- Metrics: derived fields (reference src/Metrics.jl:14-77), `@inside sim.flow.σ[I] = f(I,sim.flow.u)` -------
+def ke_field(sim, U=None):
+    """``@inside σ[I] = ke(I,u,U)`` — reference src/Metrics.jl:20-22."""
+    return sim._eng.derived("ke", U=U)
+
+
+def curl_field(sim, i):
+    """``@inside σ[I] = curl(i,I,u)`` — reference src/Metrics.jl:55 (README.md:97 uses i=3 in 2-D)."""
+    return sim._eng.derived("curl", comp=i)
+
+
+def omega_mag_field(sim):
+    """``@inside σ[I] = ω_mag(I,u)`` — reference src/Metrics.jl:67."""
+    return sim._eng.derived("omega_mag")
+
+
+def lambda2_field(sim):
+    """``@inside σ[I] = λ₂(I,u)`` — reference src/Metrics.jl:40-44."""
+    return sim._eng.derived("lambda2")
+
+
+def omega_theta_field(sim, z, center):
+    """``@inside σ[I] = ω_θ(I,z,center,u)`` — reference src/Metrics.jl:74-78."""
+    return sim._eng.derived("omega_theta", axis=z, center=center)
