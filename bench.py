@@ -224,10 +224,9 @@ def run_ours(args):
     d = kern[dom]
     achieved = d["bytes"] / (d["ms"] * 1e-3) / 1e9
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from ncu captures at 512^3 on one GPU
-    # (profiles/r01_launches_tgv512_1gpu_v3.txt, profiles/r01_ncu_full_increment_512.txt).  The "increment" class is
-    # k_increment (9 words/cell, captured: 5.61 GB) and, since the last change, k_prolong_increment_init (10.1 words,
-    # not captured yet): the figure is k_increment's.
-    ncu_traffic = {"increment": 5.61e9, "conv_diff+bdim1": 0.5 * (5.05e9 + 6.73e9), "pcg_update": 3.78e9, "pcg_mult": 4.00e9,
+    # (profiles/r01_launches_tgv512_1gpu_v4.txt, profiles/r01_ncu_full_increment_512.txt).  The "increment" class is
+    # k_increment (9 words/cell, 5.61 GB per launch) and k_prolong_increment_init (10.1 words, 6.01 GB), one each per solve
+    ncu_traffic = {"increment": 0.5 * (5.61e9 + 6.01e9), "conv_diff+bdim1": 0.5 * (5.05e9 + 6.73e9), "pcg_update": 3.78e9, "pcg_mult": 4.00e9,
                    "residual": 5.65e9}
     traffic = ncu_traffic.get(dom) if (N == 512 and world == 1) else None
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
