@@ -78,9 +78,6 @@ Range r_slice(const Grid& g, int i, int j, int low = 1) {
     else { R.lo[k] = low; R.hi[k] = g.n[k]; }
   } return R;
 }
-Range r_all(const Grid& g) {
-  Range R; for (int k = 0; k < 3; ++k) { R.lo[k] = 1; R.hi[k] = g.n[k]; } return R;
-}
 
 // @loop <body> over I ∈ R (util.jl:119-141): one parallel loop per reference loop.
 template <class F>
