@@ -43,6 +43,11 @@ def tgv_ulam(N):
     return ulam, 1.0 / (kappa * RE)
 
 
+def workload_name(N):
+    """`config.workload` — the same string on both arms (the driver compares them)."""
+    return f"3D Taylor-Green vortex {N}^3 periodic, Re=1600, Float32, MultiLevelPoisson"
+
+
 def make_tgv(cls, N, **kw):
     ulam, nu = tgv_ulam(N)
     return cls((N, N, N), (0, 0, 0), N, U=1, nu=nu, ulam=ulam, perdir=(1, 2, 3), **kw)
@@ -111,6 +116,11 @@ def cpu_oracle_run(N, steps, warmup):
     from oracle import oracle
     from oracle.oracle import OracleSimulation
     from waterlily_b200 import sim_step
+    try:
+        ncpu = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncpu = os.cpu_count() or 1
+    oracle.set_num_threads(ncpu)   # all host cores, whatever OMP_NUM_THREADS the launcher exported (torchrun: 1)
     sim = make_tgv(OracleSimulation, N)
     for _ in range(warmup):
         sim_step(sim, remeasure=False)
@@ -132,7 +142,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": "Mcell-updates/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"3D Taylor-Green vortex {args.size}^3 periodic, Re=1600, Float32", "sample": sample},
+        "config": {"workload": workload_name(args.size), "sample": sample},
         "cpu_baseline": {"value": val, "unit": "Mcell-updates/s", "cores": cores, "kind": "port", "sample": sample,
                          "note": "the reference is Julia and cannot run in this image; this is the C++/OpenMP oracle, a literal un-fused restatement of it"},
         "e2e": {"value": val, "unit": "Mcell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -285,7 +295,7 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": "Mcell-updates/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"3D Taylor-Green vortex {N}^3 periodic, Re=1600, Float32, MultiLevelPoisson {eng.nlevels()} levels",
+        "config": {"workload": workload_name(N), "multigrid_levels": eng.nlevels(),
                    "vcycles_per_solve": ns, "l2": "working set (~17 GB at 512^3) far exceeds the 126 MB L2; no flush needed",
                    "parallelism": "1 GPU" if world == 1 else f"z-slab x{world}: {info['nz_local']} planes/rank, NCCL halo exchange + all-reduce, coarse levels replicated",
                    "nccl_calls_per_step": collectives / K if world > 1 else 0},

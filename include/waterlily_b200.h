@@ -98,6 +98,9 @@ int wl_create_dist(wl_sim** out, int D, const int* N, double nu, double dt0,
                    const int* perdir, int exitBC, int pois_kind, int device,
                    int rank, int nranks, const char* nccl_id128);
 int wl_dist_info(wl_sim* s, int* rank, int* nranks, int* zoff, int* nz_local, int64_t* collectives);
+/* Destroys the NCCL communicators of this process that no live handle uses (they are cached per id so
+ * that several handles can share one).  Optional; call after the last wl_destroy. */
+int wl_dist_finalize(void);
 /* Host-only (no GPU touched): the slab plan of `rank` — per multigrid level whether it is distributed,
  * its local interior z-planes, the global z offset of local plane 0 and the halo flags of its faces. */
 int wl_dist_plan(int D, const int* N, const int* perdir, int pois_kind, int rank, int nranks, int max_levels,

@@ -37,6 +37,12 @@ def num_threads() -> int:
     return int(load().lib.wlo_num_threads())
 
 
+def set_num_threads(n: int) -> int:
+    """OpenMP threads of the oracle from here on (torchrun exports OMP_NUM_THREADS=1 to its workers)."""
+    load().lib.wlo_set_num_threads(int(n))
+    return num_threads()
+
+
 def engine(dims, **kw) -> Engine:
     return Engine(load(), dims, **kw)
 

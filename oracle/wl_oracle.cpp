@@ -775,6 +775,7 @@ int wlo_dist_info(wl_sim* s, int* rank, int* nranks, int* zoff, int* nz_local, i
   if (collectives) *collectives = 0;
   return WL_OK;
 }
+int wlo_dist_finalize(void) { return WL_OK; }
 int wlo_dist_plan(int, const int*, const int*, int, int, int, int, int*, int*, int*, int*, int*, int*) {
   return fail(WL_ERR_STATE, "the oracle is not distributed");
 }
@@ -892,6 +893,13 @@ int wlo_profile_read(wl_sim*, int, double* ms, int64_t* launches, double* bytes)
 int wlo_set_sum_mode(int mode) { g_sum_mode = mode; return WL_OK; }
 int wlo_profile_count(void) { return 0; }
 const char* wlo_profile_name(int) { return ""; }
+// torchrun exports OMP_NUM_THREADS=1 to its workers: bench.py --impl reference asks for all host cores explicitly
+int wlo_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#endif
+  return WL_OK;
+}
 int wlo_num_threads(void) {
   int n = 1;
 #ifdef _OPENMP

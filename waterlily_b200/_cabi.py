@@ -23,6 +23,7 @@ SIGNATURES = {
     "create_dist": (C.c_int, [C.POINTER(H), C.c_int, c_int_p, C.c_double, C.c_double, c_int_p, C.c_int, C.c_int, C.c_int,
                               C.c_int, C.c_int, C.c_char_p]),
     "dist_info": (C.c_int, [H, c_int_p, c_int_p, c_int_p, c_int_p, c_i64_p]),
+    "dist_finalize": (C.c_int, []),
     "dist_plan": (C.c_int, [C.c_int, c_int_p, c_int_p, C.c_int, C.c_int, C.c_int, C.c_int, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p]),
     "destroy": (C.c_int, [H]),
     "last_error": (C.c_char_p, []),

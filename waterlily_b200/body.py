@@ -107,9 +107,9 @@ class _Combined(AutoBody):
     def measure(self, x, t=0.0, fastd2=math.inf):
         da, na, Va = self.a.measure(x, t, fastd2)
         db, nb, Vb = self.b.measure(x, t, fastd2)
-        if self.op == "-":
+        if self.op == "-":  # a - b = a ∩ -b (src/AutoBody.jl:34): max(da, -db), with -b's flipped normal
             db, nb = -db, -nb
-        useb = (db < da) if self.op in "+-" else (db > da)
+        useb = (db < da) if self.op == "+" else (db > da)
         return torch.where(useb, db, da), torch.where(useb[..., None], nb, na), torch.where(useb[..., None], Vb, Va)
 
 

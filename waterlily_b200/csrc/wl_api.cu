@@ -235,7 +235,7 @@ static std::vector<std::vector<int>> level_dims(int D, const int* N, int pois_ki
   dims.push_back(g0);
   if (pois_kind == WL_POIS_MULTILEVEL) {
     auto div_ok = [&](const std::vector<int>& n) { for (int k = 0; k < D; ++k) if (!divisible(n[k])) return false; return true; };
-    while (div_ok(dims.back()) && (int)dims.size() < WL_MAXLEVELS) {  // MultiLevelPoisson.jl:53
+    while (div_ok(dims.back()) && (int)dims.size() <= 10) {  // MultiLevelPoisson.jl:53: length(levels) <= maxlevels (=10) → at most 11 levels
       std::vector<int> c(3, 1);
       for (int k = 0; k < D; ++k) c[k] = 1 + dims.back()[k] / 2;  // restrictML :20
       dims.push_back(c);
@@ -352,6 +352,7 @@ static int create_impl(wl_sim** out, int D, const int* N, double nu, double dt0,
   if (!rc) rc = pois_update(a);
   if (!rc) rc = wl_cuda_check(a, cudaStreamSynchronize(a.stream), "wl_create sync");
   if (rc) { wl_destroy((wl_sim*)sp); return rc; }
+  a.dist.ready = true;
   *out = (wl_sim*)sp;
   return WL_OK;
 }
@@ -389,6 +390,7 @@ int wl_dist_plan(int D, const int* N, const int* perdir, int pois_kind, int rank
   }
   return WL_OK;
 }
+int wl_dist_finalize(void) { return dist_finalize(); }
 int wl_dist_info(wl_sim* s, int* rank, int* nranks, int* zoff, int* nz_local, int64_t* collectives) {
   if (!s) return wl_fail(WL_ERR_ARG, "null handle");
   Sim& a = *(Sim*)s;
@@ -426,7 +428,13 @@ int wl_set_stream(wl_sim* s, void* stream) {
   S.stream = (cudaStream_t)stream;
   return WL_OK;
 }
-int wl_sync(wl_sim* s) { GUARD(s); return wl_cuda_check(S, cudaStreamSynchronize(S.stream), "wl_sync"); }
+// every collective entry point ends here: a peer wait that timed out inside one of its kernels
+// surfaces as an error of THIS call, not of some later wl_mom_step
+int wl_sync(wl_sim* s) {
+  GUARD(s);
+  const int rc = wl_cuda_check(S, cudaStreamSynchronize(S.stream), "wl_sync");
+  return rc ? rc : dist_check_p2p_error(S);
+}
 
 int wl_field_count(wl_sim* s, int field, int64_t* count) {
   GUARD(s);

@@ -23,6 +23,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <vector>
 
 #include "wl_internal.h"
@@ -66,6 +67,10 @@ int nccl_check(Sim& s, ncclResult_t r, const char* what) {
   return wl_fail(WL_ERR_NCCL, std::string("NCCL error in ") + what + ": " + (N.GetErrorString ? N.GetErrorString(r) : "?"));
 }
 #define WL_NCCL(s, call) do { int _rc = nccl_check((s), (call), #call); if (_rc) return _rc; } while (0)
+
+struct CommRef { ncclComm_t comm; int refs; };
+std::mutex g_comm_mu;                      // wl_create_dist may be called from several host threads
+std::map<std::string, CommRef> g_comms;   // NCCL unique id → communicator
 }  // namespace
 
 int dist_unique_id(char* out128) {
@@ -85,19 +90,20 @@ int dist_init(Sim& s, int rank, int nranks, const char* id128) {
   if (nranks == 1) return 0;
   std::string err;
   if (!load_nccl(err)) return wl_fail(WL_ERR_NCCL, err);
-  // a unique id creates exactly one communicator: handles made with the same id share it
-  // (it lives until the process exits)
-  static std::map<std::string, ncclComm_t> comms;
+  // a unique id creates exactly one communicator (NCCL ids are single-use): handles made with the
+  // same id share it, and it lives until wl_dist_finalize() or process exit
+  std::lock_guard<std::mutex> lock(g_comm_mu);
   const std::string key(id128, 128);
-  auto it = comms.find(key);
-  if (it == comms.end()) {
+  auto it = g_comms.find(key);
+  if (it == g_comms.end()) {
     ncclUniqueId id;
     memcpy(&id, id128, 128);
     ncclComm_t comm;
     WL_NCCL(s, N.CommInitRank(&comm, nranks, id, rank));
-    it = comms.emplace(key, comm).first;
+    it = g_comms.emplace(key, CommRef{comm, 0}).first;
   }
-  s.dist.comm = (void*)it->second;
+  ++it->second.refs;
+  s.dist.comm = (void*)it->second.comm;
   return 0;
 }
 
@@ -254,9 +260,12 @@ int dist_check_p2p_error(Sim& s) {
   return 0;
 }
 
-// all ranks leave together: nobody frees an arena a peer may still be writing to
+// all ranks leave together: nobody frees an arena a peer may still be writing to.  The farewell
+// handshake is collective, so it only runs for a handle that finished wl_create_dist on every rank
+// (s.dist.ready) and is not in a failed state — a rank that failed during create must not make its
+// peers spin until the timeout.
 void dist_destroy(Sim& s) {
-  if (s.dist.p2p && !s.sticky) {
+  if (s.dist.p2p && s.dist.ready && !s.sticky) {
     PushPlan plan{};
     for (int r = 0; r < s.dist.nranks; ++r) if (r != s.dist.rank) plan_add_peer(plan, r);
     push(s, plan, 0);
@@ -265,9 +274,27 @@ void dist_destroy(Sim& s) {
   if (s.dist.p2p)
     for (int r = 0; r < s.dist.nranks; ++r) if (r != s.dist.rank && s.dist.host.base[r]) cudaIpcCloseMemHandle(s.dist.host.base[r]);
   s.dist.p2p = false;
+  if (s.dist.comm) {
+    std::lock_guard<std::mutex> lock(g_comm_mu);
+    for (auto& kv : g_comms) if ((void*)kv.second.comm == s.dist.comm) { --kv.second.refs; break; }
+  }
   s.dist.comm = nullptr;
 }
 
+
+// destroys every cached communicator that no live handle uses (call once, after the last wl_destroy)
+int dist_finalize() {
+  std::lock_guard<std::mutex> lock(g_comm_mu);
+  for (auto it = g_comms.begin(); it != g_comms.end();) {
+    if (it->second.refs <= 0) {
+      if (N.CommDestroy) N.CommDestroy(it->second.comm);
+      it = g_comms.erase(it);
+    } else {
+      ++it;
+    }
+  }
+  return 0;
+}
 
 // Exchange `depth` z-planes per side of `ncomp` components of a field living on grid g.
 // base points at cell (0,0,0) of component 0; plane k starts at base + k*s2.

@@ -44,6 +44,7 @@ struct DistState {
   void* comm = nullptr;  // ncclComm_t (bootstrap, and the data path when peer mapping is off)
   // peer-memory path (wl_p2p.cuh): arenas of all ranks mapped over CUDA IPC
   bool p2p = false;
+  bool ready = false;            // wl_create_dist completed (the collective teardown handshake is safe)
   P2PDev host{};                 // host copy of the device context
   P2PDev* dev = nullptr;         // the same in device memory (kernels take the pointer)
   int64_t pushes = 0;            // peer-push kernels launched
@@ -115,6 +116,7 @@ int dist_init(Sim& s, int rank, int nranks, const char* id128);
 int dist_p2p_setup(Sim& s);   // after the arena exists: exchange IPC handles, map the peers
 int dist_check_p2p_error(Sim& s);  // a peer wait timed out → sticky failure
 void dist_destroy(Sim& s);
+int dist_finalize();
 int dist_halo(Sim& s, const GridD& g, float* base, int ncomp, int depth);
 int dist_allreduce(Sim& s, double* dptr, int count, bool is_max);
 int dist_allgather(Sim& s, float* base, size_t count);

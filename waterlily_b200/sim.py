@@ -84,10 +84,34 @@ def BCTuple(U, dt, N, t=None):
 
 
 def _ddt(fun, i, t):
-    """d/dt of a host closure ``U(i,t)`` (the reference uses ForwardDiff.derivative,
-    src/Flow.jl:71-72); central difference in Float64, exact for the polynomial ramps used."""
-    h = 1e-4 * max(1.0, abs(t))
-    return (float(fun(i, t + h)) - float(fun(i, t - h))) / (2 * h)
+    """d/dt of a host closure ``U(i,t)`` — the reference uses ForwardDiff.derivative (src/Flow.jl:71-72).
+
+    In order: (1) a user-supplied exact derivative ``fun.ddt(i,t)``; (2) forward-mode AD through the
+    closure when it is written with torch ops (``torch.func.jvp``, exact like ForwardDiff); (3) a
+    4th-order finite difference in Float64 — central, or one-sided forward when the two disagree,
+    i.e. at a kink such as a ramp that starts at ``t`` (ForwardDiff differentiates the branch taken
+    at ``t``, which for ``t ≥ t_kink`` conditions is the forward one)."""
+    exact = getattr(fun, "ddt", None)
+    if callable(exact):
+        return float(exact(i, t))
+    try:
+        import torch
+        tt = torch.tensor(float(t), dtype=torch.float64)
+        y, dy = torch.func.jvp(lambda s: torch.as_tensor(fun(i, s), dtype=torch.float64), (tt,), (torch.ones_like(tt),))
+        if torch.is_tensor(dy) and bool(torch.isfinite(dy)):
+            # a closure that ignores the dual part (pure-Python arithmetic on float(s)) raises above or returns 0 with y ≠ const;
+            # accept the AD result only if it agrees with a coarse difference, else fall through
+            h = 1e-3 * max(1.0, abs(t))
+            fd = (float(fun(i, t + h)) - float(fun(i, t))) / h
+            if abs(float(dy) - fd) <= 1e-2 * max(1.0, abs(fd)):
+                return float(dy)
+    except Exception:
+        pass
+    h = 1e-3 * max(1.0, abs(t))
+    f = lambda s: float(fun(i, s))
+    central = (f(t - 2 * h) - 8 * f(t - h) + 8 * f(t + h) - f(t + 2 * h)) / (12 * h)
+    forward = (-25 * f(t) + 48 * f(t + h) - 36 * f(t + 2 * h) + 16 * f(t + 3 * h) - 3 * f(t + 4 * h)) / (12 * h)
+    return forward if abs(central - forward) > 1e-6 * max(1.0, abs(forward)) else central
 
 
 class Flow:
