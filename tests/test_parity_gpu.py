@@ -344,3 +344,57 @@ def test_derived_fields_on_cuda():
                      ("lambda2", {}), ("omega_theta", {"axis": (0, 0, 1), "center": (16, 16, 16)})):
         a, b = sc._eng.derived(kind, **kw)[inside], so._eng.derived(kind, **kw)[inside]
         assert np.abs(a - b).max() <= 1e-4 * max(np.abs(b).max(), 1e-6), (kind, np.abs(a - b).max(), np.abs(b).max())
+
+
+@pytest.mark.parametrize("make,steps", [(lambda cls: tgv3d(cls, 32), 3), (lambda cls: sphere3d(cls, exitBC=True), 3), (circle2d, 6)])
+@pytest.mark.parametrize("solve_cells", ["0", "1000000000"])
+def test_uniform_coefficient_packs_are_bit_identical(make, steps, solve_cells, monkeypatch):
+    # Lvl::umask (wl_common.cuh): packs whose face coefficients all equal the level constant use constants for
+    # L, D, iD instead of loading them — same operands, same operations: every field must come out bit for bit
+    # the same as with the fast path switched off (WL_UNIFORM=0), in the per-level kernels and in the fused solver
+    monkeypatch.setenv("WL_FUSED_SOLVE_CELLS", solve_cells)
+    monkeypatch.setenv("WL_UNIFORM", "0")
+    s0 = make(Simulation)
+    monkeypatch.setenv("WL_UNIFORM", "1")
+    s1 = make(Simulation)
+    for _ in range(steps):
+        sim_step(s0, remeasure=False)
+        sim_step(s1, remeasure=False)
+    assert s0.pois.n == s1.pois.n and s0.flow.dt == s1.flow.dt
+    for f in ("u", "p", "f", "sigma"):
+        assert np.array_equal(getattr(s1.flow, f).numpy(), getattr(s0.flow, f).numpy()), f
+
+
+def test_uniform_mask_goes_stale_with_L():
+    # changing L (≡ μ₀) without update! must fall back to loading L, D, iD (the reference would use the new L with
+    # the old D); update! re-validates the mask
+    eo, ec = pair((16, 16, 16), perdir=(1, 2, 3), kind=_cabi.POIS_MULTILEVEL, random_fields=("p", "sigma"))
+    rng = np.random.default_rng(3)
+    L = np.ones(eo.shape(_cabi.FIELD_IDS["mu0"]), dtype=np.float32, order="F")
+    L[5:9, 4:7, 3:11, :] = rng.random((4, 3, 8, 3)).astype(np.float32)
+    for e in (eo, ec):
+        e.level_upload(0, "L", L)          # no update!: D, iD still describe L = 1
+        e.pois_residual(0)
+    assert rel_l2(ec.level_download(0, "r"), eo.level_download(0, "r")) < 1e-6
+    for e in (eo, ec):
+        e.pois_update()
+        e.pois_residual(0)
+    assert rel_l2(ec.level_download(0, "r"), eo.level_download(0, "r")) < 1e-6
+    assert np.array_equal(ec.level_download(0, "D"), eo.level_download(0, "D"))
+
+
+@pytest.mark.parametrize("make,steps", [(lambda cls: tgv3d(cls, 64), 3), (lambda cls: sphere3d(cls, exitBC=True), 4), (lambda cls: sphere3d(cls, n=128, m=64, exitBC=False), 2)])
+def test_z_marching_kernels_match_row_kernels(make, steps, monkeypatch):
+    # k_*_m (for_columns, wl_vec.cuh) against the (row-group, plane) kernels: same arithmetic per cell, different
+    # reduction tree; the fused solver is switched off so that the per-level kernels run on every level
+    monkeypatch.setenv("WL_FUSED_VCYCLE", "0")
+    monkeypatch.setenv("WL_MARCH", "0")
+    s0 = make(Simulation)
+    monkeypatch.setenv("WL_MARCH", "1")
+    s1 = make(Simulation)
+    for _ in range(steps):
+        sim_step(s0, remeasure=False)
+        sim_step(s1, remeasure=False)
+    assert s0.pois.n == s1.pois.n
+    for f in ("u", "p"):
+        assert rel_l2(getattr(s1.flow, f).numpy(), getattr(s0.flow, f).numpy()) < 2e-6, f

@@ -318,6 +318,17 @@ static int create_impl(wl_sim** out, int D, const int* N, double nu, double dt0,
       else { lv.L = dev_alloc(a, lv.g, D, prc); lv.x = dev_alloc(a, lv.g, 1, prc); lv.z = dev_alloc(a, lv.g, 1, prc); }
       lv.r = dev_alloc(a, lv.g, 1, prc); lv.eps = dev_alloc(a, lv.g, 1, prc);
       lv.Dg = dev_alloc(a, lv.g, 1, prc); lv.iD = dev_alloc(a, lv.g, 1, prc);
+      // uniform-coefficient pack mask (one byte per four cells) and this level's constants: L = μ₀ = 1 on the
+      // finest level, ×2^(D-2) per restrictL (½ · 2^(D-1) fine faces, MultiLevelPoisson.jl:10-16); D and iD as set_diag! computes them
+      unsigned char* um = (lv.g.n[0] - 2) % 4 == 0 ? (unsigned char*)arena_take(a, (size_t)lv.g.comp / 4 + 16, prc) : nullptr;
+      if (l < a.umask_store.size()) a.umask_store[l] = um; else a.umask_store.push_back(um);
+      lv.umask = nullptr;
+      lv.uL = l == 0 ? 1.f : a.levels[l - 1].uL * (D == 3 ? 2.f : 1.f);
+      float sD = 0.f;
+      for (int k = 0; k < D; ++k) sD -= (lv.uL + lv.uL);
+      lv.uD = sD;
+      lv.uiD = (sD * sD < 2 * 1.1920929e-07f) ? 0.f : 1.f / sD;
+      lv.upad = 0;
       a.levels.push_back(lv);
     }
   };
@@ -326,6 +337,9 @@ static int create_impl(wl_sim** out, int D, const int* N, double nu, double dt0,
   if (!rc && cudaMalloc(&tmp, sizeof(LevelScalars) * dims.size()) == cudaSuccess) { a.allocs.push_back(tmp); a.d_scalars = (LevelScalars*)tmp; cudaMemsetAsync(tmp, 0, sizeof(LevelScalars) * dims.size(), a.stream); } else if (!rc) rc = wl_fail(WL_ERR_CUDA, "cudaMalloc scalars");
   if (!rc && cudaMalloc(&tmp, sizeof(MiscScalars)) == cudaSuccess) { a.allocs.push_back(tmp); a.d_misc = (MiscScalars*)tmp; cudaMemsetAsync(tmp, 0, sizeof(MiscScalars), a.stream); } else if (!rc) rc = wl_fail(WL_ERR_CUDA, "cudaMalloc misc");
   if (!rc && cudaMalloc(&tmp, sizeof(double) * (WL_MAXBLOCKS * WL_MAXRED + 8)) == cudaSuccess) { a.allocs.push_back(tmp); a.ws.partials = (double*)tmp; } else if (!rc) rc = wl_fail(WL_ERR_CUDA, "cudaMalloc partials");
+  if (!rc && cudaMalloc(&tmp, sizeof(unsigned int) * (dims.size() + 4)) == cudaSuccess) { a.allocs.push_back(tmp); a.d_nonuni = (unsigned int*)tmp; cudaMemsetAsync(tmp, 0, sizeof(unsigned int) * (dims.size() + 4), a.stream); } else if (!rc) rc = wl_fail(WL_ERR_CUDA, "cudaMalloc counters");
+  { const char* e = getenv("WL_UNIFORM"); a.uniform_path = !(e && atoi(e) == 0); }
+  { const char* e = getenv("WL_MARCH"); a.march_on = !(e && atoi(e) == 0); }
   if (!rc && cudaMalloc(&tmp, 64) == cudaSuccess) { a.allocs.push_back(tmp); a.ws.ticket = (unsigned int*)tmp; cudaMemsetAsync(tmp, 0, 64, a.stream); } else if (!rc) rc = wl_fail(WL_ERR_CUDA, "cudaMalloc ticket");
   if (!rc && cudaMallocHost((void**)&a.h_pinned, 64 * sizeof(float)) != cudaSuccess) rc = wl_fail(WL_ERR_CUDA, "cudaMallocHost");
   if (rc) { wl_destroy((wl_sim*)sp); return rc; }
@@ -448,6 +462,7 @@ int wl_upload(wl_sim* s, int field, const float* host, int64_t count) {
   const int nzg = nz_padded_global(S, 0);
   if (!d || count != (int64_t)S.g.n[0] * S.g.n[1] * nzg * nc) return wl_fail(WL_ERR_ARG, "wl_upload: bad field or size");
   if (field == WL_V || field == WL_MU0 || field == WL_MU1) S.mask_dirty = true;
+  if (field == WL_MU0) pois_invalidate_uniform(S, 0);  // levels[1].L ≡ μ₀: stale until update!
   int rc = copy_field(S, S.g, d, const_cast<float*>(host), nc, true, nzg);
   // slab faces: refresh the halo planes from the neighbours (collective: every rank uploads the field)
   if (!rc) rc = dist_halo(S, S.g, d, nc, (field == WL_U || field == WL_U0) ? 2 : 1);
@@ -476,6 +491,7 @@ int wl_level_upload(wl_sim* s, int level, int lf, const float* host, int64_t cou
   const int nzg = nz_padded_global(S, level);
   if (count != (int64_t)g.n[0] * g.n[1] * nzg * nc) return wl_fail(WL_ERR_ARG, "wl_level_upload: bad size");
   if (level == 0 && lf == WL_LVL_L) S.mask_dirty = true;  // levels[1].L ≡ μ₀
+  if (lf == WL_LVL_L || lf == WL_LVL_D || lf == WL_LVL_ID) pois_invalidate_uniform(S, level);
   int rc = copy_field(S, g, d, const_cast<float*>(host), nc, true, nzg);
   if (!rc) rc = dist_halo(S, g, d, nc, 1);
   return rc ? rc : wl_sync(s);
@@ -499,6 +515,7 @@ int wl_bc(wl_sim* s, int field, const double* A, int saveexit, const int* perdir
   if (!d || nc != S.D) return wl_fail(WL_ERR_ARG, "wl_bc: not a vector field");
   int per[3]; per_flags(S, perdir, per);
   if (field == WL_V || field == WL_MU0) S.mask_dirty = true;
+  if (field == WL_MU0) pois_invalidate_uniform(S, 0);
   int rc = bc_vec(S, S.g, d, A, saveexit != 0, per, (field == WL_U || field == WL_U0) ? 2 : 1);
   return rc ? rc : wl_sync(s);
 }
@@ -623,10 +640,12 @@ int wl_profile(wl_sim* s, int on) {
   // pcg! kernels can be predicated off on the device: their traffic is counted from device counters
   LevelScalars* sc = S.levels[0].sc;
   const double cb = 4.0 * (double)S.g.interior;
-  S.prof[WL_PROF_PCG_MULT].d_counter = &sc->cnt_mult;     S.prof[WL_PROF_PCG_MULT].bytes_per_active = 6 * cb;
-  S.prof[WL_PROF_PCG_UPDATE].d_counter = &sc->cnt_update; S.prof[WL_PROF_PCG_UPDATE].bytes_per_active = 7 * cb;
-  S.prof[WL_PROF_PCG_DIR].d_counter = &sc->cnt_dir;       S.prof[WL_PROF_PCG_DIR].bytes_per_active = 4 * cb;
-  int rc = wl_read_scalars(S, sc, sizeof(LevelScalars));
+  int rc = pois_uniform_fraction(S);  // algorithmic bytes depend on how many packs take the uniform-coefficient path
+  if (rc) return rc;
+  S.prof[WL_PROF_PCG_MULT].d_counter = &sc->cnt_mult;     S.prof[WL_PROF_PCG_MULT].bytes_per_active = wl_words(S, S.D + 3, S.D + 1) * cb;
+  S.prof[WL_PROF_PCG_UPDATE].d_counter = &sc->cnt_update; S.prof[WL_PROF_PCG_UPDATE].bytes_per_active = wl_words(S, 7, 1) * cb;
+  S.prof[WL_PROF_PCG_DIR].d_counter = &sc->cnt_dir;       S.prof[WL_PROF_PCG_DIR].bytes_per_active = wl_words(S, 4, 1) * cb;
+  rc = wl_read_scalars(S, sc, sizeof(LevelScalars));
   if (rc) return rc;
   LevelScalars h; memcpy(&h, S.h_pinned, sizeof(h));
   S.prof[WL_PROF_PCG_MULT].counter_base = h.cnt_mult;

@@ -47,6 +47,16 @@ struct Lvl {
   GridD g;
   float *L, *Dg, *iD, *x, *eps, *r, *z;
   LevelScalars* sc;
+  // Uniform-coefficient packs.  Away from bodies and non-periodic boundaries every face coefficient of a
+  // level has the same value uL (μ₀ = 1 on the finest level, MultiLevelPoisson.jl:10-16 scales it by
+  // 2^(D-2) per coarsening), so D = uD and iD = uiD there.  umask holds one byte per aligned pack of four
+  // x-cells — 0 when all 2D faces of all four cells equal uL — written by set_diag! (k_set_diag) from the
+  // actual contents of L.  A stencil on such a pack uses the three constants instead of loading L (D words),
+  // D and iD: same operands, same operations, same bits, 5 words per cell less traffic.  Null when the
+  // mask is stale (L, D or iD changed without update!) or the level's rows are not a multiple of four.
+  const unsigned char* umask;
+  float uL, uD, uiD;
+  int upad;
 };
 
 // device scratch scalars shared by the momentum kernels

@@ -93,6 +93,14 @@ struct Sim {
   int vc_first = -1;           // first level the fused kernel covers (-1: off)
   int last_solve_n[2] = {0, 0};
   bool vc_solve = false;       // the fused kernel runs the whole solver! (one launch, no host read)
+  // uniform-coefficient packs (Lvl::umask): per-level mask storage, non-uniform pack counters, switch
+  std::vector<unsigned char*> umask_store;
+  unsigned int* d_nonuni = nullptr;  // [levels] packs that are NOT uniform, counted by k_set_diag
+  bool uniform_path = true;          // WL_UNIFORM=0 switches the fast path off (every stencil loads L, D, iD)
+  bool march_on = true;              // WL_MARCH=0: the stencil kernels iterate (row-group, plane) units instead of marching in z
+  bool nonuni_known = false;
+  unsigned int nonuni0 = 0;
+  double uni_frac0 = 0.0;            // fraction of uniform packs on the finest level (profiling: algorithmic bytes)
   int sticky = 0;  // first CUDA error, sticky per handle
   bool profiling = false;
   ProfClass prof[WL_PROF_N];
@@ -150,6 +158,14 @@ int bc_exit(Sim& s, const double* U, float dt);
 
 // ---- wl_poisson.cu ----
 int pois_set_diag(Sim& s, Lvl& l);
+void pois_invalidate_uniform(Sim& s, int level);
+int pois_uniform_fraction(Sim& s);  // refreshes s.uni_frac0 (one scalar read)
+// algorithmic words per cell of a finest-level kernel: `generic` when every pack loads its coefficients,
+// `saved` words less on uniform packs, plus the 1/16 word of the pack mask
+inline double wl_words(const Sim& s, double generic, double saved) {
+  const bool on = !s.levels.empty() && s.levels[0].umask != nullptr;
+  return on ? generic - saved * s.uni_frac0 + 0.0625 : generic;
+}
 int pois_restrictL(Sim& s, Lvl& coarse, const Lvl& fine);
 int pois_update(Sim& s);
 int pois_mult(Sim& s);

@@ -429,14 +429,19 @@ __global__ void __launch_bounds__(256) k_scale_alloc(float4* __restrict__ x, int
   }
 }
 // project!: u[I,i] -= L[I,i]*∂(i,I,x) (Flow.jl:141-143)
+// On a uniform pack (Lvl::umask) L[I,i] is the constant uL = 1 and is not loaded.
 template <int D, int V>
-__global__ void __launch_bounds__(256) k_project_correct(GridD g, float* __restrict__ u, const float* __restrict__ L, const float* __restrict__ x) {
+__global__ void __launch_bounds__(256) k_project_correct(Lvl l, float* __restrict__ u) {
+  const GridD& g = l.g;
+  const float* __restrict__ L = l.L;
+  const float* __restrict__ x = l.x;
   for_rows<V>(g, [&](int, int, int, int64_t I) {
     const Pack<V> xc = ldp<V>(x + I);
+    const bool uni = pack_uniform<V>(l, I);
 #pragma unroll
     for (int i = 0; i < D; ++i) {
       const Pack<V> xm = i == 0 ? ld_xm<V>(x + I, xc) : ldp<V>(x + I - g.s[i]);
-      const Pack<V> Lc = ldp<V>(L + I + i * g.comp);
+      const Pack<V> Lc = uni ? splat<V>(l.uL) : ldp<V>(L + I + i * g.comp);
       Pack<V> uc = ldp<V>(u + I + i * g.comp);
 #pragma unroll
       for (int q = 0; q < V; ++q) uc.v[q] -= Lc.v[q] * (xc.v[q] - xm.v[q]);
@@ -618,12 +623,12 @@ int mom_project(Sim& s, double w, int* n, int slot, bool defer_count, bool skip_
   int rc = pois_solve(s, 1e-4, s.pois_kind == WL_POIS_MULTILEVEL ? 32 : 1000, n, true, slot, defer_count);
   if (rc) return rc;
   wl_prof_begin(s, WL_PROF_PROJECT);
-  RLAUNCH(s, k_project_correct, s.g, s.g, s.u, b.L, b.x);
+  RLAUNCH(s, k_project_correct, s.g, b, s.u);
   if (!skip_unscale) {
     k_scale_alloc<<<sgrid, 256, 0, s.stream>>>(xall, n4, (float)dtw, dtw, f32 ? 1 : 0, 1, 0.f);
     ++s.launches;
   }
-  wl_prof_end(s, WL_PROF_PROJECT, 4.0 * (double)s.g.interior * (3 * s.D + 1 + (skip_unscale ? 0 : 2)));
+  wl_prof_end(s, WL_PROF_PROJECT, 4.0 * (double)s.g.interior * (wl_words(s, 3 * s.D + 1, s.D) + (skip_unscale ? 0 : 2)));
   return wl_cuda_check(s, cudaGetLastError(), "project");
 }
 // CFL(a) (Flow.jl:172-175)

@@ -41,30 +41,43 @@ __device__ __forceinline__ Pack<V> mult_row(const Lvl& l, int64_t I, const float
 }
 
 // set_diag! (Poisson.jl:42-45) with diag (:48-54)
+// Also classifies every aligned pack of four cells: umask = 0 when all its 2D·4 face coefficients equal
+// uL (then D = uD and iD = uiD exactly, see Lvl) — `umask` is the array to fill (or null), `nonuni`
+// counts the other packs (profiling: algorithmic bytes depend on it).
 template <int D, int V>
-__global__ void __launch_bounds__(256) k_set_diag(Lvl l) {
+__global__ void __launch_bounds__(256) k_set_diag(Lvl l, unsigned char* __restrict__ umask, unsigned int* __restrict__ nonuni) {
+  unsigned int mine = 0;
   for_rows<V>(l.g, [&](int, int, int, int64_t I) {
     Pack<V> s;
+    bool uni = true;
 #pragma unroll
     for (int q = 0; q < V; ++q) s.v[q] = 0.f;
     {
       const Pack<V> Lc = ldp<V>(l.L + I), Lp = ld_xp<V>(l.L + I, Lc);
 #pragma unroll
-      for (int q = 0; q < V; ++q) s.v[q] -= (Lc.v[q] + Lp.v[q]);
+      for (int q = 0; q < V; ++q) { s.v[q] -= (Lc.v[q] + Lp.v[q]); uni &= (Lc.v[q] == l.uL) & (Lp.v[q] == l.uL); }
     }
 #pragma unroll
     for (int i = 1; i < D; ++i) {
       const float* __restrict__ Li = l.L + i * l.g.comp;
       const Pack<V> Lc = ldp<V>(Li + I), Lp = ldp<V>(Li + I + l.g.s[i]);
 #pragma unroll
-      for (int q = 0; q < V; ++q) s.v[q] -= (Lc.v[q] + Lp.v[q]);
+      for (int q = 0; q < V; ++q) { s.v[q] -= (Lc.v[q] + Lp.v[q]); uni &= (Lc.v[q] == l.uL) & (Lp.v[q] == l.uL); }
     }
     Pack<V> inv;
 #pragma unroll
     for (int q = 0; q < V; ++q) inv.v[q] = (s.v[q] * s.v[q] < 2 * WL_EPS32) ? 0.f : 1.f / s.v[q];
     stp<V>(l.Dg + I, s);
     stp<V>(l.iD + I, inv);
+    if (V == 4 && umask) {
+      umask[(I + l.g.lead) >> 2] = uni ? 0 : 1;
+      mine += uni ? 0u : 1u;
+    }
   });
+  if (V == 4 && nonuni) {
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    if (((threadIdx.x + blockDim.x * threadIdx.y) & 31) == 0 && mine) atomicAdd(nonuni, mine);
+  }
 }
 
 // restrictL! interior part (MultiLevelPoisson.jl:26-30) with restrictL (:10-16), up(I,i) (:1)
@@ -96,7 +109,8 @@ template <int D, int V>
 __global__ void __launch_bounds__(256) k_residual(Lvl l, ReduceWS ws, FinArgs fa, int write_eps) {
   double acc[2] = {0.0, 0.0};
   for_rows<V>(l.g, [&](int i, int j, int k, int64_t I) {
-    const Pack<V> xc = ldp<V>(l.x + I), ax = mult_w<D, V>(l, l.x, i, j, k, I, xc), zc = ldp<V>(l.z + I), id = ldp<V>(l.iD + I);
+    const bool uni = pack_uniform<V>(l, I);
+    const Pack<V> xc = ldp<V>(l.x + I), ax = mult_w<D, V>(l, l.x, i, j, k, I, xc, uni), zc = ldp<V>(l.z + I), id = ld_iD<V>(l, I, uni);
     Pack<V> r;
 #pragma unroll
     for (int q = 0; q < V; ++q) {
@@ -127,7 +141,7 @@ __global__ void __launch_bounds__(256) k_sub_mean(Lvl l, ReduceWS ws, FinArgs fa
     for (int q = 0; q < V; ++q) { r.v[q] = r.v[q] - s; acc[0] += (double)r.v[q] * (double)r.v[q]; }
     stp<V>(l.r + I, r);
     if (write_eps) {
-      const Pack<V> id = ldp<V>(l.iD + I);
+      const Pack<V> id = ld_iD<V>(l, I, pack_uniform<V>(l, I));
       Pack<V> e;
 #pragma unroll
       for (int q = 0; q < V; ++q) e.v[q] = r.v[q] * id.v[q];
@@ -151,7 +165,7 @@ __global__ void __launch_bounds__(256) k_mult(Lvl l) {
 template <int D, int V>
 __global__ void __launch_bounds__(256) k_jacobi_eps(Lvl l) {
   for_rows<V>(l.g, [&](int, int, int, int64_t I) {
-    const Pack<V> r = ldp<V>(l.r + I), id = ldp<V>(l.iD + I);
+    const Pack<V> r = ldp<V>(l.r + I), id = ld_iD<V>(l, I, pack_uniform<V>(l, I));
     Pack<V> e;
 #pragma unroll
     for (int q = 0; q < V; ++q) e.v[q] = r.v[q] * id.v[q];
@@ -164,7 +178,7 @@ template <int D, int V>
 __global__ void __launch_bounds__(256) k_increment(Lvl l, ReduceWS ws, FinArgs fa) {
   double acc[1] = {0.0};
   for_rows<V>(l.g, [&](int i, int j, int k, int64_t I) {
-    const Pack<V> ec = ldp<V>(l.eps + I), ae = mult_w<D, V>(l, l.eps, i, j, k, I, ec);
+    const Pack<V> ec = ldp<V>(l.eps + I), ae = mult_w<D, V>(l, l.eps, i, j, k, I, ec, pack_uniform<V>(l, I));
     Pack<V> r = ldp<V>(l.r + I), x = ldp<V>(l.x + I);
 #pragma unroll
     for (int q = 0; q < V; ++q) {
@@ -220,6 +234,153 @@ __global__ void __launch_bounds__(256) k_prolong_increment_init(Lvl f, Lvl c, Pr
   if (grid_reduce<2>(acc, ws, tot)) finish_reduction(FIN_INC_INIT, fa, tot[0], tot[1]);
 }
 
+// ---- z-marching variants of the stencil kernels (3-D, V = 4; see for_columns in wl_vec.cuh) ---------
+// Same arithmetic as k_residual / k_increment / k_pcg_mult / k_prolong_increment_init, cell for cell.
+__global__ void __launch_bounds__(256) k_residual_m(Lvl l, MarchGeom mg, ReduceWS ws, FinArgs fa, int write_eps) {
+  double acc[2] = {0.0, 0.0};
+  const GridD& g = l.g;
+  for_columns(g, mg, [&](int i, int j, int k0, int k1) {
+    int64_t I = i + j * g.s[1] + (int64_t)k0 * g.s[2];
+    Pack<4> xm = ldp<4>(l.x + I + zoff_m(g, k0)), xc = ldp<4>(l.x + I);
+    for (int k = k0; k <= k1; ++k, I += g.s[2]) {
+      const Pack<4> xp = ldp<4>(l.x + I + zoff_p(g, k));
+      const bool uni = pack_uniform<4>(l, I);
+      const Pack<4> ax = mult_zreg<4>(l, l.x, i, j, I, xc, xm, xp, uni), zc = ldp<4>(l.z + I), id = ld_iD<4>(l, I, uni);
+      Pack<4> r;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        r.v[q] = id.v[q] == 0.f ? 0.f : zc.v[q] - ax.v[q];
+        acc[0] += (double)r.v[q];
+        acc[1] += (double)r.v[q] * (double)r.v[q];
+      }
+      stp<4>(l.r + I, r);
+      if (write_eps) {
+        Pack<4> e;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) e.v[q] = r.v[q] * id.v[q];
+        stp<4>(l.eps + I, e);
+      }
+      xm = xc; xc = xp;
+    }
+  });
+  double tot[2];
+  if (grid_reduce<2>(acc, ws, tot)) finish_reduction(FIN_RESIDUAL, fa, tot[0], tot[1]);
+}
+__global__ void __launch_bounds__(256) k_increment_m(Lvl l, MarchGeom mg, ReduceWS ws, FinArgs fa) {
+  double acc[1] = {0.0};
+  const GridD& g = l.g;
+  for_columns(g, mg, [&](int i, int j, int k0, int k1) {
+    int64_t I = i + j * g.s[1] + (int64_t)k0 * g.s[2];
+    Pack<4> em = ldp<4>(l.eps + I + zoff_m(g, k0)), ec = ldp<4>(l.eps + I);
+    for (int k = k0; k <= k1; ++k, I += g.s[2]) {
+      const Pack<4> ep = ldp<4>(l.eps + I + zoff_p(g, k));
+      const Pack<4> ae = mult_zreg<4>(l, l.eps, i, j, I, ec, em, ep, pack_uniform<4>(l, I));
+      Pack<4> r = ldp<4>(l.r + I), x = ldp<4>(l.x + I);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        r.v[q] = r.v[q] - ae.v[q];
+        x.v[q] = x.v[q] + ec.v[q];
+        acc[0] += (double)r.v[q] * (double)r.v[q];
+      }
+      stp<4>(l.r + I, r);
+      stp<4>(l.x + I, x);
+      em = ec; ec = ep;
+    }
+  });
+  double tot[1];
+  if (grid_reduce<1>(acc, ws, tot)) finish_reduction(FIN_R2, fa, tot[0], 0.0);
+}
+__global__ void __launch_bounds__(256) k_pcg_mult_m(Lvl l, MarchGeom mg, ReduceWS ws, FinArgs fa) {
+  if (!l.sc->active) return;
+  double acc[1] = {0.0};
+  const GridD& g = l.g;
+  for_columns(g, mg, [&](int i, int j, int k0, int k1) {
+    int64_t I = i + j * g.s[1] + (int64_t)k0 * g.s[2];
+    Pack<4> em = ldp<4>(l.eps + I + zoff_m(g, k0)), ec = ldp<4>(l.eps + I);
+    for (int k = k0; k <= k1; ++k, I += g.s[2]) {
+      const Pack<4> ep = ldp<4>(l.eps + I + zoff_p(g, k));
+      const Pack<4> z = mult_zreg<4>(l, l.eps, i, j, I, ec, em, ep, pack_uniform<4>(l, I));
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[0] += (double)z.v[q] * (double)ec.v[q];
+      stp<4>(l.z + I, z);
+      em = ec; ec = ep;
+    }
+  });
+  double tot[1];
+  if (grid_reduce<1>(acc, ws, tot)) finish_reduction(FIN_PCG_MULT, fa, tot[0], 0.0);
+}
+// prolongate! + increment! + head of pcg!: ϵ of a fine pack (i = 1+4t) is {c, c, c', c'} with (c, c') the aligned
+// coarse pair at ci = 1+2t, so a pack costs one 8-byte load per coarse row it touches
+__device__ __forceinline__ Pack<4> pro_pack(const float* __restrict__ crow, int ci) {
+  const float2 c = *reinterpret_cast<const float2*>(crow + ci);
+  Pack<4> e; e.v[0] = c.x; e.v[1] = c.x; e.v[2] = c.y; e.v[3] = c.y;
+  return e;
+}
+__global__ void __launch_bounds__(256) k_prolong_increment_init_m(Lvl f, Lvl c, ProMap m, MarchGeom mg, ReduceWS ws, FinArgs fa) {
+  double acc[2] = {0.0, 0.0};
+  const GridD& g = f.g;
+  const float* __restrict__ xc = c.x;
+  const int64_t cs1 = c.g.s[1], cs2 = c.g.s[2];
+  for_columns(g, mg, [&](int i, int j, int k0, int k1) {
+    int64_t I = i + j * g.s[1] + (int64_t)k0 * g.s[2];
+    const int ci = (i + 1) >> 1;
+    const int cim = pro_cidx(m, 0, i - 1), cip = pro_cidx(m, 0, i + 4);
+    const int64_t Jy = pro_cidx(m, 1, j) * cs1, Jym = pro_cidx(m, 1, j - 1) * cs1, Jyp = pro_cidx(m, 1, j + 1) * cs1;
+    for (int k = k0; k <= k1; ++k, I += g.s[2]) {
+      const int64_t Jz = pro_cidx(m, 2, k) * cs2, Jzm = pro_cidx(m, 2, k - 1) * cs2, Jzp = pro_cidx(m, 2, k + 1) * cs2;
+      const float* row = xc + Jy + Jz;
+      const Pack<4> e = pro_pack(row, ci);
+      Pack<4> xm, xp;
+      xm.v[0] = row[cim]; xm.v[1] = e.v[0]; xm.v[2] = e.v[1]; xm.v[3] = e.v[2];
+      xp.v[0] = e.v[1]; xp.v[1] = e.v[2]; xp.v[2] = e.v[3]; xp.v[3] = row[cip];
+      const bool uni = pack_uniform<4>(f, I);
+      const Pack<4> Dc = uni ? splat<4>(f.uD) : ldp<4>(f.Dg + I);
+      Pack<4> s;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) s.v[q] = e.v[q] * Dc.v[q];
+      {
+        Pack<4> Lc, Lp;
+        if (uni) { Lc = splat<4>(f.uL); Lp = Lc; }
+        else { Lc = ldp<4>(f.L + I); Lp = ld_xp<4>(f.L + I, Lc); }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) s.v[q] += (xm.v[q] * Lc.v[q] + xp.v[q] * Lp.v[q]);
+      }
+      {
+        const Pack<4> em = pro_pack(xc + Jym + Jz, ci), ep = pro_pack(xc + Jyp + Jz, ci);
+        Pack<4> Lc, Lp;
+        if (uni) { Lc = splat<4>(f.uL); Lp = Lc; }
+        else { Lc = ldp<4>(f.L + g.comp + I); Lp = ldp<4>(f.L + g.comp + I + g.s[1]); }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) s.v[q] += (em.v[q] * Lc.v[q] + ep.v[q] * Lp.v[q]);
+      }
+      {
+        const Pack<4> em = pro_pack(xc + Jy + Jzm, ci), ep = pro_pack(xc + Jy + Jzp, ci);
+        Pack<4> Lc, Lp;
+        if (uni) { Lc = splat<4>(f.uL); Lp = Lc; }
+        else { Lc = ldp<4>(f.L + 2 * g.comp + I); Lp = ldp<4>(f.L + 2 * g.comp + I + g.s[2]); }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) s.v[q] += (em.v[q] * Lc.v[q] + ep.v[q] * Lp.v[q]);
+      }
+      Pack<4> r = ldp<4>(f.r + I), x = ldp<4>(f.x + I);
+      const Pack<4> id = ld_iD<4>(f, I, uni);
+      Pack<4> en;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        r.v[q] = r.v[q] - s.v[q];
+        x.v[q] = x.v[q] + e.v[q];
+        en.v[q] = r.v[q] * id.v[q];
+        acc[0] += (double)r.v[q] * (double)en.v[q];
+        acc[1] += (double)r.v[q] * (double)r.v[q];
+      }
+      stp<4>(f.r + I, r);
+      stp<4>(f.x + I, x);
+      stp<4>(f.eps + I, en);
+    }
+  });
+  double tot[2];
+  if (grid_reduce<2>(acc, ws, tot)) finish_reduction(FIN_INC_INIT, fa, tot[0], tot[1]);
+}
+
 // ---- pcg! (Poisson.jl:123-144) -----------------------------------------------------------
 // :125-127  z = ϵ = r·iD ; ρ = r⋅z ; |ρ|<10eps → return      (z is rewritten by k_pcg_mult before
 // any read, so only ϵ is stored)
@@ -227,7 +388,7 @@ template <int D, int V>
 __global__ void __launch_bounds__(256) k_pcg_init(Lvl l, ReduceWS ws, FinArgs fa) {
   double acc[1] = {0.0};
   for_rows<V>(l.g, [&](int, int, int, int64_t I) {
-    const Pack<V> r = ldp<V>(l.r + I), id = ldp<V>(l.iD + I);
+    const Pack<V> r = ldp<V>(l.r + I), id = ld_iD<V>(l, I, pack_uniform<V>(l, I));
     Pack<V> e;
 #pragma unroll
     for (int q = 0; q < V; ++q) { e.v[q] = r.v[q] * id.v[q]; acc[0] += (double)r.v[q] * (double)e.v[q]; }
@@ -243,7 +404,7 @@ __global__ void __launch_bounds__(256) k_pcg_mult(Lvl l, ReduceWS ws, FinArgs fa
   if (!l.sc->active) return;
   double acc[1] = {0.0};
   for_rows<V>(l.g, [&](int i, int j, int k, int64_t I) {
-    const Pack<V> ec = ldp<V>(l.eps + I), z = mult_w<D, V>(l, l.eps, i, j, k, I, ec);
+    const Pack<V> ec = ldp<V>(l.eps + I), z = mult_w<D, V>(l, l.eps, i, j, k, I, ec, pack_uniform<V>(l, I));
 #pragma unroll
     for (int q = 0; q < V; ++q) acc[0] += (double)z.v[q] * (double)ec.v[q];
     stp<V>(l.z + I, z);
@@ -259,7 +420,7 @@ __global__ void __launch_bounds__(256) k_pcg_update(Lvl l, ReduceWS ws, FinArgs 
   const float alpha = l.sc->alpha;
   double acc[2] = {0.0, 0.0};
   for_rows<V>(l.g, [&](int, int, int, int64_t I) {
-    const Pack<V> e = ldp<V>(l.eps + I), z = ldp<V>(l.z + I), id = ldp<V>(l.iD + I);
+    const Pack<V> e = ldp<V>(l.eps + I), z = ldp<V>(l.z + I), id = ld_iD<V>(l, I, pack_uniform<V>(l, I));
     Pack<V> x = ldp<V>(l.x + I), r = ldp<V>(l.r + I);
 #pragma unroll
     for (int q = 0; q < V; ++q) {
@@ -281,7 +442,7 @@ __global__ void __launch_bounds__(256) k_pcg_dir(Lvl l) {
   const float beta = l.sc->beta;
   if (blockIdx.x == 0 && threadIdx.x + threadIdx.y + threadIdx.z == 0) atomicAdd(&l.sc->cnt_dir, 1);
   for_rows<V>(l.g, [&](int, int, int, int64_t I) {
-    const Pack<V> r = ldp<V>(l.r + I), id = ldp<V>(l.iD + I);
+    const Pack<V> r = ldp<V>(l.r + I), id = ld_iD<V>(l, I, pack_uniform<V>(l, I));
     Pack<V> e = ldp<V>(l.eps + I);
 #pragma unroll
     for (int q = 0; q < V; ++q) e.v[q] = beta * e.v[q] + r.v[q] * id.v[q];
@@ -328,7 +489,14 @@ __global__ void k_finalize(int stage, FinArgs fa) {
 
 }  // namespace
 
-static inline double cellsB(const Lvl& l, int words) { return 4.0 * words * (double)l.g.interior; }
+
+static int level_of(const Sim& s, const Lvl& l) { return (int)(&l - &s.levels[0]); }
+
+// z-marching geometry of a level, or ok = false (2-D, small or odd-sized levels, WL_MARCH=0)
+static MarchLaunch march_for(const Sim& s, const GridD& g) {
+  if (!s.march_on) { MarchLaunch m{}; return m; }
+  return march_launch(g, s.nsm);
+}
 
 FinArgs fin_level(const Sim& s, int level) {
   FinArgs fa{};
@@ -357,11 +525,34 @@ int post_reduce(Sim& s, int stage, const FinArgs& fa, bool is_max) {
   return wl_cuda_check(s, cudaGetLastError(), "k_finalize");
 }
 
-static int level_of(const Sim& s, const Lvl& l) { return (int)(&l - &s.levels[0]); }
-
 int pois_set_diag(Sim& s, Lvl& l) {
-  RLAUNCH(s, k_set_diag, l.g, l);
+  const int lv = level_of(s, l);
+  unsigned char* um = s.umask_store[lv];               // null: rows of this level are not a multiple of four
+  unsigned int* cnt = um ? s.d_nonuni + lv : nullptr;
+  if (cnt) cudaMemsetAsync(cnt, 0, sizeof(unsigned int), s.stream);
+  RLAUNCH(s, k_set_diag, l.g, l, um, cnt);
+  l.umask = s.uniform_path ? um : nullptr;             // the mask now describes L, D, iD of this level
+  s.nonuni_known = false;
   return wl_cuda_check(s, cudaGetLastError(), "k_set_diag");
+}
+int pois_uniform_fraction(Sim& s) {
+  s.uni_frac0 = 0.0;
+  if (s.levels.empty() || !s.levels[0].umask) return 0;
+  if (!s.nonuni_known) {
+    const int rc = wl_read_scalars(s, s.d_nonuni, sizeof(unsigned int));
+    if (rc) return rc;
+    unsigned int c;
+    memcpy(&c, s.h_pinned, sizeof(c));
+    s.nonuni0 = c;
+    s.nonuni_known = true;
+  }
+  const double packs = (double)s.levels[0].g.interior / 4.0;
+  s.uni_frac0 = packs > 0 ? 1.0 - (double)s.nonuni0 / packs : 0.0;
+  return 0;
+}
+// L, D or iD of a level changed behind set_diag!'s back (upload, BC! on μ₀): its kernels go back to loading them
+void pois_invalidate_uniform(Sim& s, int level) {
+  if (level >= 0 && level < (int)s.levels.size()) s.levels[level].umask = nullptr;
 }
 // restrictL! (MultiLevelPoisson.jl:26-32).  When the fine level is z-distributed and the coarse one
 // replicated, every rank restricts its own planes and the planes are all-gathered.
@@ -412,7 +603,9 @@ int pois_residual(Sim& s, Lvl& l, bool need_r2, bool ghosts_valid, bool jacobi_e
   const bool fine = lv == 0;
   const FinArgs fa = fin_level(s, lv);
   if (fine) wl_prof_begin(s, WL_PROF_RESIDUAL);
-  RLAUNCH(s, k_residual, l.g, l, s.ws, fa, jacobi_eps ? 1 : 0);
+  const MarchLaunch ml = march_for(s, l.g);
+  if (ml.ok) { k_residual_m<<<ml.grid, ml.blk, 0, s.stream>>>(l, ml.mg, s.ws, fa, jacobi_eps ? 1 : 0); ++s.launches; }
+  else RLAUNCH(s, k_residual, l.g, l, s.ws, fa, jacobi_eps ? 1 : 0);
   if ((rc = post_reduce(s, FIN_RESIDUAL, fa))) return rc;
   {
     FinArgs fb = fa;
@@ -422,7 +615,7 @@ int pois_residual(Sim& s, Lvl& l, bool need_r2, bool ghosts_valid, bool jacobi_e
   s.eps_is_jacobi = jacobi_eps;
   // r⋅r after the mean subtraction is only reported, never used for control: solver! skips its all-reduce
   if (need_r2 && (rc = post_reduce(s, FIN_R2_IF_SUB, fa))) return rc;
-  if (fine) wl_prof_end(s, WL_PROF_RESIDUAL, cellsB(l, 8));
+  if (fine) wl_prof_end(s, WL_PROF_RESIDUAL, 4.0 * (double)l.g.interior * wl_words(s, s.D + 5 + (jacobi_eps ? 1 : 0), s.D + 2));
   return wl_cuda_check(s, cudaGetLastError(), "k_residual");
 }
 // increment!(p) (Poisson.jl:99-103)
@@ -436,9 +629,11 @@ static int pois_increment(Sim& s, Lvl& l) {
   FinArgs fa = fin_level(s, lv);
   if (!fine && fa.defer == 2) fa.defer = 0;  // L₂ is only ever read on the finest level
   if (fine) wl_prof_begin(s, WL_PROF_INCREMENT);
-  RLAUNCH(s, k_increment, l.g, l, s.ws, fa);
+  const MarchLaunch ml = march_for(s, l.g);
+  if (ml.ok) { k_increment_m<<<ml.grid, ml.blk, 0, s.stream>>>(l, ml.mg, s.ws, fa); ++s.launches; }
+  else RLAUNCH(s, k_increment, l.g, l, s.ws, fa);
   if (fine && (rc = post_reduce(s, FIN_R2, fa))) return rc;  // L₂ is only ever read on the finest level
-  if (fine) wl_prof_end(s, WL_PROF_INCREMENT, cellsB(l, 9));
+  if (fine) wl_prof_end(s, WL_PROF_INCREMENT, 4.0 * (double)l.g.interior * wl_words(s, s.D + 6, s.D + 1));
   return wl_cuda_check(s, cudaGetLastError(), "k_increment");
 }
 // Jacobi!(p;it) (Poisson.jl:110-113)
@@ -467,7 +662,7 @@ int pois_pcg(Sim& s, int level, int it) {
     if (fine) wl_prof_begin(s, WL_PROF_PCG_INIT);
     RLAUNCH(s, k_pcg_init, l.g, l, s.ws, fa);
     if ((rc = post_reduce(s, FIN_PCG_INIT, fa))) return rc;
-    if (fine) wl_prof_end(s, WL_PROF_PCG_INIT, cellsB(l, 3));
+    if (fine) wl_prof_end(s, WL_PROF_PCG_INIT, 4.0 * (double)l.g.interior * wl_words(s, 3, 1));
   }
   s.pcg_init_done = -1;
   // Sweeps are enqueued speculatively: as many as the previous pcg! on this level needed, then ONE
@@ -476,6 +671,7 @@ int pois_pcg(Sim& s, int level, int it) {
   // all-reducing) work that is known to be dead.  Every rank reads the same bits.
   if ((int)s.pcg_guess.size() < (int)s.levels.size()) { s.pcg_guess.assign(s.levels.size(), std::min(it, 2)); s.pcg_cnt.assign(s.levels.size(), 0); }
   int& guess = s.pcg_guess[level];
+  const MarchLaunch mlp = march_for(s, l.g);
   int i = 1;
   while (i <= it) {
     const int upto = std::min(it, std::max(guess, i));
@@ -489,7 +685,8 @@ int pois_pcg(Sim& s, int level, int it) {
         }
       }
       if (fine) wl_prof_begin(s, WL_PROF_PCG_MULT);
-      RLAUNCH(s, k_pcg_mult, l.g, l, s.ws, fa);
+      if (mlp.ok) { k_pcg_mult_m<<<mlp.grid, mlp.blk, 0, s.stream>>>(l, mlp.mg, s.ws, fa); ++s.launches; }
+      else RLAUNCH(s, k_pcg_mult, l.g, l, s.ws, fa);
       if ((rc = post_reduce(s, FIN_PCG_MULT, fa))) return rc;
       if (fine) { wl_prof_end(s, WL_PROF_PCG_MULT, 0); wl_prof_begin(s, WL_PROF_PCG_UPDATE); }
       RLAUNCH(s, k_pcg_update, l.g, l, s.ws, fa, i == it ? 1 : 0);
@@ -546,9 +743,11 @@ int pois_vcycle(Sim& s, int level) {
     const FinArgs fa = fin_level(s, level);  // ρ steers the pcg! of this level: all-reduced on every distributed level
     const bool top = level == 0;
     if (top) wl_prof_begin(s, WL_PROF_INCREMENT);
-    RLAUNCH(s, k_prolong_increment_init, fine.g, fine, coarse, m, s.ws, fa);
+    const MarchLaunch ml = march_for(s, fine.g);
+    if (ml.ok && (coarse.g.n[0] - 2) % 2 == 0) { k_prolong_increment_init_m<<<ml.grid, ml.blk, 0, s.stream>>>(fine, coarse, m, ml.mg, s.ws, fa); ++s.launches; }
+    else RLAUNCH(s, k_prolong_increment_init, fine.g, fine, coarse, m, s.ws, fa);
     if ((rc = post_reduce(s, FIN_INC_INIT, fa))) return rc;
-    if (top) wl_prof_end(s, WL_PROF_INCREMENT, 4.0 * 10.125 * (double)fine.g.interior);
+    if (top) wl_prof_end(s, WL_PROF_INCREMENT, 4.0 * (double)fine.g.interior * wl_words(s, s.D + 7.125, s.D + 2));
     s.pcg_init_done = level;
     return wl_cuda_check(s, cudaGetLastError(), "k_prolong_increment_init");
   }

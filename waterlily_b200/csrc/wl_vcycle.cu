@@ -268,7 +268,7 @@ __device__ __forceinline__ void increment(const FusedParams& p, Run& run, int l,
   if (GRID && p.dist[l]) halo_push(p, run, l, L.eps);
   double acc[1] = {0.0};
   rows<V, GRID>(p, l, [&](int i, int j, int k, int64_t I) {
-    const Pack<V> ec = ldp<V>(L.eps + I), ae = mult_w<D, V>(L, L.eps, i, j, k, I, ec);
+    const Pack<V> ec = ldp<V>(L.eps + I), ae = mult_w<D, V>(L, L.eps, i, j, k, I, ec, pack_uniform<V>(L, I));
     Pack<V> r = ldp<V>(L.r + I), x = ldp<V>(L.x + I);
 #pragma unroll
     for (int q = 0; q < V; ++q) {
@@ -293,7 +293,7 @@ __device__ __forceinline__ void jacobi(const FusedParams& p, Run& run, int l, bo
   const Lvl& L = p.lv[l];
   if (eps_ready) { increment<D, V, GRID>(p, run, l); return; }  // residual! already stored ϵ = r·iD
   rows<V, GRID>(p, l, [&](int, int, int, int64_t I) {
-    const Pack<V> r = ldp<V>(L.r + I), id = ldp<V>(L.iD + I);
+    const Pack<V> r = ldp<V>(L.r + I), id = ld_iD<V>(L, I, pack_uniform<V>(L, I));
     Pack<V> e;
 #pragma unroll
     for (int q = 0; q < V; ++q) e.v[q] = r.v[q] * id.v[q];
@@ -316,7 +316,7 @@ __device__ __forceinline__ void pcg(const FusedParams& p, Run& run, int l, int i
   } else {
     double acc[1] = {0.0};
     rows<V, GRID>(p, l, [&](int, int, int, int64_t I) {
-      const Pack<V> r = ldp<V>(L.r + I), id = ldp<V>(L.iD + I);
+      const Pack<V> r = ldp<V>(L.r + I), id = ld_iD<V>(L, I, pack_uniform<V>(L, I));
       Pack<V> e;
 #pragma unroll
       for (int q = 0; q < V; ++q) { e.v[q] = r.v[q] * id.v[q]; acc[0] += (double)r.v[q] * (double)e.v[q]; }
@@ -332,7 +332,7 @@ __device__ __forceinline__ void pcg(const FusedParams& p, Run& run, int l, int i
     {
       double acc[1] = {0.0};
       rows<V, GRID>(p, l, [&](int ii, int j, int k, int64_t I) {
-        const Pack<V> ec = ldp<V>(L.eps + I), z = mult_w<D, V>(L, L.eps, ii, j, k, I, ec);
+        const Pack<V> ec = ldp<V>(L.eps + I), z = mult_w<D, V>(L, L.eps, ii, j, k, I, ec, pack_uniform<V>(L, I));
 #pragma unroll
         for (int q = 0; q < V; ++q) acc[0] += (double)z.v[q] * (double)ec.v[q];
         stp<V>(L.z + I, z);
@@ -360,7 +360,7 @@ __device__ __forceinline__ void pcg(const FusedParams& p, Run& run, int l, int i
     {
       double acc[2] = {0.0, 0.0};
       rows<V, GRID>(p, l, [&](int, int, int, int64_t I) {
-        const Pack<V> e = ldp<V>(L.eps + I), z = ldp<V>(L.z + I), id = ldp<V>(L.iD + I);
+        const Pack<V> e = ldp<V>(L.eps + I), z = ldp<V>(L.z + I), id = ld_iD<V>(L, I, pack_uniform<V>(L, I));
         Pack<V> x = ldp<V>(L.x + I), r = ldp<V>(L.r + I);
 #pragma unroll
         for (int q = 0; q < V; ++q) {
@@ -382,7 +382,7 @@ __device__ __forceinline__ void pcg(const FusedParams& p, Run& run, int l, int i
     const float beta = rho2 / rho;
     rho = rho2;
     rows<V, GRID>(p, l, [&](int, int, int, int64_t I) {
-      const Pack<V> r = ldp<V>(L.r + I), id = ldp<V>(L.iD + I);
+      const Pack<V> r = ldp<V>(L.r + I), id = ld_iD<V>(L, I, pack_uniform<V>(L, I));
       Pack<V> e = ldp<V>(L.eps + I);
 #pragma unroll
       for (int q = 0; q < V; ++q) e.v[q] = beta * e.v[q] + r.v[q] * id.v[q];
@@ -516,7 +516,8 @@ __device__ __forceinline__ void residual0(const FusedParams& p, Run& run, const 
   if (dist && !sa.ghosts_valid) halo_push(p, run, 0, L.x);
   double acc[2] = {0.0, 0.0};
   rows<V, true>(p, 0, [&](int i, int j, int k, int64_t I) {
-    const Pack<V> xc = ldp<V>(L.x + I), ax = mult_w<D, V>(L, L.x, i, j, k, I, xc), zc = ldp<V>(L.z + I), id = ldp<V>(L.iD + I);
+    const bool uni = pack_uniform<V>(L, I);
+    const Pack<V> xc = ldp<V>(L.x + I), ax = mult_w<D, V>(L, L.x, i, j, k, I, xc, uni), zc = ldp<V>(L.z + I), id = ld_iD<V>(L, I, uni);
     Pack<V> r, e;
 #pragma unroll
     for (int q = 0; q < V; ++q) {
@@ -535,7 +536,7 @@ __device__ __forceinline__ void residual0(const FusedParams& p, Run& run, const 
   if (fabsf(rmean) > 2 * WL_EPS32) {
     rows<V, true>(p, 0, [&](int, int, int, int64_t I) {
       Pack<V> r = ldp<V>(L.r + I);
-      const Pack<V> id = ldp<V>(L.iD + I);
+      const Pack<V> id = ld_iD<V>(L, I, pack_uniform<V>(L, I));
       Pack<V> e;
 #pragma unroll
       for (int q = 0; q < V; ++q) { r.v[q] = r.v[q] - rmean; e.v[q] = r.v[q] * id.v[q]; }
@@ -731,8 +732,13 @@ void vcycle_fused_destroy(Sim& s) {
   s.vc_fused = nullptr;
 }
 // runs levels lf … nl-1 of the V-cycle (the residual of level lf has just been restricted)
+// the uniform-pack masks are (in)validated after setup: the kernel gets the current pointers
+static void refresh_masks(Sim& s, VcycleFused* vf) {
+  for (int l = 0; l < vf->p.nl; ++l) vf->p.lv[l].umask = s.levels[l].umask;
+}
 int vcycle_fused_run(Sim& s) {
   VcycleFused* vf = (VcycleFused*)s.vc_fused;
+  refresh_masks(s, vf);
   SolveArgs sa{};
   void* args[] = {&vf->p, &sa};
   wl_prof_begin(s, WL_PROF_VCTAIL);
@@ -745,6 +751,7 @@ int vcycle_fused_run(Sim& s) {
 // solver!(ml; tol, itmx) as ONE launch; the V-cycle count lands in MiscScalars::solve_n[slot]
 int vcycle_fused_solve(Sim& s, double tol, int itmx, bool ghosts_valid, int slot) {
   VcycleFused* vf = (VcycleFused*)s.vc_fused;
+  refresh_masks(s, vf);
   const Lvl& l = s.levels[0];
   bool ghosts = l.g.zlo_halo || l.g.zhi_halo;
   for (int k = 0; k < s.D; ++k) ghosts |= l.g.per[k] != 0;

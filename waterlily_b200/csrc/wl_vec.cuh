@@ -40,17 +40,39 @@ template <int V> __device__ __forceinline__ Pack<V> ld_xp(const float* __restric
   return r;
 }
 
+// ---- uniform-coefficient packs (see Lvl in wl_common.cuh) -------------------------------------------
+// true when the pack of V=4 cells starting at I has L ≡ uL on all its faces (then D ≡ uD, iD ≡ uiD)
+template <int V>
+__device__ __forceinline__ bool pack_uniform(const Lvl& l, int64_t I) {
+  if (V != 4 || l.umask == nullptr) return false;
+  return l.umask[(I + l.g.lead) >> 2] == 0;
+}
+template <int V>
+__device__ __forceinline__ Pack<V> splat(float v) {
+  Pack<V> r;
+#pragma unroll
+  for (int q = 0; q < V; ++q) r.v[q] = v;
+  return r;
+}
+// iD of a pack: the constant on a uniform pack, a load otherwise
+template <int V>
+__device__ __forceinline__ Pack<V> ld_iD(const Lvl& l, int64_t I, bool uni) {
+  return uni ? splat<V>(l.uiD) : ldp<V>(l.iD + I);
+}
+
 // mult (Poisson.jl:69-75) for V cells at (i..i+V-1, j, k); periodic neighbours are read through a
-// wrapped index instead of a ghost copy
+// wrapped index instead of a ghost copy.  `uni`: the pack is uniform — L, D come from constants.
 template <int D, int V>
-__device__ __forceinline__ Pack<V> mult_w(const Lvl& l, const float* x, int i, int j, int k, int64_t I, const Pack<V>& xc) {
+__device__ __forceinline__ Pack<V> mult_w(const Lvl& l, const float* x, int i, int j, int k, int64_t I, const Pack<V>& xc, bool uni = false) {
   const GridD& g = l.g;
-  const Pack<V> Dc = ldp<V>(l.Dg + I);
+  const Pack<V> Dc = uni ? splat<V>(l.uD) : ldp<V>(l.Dg + I);
   Pack<V> s;
 #pragma unroll
   for (int q = 0; q < V; ++q) s.v[q] = xc.v[q] * Dc.v[q];
   {
-    const Pack<V> Lc = ldp<V>(l.L + I), Lp = ld_xp<V>(l.L + I, Lc);
+    Pack<V> Lc, Lp;
+    if (uni) { Lc = splat<V>(l.uL); Lp = Lc; }
+    else { Lc = ldp<V>(l.L + I); Lp = ld_xp<V>(l.L + I, Lc); }
     Pack<V> xm, xp;
     xm.v[0] = x[(g.per[0] && i == 1) ? I + (g.n[0] - 3) : I - 1];
 #pragma unroll
@@ -68,11 +90,85 @@ __device__ __forceinline__ Pack<V> mult_w(const Lvl& l, const float* x, int i, i
     const int64_t om = (g.per[d] && cd == 1) ? (int64_t)(n - 3) * st : -st;
     const int64_t op = (g.per[d] && cd == n - 2) ? -(int64_t)(n - 3) * st : st;
     const float* Li = l.L + d * g.comp;
-    const Pack<V> Lc = ldp<V>(Li + I), Lp = ldp<V>(Li + I + st), xm = ldp<V>(x + I + om), xp = ldp<V>(x + I + op);
+    Pack<V> Lc, Lp;
+    if (uni) { Lc = splat<V>(l.uL); Lp = Lc; }
+    else { Lc = ldp<V>(Li + I); Lp = ldp<V>(Li + I + st); }
+    const Pack<V> xm = ldp<V>(x + I + om), xp = ldp<V>(x + I + op);
 #pragma unroll
     for (int q = 0; q < V; ++q) s.v[q] += (xm.v[q] * Lc.v[q] + xp.v[q] * Lp.v[q]);
   }
   return s;
+}
+
+// mult for the z-marching kernels (3-D): the z-neighbours of the pack come from the thread's register
+// window instead of memory; operands and operation order are those of mult_w
+template <int V>
+__device__ __forceinline__ Pack<V> mult_zreg(const Lvl& l, const float* x, int i, int j, int64_t I, const Pack<V>& xc, const Pack<V>& zm,
+                                             const Pack<V>& zp, bool uni) {
+  const GridD& g = l.g;
+  const Pack<V> Dc = uni ? splat<V>(l.uD) : ldp<V>(l.Dg + I);
+  Pack<V> s;
+#pragma unroll
+  for (int q = 0; q < V; ++q) s.v[q] = xc.v[q] * Dc.v[q];
+  {
+    Pack<V> Lc, Lp;
+    if (uni) { Lc = splat<V>(l.uL); Lp = Lc; }
+    else { Lc = ldp<V>(l.L + I); Lp = ld_xp<V>(l.L + I, Lc); }
+    Pack<V> xm, xp;
+    xm.v[0] = x[(g.per[0] && i == 1) ? I + (g.n[0] - 3) : I - 1];
+#pragma unroll
+    for (int q = 1; q < V; ++q) xm.v[q] = xc.v[q - 1];
+#pragma unroll
+    for (int q = 0; q < V - 1; ++q) xp.v[q] = xc.v[q + 1];
+    xp.v[V - 1] = x[(g.per[0] && i + V - 1 == g.n[0] - 2) ? I + (V - 1) - (g.n[0] - 3) : I + V];
+#pragma unroll
+    for (int q = 0; q < V; ++q) s.v[q] += (xm.v[q] * Lc.v[q] + xp.v[q] * Lp.v[q]);
+  }
+  {
+    const int64_t st = g.s[1];
+    const int n = g.n[1];
+    const int64_t om = (g.per[1] && j == 1) ? (int64_t)(n - 3) * st : -st;
+    const int64_t op = (g.per[1] && j == n - 2) ? -(int64_t)(n - 3) * st : st;
+    const float* Li = l.L + g.comp;
+    Pack<V> Lc, Lp;
+    if (uni) { Lc = splat<V>(l.uL); Lp = Lc; }
+    else { Lc = ldp<V>(Li + I); Lp = ldp<V>(Li + I + st); }
+    const Pack<V> xm = ldp<V>(x + I + om), xp = ldp<V>(x + I + op);
+#pragma unroll
+    for (int q = 0; q < V; ++q) s.v[q] += (xm.v[q] * Lc.v[q] + xp.v[q] * Lp.v[q]);
+  }
+  {
+    const float* Li = l.L + 2 * g.comp;
+    Pack<V> Lc, Lp;
+    if (uni) { Lc = splat<V>(l.uL); Lp = Lc; }
+    else { Lc = ldp<V>(Li + I); Lp = ldp<V>(Li + I + g.s[2]); }
+#pragma unroll
+    for (int q = 0; q < V; ++q) s.v[q] += (zm.v[q] * Lc.v[q] + zp.v[q] * Lp.v[q]);
+  }
+  return s;
+}
+// offsets of the z-neighbours of plane k (periodic wrap of a level that is periodic in z on this rank)
+__device__ __forceinline__ int64_t zoff_m(const GridD& g, int k) { return (g.per[2] && k == 1) ? (int64_t)(g.n[2] - 3) * g.s[2] : -g.s[2]; }
+__device__ __forceinline__ int64_t zoff_p(const GridD& g, int k) { return (g.per[2] && k == g.n[2] - 2) ? -(int64_t)(g.n[2] - 3) * g.s[2] : g.s[2]; }
+
+// ---- z-marching iteration (3-D, V = 4) ---------------------------------------------------------------
+// With one (row-group, plane) unit per block (for_rows) every 7-point stencil pulls its four y/z neighbour
+// rows through L2 again: ~5 words per cell of L2 traffic for a kernel whose HBM traffic is 2 words (measured:
+// k_pcg_mult stalled at 5.6 TB/s of L2 reads).  Here a block owns an (mx packs × my rows) tile and marches
+// along z: a thread keeps the packs of planes k-1, k, k+1 of its column in registers (one new load per
+// step), its y-neighbours were loaded one step earlier by the adjacent threads of the same block (L1 hits),
+// and only the tile's perimeter rows come from L2.
+struct MarchGeom { int mx, my, ntx, nty, ntz, zchunk; };
+template <class F>
+__device__ __forceinline__ void for_columns(const GridD& g, const MarchGeom& mg, F&& f) {
+  const int ntiles = mg.ntx * mg.nty * mg.ntz;
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int tx = t % mg.ntx, q = t / mg.ntx;
+    const int ty = q % mg.nty, tz = q / mg.nty;
+    const int i = 1 + 4 * (tx * mg.mx + (int)threadIdx.x), j = 1 + ty * mg.my + (int)threadIdx.y;
+    const int k0 = 1 + tz * mg.zchunk, k1 = min(k0 + mg.zchunk - 1, g.n[2] - 2);
+    if (i <= g.n[0] - 2 && j <= g.n[1] - 2) f(i, j, k0, k1);
+  }
 }
 
 // ---- prolongate! + increment! + the head of pcg! in one pass -------------------------------------
@@ -116,12 +212,15 @@ __device__ __forceinline__ void prolong_increment_init(const Lvl& f, const Lvl& 
 #pragma unroll
   for (int q = 0; q < V - 1; ++q) xp.v[q] = e.v[q + 1];
   xp.v[V - 1] = xc[J + pro_cidx(m, 0, i + V)];
-  const Pack<V> Dc = ldp<V>(f.Dg + I);
+  const bool uni = pack_uniform<V>(f, I);
+  const Pack<V> Dc = uni ? splat<V>(f.uD) : ldp<V>(f.Dg + I);
   Pack<V> s;
 #pragma unroll
   for (int q = 0; q < V; ++q) s.v[q] = e.v[q] * Dc.v[q];
   {
-    const Pack<V> Lc = ldp<V>(f.L + I), Lp = ld_xp<V>(f.L + I, Lc);
+    Pack<V> Lc, Lp;
+    if (uni) { Lc = splat<V>(f.uL); Lp = Lc; }
+    else { Lc = ldp<V>(f.L + I); Lp = ld_xp<V>(f.L + I, Lc); }
 #pragma unroll
     for (int q = 0; q < V; ++q) s.v[q] += (xm.v[q] * Lc.v[q] + xp.v[q] * Lp.v[q]);
   }
@@ -132,12 +231,14 @@ __device__ __forceinline__ void prolong_increment_init(const Lvl& f, const Lvl& 
     const int64_t Jo = J - pro_cidx(m, d, cd) * cst;  // J without dimension d's term
     const int64_t Jm = Jo + pro_cidx(m, d, cd - 1) * cst, Jp = Jo + pro_cidx(m, d, cd + 1) * cst;
     const float* Li = f.L + d * f.g.comp;
-    const Pack<V> Lc = ldp<V>(Li + I), Lp = ldp<V>(Li + I + f.g.s[d]);
+    Pack<V> Lc, Lp;
+    if (uni) { Lc = splat<V>(f.uL); Lp = Lc; }
+    else { Lc = ldp<V>(Li + I); Lp = ldp<V>(Li + I + f.g.s[d]); }
 #pragma unroll
     for (int q = 0; q < V; ++q) s.v[q] += (xc[Jm + ci[q]] * Lc.v[q] + xc[Jp + ci[q]] * Lp.v[q]);
   }
   Pack<V> r = ldp<V>(f.r + I), x = ldp<V>(f.x + I);
-  const Pack<V> id = ldp<V>(f.iD + I);
+  const Pack<V> id = ld_iD<V>(f, I, uni);
   Pack<V> en;
 #pragma unroll
   for (int q = 0; q < V; ++q) {
@@ -183,6 +284,30 @@ inline RowLaunch row_launch(const GridD& g) {
   const int nj = g.D > 1 ? g.n[1] - 2 : 1, nk = g.D > 2 ? g.n[2] - 2 : 1;
   r.nunits = ((nj + (int)r.blk.y - 1) / (int)r.blk.y) * nk;
   return r;
+}
+
+// host-side geometry of the z-marching kernels; ok = false when the level should use for_rows
+struct MarchLaunch { bool ok; MarchGeom mg; dim3 blk; int grid; };
+inline MarchLaunch march_launch(const GridD& g, int nsm) {
+  MarchLaunch m{};
+  const int nxi = g.n[0] - 2, nyi = g.n[1] - 2, nzi = g.D > 2 ? g.n[2] - 2 : 0;
+  m.ok = g.D == 3 && nxi % 4 == 0 && nxi >= 32 && nyi >= 8 && nzi >= 8;
+  if (!m.ok) return m;
+  const int packs = nxi / 4;
+  int mx = 8;
+  while (mx < packs && mx < 32) mx <<= 1;
+  const int my = 256 / mx;
+  m.mg.mx = mx; m.mg.my = my;
+  m.mg.ntx = (packs + mx - 1) / mx;
+  m.mg.nty = (nyi + my - 1) / my;
+  int zc = 64;
+  while (zc > 8 && (int64_t)m.mg.ntx * m.mg.nty * ((nzi + zc - 1) / zc) < (int64_t)nsm * 8) zc >>= 1;  // enough blocks to fill the machine
+  m.mg.zchunk = zc;
+  m.mg.ntz = (nzi + zc - 1) / zc;
+  m.blk = dim3(mx, my, 1);
+  const int64_t ntiles = (int64_t)m.mg.ntx * m.mg.nty * m.mg.ntz;
+  m.grid = (int)(ntiles < WL_MAXBLOCKS ? ntiles : WL_MAXBLOCKS);
+  return m;
 }
 
 // launch a for_rows kernel<D,V> on the interior of grid `grd`
