@@ -384,13 +384,15 @@ def test_uniform_mask_goes_stale_with_L():
 
 
 @pytest.mark.parametrize("make,steps", [(lambda cls: tgv3d(cls, 64), 3), (lambda cls: sphere3d(cls, exitBC=True), 4), (lambda cls: sphere3d(cls, n=128, m=64, exitBC=False), 2)])
-def test_z_marching_kernels_match_row_kernels(make, steps, monkeypatch):
-    # k_*_m (for_columns, wl_vec.cuh) against the (row-group, plane) kernels: same arithmetic per cell, different
-    # reduction tree; the fused solver is switched off so that the per-level kernels run on every level
+@pytest.mark.parametrize("stage", ["0", "1"])   # z-window in registers / operand planes staged in shared memory by cp.async
+def test_z_marching_kernels_match_row_kernels(make, steps, stage, monkeypatch):
+    # k_*_m / k_*_s (for_columns, march_staged in wl_vec.cuh) against the (row-group, plane) kernels: same arithmetic
+    # per cell, different reduction tree; the fused solver is switched off so that the per-level kernels run on every level
     monkeypatch.setenv("WL_FUSED_VCYCLE", "0")
     monkeypatch.setenv("WL_MARCH", "0")
     s0 = make(Simulation)
     monkeypatch.setenv("WL_MARCH", "1")
+    monkeypatch.setenv("WL_STAGE", stage)
     s1 = make(Simulation)
     for _ in range(steps):
         sim_step(s0, remeasure=False)

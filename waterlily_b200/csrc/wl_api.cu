@@ -340,6 +340,7 @@ static int create_impl(wl_sim** out, int D, const int* N, double nu, double dt0,
   if (!rc && cudaMalloc(&tmp, sizeof(unsigned int) * (dims.size() + 4)) == cudaSuccess) { a.allocs.push_back(tmp); a.d_nonuni = (unsigned int*)tmp; cudaMemsetAsync(tmp, 0, sizeof(unsigned int) * (dims.size() + 4), a.stream); } else if (!rc) rc = wl_fail(WL_ERR_CUDA, "cudaMalloc counters");
   { const char* e = getenv("WL_UNIFORM"); a.uniform_path = !(e && atoi(e) == 0); }
   { const char* e = getenv("WL_MARCH"); a.march_on = !(e && atoi(e) == 0); }
+  { const char* e = getenv("WL_STAGE"); a.stage_on = !(e && atoi(e) == 0); }
   if (!rc && cudaMalloc(&tmp, 64) == cudaSuccess) { a.allocs.push_back(tmp); a.ws.ticket = (unsigned int*)tmp; cudaMemsetAsync(tmp, 0, 64, a.stream); } else if (!rc) rc = wl_fail(WL_ERR_CUDA, "cudaMalloc ticket");
   if (!rc && cudaMallocHost((void**)&a.h_pinned, 64 * sizeof(float)) != cudaSuccess) rc = wl_fail(WL_ERR_CUDA, "cudaMallocHost");
   if (rc) { wl_destroy((wl_sim*)sp); return rc; }

@@ -98,6 +98,7 @@ struct Sim {
   unsigned int* d_nonuni = nullptr;  // [levels] packs that are NOT uniform, counted by k_set_diag
   bool uniform_path = true;          // WL_UNIFORM=0 switches the fast path off (every stencil loads L, D, iD)
   bool march_on = true;              // WL_MARCH=0: the stencil kernels iterate (row-group, plane) units instead of marching in z
+  bool stage_on = true;              // WL_STAGE=0: marching kernels keep their z-window in registers instead of a shared-memory ring
   bool nonuni_known = false;
   unsigned int nonuni0 = 0;
   double uni_frac0 = 0.0;            // fraction of uniform packs on the finest level (profiling: algorithmic bytes)

@@ -309,6 +309,78 @@ __global__ void __launch_bounds__(256) k_pcg_mult_m(Lvl l, MarchGeom mg, ReduceW
   double tot[1];
   if (grid_reduce<1>(acc, ws, tot)) finish_reduction(FIN_PCG_MULT, fa, tot[0], 0.0);
 }
+// ---- the same with the stencil operand staged through shared memory (march_staged, wl_vec.cuh) ------
+extern __shared__ __align__(16) float wl_ring[];
+__global__ void __launch_bounds__(256) k_pcg_mult_s(Lvl l, MarchGeom mg, ReduceWS ws, FinArgs fa) {
+  if (!l.sc->active) return;
+  double acc[1] = {0.0};
+  const GridD& g = l.g;
+  for_columns(g, mg, [&](int i, int j, int k0, int k1) {
+    bool uni = false;
+    march_staged(g, l.eps, wl_ring, i, j, k0, k1,
+      [&](int, int64_t I) { uni = pack_uniform<4>(l, I); },
+      [&](int, int64_t I, const Pack<4>& ec, float xm1, float xp4, const Pack<4>& ym, const Pack<4>& yp, const Pack<4>& zm, const Pack<4>& zp) {
+        const Pack<4> z = mult_vals<4>(l, I, ec, xm1, xp4, ym, yp, zm, zp, uni);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[0] += (double)z.v[q] * (double)ec.v[q];
+        stp<4>(l.z + I, z);
+      });
+  });
+  double tot[1];
+  if (grid_reduce<1>(acc, ws, tot)) finish_reduction(FIN_PCG_MULT, fa, tot[0], 0.0);
+}
+__global__ void __launch_bounds__(256) k_increment_s(Lvl l, MarchGeom mg, ReduceWS ws, FinArgs fa) {
+  double acc[1] = {0.0};
+  const GridD& g = l.g;
+  for_columns(g, mg, [&](int i, int j, int k0, int k1) {
+    bool uni = false;
+    Pack<4> r, x;
+    march_staged(g, l.eps, wl_ring, i, j, k0, k1,
+      [&](int, int64_t I) { uni = pack_uniform<4>(l, I); r = ldp<4>(l.r + I); x = ldp<4>(l.x + I); },
+      [&](int, int64_t I, const Pack<4>& ec, float xm1, float xp4, const Pack<4>& ym, const Pack<4>& yp, const Pack<4>& zm, const Pack<4>& zp) {
+        const Pack<4> ae = mult_vals<4>(l, I, ec, xm1, xp4, ym, yp, zm, zp, uni);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          r.v[q] = r.v[q] - ae.v[q];
+          x.v[q] = x.v[q] + ec.v[q];
+          acc[0] += (double)r.v[q] * (double)r.v[q];
+        }
+        stp<4>(l.r + I, r);
+        stp<4>(l.x + I, x);
+      });
+  });
+  double tot[1];
+  if (grid_reduce<1>(acc, ws, tot)) finish_reduction(FIN_R2, fa, tot[0], 0.0);
+}
+__global__ void __launch_bounds__(256) k_residual_s(Lvl l, MarchGeom mg, ReduceWS ws, FinArgs fa, int write_eps) {
+  double acc[2] = {0.0, 0.0};
+  const GridD& g = l.g;
+  for_columns(g, mg, [&](int i, int j, int k0, int k1) {
+    bool uni = false;
+    Pack<4> zc;
+    march_staged(g, l.x, wl_ring, i, j, k0, k1,
+      [&](int, int64_t I) { uni = pack_uniform<4>(l, I); zc = ldp<4>(l.z + I); },
+      [&](int, int64_t I, const Pack<4>& xc, float xm1, float xp4, const Pack<4>& ym, const Pack<4>& yp, const Pack<4>& zm, const Pack<4>& zp) {
+        const Pack<4> ax = mult_vals<4>(l, I, xc, xm1, xp4, ym, yp, zm, zp, uni), id = ld_iD<4>(l, I, uni);
+        Pack<4> r;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          r.v[q] = id.v[q] == 0.f ? 0.f : zc.v[q] - ax.v[q];
+          acc[0] += (double)r.v[q];
+          acc[1] += (double)r.v[q] * (double)r.v[q];
+        }
+        stp<4>(l.r + I, r);
+        if (write_eps) {
+          Pack<4> e;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) e.v[q] = r.v[q] * id.v[q];
+          stp<4>(l.eps + I, e);
+        }
+      });
+  });
+  double tot[2];
+  if (grid_reduce<2>(acc, ws, tot)) finish_reduction(FIN_RESIDUAL, fa, tot[0], tot[1]);
+}
 // prolongate! + increment! + head of pcg!: ϵ of a fine pack (i = 1+4t) is {c, c, c', c'} with (c, c') the aligned
 // coarse pair at ci = 1+2t, so a pack costs one 8-byte load per coarse row it touches
 __device__ __forceinline__ Pack<4> pro_pack(const float* __restrict__ crow, int ci) {
@@ -604,7 +676,8 @@ int pois_residual(Sim& s, Lvl& l, bool need_r2, bool ghosts_valid, bool jacobi_e
   const FinArgs fa = fin_level(s, lv);
   if (fine) wl_prof_begin(s, WL_PROF_RESIDUAL);
   const MarchLaunch ml = march_for(s, l.g);
-  if (ml.ok) { k_residual_m<<<ml.grid, ml.blk, 0, s.stream>>>(l, ml.mg, s.ws, fa, jacobi_eps ? 1 : 0); ++s.launches; }
+  if (ml.ok && ml.staged && s.stage_on) { k_residual_s<<<ml.grid, ml.blk, ml.smem, s.stream>>>(l, ml.mg, s.ws, fa, jacobi_eps ? 1 : 0); ++s.launches; }
+  else if (ml.ok) { k_residual_m<<<ml.grid, ml.blk, 0, s.stream>>>(l, ml.mg, s.ws, fa, jacobi_eps ? 1 : 0); ++s.launches; }
   else RLAUNCH(s, k_residual, l.g, l, s.ws, fa, jacobi_eps ? 1 : 0);
   if ((rc = post_reduce(s, FIN_RESIDUAL, fa))) return rc;
   {
@@ -630,7 +703,8 @@ static int pois_increment(Sim& s, Lvl& l) {
   if (!fine && fa.defer == 2) fa.defer = 0;  // L₂ is only ever read on the finest level
   if (fine) wl_prof_begin(s, WL_PROF_INCREMENT);
   const MarchLaunch ml = march_for(s, l.g);
-  if (ml.ok) { k_increment_m<<<ml.grid, ml.blk, 0, s.stream>>>(l, ml.mg, s.ws, fa); ++s.launches; }
+  if (ml.ok && ml.staged && s.stage_on) { k_increment_s<<<ml.grid, ml.blk, ml.smem, s.stream>>>(l, ml.mg, s.ws, fa); ++s.launches; }
+  else if (ml.ok) { k_increment_m<<<ml.grid, ml.blk, 0, s.stream>>>(l, ml.mg, s.ws, fa); ++s.launches; }
   else RLAUNCH(s, k_increment, l.g, l, s.ws, fa);
   if (fine && (rc = post_reduce(s, FIN_R2, fa))) return rc;  // L₂ is only ever read on the finest level
   if (fine) wl_prof_end(s, WL_PROF_INCREMENT, 4.0 * (double)l.g.interior * wl_words(s, s.D + 6, s.D + 1));
@@ -685,7 +759,8 @@ int pois_pcg(Sim& s, int level, int it) {
         }
       }
       if (fine) wl_prof_begin(s, WL_PROF_PCG_MULT);
-      if (mlp.ok) { k_pcg_mult_m<<<mlp.grid, mlp.blk, 0, s.stream>>>(l, mlp.mg, s.ws, fa); ++s.launches; }
+      if (mlp.ok && mlp.staged && s.stage_on) { k_pcg_mult_s<<<mlp.grid, mlp.blk, mlp.smem, s.stream>>>(l, mlp.mg, s.ws, fa); ++s.launches; }
+      else if (mlp.ok) { k_pcg_mult_m<<<mlp.grid, mlp.blk, 0, s.stream>>>(l, mlp.mg, s.ws, fa); ++s.launches; }
       else RLAUNCH(s, k_pcg_mult, l.g, l, s.ws, fa);
       if ((rc = post_reduce(s, FIN_PCG_MULT, fa))) return rc;
       if (fine) { wl_prof_end(s, WL_PROF_PCG_MULT, 0); wl_prof_begin(s, WL_PROF_PCG_UPDATE); }

@@ -100,11 +100,12 @@ __device__ __forceinline__ Pack<V> mult_w(const Lvl& l, const float* x, int i, i
   return s;
 }
 
-// mult for the z-marching kernels (3-D): the z-neighbours of the pack come from the thread's register
-// window instead of memory; operands and operation order are those of mult_w
+// mult (Poisson.jl:69-75) of one pack in 3-D with every neighbour value supplied by the caller (registers or
+// shared memory): xm1/xp4 are the x-neighbours of the pack's ends, ym/yp/zm/zp the neighbour packs.  Operands
+// and operation order are those of mult_w.
 template <int V>
-__device__ __forceinline__ Pack<V> mult_zreg(const Lvl& l, const float* x, int i, int j, int64_t I, const Pack<V>& xc, const Pack<V>& zm,
-                                             const Pack<V>& zp, bool uni) {
+__device__ __forceinline__ Pack<V> mult_vals(const Lvl& l, int64_t I, const Pack<V>& xc, float xm1, float xp4, const Pack<V>& ym, const Pack<V>& yp,
+                                             const Pack<V>& zm, const Pack<V>& zp, bool uni) {
   const GridD& g = l.g;
   const Pack<V> Dc = uni ? splat<V>(l.uD) : ldp<V>(l.Dg + I);
   Pack<V> s;
@@ -115,27 +116,22 @@ __device__ __forceinline__ Pack<V> mult_zreg(const Lvl& l, const float* x, int i
     if (uni) { Lc = splat<V>(l.uL); Lp = Lc; }
     else { Lc = ldp<V>(l.L + I); Lp = ld_xp<V>(l.L + I, Lc); }
     Pack<V> xm, xp;
-    xm.v[0] = x[(g.per[0] && i == 1) ? I + (g.n[0] - 3) : I - 1];
+    xm.v[0] = xm1;
 #pragma unroll
     for (int q = 1; q < V; ++q) xm.v[q] = xc.v[q - 1];
 #pragma unroll
     for (int q = 0; q < V - 1; ++q) xp.v[q] = xc.v[q + 1];
-    xp.v[V - 1] = x[(g.per[0] && i + V - 1 == g.n[0] - 2) ? I + (V - 1) - (g.n[0] - 3) : I + V];
+    xp.v[V - 1] = xp4;
 #pragma unroll
     for (int q = 0; q < V; ++q) s.v[q] += (xm.v[q] * Lc.v[q] + xp.v[q] * Lp.v[q]);
   }
   {
-    const int64_t st = g.s[1];
-    const int n = g.n[1];
-    const int64_t om = (g.per[1] && j == 1) ? (int64_t)(n - 3) * st : -st;
-    const int64_t op = (g.per[1] && j == n - 2) ? -(int64_t)(n - 3) * st : st;
     const float* Li = l.L + g.comp;
     Pack<V> Lc, Lp;
     if (uni) { Lc = splat<V>(l.uL); Lp = Lc; }
-    else { Lc = ldp<V>(Li + I); Lp = ldp<V>(Li + I + st); }
-    const Pack<V> xm = ldp<V>(x + I + om), xp = ldp<V>(x + I + op);
+    else { Lc = ldp<V>(Li + I); Lp = ldp<V>(Li + I + g.s[1]); }
 #pragma unroll
-    for (int q = 0; q < V; ++q) s.v[q] += (xm.v[q] * Lc.v[q] + xp.v[q] * Lp.v[q]);
+    for (int q = 0; q < V; ++q) s.v[q] += (ym.v[q] * Lc.v[q] + yp.v[q] * Lp.v[q]);
   }
   {
     const float* Li = l.L + 2 * g.comp;
@@ -146,6 +142,20 @@ __device__ __forceinline__ Pack<V> mult_zreg(const Lvl& l, const float* x, int i
     for (int q = 0; q < V; ++q) s.v[q] += (zm.v[q] * Lc.v[q] + zp.v[q] * Lp.v[q]);
   }
   return s;
+}
+// the same with the x/y neighbours read from memory (wrapped indices) and the z-neighbours from registers
+template <int V>
+__device__ __forceinline__ Pack<V> mult_zreg(const Lvl& l, const float* x, int i, int j, int64_t I, const Pack<V>& xc, const Pack<V>& zm,
+                                             const Pack<V>& zp, bool uni) {
+  const GridD& g = l.g;
+  const float xm1 = x[(g.per[0] && i == 1) ? I + (g.n[0] - 3) : I - 1];
+  const float xp4 = x[(g.per[0] && i + V - 1 == g.n[0] - 2) ? I + (V - 1) - (g.n[0] - 3) : I + V];
+  const int64_t st = g.s[1];
+  const int n = g.n[1];
+  const int64_t om = (g.per[1] && j == 1) ? (int64_t)(n - 3) * st : -st;
+  const int64_t op = (g.per[1] && j == n - 2) ? -(int64_t)(n - 3) * st : st;
+  const Pack<V> ym = ldp<V>(x + I + om), yp = ldp<V>(x + I + op);
+  return mult_vals<V>(l, I, xc, xm1, xp4, ym, yp, zm, zp, uni);
 }
 // offsets of the z-neighbours of plane k (periodic wrap of a level that is periodic in z on this rank)
 __device__ __forceinline__ int64_t zoff_m(const GridD& g, int k) { return (g.per[2] && k == 1) ? (int64_t)(g.n[2] - 3) * g.s[2] : -g.s[2]; }
@@ -169,6 +179,99 @@ __device__ __forceinline__ void for_columns(const GridD& g, const MarchGeom& mg,
     const int k0 = 1 + tz * mg.zchunk, k1 = min(k0 + mg.zchunk - 1, g.n[2] - 2);
     if (i <= g.n[0] - 2 && j <= g.n[1] - 2) f(i, j, k0, k1);
   }
+}
+
+// ---- z-marching with the stencil operand staged in shared memory --------------------------------------
+// A kernel whose only HBM input is the stencil operand (pcg!'s z = Aϵ reads ϵ and nothing else) has one
+// 16-byte load per thread and step in flight — at 32 warps per SM that is a quarter of what HBM latency ×
+// bandwidth needs, and the kernel ran at 2.7 TB/s.  Here the planes of the operand travel through a ring of
+// WL_NST shared-memory stages filled by cp.async (LDGSTS: no registers held while the miss is outstanding),
+// two planes ahead of the one being differenced; every neighbour read is then an LDS with a compile-time
+// shape: [my + 2 rows][4 pad | 4·mx | 4 pad floats], the x-halo cells in the inner float of each pad.
+// Each thread copies its own pack; edge threads add the tile's halo rows / cells (periodic wrap in the address).
+#define WL_NST 5
+__device__ __forceinline__ unsigned int wl_smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(float* smem, const float* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(wl_smem_u32(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async4(float* smem, const float* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(wl_smem_u32(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+struct StageCtx {
+  float* ring;       // WL_NST planes
+  int row, plane;    // floats per staged row / plane
+  int mine;          // offset of this thread's pack inside a staged plane
+  int64_t col;       // i + j*s1 of the thread's pack
+  int64_t colm, colp;  // the same for the y-neighbour rows (wrapped)
+  int64_t xm, xp;    // i-1 / i+4 (wrapped) + j*s1
+  bool ylo, yhi, xlo, xhi;  // this thread also copies the tile's lower/upper halo row, left/right halo cell
+};
+__device__ __forceinline__ StageCtx stage_ctx(const GridD& g, float* ring, int i, int j) {
+  StageCtx c;
+  c.ring = ring;
+  c.row = 4 * blockDim.x + 8;
+  c.plane = (blockDim.y + 2) * c.row;
+  c.mine = (threadIdx.y + 1) * c.row + 4 + 4 * threadIdx.x;
+  const int64_t s1 = g.s[1];
+  c.col = i + j * s1;
+  const int n1 = g.n[1], n0 = g.n[0];
+  c.colm = i + (int64_t)((g.per[1] && j == 1) ? n1 - 2 : j - 1) * s1;
+  c.colp = i + (int64_t)((g.per[1] && j == n1 - 2) ? 1 : j + 1) * s1;
+  c.xm = ((g.per[0] && i == 1) ? n0 - 2 : i - 1) + j * s1;
+  c.xp = ((g.per[0] && i + 3 == n0 - 2) ? 1 : i + 4) + j * s1;
+  c.ylo = threadIdx.y == 0; c.yhi = threadIdx.y == blockDim.y - 1;
+  c.xlo = threadIdx.x == 0; c.xhi = threadIdx.x == blockDim.x - 1;
+  return c;
+}
+// requests plane P (0 … n2-1; wrapped if the level is periodic in z) of field S into ring stage `st`
+__device__ __forceinline__ void stage_issue(const StageCtx& c, const GridD& g, const float* __restrict__ S, int P, int st) {
+  if (g.per[2]) P = P == 0 ? g.n[2] - 2 : (P == g.n[2] - 1 ? 1 : P);
+  const float* src = S + (int64_t)P * g.s[2];
+  float* dst = c.ring + st * c.plane;
+  cp_async16(dst + c.mine, src + c.col);
+  if (c.ylo) cp_async16(dst + c.mine - c.row, src + c.colm);
+  if (c.yhi) cp_async16(dst + c.mine + c.row, src + c.colp);
+  if (c.xlo) cp_async4(dst + c.mine - 1, src + c.xm);
+  if (c.xhi) cp_async4(dst + c.mine + 4, src + c.xp);
+}
+__device__ __forceinline__ Pack<4> lds4(const float* p) {
+  const float4 t = *reinterpret_cast<const float4*>(p);
+  Pack<4> r; r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w; return r;
+}
+// Marches a column block over planes k0 … k1 with field S staged: body(k, I, xc, Ax-operands…) is called with
+// the seven neighbour values of the thread's pack.  `pre(k, I)` runs before the step's wait + barrier (issue the
+// step's own global loads there: they overlap the wait).  All threads of the block must call it (barriers).
+template <class Pre, class Body>
+__device__ __forceinline__ void march_staged(const GridD& g, const float* __restrict__ S, float* ring, int i, int j, int k0, int k1, Pre&& pre, Body&& body) {
+  const StageCtx c = stage_ctx(g, ring, i, j);
+  // planes k0-1, k0, k0+1, k0+2 → stages 0, 1, 2, 3 (one group each)
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    if (k0 - 1 + q <= k1 + 1) stage_issue(c, g, S, k0 - 1 + q, q);
+    cp_async_commit_group();
+  }
+  int st = 1;  // stage of plane k
+  int64_t I = c.col + (int64_t)k0 * g.s[2];
+  for (int k = k0; k <= k1; ++k, I += g.s[2]) {
+    pre(k, I);
+    cp_async_wait_group<1>();   // planes ≤ k+1 have landed (the newest group, k+2, may still be in flight)
+    __syncthreads();             // … for every thread of the block; and everyone is done with plane k-2
+    {                            // plane k+3 takes the stage plane k-2 occupied
+      const int P = k + 3;
+      if (P <= k1 + 1) stage_issue(c, g, S, P, (st + 3) % WL_NST);
+      cp_async_commit_group();
+    }
+    const float* pc = c.ring + st * c.plane + c.mine;
+    const float* pm = c.ring + ((st + WL_NST - 1) % WL_NST) * c.plane + c.mine;
+    const float* pp = c.ring + ((st + 1) % WL_NST) * c.plane + c.mine;
+    body(k, I, lds4(pc), pc[-1], pc[4], lds4(pc - c.row), lds4(pc + c.row), lds4(pm), lds4(pp));
+    st = (st + 1) % WL_NST;
+  }
+  cp_async_wait_group<0>();
+  __syncthreads();  // the ring is reused by the block's next tile
 }
 
 // ---- prolongate! + increment! + the head of pcg! in one pass -------------------------------------
@@ -287,7 +390,7 @@ inline RowLaunch row_launch(const GridD& g) {
 }
 
 // host-side geometry of the z-marching kernels; ok = false when the level should use for_rows
-struct MarchLaunch { bool ok; MarchGeom mg; dim3 blk; int grid; };
+struct MarchLaunch { bool ok; bool staged; MarchGeom mg; dim3 blk; int grid; size_t smem; };
 inline MarchLaunch march_launch(const GridD& g, int nsm) {
   MarchLaunch m{};
   const int nxi = g.n[0] - 2, nyi = g.n[1] - 2, nzi = g.D > 2 ? g.n[2] - 2 : 0;
@@ -307,6 +410,9 @@ inline MarchLaunch march_launch(const GridD& g, int nsm) {
   m.blk = dim3(mx, my, 1);
   const int64_t ntiles = (int64_t)m.mg.ntx * m.mg.nty * m.mg.ntz;
   m.grid = (int)(ntiles < WL_MAXBLOCKS ? ntiles : WL_MAXBLOCKS);
+  // the shared-memory staged kernels have block-wide barriers in the march: every thread of every tile must own a pack
+  m.staged = packs % mx == 0 && nyi % my == 0;
+  m.smem = sizeof(float) * (size_t)WL_NST * (my + 2) * (4 * mx + 8);
   return m;
 }
 

@@ -10,7 +10,8 @@ import os
 
 from ._cabi import CABI
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libwaterlily_b200.so")
+# WL_LIB_PATH: a differently-built copy of the same library (kernel tuning experiments, tools/build_variant.sh)
+LIB_PATH = os.environ.get("WL_LIB_PATH") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libwaterlily_b200.so")
 _lib = None
 
 
