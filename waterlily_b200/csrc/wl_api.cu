@@ -302,12 +302,15 @@ static int create_impl(wl_sim** out, int D, const int* N, double nu, double dt0,
   // levels[1] aliases the flow arrays (WaterLily.jl:77); r, ϵ, D, iD are its own (Poisson.jl:33-34)
   auto alloc_fields = [&](int* prc) {
     a.arena_used = WL_P2P_FLAG_BYTES;  // the peer-communication flag block leads the arena
-    a.u = dev_alloc(a, a.g, D, prc); a.u0 = dev_alloc(a, a.g, D, prc); a.f = dev_alloc(a, a.g, D, prc);
+    a.u = dev_alloc(a, a.g, D, prc); a.u0 = dev_alloc(a, a.g, D, prc); a.f = dev_alloc(a, a.g, D, prc); a.w = dev_alloc(a, a.g, D, prc);
     a.p = dev_alloc(a, a.g, 1, prc); a.sigma = dev_alloc(a, a.g, 1, prc); a.V = dev_alloc(a, a.g, D, prc);
     a.mu0 = dev_alloc(a, a.g, D, prc); a.mu1 = dev_alloc(a, a.g, D * D, prc);
     {
       unsigned char* m = (unsigned char*)arena_take(a, (size_t)a.g.comp, prc);
       a.body_mask = m ? m + a.g.lead : nullptr;
+      // clean map of the conv_diff! core tiles (64 x 8 cells): one byte per tile and plane
+      const size_t ntile = (size_t)((a.g.n[0] + 63) / 64 + 1) * ((a.g.n[1] + 7) / 8 + 1) * (size_t)a.g.n[2];
+      a.tile_clean = (unsigned char*)arena_take(a, ntile + 16, prc);
     }
     a.levels.clear();
     for (size_t l = 0; l < dims.size(); ++l) {
@@ -341,6 +344,7 @@ static int create_impl(wl_sim** out, int D, const int* N, double nu, double dt0,
   { const char* e = getenv("WL_UNIFORM"); a.uniform_path = !(e && atoi(e) == 0); }
   { const char* e = getenv("WL_MARCH"); a.march_on = !(e && atoi(e) == 0); }
   { const char* e = getenv("WL_STAGE"); a.stage_on = !(e && atoi(e) == 0); }
+  { const char* e = getenv("WL_BDIM_FUSE"); a.bdim_fuse = !(e && atoi(e) == 0); }
   if (!rc && cudaMalloc(&tmp, 64) == cudaSuccess) { a.allocs.push_back(tmp); a.ws.ticket = (unsigned int*)tmp; cudaMemsetAsync(tmp, 0, 64, a.stream); } else if (!rc) rc = wl_fail(WL_ERR_CUDA, "cudaMalloc ticket");
   if (!rc && cudaMallocHost((void**)&a.h_pinned, 64 * sizeof(float)) != cudaSuccess) rc = wl_fail(WL_ERR_CUDA, "cudaMallocHost");
   if (rc) { wl_destroy((wl_sim*)sp); return rc; }
@@ -464,7 +468,11 @@ int wl_upload(wl_sim* s, int field, const float* host, int64_t count) {
   if (!d || count != (int64_t)S.g.n[0] * S.g.n[1] * nzg * nc) return wl_fail(WL_ERR_ARG, "wl_upload: bad field or size");
   if (field == WL_V || field == WL_MU0 || field == WL_MU1) S.mask_dirty = true;
   if (field == WL_MU0) pois_invalidate_uniform(S, 0);  // levels[1].L ≡ μ₀: stale until update!
-  int rc = copy_field(S, S.g, d, const_cast<float*>(host), nc, true, nzg);
+  int rc = 0;
+  if (field == WL_F) S.f_stale = false;                                   // replaced wholesale
+  else if (field == WL_U0 || field == WL_V) rc = mom_materialize_f(S);     // inputs of the on-demand f are about to change
+  if (rc) return rc;
+  rc = copy_field(S, S.g, d, const_cast<float*>(host), nc, true, nzg);
   // slab faces: refresh the halo planes from the neighbours (collective: every rank uploads the field)
   if (!rc) rc = dist_halo(S, S.g, d, nc, (field == WL_U || field == WL_U0) ? 2 : 1);
   return rc ? rc : wl_sync(s);
@@ -474,6 +482,7 @@ int wl_download(wl_sim* s, int field, float* host, int64_t count) {
   int nc; float* d = field_ptr(S, field, &nc);
   const int nzg = nz_padded_global(S, 0);
   if (!d || count != (int64_t)S.g.n[0] * S.g.n[1] * nzg * nc) return wl_fail(WL_ERR_ARG, "wl_download: bad field or size");
+  if (field == WL_F) { const int rc = mom_materialize_f(S); if (rc) return rc; }
   return copy_field(S, S.g, d, host, nc, false, nzg);
 }
 int wl_nlevels(wl_sim* s) { return s ? (int)S.levels.size() : 0; }
@@ -517,6 +526,7 @@ int wl_bc(wl_sim* s, int field, const double* A, int saveexit, const int* perdir
   int per[3]; per_flags(S, perdir, per);
   if (field == WL_V || field == WL_MU0) S.mask_dirty = true;
   if (field == WL_MU0) pois_invalidate_uniform(S, 0);
+  if (field == WL_F || field == WL_U0 || field == WL_V) { const int rc0 = mom_materialize_f(S); if (rc0) return rc0; }
   int rc = bc_vec(S, S.g, d, A, saveexit != 0, per, (field == WL_U || field == WL_U0) ? 2 : 1);
   return rc ? rc : wl_sync(s);
 }
@@ -536,13 +546,15 @@ int wl_per_bc(wl_sim* s, int field, const int* perdir) {
 int wl_conv_diff(wl_sim* s, int src) {
   GUARD(s);
   if (src != WL_U && src != WL_U0) return wl_fail(WL_ERR_ARG, "wl_conv_diff: src must be WL_U or WL_U0");
+  S.f_stale = false;  // f is overwritten
   int rc = mom_conv_diff(S, src == WL_U ? S.u : S.u0, false, nullptr);
   return rc ? rc : wl_sync(s);
 }
-int wl_accelerate(wl_sim* s, const double* g) { GUARD(s); int rc = mom_accelerate(S, g); return rc ? rc : wl_sync(s); }
+int wl_accelerate(wl_sim* s, const double* g) { GUARD(s); int rc = mom_materialize_f(S); if (!rc) rc = mom_accelerate(S, g); return rc ? rc : wl_sync(s); }
 int wl_bdim(wl_sim* s) {
   GUARD(s);
-  int rc = mom_bdim1(S);
+  int rc = mom_materialize_f(S);
+  if (!rc) rc = mom_bdim1(S);
   if (!rc) rc = mom_bdim2(S, true, 1.f);
   return rc ? rc : wl_sync(s);
 }

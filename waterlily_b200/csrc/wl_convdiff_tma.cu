@@ -370,24 +370,37 @@ __global__ void __launch_bounds__(32 * TY, MINB)
   // copies the values of its own two cells asynchronously into shared memory one plane ahead
   // (cp.async, no registers held) and picks them up after cp.async.wait_group
   float* const vu = VU + tiy * TX + 2 * lane;
-  auto fetch_plane = [&](int st, int64_t o) {
+  // clean tile-planes (CDArgs::clean): V is zero there and is not fetched.  The flags of the block's z-chunk are
+  // copied to shared memory up front: a global load per step sat on the critical path of the march (+0.3 ms per launch)
+  __shared__ unsigned char cflag[128];
+  if (a.ufused) {
+    const int t = tiy * 32 + lane;
+    if (t < 128) cflag[t] = (t < z1 - z0) ? a.clean[((size_t)(z0 + t) * nty + ty) * ntx + tx] : 0;
+  }
+  __syncthreads();
+  auto is_clean = [&](int z) -> bool { return a.ufused != nullptr && cflag[z - z0] != 0; };
+  auto fetch_plane = [&](int st, int64_t o, bool cl) {
     if (a.fuse_bdim1) {
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
-        cp_async8(vu + (st * 6 + i) * TY * TX, vb[i] + o);
+        if (!cl) cp_async8(vu + (st * 6 + i) * TY * TX, vb[i] + o);
         if (CORR) cp_async8(vu + (st * 6 + 3 + i) * TY * TX, ub[i] + o);
       }
     }
     cp_async_commit();
   };
-  fetch_plane(0, off);
+  bool cl_cur = is_clean(z0);
+  fetch_plane(0, off, cl_cur);
+  const char* const qb[3] = {(const char*)a.ufused, (const char*)(a.ufused + g.comp), (const char*)(a.ufused + 2 * g.comp)};
   auto step = [&](auto stage_tag, int z) {
     constexpr int S = decltype(stage_tag)::value;
     constexpr int SM1 = (S + 3) & 3, SP1 = (S + 1) & 3, SP2 = (S + 2) & 3;
     const float* C = tb + S * STAGE;
     const float* N = tb + SP1 * STAGE;
     const float* NN = tb + SP2 * STAGE;
-    fetch_plane(buf ^ 1, off + doff);
+    const bool cl = cl_cur;
+    cl_cur = z + 1 < z1 ? is_clean(z + 1) : false;
+    fetch_plane(buf ^ 1, off + doff, cl_cur);
     float2 fx[3], fxh[3], fy[3], fyh[3];
     float2 ym1[3], yp1[3];
     float2 xm[3];
@@ -484,11 +497,18 @@ __global__ void __launch_bounds__(32 * TY, MINB)
         if (HASG) { v.x = (float)((double)v.x + a.gacc[i]); v.y = (float)((double)v.y + a.gacc[i]); }
         if (a.fuse_bdim1) {
           const float2 u0v = CORR ? ld2(vu + (buf * 6 + 3 + i) * TY * TX) : R[i][S];
-          const float2 Vv = ld2(vu + (buf * 6 + i) * TY * TX);
+          const float2 Vv = cl ? make_float2(0.f, 0.f) : ld2(vu + (buf * 6 + i) * TY * TX);
           v.x = u0v.x + a.dt * v.x - Vv.x;
           v.y = u0v.y + a.dt * v.y - Vv.y;
         }
         float* dst = reinterpret_cast<float*>(const_cast<char*>(fb[i]) + off);
+        if (cl) {  // BDIM! stage 2 away from bodies: u = (u_acc + f)·scale with u_acc = 0 (predictor) or u (corrector)
+          // the reference adds in Float64 and rounds once; for the sum of two Float32 that is the Float32 sum (53 ≥ 2·24+2 bits:
+          // the double rounding is innocuous), so the Float32 add below has the same bits — and no FP64 conversions to issue
+          v.x = ((CORR ? R[i][S].x : 0.f) + v.x) * a.bscale;
+          v.y = ((CORR ? R[i][S].y : 0.f) + v.y) * a.bscale;
+          dst = reinterpret_cast<float*>(const_cast<char*>(qb[i]) + off);
+        }
         if (valid_b) *reinterpret_cast<float2*>(dst) = v;
         else dst[0] = v.x;
       }
@@ -515,9 +535,8 @@ constexpr size_t kSmem2 = sizeof(float) * (4 * Tile<64, kTY2>::STAGE + 2 * 3 * k
 }  // namespace
 
 struct ConvDiffTma {
-  CUtensorMap map_u, map_u0;  // the two velocity buffers (mom_step swaps the pointers, not the data)
-  const float* ptr_u;
-  const float* ptr_u0;
+  CUtensorMap map[4];         // the velocity-sized buffers u, u⁰, f, w (mom_step rotates the pointers, not the data)
+  const float* ptr[4];
   int cells_per_thread;       // 1: k_conv_diff3_tma (core from x = 2), 2: k_conv_diff3_tma2 (core from x = 3)
 };
 
@@ -551,7 +570,8 @@ int convdiff_tma_setup(Sim& s) {
     return encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
   };
-  if (!make(&t->map_u, s.u) || !make(&t->map_u0, s.u0)) {
+  t->ptr[0] = s.u; t->ptr[1] = s.u0; t->ptr[2] = s.f; t->ptr[3] = s.w;
+  if (!make(&t->map[0], s.u) || !make(&t->map[1], s.u0) || !make(&t->map[2], s.f) || !make(&t->map[3], s.w)) {
     if (getenv("WL_VERBOSE")) fprintf(stderr, "[waterlily_b200] cuTensorMapEncodeTiled failed: conv_diff! uses the untiled kernel\n");
     delete t;
     return 0;
@@ -566,8 +586,6 @@ int convdiff_tma_setup(Sim& s) {
     if (e != cudaSuccess) { cudaGetLastError(); delete t; return 0; }
   }
   if (getenv("WL_VERBOSE")) fprintf(stderr, "[waterlily_b200] conv_diff!: TMA-staged kernel, %d cell(s) per thread\n", t->cells_per_thread);
-  t->ptr_u = s.u;
-  t->ptr_u0 = s.u0;
   s.cd_tma = t;
   return 0;
 }
@@ -594,7 +612,8 @@ static void launch_tma(Sim& s, const CUtensorMap& m, const CDArgs& a, int zchunk
 bool convdiff_tma_launch(Sim& s, const CDArgs& a, int zchunk, bool corr) {
   ConvDiffTma* t = (ConvDiffTma*)s.cd_tma;
   if (!t) return false;
-  const CUtensorMap* m = a.u == t->ptr_u ? &t->map_u : (a.u == t->ptr_u0 ? &t->map_u0 : nullptr);
+  const CUtensorMap* m = nullptr;
+  for (int q = 0; q < 4; ++q) if (a.u == t->ptr[q]) m = &t->map[q];
   if (!m) return false;
   if (t->cells_per_thread == 2) {
     if (a.has_g) {
@@ -612,6 +631,14 @@ bool convdiff_tma_launch(Sim& s, const CDArgs& a, int zchunk, bool corr) {
     else launch_tma<false, false>(s, *m, a, zchunk);
   }
   ++s.launches;
+  return true;
+}
+// tile grid of the two-cells-per-thread kernel (the `clean` map of CDArgs is indexed with it); false if another kernel runs
+bool convdiff_tma_tiles(const Sim& s, int* ntx, int* nty) {
+  const ConvDiffTma* t = (const ConvDiffTma*)s.cd_tma;
+  if (!t || t->cells_per_thread != 2) return false;
+  *ntx = (s.g.n[0] - 5 + 63) / 64;
+  *nty = (s.g.n[1] - 4 + kTY2 - 1) / kTY2;
   return true;
 }
 // first x index of the core the TMA kernel covers (the boundary-shell kernel takes everything below it)

@@ -25,6 +25,12 @@ __device__ __forceinline__ float quick(float u, float c, float d) {
   return fminf(fmaxf(c, lo), hi);
 }
 
+// tile of the two-cells-per-thread core kernel (wl_convdiff_tma.cu): 64 x 8 cells starting at cell (3, 2)
+#define WL_CD_TX 64
+#define WL_CD_TY 8
+#define WL_CD_X0 3
+#define WL_CD_Y0 2
+
 struct CDArgs {
   GridD g;
   const float* u;    // field being differenced (u⁰ in the predictor, u in the corrector)
@@ -36,6 +42,17 @@ struct CDArgs {
   double gacc[3];
   int has_g;
   int fuse_bdim1;
+  // BDIM! stage 2 folded into the store (3-D core kernel only): on a tile-plane whose cells — and, for μ₁, whose
+  // neighbours — are away from every body (`clean` map, see k_tile_clean) stage 2 is u = (u_acc + f)·scale, so the
+  // kernel writes u straight to `ufused` and neither f nor V is touched there.  Null = write f everywhere.
+  float* ufused;
+  const unsigned char* clean;   // [plane][tile row][tile column], 1 = clean
+  float bscale;                 // scale_u! folded into stage 2: 1 (predictor), 0.5 (corrector)
+  // boundary-shell cells (k_conv_diff_shell): f is always stored; where the cell's own μ₁ is zero (mask bit 1 clear) stage 2
+  // needs no neighbour and is applied on the spot: u_dst = (u_acc + V + μ₀·f)·scale
+  const unsigned char* mask;
+  const float* mu0;
+  const float* uacc;            // null: predictor (u_acc = 0)
 };
 
 // one face flux Φ = uf·quick(upwind samples) − ν(u_c − u_{c-1}) (Flow.jl:45): the reference rounds the

@@ -58,6 +58,7 @@ struct Sim {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   // flow fields (pointers already offset by WL_OX); u/u0 are swapped by mom_step
+  float* w = nullptr;  // fourth velocity-sized buffer: the corrector writes the new u here (BDIM! stage 2 folded into conv_diff!), then u ↔ w
   float *u = nullptr, *u0 = nullptr, *f = nullptr, *p = nullptr, *sigma = nullptr, *V = nullptr, *mu0 = nullptr, *mu1 = nullptr;
   std::vector<void*> allocs;
   char* arena = nullptr;       // all fields live in one allocation (symmetric across ranks, wl_p2p.cuh)
@@ -67,6 +68,15 @@ struct Sim {
   size_t stage_bytes = 0;
   unsigned char* body_mask = nullptr;  // 1 byte per cell, same indexing as a scalar field (see k_body_mask)
   bool mask_dirty = true;              // V, μ₀ or μ₁ changed since the mask was built
+  unsigned char* tile_clean = nullptr; // [plane][tile row][tile column] of the conv_diff! core kernel: 1 = BDIM! stage 2 folds into its store
+  bool bdim_fuse = true;               // WL_BDIM_FUSE=0: conv_diff! writes f everywhere and BDIM! stage 2 runs on every cell
+  // flow.f after a fused step: the clean tiles never received the corrector's f.  It is recomputed on demand
+  // (download of f, wl_bdim, …) from the inputs the corrector used, which are all still in memory: u' in w, u⁰, V.
+  bool f_stale = false;
+  float f_dt = 0.f;
+  double f_g[3] = {0, 0, 0};
+  bool f_has_g = false;
+  bool last_cd_fused = false;          // the last conv_diff! folded BDIM! stage 2 into its store on the clean tile-planes
   float nu = 0.f;
   std::vector<float> dt;
   bool exitBC = false;
@@ -140,6 +150,7 @@ int convdiff_tma_setup(Sim& s);
 void convdiff_tma_destroy(Sim& s);
 bool convdiff_tma_launch(Sim& s, const CDArgs& a, int zchunk, bool corr);
 int convdiff_tma_core_x0(const Sim& s);
+bool convdiff_tma_tiles(const Sim& s, int* ntx, int* nty);
 
 // ---- wl_metrics.cu ----
 // which: 0 pressure_force, 1 viscous_force, 2 pressure_moment (x0 required); out has D entries
@@ -179,10 +190,11 @@ int pois_materialize_eps(Sim& s, int level);
 int pois_dot_rr(Sim& s, Lvl& l, double* out);
 
 // ---- wl_momentum.cu ----
-int mom_conv_diff(Sim& s, const float* src, bool fuse_bdim1, const double* g);
+int mom_conv_diff(Sim& s, const float* src, bool fuse_bdim1, const double* g, int bdim2_mode = 0, float dt_override = 0.f);
+int mom_materialize_f(Sim& s);  // flow.f of the last fused step, on demand (see Sim::f_stale)
 int mom_accelerate(Sim& s, const double* g);
 int mom_bdim1(Sim& s);
-int mom_bdim2(Sim& s, bool accumulate, float scale);
+int mom_bdim2(Sim& s, bool accumulate, float scale, bool fused = false);
 int mom_scale_u(Sim& s, double scale);
 int mom_project(Sim& s, double w, int* n, int slot = 0, bool defer_count = false, bool skip_unscale = false, float prediv = 0.f);
 int mom_cfl(Sim& s, double* dt);

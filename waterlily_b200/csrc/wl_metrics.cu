@@ -206,6 +206,7 @@ int metrics_run(Sim& s, int which, const double* x0, double* out) {
   for (int k = 0; k < 3; ++k) a.x0[k] = (x0 && k < s.D) ? x0[k] : 0.0;
   a.out = s.ws.partials + (size_t)WL_MAXBLOCKS * WL_MAXRED;  // spare slots behind the partials (8 doubles)
   // df .= 0 (Metrics.jl:97,115,138): ghost cells included
+  s.f_stale = false;  // flow.f is the scratch of the Metrics functions (Metrics.jl:96): overwritten whole
   int rc = wl_fill(s, s.f - s.g.lead, 0.f, s.g.comp * s.D);
   if (rc) return rc;
   const dim3 blk = wl_pick_block(s.g);

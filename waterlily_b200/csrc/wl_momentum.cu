@@ -106,12 +106,31 @@ __device__ __forceinline__ void convdiff_store_cell(const CDArgs& a, const int (
       }
     }
   }
+  // BDIM! stage 2 on the spot (fused step, interior cell whose own μ₁ is zero: no neighbour of f is needed)
+  bool stage2 = false;
+  unsigned char mk = 0;
+  if (a.ufused) {
+    stage2 = true;
+#pragma unroll
+    for (int k = 0; k < D; ++k) stage2 &= c[k] >= 1 && c[k] <= g.n[k] - 2;
+    if (stage2) { mk = a.mask[I]; stage2 = (mk & 2) == 0; }
+  }
 #pragma unroll
   for (int i = 0; i < D; ++i) {
     float v = r[i];
     if (a.has_g) v = (float)((double)v + a.gacc[i]);          // accelerate! (Flow.jl:68-70)
     if (a.fuse_bdim1) v = a.u0[I + i * g.comp] + a.dt * v - a.V[I + i * g.comp];  // BDIM! stage 1 (:133)
     a.f[I + i * g.comp] = v;
+    if (stage2) {  // the expressions of k_bdim2 with μ₁ = 0 (s = 0.f + 0·(…) = +0)
+      const int64_t Ii = I + i * g.comp;
+      const double acc = a.uacc ? (double)a.uacc[Ii] : 0.0;
+      if (mk == 0) {
+        a.ufused[Ii] = (float)(acc + (double)v) * a.bscale;
+      } else {
+        const double add = (0.5 * (double)0.f + (double)a.V[Ii]) + (double)(a.mu0[Ii] * v);
+        a.ufused[Ii] = (float)(acc + add) * a.bscale;
+      }
+    }
   }
 }
 
@@ -295,10 +314,11 @@ __global__ void __launch_bounds__(256) k_bdim1(GridD g, float* f, const float* u
 }
 
 // "Body band" mask: 0 where BDIM! stage 2 degenerates to u += f (μ₁ = 0, V = 0, μ₀ = 1 for every
-// component — everywhere except within 2+ϵ cells of a body and on the domain-boundary faces), 1
-// elsewhere.  One byte per cell replaces 15 words of μ₁/V/μ₀ reads; rebuilt whenever one of the three
-// fields changes (upload, BC!).  The result is bit-identical: with those values the general
-// expression reduces to (Float64)u + (Float64)f exactly.
+// component — everywhere except within 2+ϵ cells of a body and on the domain-boundary faces), non-zero
+// elsewhere (bit 1 set where some μ₁ ≠ 0, i.e. where stage 2 also reads f of the six neighbours).  One
+// byte per cell replaces 15 words of μ₁/V/μ₀ reads; rebuilt whenever one of the three fields changes
+// (upload, BC!).  The result is bit-identical: with those values the general expression reduces to
+// (Float64)u + (Float64)f exactly.
 template <int D, int V>
 __global__ void __launch_bounds__(256) k_body_mask(GridD g, const float* __restrict__ Vb, const float* __restrict__ mu0,
                                                    const float* __restrict__ mu1, unsigned char* __restrict__ mask) {
@@ -315,7 +335,7 @@ __global__ void __launch_bounds__(256) k_body_mask(GridD g, const float* __restr
       for (int j = 0; j < D; ++j) {
         const Pack<V> m1 = ldp<V>(mu1 + I + (int64_t)(i + D * j) * g.comp);
 #pragma unroll
-        for (int q = 0; q < V; ++q) m[q] |= (m1.v[q] != 0.f);
+        for (int q = 0; q < V; ++q) m[q] |= (m1.v[q] != 0.f) ? 3 : 0;
       }
     }
 #pragma unroll
@@ -323,13 +343,77 @@ __global__ void __launch_bounds__(256) k_body_mask(GridD g, const float* __restr
   });
 }
 
+// slab decomposition: the same for the interior cells of one z-plane (the neighbour's cells in a halo plane —
+// their μ₁ decides whether this rank's adjacent tiles may skip f, see k_tile_clean)
+template <int D>
+__global__ void __launch_bounds__(256) k_body_mask_plane(GridD g, const float* __restrict__ Vb, const float* __restrict__ mu0,
+                                                         const float* __restrict__ mu1, unsigned char* __restrict__ mask, int k) {
+  Box b = box_interior(g);
+  b.lo[2] = b.hi[2] = k;
+  for_cells(g, b, [&](int, int, int, int64_t I) {
+    unsigned char m = 0;
+    for (int i = 0; i < D; ++i) {
+      m |= (Vb[I + i * g.comp] != 0.f) | (mu0[I + i * g.comp] != 1.f);
+      for (int j = 0; j < D; ++j) m |= (mu1[I + (int64_t)(i + D * j) * g.comp] != 0.f) ? 3 : 0;
+    }
+    mask[I] = m;
+  });
+}
+// Which (tile, plane) units of the conv_diff! core kernel may fold BDIM! stage 2 into their store: every cell of
+// the tile in that plane is plain (mask = 0), and no cell within one cell of the tile — in x, y or z — has μ₁ ≠ 0
+// (such a cell reads f of its six neighbours, so the tile must deliver f).  One warp per unit.
+__global__ void __launch_bounds__(256) k_tile_clean(GridD g, const unsigned char* __restrict__ mask, unsigned char* __restrict__ clean, int ntx,
+                                                    int nty, int zlo, int zhi) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nunits = (int64_t)ntx * nty * g.n[2];
+  for (int64_t unit = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); unit < nunits; unit += (int64_t)gridDim.x * (blockDim.x >> 5)) {
+    const int tx = (int)(unit % ntx), ty = (int)((unit / ntx) % nty), z = (int)(unit / ((int64_t)ntx * nty));
+    bool ok = z >= zlo && z <= zhi;
+    if (ok) {
+      const int x0 = WL_CD_X0 + tx * WL_CD_TX, x1 = min(x0 + WL_CD_TX - 1, g.n[0] - 3);
+      const int y0 = WL_CD_Y0 + ty * WL_CD_TY, y1 = min(y0 + WL_CD_TY - 1, g.n[1] - 3);
+      const int wx = x1 - x0 + 3, wy = y1 - y0 + 3;
+      bool bad = false;
+      for (int t = lane; t < wx * wy * 3; t += 32) {
+        const int dx = t % wx, q = t / wx, dy = q % wy, dz = q / wy;
+        const int x = x0 - 1 + dx, y = y0 - 1 + dy, zz = z - 1 + dz;
+        const unsigned char m = mask[x + y * g.s[1] + zz * g.s[2]];
+        const bool inside = dx >= 1 && dx <= wx - 2 && dy >= 1 && dy <= wy - 2 && dz == 1;
+        bad |= inside ? (m != 0) : ((m & 2) != 0);
+      }
+      ok = !__any_sync(0xffffffffu, bad);
+    }
+    if (lane == 0) clean[unit] = ok ? 1 : 0;
+  }
+}
+
 // BDIM! stage 2 (Flow.jl:134) with μddn (:18-24); `accumulate`=0 folds the predictor's
 // scale_u!(a,0), `scale` folds the corrector's scale_u!(a,0.5)
+// `u` receives the result, `ua` is the u that is accumulated (the same buffer unless the corrector writes the new
+// u elsewhere, see mom_step).  Cells of a clean tile-plane (k_tile_clean) were already finished by the conv_diff! core
+// kernel: they are skipped (`clean` null = none).
+struct FusedTiles { const unsigned char* clean; int ntx, nty, zlo, zhi; };
 template <int D, int V>
-__global__ void __launch_bounds__(256) k_bdim2(GridD g, float* __restrict__ u, const float* __restrict__ f, const float* __restrict__ Vb,
-                                               const float* __restrict__ mu0, const float* __restrict__ mu1,
-                                               const unsigned char* __restrict__ mask, int accumulate, float scale) {
-  for_rows<V>(g, [&](int, int, int, int64_t I) {
+__global__ void __launch_bounds__(256) k_bdim2(GridD g, float* __restrict__ u, const float* __restrict__ ua, const float* __restrict__ f,
+                                               const float* __restrict__ Vb, const float* __restrict__ mu0, const float* __restrict__ mu1,
+                                               const unsigned char* __restrict__ mask, FusedTiles ft, int accumulate, float scale) {
+  for_rows<V>(g, [&](int i0, int j0, int k0, int64_t I) {
+    // bit q set: cell i0+q is done already
+    unsigned int done = 0;
+    if (D == 3 && ft.clean && k0 >= ft.zlo && k0 <= ft.zhi && j0 >= WL_CD_Y0 && j0 <= g.n[1] - 3) {
+      const unsigned char* row = ft.clean + ((size_t)k0 * ft.nty + ((j0 - WL_CD_Y0) / WL_CD_TY)) * ft.ntx;
+#pragma unroll
+      for (int q = 0; q < V; ++q) {
+        const int x = i0 + q;
+        if (x >= WL_CD_X0 && x <= g.n[0] - 3 && row[(x - WL_CD_X0) / WL_CD_TX]) done |= 1u << q;
+      }
+      if (done == (1u << V) - 1u) return;
+    }
+    auto store = [&](float* dst, const Pack<V>& a) {
+      if (done == 0) { stp<V>(dst, a); return; }
+#pragma unroll
+      for (int q = 0; q < V; ++q) if (!((done >> q) & 1u)) dst[q] = a.v[q];
+    };
     // one 32-bit load covers the 4 cells of a pack (mask + I is 4-byte aligned like the fields are 16-byte aligned)
     const bool plain = V == 4 ? (*reinterpret_cast<const unsigned int*>(mask + I) == 0u) : (mask[I] == 0);
     if (plain) {  // away from any body and boundary face: u = (u + f)·scale
@@ -340,10 +424,10 @@ __global__ void __launch_bounds__(256) k_bdim2(GridD g, float* __restrict__ u, c
         Pack<V> un;
 #pragma unroll
         for (int q = 0; q < V; ++q) un.v[q] = 0.f;
-        if (accumulate) un = ldp<V>(u + Ii);
+        if (accumulate) un = ldp<V>(ua + Ii);
 #pragma unroll
         for (int q = 0; q < V; ++q) un.v[q] = (float)((accumulate ? (double)un.v[q] : 0.0) + (double)fc.v[q]) * scale;
-        stp<V>(u + Ii, un);
+        store(u + Ii, un);
       }
       return;
     }
@@ -367,16 +451,103 @@ __global__ void __launch_bounds__(256) k_bdim2(GridD g, float* __restrict__ u, c
       Pack<V> un;
 #pragma unroll
       for (int q = 0; q < V; ++q) un.v[q] = 0.f;
-      if (accumulate) un = ldp<V>(u + Ii);
+      if (accumulate) un = ldp<V>(ua + Ii);
 #pragma unroll
       for (int q = 0; q < V; ++q) {
         const double add = (0.5 * (double)s.v[q] + (double)vb.v[q]) + (double)(m0.v[q] * fc.v[q]);
         un.v[q] = (float)((accumulate ? (double)un.v[q] : 0.0) + add) * scale;
       }
-      stp<V>(u + Ii, un);
+      store(u + Ii, un);
     }
   });
 }
+// ---- BDIM! stage 2 on what the fused conv_diff! left over (3-D) -----------------------------------
+// one cell, all components: the expressions of k_bdim2
+__device__ __forceinline__ void bdim2_cell(const GridD& g, float* __restrict__ u, const float* __restrict__ ua, const float* __restrict__ f,
+                                           const float* __restrict__ Vb, const float* __restrict__ mu0, const float* __restrict__ mu1,
+                                           const unsigned char* __restrict__ mask, int64_t I, int accumulate, float scale) {
+  const bool plain = mask[I] == 0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const int64_t Ii = I + i * g.comp;
+    const float fc = f[Ii];
+    const double acc = accumulate ? (double)ua[Ii] : 0.0;
+    if (plain) {
+      u[Ii] = (float)(acc + (double)fc) * scale;
+    } else {
+      float s = 0.f + mu1[I + (int64_t)i * g.comp] * (f[Ii + 1] - f[Ii - 1]);
+#pragma unroll
+      for (int j = 1; j < 3; ++j) s += mu1[I + (int64_t)(i + 3 * j) * g.comp] * (f[Ii + g.s[j]] - f[Ii - g.s[j]]);
+      const double add = (0.5 * (double)s + (double)Vb[Ii]) + (double)(mu0[Ii] * fc);
+      u[Ii] = (float)(acc + add) * scale;
+    }
+  }
+}
+// the interior cells outside the core of the conv_diff! kernel (the enumeration of k_conv_diff_shell, ghost cells skipped)
+__global__ void __launch_bounds__(256) k_bdim2_shell(GridD g, float* __restrict__ u, const float* __restrict__ ua, const float* __restrict__ f,
+                                                     const float* __restrict__ Vb, const float* __restrict__ mu0, const float* __restrict__ mu1,
+                                                     const unsigned char* __restrict__ mask, unsigned int nZ, unsigned int nY, unsigned int nX,
+                                                     int xlow, int accumulate, float scale) {
+  const int n0 = g.n[0], n1 = g.n[1], n2 = g.n[2];
+  const int zc0 = g.zlo_halo ? 1 : 2, zc1 = g.zhi_halo ? n2 - 2 : n2 - 3;
+  const unsigned int total = nZ + nY + nX;
+  for (unsigned int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    int c[3];
+    if (idx < nZ) {
+      const unsigned int row = idx / (unsigned int)n0, kk = row / (unsigned int)n1;
+      c[0] = (int)(idx - row * n0);
+      c[1] = (int)(row - kk * n1);
+      c[2] = (int)kk < zc0 ? (int)kk : zc1 + 1 + ((int)kk - zc0);
+    } else if (idx < nZ + nY) {
+      const unsigned int t = idx - nZ, row = t / (unsigned int)n0, kk = row >> 2, jj = row & 3u;
+      c[0] = (int)(t - row * n0);
+      c[1] = jj < 2 ? (int)jj : n1 - 4 + (int)jj;
+      c[2] = zc0 + (int)kk;
+    } else {
+      const unsigned int t = idx - nZ - nY, nxs = (unsigned int)xlow + 2u, row = t / nxs, ii = t - row * nxs, kk = row / (unsigned int)(n1 - 4);
+      c[0] = (int)ii < xlow ? (int)ii : n0 - 2 + ((int)ii - xlow);
+      c[1] = 2 + (int)(row - kk * (n1 - 4));
+      c[2] = zc0 + (int)kk;
+    }
+    if (c[0] < 1 || c[0] > n0 - 2 || c[1] < 1 || c[1] > n1 - 2 || c[2] < 1 || c[2] > n2 - 2) continue;  // BDIM! stage 2 is @inside
+    const int64_t I = c[0] + c[1] * g.s[1] + c[2] * g.s[2];
+    if ((mask[I] & 2) == 0) continue;  // no μ₁ here: k_conv_diff_shell applied stage 2 itself
+    bdim2_cell(g, u, ua, f, Vb, mu0, mu1, mask, I, accumulate, scale);
+  }
+}
+// the core tile-planes that are not clean: one block per (tile, plane) unit, two cells per thread
+__global__ void __launch_bounds__(256) k_bdim2_tiles(GridD g, float* __restrict__ u, const float* __restrict__ ua, const float* __restrict__ f,
+                                                     const float* __restrict__ Vb, const float* __restrict__ mu0, const float* __restrict__ mu1,
+                                                     const unsigned char* __restrict__ mask, FusedTiles ft, int accumulate, float scale) {
+  // the flags of 256 consecutive units are read with one coalesced load; the (few) units that are not clean are
+  // collected in shared memory and worked off by the whole block
+  __shared__ int todo[256];
+  __shared__ int ntodo;
+  const int per_plane = ft.ntx * ft.nty;
+  const int nunits = per_plane * (ft.zhi - ft.zlo + 1);
+  const int base0 = per_plane * ft.zlo;  // the map starts at plane 0
+  for (int chunk = blockIdx.x * 256; chunk < nunits; chunk += gridDim.x * 256) {
+    if (threadIdx.x == 0) ntodo = 0;
+    __syncthreads();
+    const int mine = chunk + (int)threadIdx.x;
+    if (mine < nunits && ft.clean[base0 + mine] == 0) todo[atomicAdd(&ntodo, 1)] = mine;
+    __syncthreads();
+    const int n = ntodo;
+    for (int t = 0; t < n; ++t) {
+      const int unit = todo[t];
+      const int tx = unit % ft.ntx, q = unit / ft.ntx, ty = q % ft.nty, z = ft.zlo + q / ft.nty;
+      const int y = WL_CD_Y0 + ty * WL_CD_TY + (int)(threadIdx.x >> 5);
+      if (y > g.n[1] - 3) continue;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int x = WL_CD_X0 + tx * WL_CD_TX + (int)(threadIdx.x & 31) + 32 * h;
+        if (x <= g.n[0] - 3) bdim2_cell(g, u, ua, f, Vb, mu0, mu1, mask, x + y * g.s[1] + (int64_t)z * g.s[2], accumulate, scale);
+      }
+    }
+    __syncthreads();
+  }
+}
+
 template <int D, int V>
 __global__ void __launch_bounds__(256) k_scale_u(GridD g, float* u, double scale) {
   for_rows<V>(g, [&](int, int, int, int64_t I) {
@@ -536,10 +707,45 @@ static void launch_march(Sim& s, const CDArgs& a, int variant, int zchunk, bool 
   }
 }
 
-int mom_conv_diff(Sim& s, const float* src, bool fuse_bdim1, const double* gacc) {
+// the body-band mask and, from it, the clean map of the core tiles (when one of V, μ₀, μ₁ changed)
+static int refresh_masks(Sim& s) {
+  if (!s.mask_dirty) return 0;
+  RLAUNCH(s, k_body_mask, s.g, s.g, s.V, s.mu0, s.mu1, s.body_mask);
+  int ntx = 0, nty = 0;
+  if (s.D == 3 && s.bdim_fuse && convdiff_tma_tiles(s, &ntx, &nty)) {
+    const GridD& g = s.g;
+    const dim3 blk = wl_pick_block(g);
+    Box b = box_interior(g);
+    b.lo[2] = b.hi[2] = 0;
+    if (g.zlo_halo) LAUNCH(s, k_body_mask_plane<3>, box_tiles(b, blk), blk, g, s.V, s.mu0, s.mu1, s.body_mask, 0);
+    if (g.zhi_halo) LAUNCH(s, k_body_mask_plane<3>, box_tiles(b, blk), blk, g, s.V, s.mu0, s.mu1, s.body_mask, g.n[2] - 1);
+    const int zlo = g.zlo_halo ? 1 : 2, zhi = g.zhi_halo ? g.n[2] - 2 : g.n[2] - 3;
+    const int64_t nunits = (int64_t)ntx * nty * g.n[2];
+    k_tile_clean<<<(int)std::min<int64_t>((nunits + 7) / 8, (int64_t)s.nsm * 16), 256, 0, s.stream>>>(g, s.body_mask, s.tile_clean, ntx, nty, zlo, zhi);
+    ++s.launches;
+  }
+  s.mask_dirty = false;
+  return wl_cuda_check(s, cudaGetLastError(), "k_body_mask");
+}
+
+// bdim2_mode (3-D core kernel, with fuse_bdim1): 1 = the predictor's BDIM! stage 2 (u = f·1), 2 = the corrector's
+// (w = (u + f)·½) is folded into the store on clean tile-planes; 0 = f is written everywhere
+int mom_conv_diff(Sim& s, const float* src, bool fuse_bdim1, const double* gacc, int bdim2_mode, float dt_override) {
   CDArgs a;
   a.g = s.g; a.u = src; a.u0 = s.u0; a.V = s.V; a.f = s.f; a.sigma = s.sigma;
-  a.nu = s.nu; a.dt = s.dt.back();
+  a.nu = s.nu; a.dt = dt_override > 0.f ? dt_override : s.dt.back();
+  a.ufused = nullptr; a.clean = nullptr; a.bscale = 1.f; a.mask = s.body_mask; a.mu0 = s.mu0; a.uacc = nullptr;
+  {
+    int ntx, nty;
+    if (bdim2_mode && fuse_bdim1 && s.D == 3 && s.bdim_fuse && convdiff_tma_tiles(s, &ntx, &nty)) {
+      const int rc0 = refresh_masks(s);
+      if (rc0) return rc0;
+      a.ufused = bdim2_mode == 1 ? s.u : s.w;
+      a.clean = s.tile_clean;
+      a.bscale = bdim2_mode == 1 ? 1.f : 0.5f;
+      a.uacc = bdim2_mode == 1 ? nullptr : s.u;
+    }
+  }
   a.has_g = gacc ? 1 : 0;
   for (int k = 0; k < 3; ++k) a.gacc[k] = (gacc && k < s.D) ? gacc[k] : 0.0;
   a.fuse_bdim1 = fuse_bdim1 ? 1 : 0;
@@ -548,16 +754,19 @@ int mom_conv_diff(Sim& s, const float* src, bool fuse_bdim1, const double* gacc)
   if (s.D == 3 && g.n[0] >= 8 && g.n[1] >= 8 && g.n[2] >= 8) {
     // core [2,n-3]³ by the marching kernel, boundary shell of thickness 2 by the generic one
     const bool corr = src != s.u0;
+    s.last_cd_fused = false;
     static int variant = -1;
     if (variant < 0) { const char* e = getenv("WL_CD_VARIANT"); variant = e ? atoi(e) : 4; }
     static int zchunk = 0;
     if (!zchunk) { const char* e = getenv("WL_CD_ZCHUNK"); zchunk = e ? atoi(e) : 32; }
     static int zchunk_tma = 0;
-    if (!zchunk_tma) { const char* e = getenv("WL_CD_TMA_ZCHUNK"); zchunk_tma = e ? atoi(e) : 64; }
+    if (!zchunk_tma) { const char* e = getenv("WL_CD_TMA_ZCHUNK"); zchunk_tma = std::min(128, std::max(4, e ? atoi(e) : 64)); }
     const bool used_tma = convdiff_tma_launch(s, a, zchunk_tma, corr);
-    if (!used_tma) launch_march(s, a, variant, zchunk, corr);
+    if (!used_tma) { a.ufused = nullptr; launch_march(s, a, variant, zchunk, corr); }
+    s.last_cd_fused = a.ufused != nullptr;
     // the profiled "dominant kernel" is the core march alone: algorithmic words/cell = read u (D) [+ u⁰, V (2D)], write f (D)
-    wl_prof_end(s, WL_PROF_CONVDIFF, 4.0 * (double)s.g.interior * (fuse_bdim1 ? (src == s.u0 ? 3 : 4) * s.D : 2 * s.D));
+    // with stage 2 folded in (clean tile-planes): read u [+ u⁰], write u — neither V nor f
+    wl_prof_end(s, WL_PROF_CONVDIFF, 4.0 * (double)s.g.interior * (fuse_bdim1 ? ((src == s.u0 ? 3 : 4) - (a.ufused ? 1 : 0)) * s.D : 2 * s.D));
     {
       const int zc0 = g.zlo_halo ? 1 : 2, zc1 = g.zhi_halo ? g.n[2] - 2 : g.n[2] - 3, nzc = zc1 - zc0 + 1;
       const unsigned int nZ = (unsigned int)g.n[0] * g.n[1] * (unsigned int)(g.n[2] - nzc);
@@ -569,6 +778,7 @@ int mom_conv_diff(Sim& s, const float* src, bool fuse_bdim1, const double* gacc)
       ++s.launches;
     }
   } else {
+    s.last_cd_fused = false;
     const dim3 blk = wl_pick_block(s.g);
     LAUNCH_D(s, k_conv_diff, s.D, box_tiles(box_all(s.g), blk), blk, a);
     wl_prof_end(s, WL_PROF_CONVDIFF, 4.0 * (double)s.g.interior * (fuse_bdim1 ? (src == s.u0 ? 3 : 4) * s.D : 2 * s.D));
@@ -588,17 +798,48 @@ int mom_bdim1(Sim& s) {
   LAUNCH(s, k_bdim1, box_tiles(box_all(s.g), blk), blk, s.g, s.f, s.u0, s.V, s.dt.back());
   return wl_cuda_check(s, cudaGetLastError(), "k_bdim1");
 }
-int mom_bdim2(Sim& s, bool accumulate, float scale) {
-  if (s.mask_dirty) {
-    RLAUNCH(s, k_body_mask, s.g, s.g, s.V, s.mu0, s.mu1, s.body_mask);
-    s.mask_dirty = false;
+// `fused`: called by mom_step! after a conv_diff! that may have folded stage 2 into its store on the clean
+// tile-planes: those cells are skipped, and the corrector's result goes to the spare buffer w (the kernel that
+// wrote the clean cells could not update u in place while other blocks still read it)
+int mom_bdim2(Sim& s, bool accumulate, float scale, bool fused) {
+  int rc = refresh_masks(s);
+  if (rc) return rc;
+  FusedTiles ft{};
+  float* dst = s.u;
+  if (fused && s.last_cd_fused) {
+    ft.clean = s.tile_clean;
+    convdiff_tma_tiles(s, &ft.ntx, &ft.nty);
+    ft.zlo = s.g.zlo_halo ? 1 : 2; ft.zhi = s.g.zhi_halo ? s.g.n[2] - 2 : s.g.n[2] - 3;
+    if (accumulate) dst = s.w;
   }
   wl_prof_begin(s, WL_PROF_BDIM2);
-  RLAUNCH(s, k_bdim2, s.g, s.g, s.u, s.f, s.V, s.mu0, s.mu1, s.body_mask, accumulate ? 1 : 0, scale);
-  // read f, V, μ₀ (3D), μ₁ (D²) [+ u (D)], write u (D)
-  // algorithmic traffic away from a body: read f (D) [+ u (D)] + mask (¼), write u (D)
-  wl_prof_end(s, WL_PROF_BDIM2, 4.0 * (double)s.g.interior * ((accumulate ? 3 : 2) * s.D + 0.25));
+  if (ft.clean) {
+    // what conv_diff! did not finish: the interior cells of its boundary shell, and the core tile-planes near a body
+    const GridD& g = s.g;
+    const int nzc = ft.zhi - ft.zlo + 1, xlow = convdiff_tma_core_x0(s);
+    const unsigned int nZ = (unsigned int)g.n[0] * g.n[1] * (unsigned int)(g.n[2] - nzc);
+    const unsigned int nY = (unsigned int)g.n[0] * 4u * (unsigned int)nzc;
+    const unsigned int nX = (unsigned int)(xlow + 2) * (unsigned int)(g.n[1] - 4) * (unsigned int)nzc;
+    const int64_t cnt = (int64_t)nZ + nY + nX;
+    k_bdim2_shell<<<(int)std::min<int64_t>((cnt + 255) / 256, s.nsm * 16), 256, 0, s.stream>>>(g, dst, s.u, s.f, s.V, s.mu0, s.mu1, s.body_mask, nZ, nY, nX,
+                                                                                         xlow, accumulate ? 1 : 0, scale);
+    const int64_t nunits = (int64_t)ft.ntx * ft.nty * nzc;
+    k_bdim2_tiles<<<(int)std::min<int64_t>((nunits + 255) / 256, (int64_t)s.nsm * 8), 256, 0, s.stream>>>(g, dst, s.u, s.f, s.V, s.mu0, s.mu1, s.body_mask, ft,
+                                                                                           accumulate ? 1 : 0, scale);
+    s.launches += 2;
+  } else {
+    RLAUNCH(s, k_bdim2, s.g, s.g, dst, s.u, s.f, s.V, s.mu0, s.mu1, s.body_mask, ft, accumulate ? 1 : 0, scale);
+  }
+  // algorithmic traffic away from a body: read f (D) [+ u (D)] + mask (¼), write u (D); nothing but the tile flag on fused cells
+  wl_prof_end(s, WL_PROF_BDIM2, 4.0 * (double)s.g.interior * (ft.clean ? 0.02 : (accumulate ? 3 : 2) * s.D + 0.25));
   return wl_cuda_check(s, cudaGetLastError(), "k_bdim2");
+}
+// flow.f as the reference leaves it after mom_step! (the corrector's BDIM! stage-1 f on every cell): after a fused
+// step the clean tiles never received it, so it is recomputed here, on demand, from the inputs the corrector used
+int mom_materialize_f(Sim& s) {
+  if (!s.f_stale) return 0;
+  s.f_stale = false;
+  return mom_conv_diff(s, s.w, true, s.f_has_g ? s.f_g : nullptr, 0, s.f_dt);
 }
 int mom_scale_u(Sim& s, double scale) {
   RLAUNCH(s, k_scale_u, s.g, s.g, s.u, scale);
@@ -666,8 +907,9 @@ int mom_step(Sim& s, const double* U, const double* gp, const double* gc, double
     ++s.launches;
   }
   // predictor u → u'
-  if ((rc = mom_conv_diff(s, s.u0, true, gp))) return rc;
-  if ((rc = mom_bdim2(s, false, 1.f))) return rc;
+  s.f_stale = false;
+  if ((rc = mom_conv_diff(s, s.u0, true, gp, 1))) return rc;
+  if ((rc = mom_bdim2(s, false, 1.f, true))) return rc;
   if ((rc = bc_vec(s, s.g, s.u, U, s.exitBC, s.g.per, 2))) return rc;
   if (s.exitBC) {
     if ((rc = bc_exit(s, U, s.dt.back()))) return rc;
@@ -679,8 +921,23 @@ int mom_step(Sim& s, const double* U, const double* gp, const double* gc, double
   if ((rc = mom_project(s, 1.0, n_pred, 0, defer, true, 0.f))) return rc;
   if ((rc = bc_vec(s, s.g, s.u, U, s.exitBC, s.g.per, 2))) return rc;
   // corrector u → u¹
-  if ((rc = mom_conv_diff(s, s.u, true, gc))) return rc;
-  if ((rc = mom_bdim2(s, true, 0.5f))) return rc;
+  if ((rc = mom_conv_diff(s, s.u, true, gc, 2))) return rc;
+  if ((rc = mom_bdim2(s, true, 0.5f, true))) return rc;
+  if (s.last_cd_fused) {
+    // the new u was assembled in w (clean tile-planes by conv_diff!, the rest by BDIM! stage 2): u ↔ w.  BC! below rewrites
+    // every ghost cell of it except the saved exit plane, which is carried over; w keeps u' — with u⁰, V and Δt that is all
+    // an on-demand flow.f needs (mom_materialize_f)
+    if (s.exitBC) {
+      const int64_t cnt = (int64_t)s.g.n[1] * s.g.n[2];
+      k_copy_exit_plane<<<(int)std::min<int64_t>((cnt + 255) / 256, 256), 256, 0, s.stream>>>(s.g, s.w, s.u);
+      ++s.launches;
+    }
+    float* t2 = s.u; s.u = s.w; s.w = t2;
+    s.f_stale = true;
+    s.f_dt = s.dt.back();
+    s.f_has_g = gc != nullptr;
+    for (int k = 0; k < 3; ++k) s.f_g[k] = (gc && k < s.D) ? gc[k] : 0.0;
+  }
   if ((rc = bc_vec(s, s.g, s.u, U, s.exitBC, s.g.per, 2))) return rc;
   if ((rc = mom_project(s, 0.5, n_corr, 1, defer, false, s.dt.back()))) return rc;
   if ((rc = bc_vec(s, s.g, s.u, U, s.exitBC, s.g.per, 2))) return rc;
