@@ -469,6 +469,7 @@ int wl_upload(wl_sim* s, int field, const float* host, int64_t count) {
   if (field == WL_V || field == WL_MU0 || field == WL_MU1) S.mask_dirty = true;
   if (field == WL_MU0) pois_invalidate_uniform(S, 0);  // levels[1].L ≡ μ₀: stale until update!
   int rc = 0;
+  if (field == WL_P) S.p_pend = 0;                                        // replaced wholesale
   if (field == WL_F) S.f_stale = false;                                   // replaced wholesale
   else if (field == WL_U0 || field == WL_V) rc = mom_materialize_f(S);     // inputs of the on-demand f are about to change
   if (rc) return rc;
@@ -483,6 +484,7 @@ int wl_download(wl_sim* s, int field, float* host, int64_t count) {
   const int nzg = nz_padded_global(S, 0);
   if (!d || count != (int64_t)S.g.n[0] * S.g.n[1] * nzg * nc) return wl_fail(WL_ERR_ARG, "wl_download: bad field or size");
   if (field == WL_F) { const int rc = mom_materialize_f(S); if (rc) return rc; }
+  if (field == WL_P) { const int rc = mom_materialize_p(S); if (rc) return rc; }
   return copy_field(S, S.g, d, host, nc, false, nzg);
 }
 int wl_nlevels(wl_sim* s) { return s ? (int)S.levels.size() : 0; }
@@ -500,6 +502,7 @@ int wl_level_upload(wl_sim* s, int level, int lf, const float* host, int64_t cou
   const GridD& g = S.levels[level].g;
   const int nzg = nz_padded_global(S, level);
   if (count != (int64_t)g.n[0] * g.n[1] * nzg * nc) return wl_fail(WL_ERR_ARG, "wl_level_upload: bad size");
+  if (level == 0 && lf == WL_LVL_X) S.p_pend = 0;         // levels[1].x ≡ p, replaced wholesale
   if (level == 0 && lf == WL_LVL_L) S.mask_dirty = true;  // levels[1].L ≡ μ₀
   if (lf == WL_LVL_L || lf == WL_LVL_D || lf == WL_LVL_ID) pois_invalidate_uniform(S, level);
   int rc = copy_field(S, g, d, const_cast<float*>(host), nc, true, nzg);
@@ -513,6 +516,7 @@ int wl_level_download(wl_sim* s, int level, int lf, float* host, int64_t count) 
   const GridD& g = S.levels[level].g;
   const int nzg = nz_padded_global(S, level);
   if (count != (int64_t)g.n[0] * g.n[1] * nzg * nc) return wl_fail(WL_ERR_ARG, "wl_level_download: bad size");
+  if (level == 0 && lf == WL_LVL_X) { const int rc = mom_materialize_p(S); if (rc) return rc; }
   return copy_field(S, g, d, host, nc, false, nzg);
 }
 
@@ -540,7 +544,8 @@ int wl_per_bc(wl_sim* s, int field, const int* perdir) {
   int nc; float* d = field_ptr(S, field, &nc);
   if (!d || nc != 1) return wl_fail(WL_ERR_ARG, "wl_per_bc: not a scalar field");
   int per[3]; per_flags(S, perdir, per);
-  int rc = bc_per(S, S.g, d, per);
+  int rc = field == WL_P ? mom_materialize_p(S) : 0;
+  if (!rc) rc = bc_per(S, S.g, d, per);
   return rc ? rc : wl_sync(s);
 }
 int wl_conv_diff(wl_sim* s, int src) {
@@ -559,36 +564,41 @@ int wl_bdim(wl_sim* s) {
   return rc ? rc : wl_sync(s);
 }
 int wl_scale_u(wl_sim* s, double scale) { GUARD(s); int rc = mom_scale_u(S, scale); return rc ? rc : wl_sync(s); }
-int wl_project(wl_sim* s, double w, int* n) { GUARD(s); int rc = mom_project(S, w, n); return rc ? rc : wl_sync(s); }
+int wl_project(wl_sim* s, double w, int* n) { GUARD(s); int rc = mom_materialize_p(S); if (!rc) rc = mom_project(S, w, n); return rc ? rc : wl_sync(s); }
 int wl_cfl(wl_sim* s, double* dt) { GUARD(s); return mom_cfl(S, dt); }
 
 int wl_pois_update(wl_sim* s) { GUARD(s); int rc = pois_update(S); return rc ? rc : wl_sync(s); }
-int wl_pois_mult(wl_sim* s) { GUARD(s); int rc = pois_mult(S); return rc ? rc : wl_sync(s); }
+int wl_pois_mult(wl_sim* s) { GUARD(s); int rc = mom_materialize_p(S);
+  if (!rc) rc = pois_mult(S); return rc ? rc : wl_sync(s); }
 int wl_pois_residual(wl_sim* s, int level, double* r2) {
   GUARD(s);
   if (level < 0 || level >= (int)S.levels.size()) return wl_fail(WL_ERR_ARG, "bad level");
-  int rc = pois_residual(S, S.levels[level]);
+  int rc = mom_materialize_p(S);
+  if (!rc) rc = pois_residual(S, S.levels[level]);
   if (!rc && r2) rc = pois_dot_rr(S, S.levels[level], r2);
   return rc ? rc : wl_sync(s);
 }
 int wl_pois_jacobi(wl_sim* s, int level, int it) {
   GUARD(s);
   if (level < 0 || level >= (int)S.levels.size()) return wl_fail(WL_ERR_ARG, "bad level");
-  int rc = pois_jacobi(S, S.levels[level], it);
+  int rc = mom_materialize_p(S);
+  if (!rc) rc = pois_jacobi(S, S.levels[level], it);
   if (!rc) rc = bc_per(S, S.levels[level].g, S.levels[level].eps, S.levels[level].g.per);  // perBC!(ϵ) made visible
   return rc ? rc : wl_sync(s);
 }
 int wl_pois_pcg(wl_sim* s, int level, int it) {
   GUARD(s);
   if (level < 0 || level >= (int)S.levels.size()) return wl_fail(WL_ERR_ARG, "bad level");
-  int rc = pois_pcg(S, level, it);
+  int rc = mom_materialize_p(S);
+  if (!rc) rc = pois_pcg(S, level, it);
   if (!rc) rc = bc_per(S, S.levels[level].g, S.levels[level].eps, S.levels[level].g.per);
   return rc ? rc : wl_sync(s);
 }
 int wl_pois_vcycle(wl_sim* s, int level) {
   GUARD(s);
   if (level < 0 || level + 1 >= (int)S.levels.size()) return wl_fail(WL_ERR_ARG, "bad level");
-  int rc = pois_vcycle(S, level);
+  int rc = mom_materialize_p(S);
+  if (!rc) rc = pois_vcycle(S, level);
   if (!rc) rc = pois_materialize_eps(S, level);
   return rc ? rc : wl_sync(s);
 }
@@ -596,7 +606,8 @@ int wl_pois_solve(wl_sim* s, double tol, int itmx, int* n) {
   GUARD(s);
   if (tol < 0) tol = 1e-4;
   if (itmx < 0) itmx = S.pois_kind == WL_POIS_MULTILEVEL ? 32 : 1000;
-  int rc = pois_solve(S, tol, itmx, n);
+  int rc = mom_materialize_p(S);
+  if (!rc) rc = pois_solve(S, tol, itmx, n);
   return rc ? rc : wl_sync(s);
 }
 // nds(body, loc(0,I,Float64), t) from the host → device (same re-pitched indexing as the fields, Float64)
@@ -618,7 +629,8 @@ static int metrics_nds(Sim& a, const double* nds, int64_t count) {
 int wl_pressure_force(wl_sim* s, const double* nds, int64_t count, double* force) {
   GUARD(s);
   if (!force) return wl_fail(WL_ERR_ARG, "null output");
-  int rc = metrics_nds(S, nds, count);
+  int rc = mom_materialize_p(S);
+  if (!rc) rc = metrics_nds(S, nds, count);
   return rc ? rc : metrics_run(S, 0, nullptr, force);
 }
 int wl_viscous_force(wl_sim* s, const double* nds, int64_t count, double* force) {
@@ -630,7 +642,8 @@ int wl_viscous_force(wl_sim* s, const double* nds, int64_t count, double* force)
 int wl_pressure_moment(wl_sim* s, const double* x0, const double* nds, int64_t count, double* moment) {
   GUARD(s);
   if (!moment || !x0) return wl_fail(WL_ERR_ARG, "null argument");
-  int rc = metrics_nds(S, nds, count);
+  int rc = mom_materialize_p(S);
+  if (!rc) rc = metrics_nds(S, nds, count);
   return rc ? rc : metrics_run(S, 2, x0, moment);
 }
 int wl_derived(wl_sim* s, int kind, int comp, const double* U, const double* axis, const double* center) {

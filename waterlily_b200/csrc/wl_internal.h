@@ -76,6 +76,10 @@ struct Sim {
   float f_dt = 0.f;
   double f_g[3] = {0, 0, 0};
   bool f_has_g = false;
+  // flow.p between project! calls of mom_step!: still scaled by dt, the division is pending (k_scale_alloc)
+  int p_pend = 0;                      // 0 none, 1 divide by p_pend32 (Float32 dt), 2 divide by p_pend64 (Float64 dt)
+  float p_pend32 = 0.f;
+  double p_pend64 = 0.0;
   bool last_cd_fused = false;          // the last conv_diff! folded BDIM! stage 2 into its store on the clean tile-planes
   float nu = 0.f;
   std::vector<float> dt;
@@ -161,7 +165,7 @@ int derived_run(Sim& s, int kind, int comp, const double* U, const double* axis,
 int vcycle_fused_setup(Sim& s);
 void vcycle_fused_destroy(Sim& s);
 int vcycle_fused_run(Sim& s);
-int vcycle_fused_solve(Sim& s, double tol, int itmx, bool ghosts_valid, int slot);
+int vcycle_fused_solve(Sim& s, double tol, int itmx, bool ghosts_valid, int slot, const float* divu = nullptr);
 
 // ---- wl_bc.cu ----
 int bc_vec(Sim& s, const GridD& g, float* a, const double* A, bool saveexit, const int* per, int halo_depth = 1);
@@ -181,11 +185,11 @@ inline double wl_words(const Sim& s, double generic, double saved) {
 int pois_restrictL(Sim& s, Lvl& coarse, const Lvl& fine);
 int pois_update(Sim& s);
 int pois_mult(Sim& s);
-int pois_residual(Sim& s, Lvl& l, bool need_r2 = true, bool ghosts_valid = false, bool jacobi_eps = false);
+int pois_residual(Sim& s, Lvl& l, bool need_r2 = true, bool ghosts_valid = false, bool jacobi_eps = false, const float* divu = nullptr);
 int pois_jacobi(Sim& s, Lvl& l, int it);
 int pois_pcg(Sim& s, int level, int it);
 int pois_vcycle(Sim& s, int level);
-int pois_solve(Sim& s, double tol, int itmx, int* n, bool ghosts_valid = false, int slot = 0, bool defer_count = false);
+int pois_solve(Sim& s, double tol, int itmx, int* n, bool ghosts_valid = false, int slot = 0, bool defer_count = false, const float* divu = nullptr);
 int pois_materialize_eps(Sim& s, int level);
 int pois_dot_rr(Sim& s, Lvl& l, double* out);
 
@@ -196,7 +200,8 @@ int mom_accelerate(Sim& s, const double* g);
 int mom_bdim1(Sim& s);
 int mom_bdim2(Sim& s, bool accumulate, float scale, bool fused = false);
 int mom_scale_u(Sim& s, double scale);
-int mom_project(Sim& s, double w, int* n, int slot = 0, bool defer_count = false, bool skip_unscale = false, float prediv = 0.f);
+int mom_project(Sim& s, double w, int* n, int slot = 0, bool defer_count = false, bool in_step = false);
+int mom_materialize_p(Sim& s);  // applies a pending x ./= dt (see Sim::p_pend)
 int mom_cfl(Sim& s, double* dt);
 int mom_step(Sim& s, const double* U, const double* gp, const double* gc, double* dt_next, int* n_pred, int* n_corr);
 

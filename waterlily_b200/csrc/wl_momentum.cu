@@ -564,37 +564,26 @@ __global__ void __launch_bounds__(256) k_scale_u(GridD g, float* u, double scale
 // project!: z = div(u) (Flow.jl:139, :11-17)
 template <int D, int V>
 __global__ void __launch_bounds__(256) k_project_pre(GridD g, const float* __restrict__ u, float* __restrict__ z) {
-  for_rows<V>(g, [&](int, int, int, int64_t I) {
-    Pack<V> s;
-    {
-      const Pack<V> uc = ldp<V>(u + I), up = ld_xp<V>(u + I, uc);
-#pragma unroll
-      for (int q = 0; q < V; ++q) s.v[q] = 0.f + (up.v[q] - uc.v[q]);
-    }
-#pragma unroll
-    for (int i = 1; i < D; ++i) {
-      const Pack<V> uc = ldp<V>(u + I + i * g.comp), up = ldp<V>(u + I + g.s[i] + i * g.comp);
-#pragma unroll
-      for (int q = 0; q < V; ++q) s.v[q] += up.v[q] - uc.v[q];
-    }
-    stp<V>(z + I, s);
-  });
+  for_rows<V>(g, [&](int, int, int, int64_t I) { stp<V>(z + I, div_pack<D, V>(g, u, I)); });
 }
 // project!: x .*= dt (Flow.jl:139) / x ./= dt (:144) over the WHOLE allocation of x — interior, ghost
 // cells and slab halo planes alike.  A ghost cell holds a copy of an interior value, and scaling a
 // copy gives the bits of the scaled original, so the ghosts stay consistent and neither the perBC!
 // of residual! (Poisson.jl:92) nor a halo exchange is needed afterwards.
-// `prediv` > 0: first undo the PREVIOUS project!'s scaling (x ./= dt with its Float32 dt, w = 1) — mom_step!
-// merges the predictor's x ./= dt with the corrector's x .*= dt (two roundings in one pass, same bits)
-__global__ void __launch_bounds__(256) k_scale_alloc(float4* __restrict__ x, int64_t n4, float f32v, double f64v, int f32, int divide, float prediv) {
+// Inside mom_step! a project! leaves x scaled and records the pending x ./= dt (Sim::p_pend); the next scaling pass
+// applies it first — the reference's roundings, in its order, in one pass instead of two: `pre` 1 divides by the
+// Float32 pre32 (w = 1: dt is Float32), 2 by the Float64 pre64 (w = 0.5: dt = 0.5Δt is Float64), then `op` 1 / 2
+// multiplies by f32v / f64v (0: nothing, i.e. only the pending division is materialised).
+__global__ void __launch_bounds__(256) k_scale_alloc(float4* __restrict__ x, int64_t n4, int op, float f32v, double f64v, int pre, float pre32, double pre64) {
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n4; t += (int64_t)gridDim.x * blockDim.x) {
     float4 v = x[t];
     float* p = reinterpret_cast<float*>(&v);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      if (prediv > 0.f) p[q] = p[q] / prediv;
-      if (divide) p[q] = f32 ? p[q] / f32v : (float)((double)p[q] / f64v);
-      else p[q] = f32 ? p[q] * f32v : (float)((double)p[q] * f64v);
+      if (pre == 1) p[q] = p[q] / pre32;
+      else if (pre == 2) p[q] = (float)((double)p[q] / pre64);
+      if (op == 1) p[q] = p[q] * f32v;
+      else if (op == 2) p[q] = (float)((double)p[q] * f64v);
     }
     x[t] = v;
   }
@@ -845,31 +834,42 @@ int mom_scale_u(Sim& s, double scale) {
   RLAUNCH(s, k_scale_u, s.g, s.g, s.u, scale);
   return wl_cuda_check(s, cudaGetLastError(), "k_scale_u");
 }
-// project!(a,b,w) (Flow.jl:137-145)
-// `skip_unscale`: leave x scaled by dt (the caller's next project! undoes it in its own first pass);
-// `prediv`: the Float32 dt such a previous project! left in x
-int mom_project(Sim& s, double w, int* n, int slot, bool defer_count, bool skip_unscale, float prediv) {
-  const float dt32 = s.dt.back();
-  const bool f32 = (w == 1.0);                 // dt = w*Δt: Float32 for the Int w=1, Float64 for w=0.5
-  const double dtw = f32 ? (double)dt32 : w * (double)dt32;
+static int scale_pressure(Sim& s, int op, float f32v, double f64v) {
   Lvl& b = s.levels[0];
   float4* xall = reinterpret_cast<float4*>(b.x - s.g.lead);
   const int64_t n4 = s.g.comp / 4;
   const int sgrid = (int)std::min<int64_t>((n4 + 255) / 256, (int64_t)s.nsm * 8);
-  wl_prof_begin(s, WL_PROF_PROJECT);
-  RLAUNCH(s, k_project_pre, s.g, s.g, s.u, b.z);
-  k_scale_alloc<<<sgrid, 256, 0, s.stream>>>(xall, n4, (float)dtw, dtw, f32 ? 1 : 0, 0, prediv);
+  k_scale_alloc<<<sgrid, 256, 0, s.stream>>>(xall, n4, op, f32v, f64v, s.p_pend, s.p_pend32, s.p_pend64);
   ++s.launches;
-  wl_prof_end(s, WL_PROF_PROJECT, 4.0 * (double)s.g.interior * (s.D + 1 + 2));
-  int rc = pois_solve(s, 1e-4, s.pois_kind == WL_POIS_MULTILEVEL ? 32 : 1000, n, true, slot, defer_count);
+  s.p_pend = 0;
+  return wl_cuda_check(s, cudaGetLastError(), "k_scale_alloc");
+}
+// the pressure as the reference leaves it after project! (x ./= dt applied): on demand, before anything outside
+// mom_step! looks at it
+int mom_materialize_p(Sim& s) {
+  if (!s.p_pend) return 0;
+  return scale_pressure(s, 0, 0.f, 0.0);
+}
+// project!(a,b,w) (Flow.jl:137-145)
+// `in_step` (mom_step!): z = div u is evaluated inside residual! instead of by a pass of its own, and the closing
+// x ./= dt is left pending for the next project! (or mom_materialize_p)
+int mom_project(Sim& s, double w, int* n, int slot, bool defer_count, bool in_step) {
+  const float dt32 = s.dt.back();
+  const bool f32 = (w == 1.0);                 // dt = w*Δt: Float32 for the Int w=1, Float64 for w=0.5
+  const double dtw = f32 ? (double)dt32 : w * (double)dt32;
+  Lvl& b = s.levels[0];
+  int rc;
+  wl_prof_begin(s, WL_PROF_PROJECT);
+  if (!in_step) RLAUNCH(s, k_project_pre, s.g, s.g, s.u, b.z);
+  if ((rc = scale_pressure(s, f32 ? 1 : 2, (float)dtw, dtw))) return rc;
+  wl_prof_end(s, WL_PROF_PROJECT, 4.0 * (double)s.g.interior * ((in_step ? 0 : s.D + 1) + 2));
+  rc = pois_solve(s, 1e-4, s.pois_kind == WL_POIS_MULTILEVEL ? 32 : 1000, n, true, slot, defer_count, in_step ? s.u : nullptr);
   if (rc) return rc;
   wl_prof_begin(s, WL_PROF_PROJECT);
   RLAUNCH(s, k_project_correct, s.g, b, s.u);
-  if (!skip_unscale) {
-    k_scale_alloc<<<sgrid, 256, 0, s.stream>>>(xall, n4, (float)dtw, dtw, f32 ? 1 : 0, 1, 0.f);
-    ++s.launches;
-  }
-  wl_prof_end(s, WL_PROF_PROJECT, 4.0 * (double)s.g.interior * (wl_words(s, 3 * s.D + 1, s.D) + (skip_unscale ? 0 : 2)));
+  s.p_pend = f32 ? 1 : 2; s.p_pend32 = (float)dtw; s.p_pend64 = dtw;
+  if (!in_step && (rc = mom_materialize_p(s))) return rc;
+  wl_prof_end(s, WL_PROF_PROJECT, 4.0 * (double)s.g.interior * (wl_words(s, 3 * s.D + 1, s.D) + (in_step ? 0 : 2)));
   return wl_cuda_check(s, cudaGetLastError(), "project");
 }
 // CFL(a) (Flow.jl:172-175)
@@ -918,7 +918,7 @@ int mom_step(Sim& s, const double* U, const double* gp, const double* gc, double
   const bool defer = s.vc_solve && s.pois_kind == WL_POIS_MULTILEVEL;
   // the pressure is not observable between the two project! calls of a step: the predictor leaves it scaled
   // and the corrector's first pass does x = (x / Δt) * (Δt/2) with the reference's two roundings
-  if ((rc = mom_project(s, 1.0, n_pred, 0, defer, true, 0.f))) return rc;
+  if ((rc = mom_project(s, 1.0, n_pred, 0, defer, true))) return rc;
   if ((rc = bc_vec(s, s.g, s.u, U, s.exitBC, s.g.per, 2))) return rc;
   // corrector u → u¹
   if ((rc = mom_conv_diff(s, s.u, true, gc, 2))) return rc;
@@ -939,7 +939,7 @@ int mom_step(Sim& s, const double* U, const double* gp, const double* gc, double
     for (int k = 0; k < 3; ++k) s.f_g[k] = (gc && k < s.D) ? gc[k] : 0.0;
   }
   if ((rc = bc_vec(s, s.g, s.u, U, s.exitBC, s.g.per, 2))) return rc;
-  if ((rc = mom_project(s, 0.5, n_corr, 1, defer, false, s.dt.back()))) return rc;
+  if ((rc = mom_project(s, 0.5, n_corr, 1, defer, true))) return rc;
   if ((rc = bc_vec(s, s.g, s.u, U, s.exitBC, s.g.per, 2))) return rc;
   double dt;
   if ((rc = mom_cfl(s, &dt))) return rc;

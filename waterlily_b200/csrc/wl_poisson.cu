@@ -105,12 +105,15 @@ __global__ void __launch_bounds__(256) k_restrictL(Lvl c, Lvl f, int ck0, int ck
 }
 
 // residual! first loop + sum (Poisson.jl:93-94)
+// `divu` non-null: z is not read but evaluated on the spot as div(u) (project! inside mom_step!: the separate z = div u
+// pass and its 4 words per cell disappear; z's interior is rewritten by pcg! before anything reads it)
 template <int D, int V>
-__global__ void __launch_bounds__(256) k_residual(Lvl l, ReduceWS ws, FinArgs fa, int write_eps) {
+__global__ void __launch_bounds__(256) k_residual(Lvl l, ReduceWS ws, FinArgs fa, int write_eps, const float* __restrict__ divu) {
   double acc[2] = {0.0, 0.0};
   for_rows<V>(l.g, [&](int i, int j, int k, int64_t I) {
     const bool uni = pack_uniform<V>(l, I);
-    const Pack<V> xc = ldp<V>(l.x + I), ax = mult_w<D, V>(l, l.x, i, j, k, I, xc, uni), zc = ldp<V>(l.z + I), id = ld_iD<V>(l, I, uni);
+    const Pack<V> xc = ldp<V>(l.x + I), ax = mult_w<D, V>(l, l.x, i, j, k, I, xc, uni), zc = divu ? div_pack<D, V>(l.g, divu, I) : ldp<V>(l.z + I),
+                  id = ld_iD<V>(l, I, uni);
     Pack<V> r;
 #pragma unroll
     for (int q = 0; q < V; ++q) {
@@ -236,7 +239,7 @@ __global__ void __launch_bounds__(256) k_prolong_increment_init(Lvl f, Lvl c, Pr
 
 // ---- z-marching variants of the stencil kernels (3-D, V = 4; see for_columns in wl_vec.cuh) ---------
 // Same arithmetic as k_residual / k_increment / k_pcg_mult / k_prolong_increment_init, cell for cell.
-__global__ void __launch_bounds__(256) k_residual_m(Lvl l, MarchGeom mg, ReduceWS ws, FinArgs fa, int write_eps) {
+__global__ void __launch_bounds__(256) k_residual_m(Lvl l, MarchGeom mg, ReduceWS ws, FinArgs fa, int write_eps, const float* __restrict__ divu) {
   double acc[2] = {0.0, 0.0};
   const GridD& g = l.g;
   for_columns(g, mg, [&](int i, int j, int k0, int k1) {
@@ -245,7 +248,7 @@ __global__ void __launch_bounds__(256) k_residual_m(Lvl l, MarchGeom mg, ReduceW
     for (int k = k0; k <= k1; ++k, I += g.s[2]) {
       const Pack<4> xp = ldp<4>(l.x + I + zoff_p(g, k));
       const bool uni = pack_uniform<4>(l, I);
-      const Pack<4> ax = mult_zreg<4>(l, l.x, i, j, I, xc, xm, xp, uni), zc = ldp<4>(l.z + I), id = ld_iD<4>(l, I, uni);
+      const Pack<4> ax = mult_zreg<4>(l, l.x, i, j, I, xc, xm, xp, uni), zc = divu ? div_pack<3, 4>(g, divu, I) : ldp<4>(l.z + I), id = ld_iD<4>(l, I, uni);
       Pack<4> r;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
@@ -352,14 +355,14 @@ __global__ void __launch_bounds__(256) k_increment_s(Lvl l, MarchGeom mg, Reduce
   double tot[1];
   if (grid_reduce<1>(acc, ws, tot)) finish_reduction(FIN_R2, fa, tot[0], 0.0);
 }
-__global__ void __launch_bounds__(256) k_residual_s(Lvl l, MarchGeom mg, ReduceWS ws, FinArgs fa, int write_eps) {
+__global__ void __launch_bounds__(256) k_residual_s(Lvl l, MarchGeom mg, ReduceWS ws, FinArgs fa, int write_eps, const float* __restrict__ divu) {
   double acc[2] = {0.0, 0.0};
   const GridD& g = l.g;
   for_columns(g, mg, [&](int i, int j, int k0, int k1) {
     bool uni = false;
     Pack<4> zc;
     march_staged(g, l.x, wl_ring, i, j, k0, k1,
-      [&](int, int64_t I) { uni = pack_uniform<4>(l, I); zc = ldp<4>(l.z + I); },
+      [&](int, int64_t I) { uni = pack_uniform<4>(l, I); zc = divu ? div_pack<3, 4>(g, divu, I) : ldp<4>(l.z + I); },
       [&](int, int64_t I, const Pack<4>& xc, float xm1, float xp4, const Pack<4>& ym, const Pack<4>& yp, const Pack<4>& zm, const Pack<4>& zp) {
         const Pack<4> ax = mult_vals<4>(l, I, xc, xm1, xp4, ym, yp, zm, zp, uni), id = ld_iD<4>(l, I, uni);
         Pack<4> r;
@@ -666,7 +669,7 @@ int pois_mult(Sim& s) {
   return wl_cuda_check(s, cudaGetLastError(), "k_mult");
 }
 // residual!(p) (Poisson.jl:91-97)
-int pois_residual(Sim& s, Lvl& l, bool need_r2, bool ghosts_valid, bool jacobi_eps) {
+int pois_residual(Sim& s, Lvl& l, bool need_r2, bool ghosts_valid, bool jacobi_eps, const float* divu) {
   // perBC!(x) (Poisson.jl:92).  project! hands over an x whose ghost cells and halo planes were scaled
   // together with the interior, i.e. are already consistent: nothing to refresh then.
   int rc = ghosts_valid ? 0 : bc_per(s, l.g, l.x, l.g.per);
@@ -676,9 +679,9 @@ int pois_residual(Sim& s, Lvl& l, bool need_r2, bool ghosts_valid, bool jacobi_e
   const FinArgs fa = fin_level(s, lv);
   if (fine) wl_prof_begin(s, WL_PROF_RESIDUAL);
   const MarchLaunch ml = march_for(s, l.g);
-  if (ml.ok && ml.staged && s.stage_on) { k_residual_s<<<ml.grid, ml.blk, ml.smem, s.stream>>>(l, ml.mg, s.ws, fa, jacobi_eps ? 1 : 0); ++s.launches; }
-  else if (ml.ok) { k_residual_m<<<ml.grid, ml.blk, 0, s.stream>>>(l, ml.mg, s.ws, fa, jacobi_eps ? 1 : 0); ++s.launches; }
-  else RLAUNCH(s, k_residual, l.g, l, s.ws, fa, jacobi_eps ? 1 : 0);
+  if (ml.ok && ml.staged && s.stage_on) { k_residual_s<<<ml.grid, ml.blk, ml.smem, s.stream>>>(l, ml.mg, s.ws, fa, jacobi_eps ? 1 : 0, divu); ++s.launches; }
+  else if (ml.ok) { k_residual_m<<<ml.grid, ml.blk, 0, s.stream>>>(l, ml.mg, s.ws, fa, jacobi_eps ? 1 : 0, divu); ++s.launches; }
+  else RLAUNCH(s, k_residual, l.g, l, s.ws, fa, jacobi_eps ? 1 : 0, divu);
   if ((rc = post_reduce(s, FIN_RESIDUAL, fa))) return rc;
   {
     FinArgs fb = fa;
@@ -688,7 +691,7 @@ int pois_residual(Sim& s, Lvl& l, bool need_r2, bool ghosts_valid, bool jacobi_e
   s.eps_is_jacobi = jacobi_eps;
   // r⋅r after the mean subtraction is only reported, never used for control: solver! skips its all-reduce
   if (need_r2 && (rc = post_reduce(s, FIN_R2_IF_SUB, fa))) return rc;
-  if (fine) wl_prof_end(s, WL_PROF_RESIDUAL, 4.0 * (double)l.g.interior * wl_words(s, s.D + 5 + (jacobi_eps ? 1 : 0), s.D + 2));
+  if (fine) wl_prof_end(s, WL_PROF_RESIDUAL, 4.0 * (double)l.g.interior * wl_words(s, s.D + 5 + (jacobi_eps ? 1 : 0) + (divu ? s.D - 1 : 0), s.D + 2));
   return wl_cuda_check(s, cudaGetLastError(), "k_residual");
 }
 // increment!(p) (Poisson.jl:99-103)
@@ -830,13 +833,13 @@ int pois_vcycle(Sim& s, int level) {
   return pois_increment(s, fine);
 }
 // solver!(ml;tol,itmx) (MultiLevelPoisson.jl:87-99) / solver!(p::Poisson;tol,itmx) (Poisson.jl:162-172)
-int pois_solve(Sim& s, double tol, int itmx, int* n_out, bool ghosts_valid, int slot, bool defer_count) {
+int pois_solve(Sim& s, double tol, int itmx, int* n_out, bool ghosts_valid, int slot, bool defer_count, const float* divu) {
   Lvl& p = s.levels[0];
   wl_prof_begin(s, WL_PROF_SOLVER);
   if (s.vc_solve && s.pois_kind == WL_POIS_MULTILEVEL) {
     // the whole solver! is one persistent kernel (wl_vcycle.cu); its V-cycle count stays on the device
     // until the caller reads it (mom_step! reads both counts together with CFL's maximum)
-    int rc = vcycle_fused_solve(s, tol, itmx, ghosts_valid, slot);
+    int rc = vcycle_fused_solve(s, tol, itmx, ghosts_valid, slot, divu);
     wl_prof_end(s, WL_PROF_SOLVER, 0.0);
     if (rc || defer_count) return rc;
     if ((rc = wl_read_scalars(s, &s.d_misc->solve_n[slot], sizeof(int)))) return rc;
@@ -846,7 +849,7 @@ int pois_solve(Sim& s, double tol, int itmx, int* n_out, bool ghosts_valid, int 
     if (n_out) *n_out = n;
     return 0;
   }
-  int rc = pois_residual(s, p, false, ghosts_valid, s.pois_kind == WL_POIS_MULTILEVEL && itmx > 0);
+  int rc = pois_residual(s, p, false, ghosts_valid, s.pois_kind == WL_POIS_MULTILEVEL && itmx > 0, divu);
   if (rc) return rc;
   int n = 0;
   static int fuse_env = -1;

@@ -54,6 +54,7 @@ struct SolveArgs {
   int ghosts_valid;  // x's ghost cells / halo planes are consistent (project! scaled them with the interior)
   int has_ghost;     // z⋅ϵ has a ghost-shell part (z ≡ σ keeps conv_diff!'s stale Φ)
   int slot;          // which entry of MiscScalars::solve_n receives the count
+  const float* divu; // non-null: residual! evaluates z = div(u) on the spot instead of reading z (project! inside mom_step!)
 };
 
 struct Shared {
@@ -517,7 +518,8 @@ __device__ __forceinline__ void residual0(const FusedParams& p, Run& run, const 
   double acc[2] = {0.0, 0.0};
   rows<V, true>(p, 0, [&](int i, int j, int k, int64_t I) {
     const bool uni = pack_uniform<V>(L, I);
-    const Pack<V> xc = ldp<V>(L.x + I), ax = mult_w<D, V>(L, L.x, i, j, k, I, xc, uni), zc = ldp<V>(L.z + I), id = ld_iD<V>(L, I, uni);
+    const Pack<V> xc = ldp<V>(L.x + I), ax = mult_w<D, V>(L, L.x, i, j, k, I, xc, uni), zc = sa.divu ? div_pack<D, V>(L.g, sa.divu, I) : ldp<V>(L.z + I),
+                  id = ld_iD<V>(L, I, uni);
     Pack<V> r, e;
 #pragma unroll
     for (int q = 0; q < V; ++q) {
@@ -749,7 +751,7 @@ int vcycle_fused_run(Sim& s) {
 }
 
 // solver!(ml; tol, itmx) as ONE launch; the V-cycle count lands in MiscScalars::solve_n[slot]
-int vcycle_fused_solve(Sim& s, double tol, int itmx, bool ghosts_valid, int slot) {
+int vcycle_fused_solve(Sim& s, double tol, int itmx, bool ghosts_valid, int slot, const float* divu) {
   VcycleFused* vf = (VcycleFused*)s.vc_fused;
   refresh_masks(s, vf);
   const Lvl& l = s.levels[0];
@@ -762,6 +764,7 @@ int vcycle_fused_solve(Sim& s, double tol, int itmx, bool ghosts_valid, int slot
   sa.ghosts_valid = ghosts_valid ? 1 : 0;
   sa.has_ghost = ghosts ? 1 : 0;
   sa.slot = slot;
+  sa.divu = divu;
   void* args[] = {&vf->p, &sa};
   cudaError_t e = cudaLaunchCooperativeKernel(tail_kernel(s.D, vf->minb), dim3(vf->grid), dim3(VC_THREADS), args, 0, s.stream);
   ++s.launches;

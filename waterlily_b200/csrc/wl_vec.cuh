@@ -40,6 +40,24 @@ template <int V> __device__ __forceinline__ Pack<V> ld_xp(const float* __restric
   return r;
 }
 
+// div(I,u) (Flow.jl:11-17) of V cells — project!'s z = div u evaluated where residual! consumes it
+template <int D, int V>
+__device__ __forceinline__ Pack<V> div_pack(const GridD& g, const float* __restrict__ u, int64_t I) {
+  Pack<V> s;
+  {
+    const Pack<V> uc = ldp<V>(u + I), up = ld_xp<V>(u + I, uc);
+#pragma unroll
+    for (int q = 0; q < V; ++q) s.v[q] = 0.f + (up.v[q] - uc.v[q]);
+  }
+#pragma unroll
+  for (int i = 1; i < D; ++i) {
+    const Pack<V> uc = ldp<V>(u + I + i * g.comp), up = ldp<V>(u + I + g.s[i] + i * g.comp);
+#pragma unroll
+    for (int q = 0; q < V; ++q) s.v[q] += up.v[q] - uc.v[q];
+  }
+  return s;
+}
+
 // ---- uniform-coefficient packs (see Lvl in wl_common.cuh) -------------------------------------------
 // true when the pack of V=4 cells starting at I has L ≡ uL on all its faces (then D ≡ uD, iD ≡ uiD)
 template <int V>
