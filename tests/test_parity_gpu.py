@@ -284,6 +284,7 @@ def test_fused_vcycle_matches_per_level_kernels(make, steps, solve_cells, monkey
     s0 = make(Simulation)
     monkeypatch.setenv("WL_FUSED_VCYCLE", "1")
     monkeypatch.setenv("WL_FUSED_SOLVE_CELLS", solve_cells)
+    monkeypatch.setenv("WL_FUSED_MARCH_CELLS", "0")   # z-marching / staged tile phases inside the persistent kernel even on these small grids
     s1 = make(Simulation)
     l0, l1 = s0._eng.launch_count(), s1._eng.launch_count()
     for _ in range(steps):
@@ -424,3 +425,23 @@ def test_bdim_stage2_folded_into_conv_diff_is_bit_identical(make, steps, monkeyp
     sim_step(s0, remeasure=False)
     sim_step(s1, remeasure=False)
     assert np.array_equal(s1.flow.u.numpy(), s0.flow.u.numpy())
+
+
+@pytest.mark.parametrize("dims,perdir", [((64, 32, 40), ()), ((64, 32, 32), (1, 2, 3)), ((136, 24, 16), (2,))])
+def test_conv_diff_kernels_agree_bitwise(dims, perdir, monkeypatch):
+    # the three 3-D core kernels of conv_diff! — untiled marching (WL_CD_TMA=0), TMA-staged one cell per thread, and the default
+    # two cells per thread with packed FADD2/FMUL2/FFMA2 arithmetic (wl_flux.cuh: flux2) — must produce the same bits: every lane
+    # of a packed instruction rounds like the scalar one, and no product is contracted into an fma the reference does not have
+    outs = []
+    for env in ({"WL_CD_TMA": "0"}, {"WL_CD_TMA": "1", "WL_CD_CELLS": "1"}, {"WL_CD_TMA": "1", "WL_CD_CELLS": "2"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        ec = cuda_engine(dims, nu=0.013, dt0=0.25, perdir=perdir)
+        rng = np.random.default_rng(11)
+        for name in ("u", "u0", "V"):
+            ec.upload(name, (rng.random(ec.shape(_cabi.FIELD_IDS[name])) * 2 - 1).astype(np.float32))
+        ec.conv_diff("u")
+        outs.append(ec.download("f"))
+        ec.close()
+    assert np.array_equal(outs[0], outs[1])
+    assert np.array_equal(outs[0], outs[2])

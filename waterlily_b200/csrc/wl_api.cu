@@ -702,6 +702,8 @@ int wl_profile_read(wl_sim* s, int which, double* ms, int64_t* launches, double*
   return WL_OK;
 }
 
+// development aid, not part of the header: phase log of the persistent solver kernel (WL_VC_TRACE=1)
+int wl_debug_vc_trace(wl_sim* s, unsigned long long* out, int max_pairs, int* n) { GUARD(s); return vcycle_fused_trace(S, out, max_pairs, n); }
 int wl_profile_count(void) { return WL_PROF_N; }
 const char* wl_profile_name(int which) {
   static const char* names[WL_PROF_N] = {"conv_diff+bdim1", "bdim2", "pcg_mult", "pcg_update", "pcg_dir", "pcg_init",

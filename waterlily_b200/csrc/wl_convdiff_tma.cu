@@ -348,12 +348,9 @@ __global__ void __launch_bounds__(32 * TY, MINB)
     const float2 uz = R[2][2];
     const float2 nzy = ld2(N + 2 * PP - PX);
     const float nzx = N[2 * PP - 1];
-    Fz[0][0].x = flux1((uz.x + nzx) * 0.5f, R[0][0].x, R[0][1].x, R[0][2].x, R[0][3].x, nu);
-    Fz[0][0].y = flux1((uz.y + uz.x) * 0.5f, R[0][0].y, R[0][1].y, R[0][2].y, R[0][3].y, nu);
-    Fz[0][1].x = flux1((uz.x + nzy.x) * 0.5f, R[1][0].x, R[1][1].x, R[1][2].x, R[1][3].x, nu);
-    Fz[0][1].y = flux1((uz.y + nzy.y) * 0.5f, R[1][0].y, R[1][1].y, R[1][2].y, R[1][3].y, nu);
-    Fz[0][2].x = flux1((uz.x + R[2][1].x) * 0.5f, R[2][0].x, R[2][1].x, R[2][2].x, R[2][3].x, nu);
-    Fz[0][2].y = flux1((uz.y + R[2][1].y) * 0.5f, R[2][0].y, R[2][1].y, R[2][2].y, R[2][3].y, nu);
+    Fz[0][0] = flux2(half_sum2(uz, make_float2(nzx, uz.x)), R[0][0], R[0][1], R[0][2], R[0][3], nu);
+    Fz[0][1] = flux2(half_sum2(uz, nzy), R[1][0], R[1][1], R[1][2], R[1][3], nu);
+    Fz[0][2] = flux2(half_sum2(uz, R[2][1]), R[2][0], R[2][1], R[2][2], R[2][3], nu);
   }
   __syncthreads();
   if (leader) {
@@ -415,20 +412,14 @@ __global__ void __launch_bounds__(32 * TY, MINB)
         yp1[c] = ld2(C + c * PP + PX);
       }
       const float2 ux = R[0][S], uy = R[1][S];
-      // lower x-faces of A and B
-      fx[0].x = flux1((ux.x + xm[0].y) * 0.5f, xm[0].x, xm[0].y, R[0][S].x, R[0][S].y, nu);
-      fx[0].y = flux1((ux.y + ux.x) * 0.5f, xm[0].y, R[0][S].x, R[0][S].y, xq[0].x, nu);
-      fx[1].x = flux1((ux.x + ym1[0].x) * 0.5f, xm[1].x, xm[1].y, R[1][S].x, R[1][S].y, nu);
-      fx[1].y = flux1((ux.y + ym1[0].y) * 0.5f, xm[1].y, R[1][S].x, R[1][S].y, xq[1].x, nu);
-      fx[2].x = flux1((ux.x + R[0][SM1].x) * 0.5f, xm[2].x, xm[2].y, R[2][S].x, R[2][S].y, nu);
-      fx[2].y = flux1((ux.y + R[0][SM1].y) * 0.5f, xm[2].y, R[2][S].x, R[2][S].y, xq[2].x, nu);
+      // lower x-faces of A and B (cell pair = one packed evaluation): stencil (x-2, x-1, x, x+1) for A, shifted by one for B
+      fx[0] = flux2(half_sum2(ux, make_float2(xm[0].y, ux.x)), xm[0], make_float2(xm[0].y, R[0][S].x), R[0][S], make_float2(R[0][S].y, xq[0].x), nu);
+      fx[1] = flux2(half_sum2(ux, ym1[0]), xm[1], make_float2(xm[1].y, R[1][S].x), R[1][S], make_float2(R[1][S].y, xq[1].x), nu);
+      fx[2] = flux2(half_sum2(ux, R[0][SM1]), xm[2], make_float2(xm[2].y, R[2][S].x), R[2][S], make_float2(R[2][S].y, xq[2].x), nu);
       // lower y-faces
-      fy[0].x = flux1((uy.x + xm[1].y) * 0.5f, ym2[0].x, ym1[0].x, R[0][S].x, yp1[0].x, nu);
-      fy[0].y = flux1((uy.y + uy.x) * 0.5f, ym2[0].y, ym1[0].y, R[0][S].y, yp1[0].y, nu);
-      fy[1].x = flux1((uy.x + ym1[1].x) * 0.5f, ym2[1].x, ym1[1].x, R[1][S].x, yp1[1].x, nu);
-      fy[1].y = flux1((uy.y + ym1[1].y) * 0.5f, ym2[1].y, ym1[1].y, R[1][S].y, yp1[1].y, nu);
-      fy[2].x = flux1((uy.x + R[1][SM1].x) * 0.5f, ym2[2].x, ym1[2].x, R[2][S].x, yp1[2].x, nu);
-      fy[2].y = flux1((uy.y + R[1][SM1].y) * 0.5f, ym2[2].y, ym1[2].y, R[2][S].y, yp1[2].y, nu);
+      fy[0] = flux2(half_sum2(uy, make_float2(xm[1].y, uy.x)), ym2[0], ym1[0], R[0][S], yp1[0], nu);
+      fy[1] = flux2(half_sum2(uy, ym1[1]), ym2[1], ym1[1], R[1][S], yp1[1], nu);
+      fy[2] = flux2(half_sum2(uy, R[1][SM1]), ym2[2], ym1[2], R[2][S], yp1[2], nu);
     }
 #pragma unroll
     for (int i = 0; i < 3; ++i) *reinterpret_cast<float2*>(Fy + ((buf * 3 + i) * TY + tiy) * TX + 2 * lane) = fy[i];
@@ -449,12 +440,8 @@ __global__ void __launch_bounds__(32 * TY, MINB)
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         const float2 yp2 = ld2(C + c * PP + 2 * PX);
-        float2 uf;
-        if (c == 0) { uf.x = (uyp.x + uyxm) * 0.5f; uf.y = (uyp.y + uyp.x) * 0.5f; }
-        else if (c == 1) { uf.x = (uyp.x + R[1][S].x) * 0.5f; uf.y = (uyp.y + R[1][S].y) * 0.5f; }
-        else { uf.x = (uyp.x + cyp.x) * 0.5f; uf.y = (uyp.y + cyp.y) * 0.5f; }
-        fyh[c].x = flux1(uf.x, ym1[c].x, R[c][S].x, yp1[c].x, yp2.x, nu);
-        fyh[c].y = flux1(uf.y, ym1[c].y, R[c][S].y, yp1[c].y, yp2.y, nu);
+        const float2 other = c == 0 ? make_float2(uyxm, uyp.x) : (c == 1 ? R[1][S] : cyp);
+        fyh[c] = flux2(half_sum2(uyp, other), ym1[c], R[c][S], yp1[c], yp2, nu);
       }
     }
     cyp = yp1[1];
@@ -471,12 +458,9 @@ __global__ void __launch_bounds__(32 * TY, MINB)
       const float2 nzy = ld2(N + 2 * PP - PX);
       const float nzx = N[2 * PP - 1];
       constexpr int Q = (S + 1) & 1;
-      Fz[Q][0].x = flux1((uz.x + nzx) * 0.5f, R[0][SM1].x, R[0][S].x, R[0][SP1].x, R[0][SP2].x, nu);
-      Fz[Q][0].y = flux1((uz.y + uz.x) * 0.5f, R[0][SM1].y, R[0][S].y, R[0][SP1].y, R[0][SP2].y, nu);
-      Fz[Q][1].x = flux1((uz.x + nzy.x) * 0.5f, R[1][SM1].x, R[1][S].x, R[1][SP1].x, R[1][SP2].x, nu);
-      Fz[Q][1].y = flux1((uz.y + nzy.y) * 0.5f, R[1][SM1].y, R[1][S].y, R[1][SP1].y, R[1][SP2].y, nu);
-      Fz[Q][2].x = flux1((uz.x + R[2][S].x) * 0.5f, R[2][SM1].x, R[2][S].x, R[2][SP1].x, R[2][SP2].x, nu);
-      Fz[Q][2].y = flux1((uz.y + R[2][S].y) * 0.5f, R[2][SM1].y, R[2][S].y, R[2][SP1].y, R[2][SP2].y, nu);
+      Fz[Q][0] = flux2(half_sum2(uz, make_float2(nzx, uz.x)), R[0][SM1], R[0][S], R[0][SP1], R[0][SP2], nu);
+      Fz[Q][1] = flux2(half_sum2(uz, nzy), R[1][SM1], R[1][S], R[1][SP1], R[1][SP2], nu);
+      Fz[Q][2] = flux2(half_sum2(uz, R[2][S]), R[2][SM1], R[2][S], R[2][SP1], R[2][SP2], nu);
     }
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
@@ -491,22 +475,19 @@ __global__ void __launch_bounds__(32 * TY, MINB)
     if (valid_a) {
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
-        float2 v;
-        v.x = 0.f; v.x += fx[i].x; v.x -= fxh[i].x; v.x += fy[i].x; v.x -= fyh[i].x; v.x += Fz[S & 1][i].x; v.x -= Fz[(S + 1) & 1][i].x;
-        v.y = 0.f; v.y += fx[i].y; v.y -= fxh[i].y; v.y += fy[i].y; v.y -= fyh[i].y; v.y += Fz[S & 1][i].y; v.y -= Fz[(S + 1) & 1][i].y;
+        float2 v = add2(splat2(0.f), fx[i]);
+        v = sub2(v, fxh[i]); v = add2(v, fy[i]); v = sub2(v, fyh[i]); v = add2(v, Fz[S & 1][i]); v = sub2(v, Fz[(S + 1) & 1][i]);
         if (HASG) { v.x = (float)((double)v.x + a.gacc[i]); v.y = (float)((double)v.y + a.gacc[i]); }
         if (a.fuse_bdim1) {
           const float2 u0v = CORR ? ld2(vu + (buf * 6 + 3 + i) * TY * TX) : R[i][S];
           const float2 Vv = cl ? make_float2(0.f, 0.f) : ld2(vu + (buf * 6 + i) * TY * TX);
-          v.x = u0v.x + a.dt * v.x - Vv.x;
-          v.y = u0v.y + a.dt * v.y - Vv.y;
+          v = sub2(add2(u0v, mul2_sep(v, a.dt)), Vv);   // u⁰ + Δt·f - V: the product is rounded on its own
         }
         float* dst = reinterpret_cast<float*>(const_cast<char*>(fb[i]) + off);
         if (cl) {  // BDIM! stage 2 away from bodies: u = (u_acc + f)·scale with u_acc = 0 (predictor) or u (corrector)
           // the reference adds in Float64 and rounds once; for the sum of two Float32 that is the Float32 sum (53 ≥ 2·24+2 bits:
           // the double rounding is innocuous), so the Float32 add below has the same bits — and no FP64 conversions to issue
-          v.x = ((CORR ? R[i][S].x : 0.f) + v.x) * a.bscale;
-          v.y = ((CORR ? R[i][S].y : 0.f) + v.y) * a.bscale;
+          v = mul2(add2(CORR ? R[i][S] : splat2(0.f), v), splat2(a.bscale));
           dst = reinterpret_cast<float*>(const_cast<char*>(qb[i]) + off);
         }
         if (valid_b) *reinterpret_cast<float2*>(dst) = v;

@@ -61,3 +61,53 @@ __device__ __forceinline__ float flux1(float uf, float um2, float um1, float uc,
   const float q = uf > 0 ? quick(um2, um1, uc) : quick(up1, uc, um1);
   return fmaf(uf, q, -(nu * (uc - um1)));
 }
+
+// ---- packed Float32 pairs (Blackwell FADD2 / FMUL2 / FFMA2: add/mul/fma.rn.f32x2) -------------------------
+// The two-cells-per-thread conv_diff! kernel evaluates every flux for the cell pair (x, x+1) with identical
+// operations: issued as packed instructions they take one issue slot per pair instead of two (the kernel is bound
+// by instruction issue).  Each lane rounds to nearest exactly like the scalar instruction, so results are bit-identical.
+// CAUTION: ptxas (12.9) contracts mul.rn.f32x2 feeding add/sub.rn.f32x2 into FFMA2 even with --fmad=false; wherever
+// the reference rounds a product before adding it, the product is formed with the scalar __fmul_rn below.
+typedef unsigned long long wl_u64;
+__device__ __forceinline__ wl_u64 pk2(float2 a) { wl_u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y)); return r; }
+__device__ __forceinline__ float2 upk2(wl_u64 a) { float2 r; asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(a)); return r; }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { wl_u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2(a)), "l"(pk2(b))); return upk2(r); }
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) { wl_u64 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2(a)), "l"(pk2(b))); return upk2(r); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { wl_u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2(a)), "l"(pk2(b))); return upk2(r); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  wl_u64 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(pk2(a)), "l"(pk2(b)), "l"(pk2(c)));
+  return upk2(r);
+}
+__device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
+// scalar products that must be rounded on their own (see CAUTION above)
+__device__ __forceinline__ float2 mul2_sep(float2 a, float b) { return make_float2(__fmul_rn(a.x, b), __fmul_rn(a.y, b)); }
+// div6 (above) for a pair: q is consumed by fma only
+__device__ __forceinline__ float2 div6x2(float2 x) {
+  const float2 y = splat2(1.0f / 6.0f);
+  const float2 q = mul2(x, y);
+  return fma2(fma2(splat2(-6.0f), q, x), y, q);
+}
+// flux1 (above) for the cell pair: same operations per lane
+__device__ __forceinline__ float2 flux2(float2 uf, float2 um2, float2 um1, float2 uc, float2 up1, float nu) {
+  float2 u, c, d;
+  u.x = uf.x > 0 ? um2.x : up1.x; c.x = uf.x > 0 ? um1.x : uc.x; d.x = uf.x > 0 ? uc.x : um1.x;
+  u.y = uf.y > 0 ? um2.y : up1.y; c.y = uf.y > 0 ? um1.y : uc.y; d.y = uf.y > 0 ? uc.y : um1.y;
+  // q1 = (5c + 2d - u)/6: 2d is exact, so fma(2, d, RN(5c)) = RN(RN(5c) + 2d)
+  const float2 q1 = div6x2(sub2(fma2(splat2(2.f), d, mul2(splat2(5.f), c)), u));
+  // q2 = 10c - 9u: both products rounded on their own
+  const float2 q2 = sub2(mul2_sep(c, 10.f), mul2_sep(u, 9.f));
+  float2 q;
+  {
+    const float lo = fminf(fminf(q1.x, q2.x), d.x), hi = fmaxf(fmaxf(q1.x, q2.x), d.x);
+    q.x = fminf(fmaxf(c.x, lo), hi);
+  }
+  {
+    const float lo = fminf(fminf(q1.y, q2.y), d.y), hi = fmaxf(fmaxf(q1.y, q2.y), d.y);
+    q.y = fminf(fmaxf(c.y, lo), hi);
+  }
+  // Φ = fma(uf, q, -(ν·(uc - um1))): the product ν·∂ is the addend of the fma (no contraction possible)
+  return fma2(uf, q, mul2(sub2(uc, um1), splat2(-nu)));
+}
+// uf = (a + b)·0.5
+__device__ __forceinline__ float2 half_sum2(float2 a, float2 b) { return mul2(add2(a, b), splat2(0.5f)); }

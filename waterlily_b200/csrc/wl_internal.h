@@ -165,6 +165,7 @@ int derived_run(Sim& s, int kind, int comp, const double* U, const double* axis,
 int vcycle_fused_setup(Sim& s);
 void vcycle_fused_destroy(Sim& s);
 int vcycle_fused_run(Sim& s);
+int vcycle_fused_trace(Sim& s, unsigned long long* out, int max_pairs, int* n);
 int vcycle_fused_solve(Sim& s, double tol, int itmx, bool ghosts_valid, int slot, const float* divu = nullptr);
 
 // ---- wl_bc.cu ----

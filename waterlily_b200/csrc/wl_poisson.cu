@@ -312,146 +312,33 @@ __global__ void __launch_bounds__(256) k_pcg_mult_m(Lvl l, MarchGeom mg, ReduceW
   double tot[1];
   if (grid_reduce<1>(acc, ws, tot)) finish_reduction(FIN_PCG_MULT, fa, tot[0], 0.0);
 }
-// ---- the same with the stencil operand staged through shared memory (march_staged, wl_vec.cuh) ------
+// ---- the same with the stencil operand staged through shared memory (march_staged / tile_* in wl_vec.cuh) ------
+#ifndef WL_STAGE_MINB
+#define WL_STAGE_MINB 3  // 80 registers, no spills: three resident blocks of the staged kernels per SM (measured: 2 and 4 are slower)
+#endif
 extern __shared__ __align__(16) float wl_ring[];
-__global__ void __launch_bounds__(256) k_pcg_mult_s(Lvl l, MarchGeom mg, ReduceWS ws, FinArgs fa) {
+__global__ void __launch_bounds__(256, WL_STAGE_MINB) k_pcg_mult_s(Lvl l, MarchGeom mg, ReduceWS ws, FinArgs fa) {
   if (!l.sc->active) return;
   double acc[1] = {0.0};
-  const GridD& g = l.g;
-  for_columns(g, mg, [&](int i, int j, int k0, int k1) {
-    bool uni = false;
-    march_staged(g, l.eps, wl_ring, i, j, k0, k1,
-      [&](int, int64_t I) { uni = pack_uniform<4>(l, I); },
-      [&](int, int64_t I, const Pack<4>& ec, float xm1, float xp4, const Pack<4>& ym, const Pack<4>& yp, const Pack<4>& zm, const Pack<4>& zp) {
-        const Pack<4> z = mult_vals<4>(l, I, ec, xm1, xp4, ym, yp, zm, zp, uni);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) acc[0] += (double)z.v[q] * (double)ec.v[q];
-        stp<4>(l.z + I, z);
-      });
-  });
+  for_columns(l.g, mg, [&](int i, int j, int k0, int k1) { tile_pcg_mult(l, mg, wl_ring, i, j, k0, k1, acc[0]); });
   double tot[1];
   if (grid_reduce<1>(acc, ws, tot)) finish_reduction(FIN_PCG_MULT, fa, tot[0], 0.0);
 }
-__global__ void __launch_bounds__(256) k_increment_s(Lvl l, MarchGeom mg, ReduceWS ws, FinArgs fa) {
+__global__ void __launch_bounds__(256, WL_STAGE_MINB) k_increment_s(Lvl l, MarchGeom mg, ReduceWS ws, FinArgs fa) {
   double acc[1] = {0.0};
-  const GridD& g = l.g;
-  for_columns(g, mg, [&](int i, int j, int k0, int k1) {
-    bool uni = false;
-    Pack<4> r, x;
-    march_staged(g, l.eps, wl_ring, i, j, k0, k1,
-      [&](int, int64_t I) { uni = pack_uniform<4>(l, I); r = ldp<4>(l.r + I); x = ldp<4>(l.x + I); },
-      [&](int, int64_t I, const Pack<4>& ec, float xm1, float xp4, const Pack<4>& ym, const Pack<4>& yp, const Pack<4>& zm, const Pack<4>& zp) {
-        const Pack<4> ae = mult_vals<4>(l, I, ec, xm1, xp4, ym, yp, zm, zp, uni);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          r.v[q] = r.v[q] - ae.v[q];
-          x.v[q] = x.v[q] + ec.v[q];
-          acc[0] += (double)r.v[q] * (double)r.v[q];
-        }
-        stp<4>(l.r + I, r);
-        stp<4>(l.x + I, x);
-      });
-  });
+  for_columns(l.g, mg, [&](int i, int j, int k0, int k1) { tile_increment(l, mg, wl_ring, i, j, k0, k1, acc[0]); });
   double tot[1];
   if (grid_reduce<1>(acc, ws, tot)) finish_reduction(FIN_R2, fa, tot[0], 0.0);
 }
-__global__ void __launch_bounds__(256) k_residual_s(Lvl l, MarchGeom mg, ReduceWS ws, FinArgs fa, int write_eps, const float* __restrict__ divu) {
+__global__ void __launch_bounds__(256, WL_STAGE_MINB) k_residual_s(Lvl l, MarchGeom mg, ReduceWS ws, FinArgs fa, int write_eps, const float* __restrict__ divu) {
   double acc[2] = {0.0, 0.0};
-  const GridD& g = l.g;
-  for_columns(g, mg, [&](int i, int j, int k0, int k1) {
-    bool uni = false;
-    Pack<4> zc;
-    march_staged(g, l.x, wl_ring, i, j, k0, k1,
-      [&](int, int64_t I) { uni = pack_uniform<4>(l, I); zc = divu ? div_pack<3, 4>(g, divu, I) : ldp<4>(l.z + I); },
-      [&](int, int64_t I, const Pack<4>& xc, float xm1, float xp4, const Pack<4>& ym, const Pack<4>& yp, const Pack<4>& zm, const Pack<4>& zp) {
-        const Pack<4> ax = mult_vals<4>(l, I, xc, xm1, xp4, ym, yp, zm, zp, uni), id = ld_iD<4>(l, I, uni);
-        Pack<4> r;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          r.v[q] = id.v[q] == 0.f ? 0.f : zc.v[q] - ax.v[q];
-          acc[0] += (double)r.v[q];
-          acc[1] += (double)r.v[q] * (double)r.v[q];
-        }
-        stp<4>(l.r + I, r);
-        if (write_eps) {
-          Pack<4> e;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) e.v[q] = r.v[q] * id.v[q];
-          stp<4>(l.eps + I, e);
-        }
-      });
-  });
+  for_columns(l.g, mg, [&](int i, int j, int k0, int k1) { tile_residual(l, mg, wl_ring, i, j, k0, k1, write_eps, divu, acc[0], acc[1]); });
   double tot[2];
   if (grid_reduce<2>(acc, ws, tot)) finish_reduction(FIN_RESIDUAL, fa, tot[0], tot[1]);
 }
-// prolongate! + increment! + head of pcg!: ϵ of a fine pack (i = 1+4t) is {c, c, c', c'} with (c, c') the aligned
-// coarse pair at ci = 1+2t, so a pack costs one 8-byte load per coarse row it touches
-__device__ __forceinline__ Pack<4> pro_pack(const float* __restrict__ crow, int ci) {
-  const float2 c = *reinterpret_cast<const float2*>(crow + ci);
-  Pack<4> e; e.v[0] = c.x; e.v[1] = c.x; e.v[2] = c.y; e.v[3] = c.y;
-  return e;
-}
 __global__ void __launch_bounds__(256) k_prolong_increment_init_m(Lvl f, Lvl c, ProMap m, MarchGeom mg, ReduceWS ws, FinArgs fa) {
   double acc[2] = {0.0, 0.0};
-  const GridD& g = f.g;
-  const float* __restrict__ xc = c.x;
-  const int64_t cs1 = c.g.s[1], cs2 = c.g.s[2];
-  for_columns(g, mg, [&](int i, int j, int k0, int k1) {
-    int64_t I = i + j * g.s[1] + (int64_t)k0 * g.s[2];
-    const int ci = (i + 1) >> 1;
-    const int cim = pro_cidx(m, 0, i - 1), cip = pro_cidx(m, 0, i + 4);
-    const int64_t Jy = pro_cidx(m, 1, j) * cs1, Jym = pro_cidx(m, 1, j - 1) * cs1, Jyp = pro_cidx(m, 1, j + 1) * cs1;
-    for (int k = k0; k <= k1; ++k, I += g.s[2]) {
-      const int64_t Jz = pro_cidx(m, 2, k) * cs2, Jzm = pro_cidx(m, 2, k - 1) * cs2, Jzp = pro_cidx(m, 2, k + 1) * cs2;
-      const float* row = xc + Jy + Jz;
-      const Pack<4> e = pro_pack(row, ci);
-      Pack<4> xm, xp;
-      xm.v[0] = row[cim]; xm.v[1] = e.v[0]; xm.v[2] = e.v[1]; xm.v[3] = e.v[2];
-      xp.v[0] = e.v[1]; xp.v[1] = e.v[2]; xp.v[2] = e.v[3]; xp.v[3] = row[cip];
-      const bool uni = pack_uniform<4>(f, I);
-      const Pack<4> Dc = uni ? splat<4>(f.uD) : ldp<4>(f.Dg + I);
-      Pack<4> s;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) s.v[q] = e.v[q] * Dc.v[q];
-      {
-        Pack<4> Lc, Lp;
-        if (uni) { Lc = splat<4>(f.uL); Lp = Lc; }
-        else { Lc = ldp<4>(f.L + I); Lp = ld_xp<4>(f.L + I, Lc); }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) s.v[q] += (xm.v[q] * Lc.v[q] + xp.v[q] * Lp.v[q]);
-      }
-      {
-        const Pack<4> em = pro_pack(xc + Jym + Jz, ci), ep = pro_pack(xc + Jyp + Jz, ci);
-        Pack<4> Lc, Lp;
-        if (uni) { Lc = splat<4>(f.uL); Lp = Lc; }
-        else { Lc = ldp<4>(f.L + g.comp + I); Lp = ldp<4>(f.L + g.comp + I + g.s[1]); }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) s.v[q] += (em.v[q] * Lc.v[q] + ep.v[q] * Lp.v[q]);
-      }
-      {
-        const Pack<4> em = pro_pack(xc + Jy + Jzm, ci), ep = pro_pack(xc + Jy + Jzp, ci);
-        Pack<4> Lc, Lp;
-        if (uni) { Lc = splat<4>(f.uL); Lp = Lc; }
-        else { Lc = ldp<4>(f.L + 2 * g.comp + I); Lp = ldp<4>(f.L + 2 * g.comp + I + g.s[2]); }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) s.v[q] += (em.v[q] * Lc.v[q] + ep.v[q] * Lp.v[q]);
-      }
-      Pack<4> r = ldp<4>(f.r + I), x = ldp<4>(f.x + I);
-      const Pack<4> id = ld_iD<4>(f, I, uni);
-      Pack<4> en;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        r.v[q] = r.v[q] - s.v[q];
-        x.v[q] = x.v[q] + e.v[q];
-        en.v[q] = r.v[q] * id.v[q];
-        acc[0] += (double)r.v[q] * (double)en.v[q];
-        acc[1] += (double)r.v[q] * (double)r.v[q];
-      }
-      stp<4>(f.r + I, r);
-      stp<4>(f.x + I, x);
-      stp<4>(f.eps + I, en);
-    }
-  });
+  for_columns(f.g, mg, [&](int i, int j, int k0, int k1) { tile_prolong(f, c, m, i, j, k0, k1, acc[0], acc[1]); });
   double tot[2];
   if (grid_reduce<2>(acc, ws, tot)) finish_reduction(FIN_INC_INIT, fa, tot[0], tot[1]);
 }

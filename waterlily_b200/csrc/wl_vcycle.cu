@@ -33,6 +33,9 @@
 namespace {
 
 #define VC_THREADS 256
+#ifndef WL_VC_MINB
+#define WL_VC_MINB 2  // resident blocks per SM the register allocation aims for
+#endif
 
 struct FusedParams {
   int D, nl, lf, lb;          // dims, levels, first fused level, first single-block level
@@ -45,6 +48,11 @@ struct FusedParams {
   const P2PDev* p2p;          // null on one rank
   MiscScalars* misc;          // solve mode: V-cycle count out
   int nzg0, perz_global;      // interior z-planes of the whole finest level; the global domain is periodic in z
+  // z-marching tiles (for_columns / march_staged, wl_vec.cuh) of the levels large enough to be bandwidth-bound:
+  // march[l] = 1: tile_prolong runs on column tiles; 2: also the shared-memory staged stencil phases
+  MarchGeom mg[WL_MAXLEVELS];
+  int march[WL_MAXLEVELS];
+  unsigned long long* trace;  // WL_VC_TRACE=1: block 0 logs (tag, globaltimer) after every phase (development aid), else null
 };
 // per-launch arguments of the whole-solver mode (solver!(ml), MultiLevelPoisson.jl:87-99)
 struct SolveArgs {
@@ -56,6 +64,8 @@ struct SolveArgs {
   int slot;          // which entry of MiscScalars::solve_n receives the count
   const float* divu; // non-null: residual! evaluates z = div(u) on the spot instead of reading z (project! inside mom_step!)
 };
+
+extern __shared__ __align__(16) float vc_ring[];  // operand ring of the staged stencil phases
 
 struct Shared {
   double red[2][VC_THREADS / 32];
@@ -69,7 +79,18 @@ struct Run {
   Shared* sh;
   unsigned long long push_epoch, ar_epoch;
   unsigned int bar_gen;
+  int trn;
 };
+#define VC_TRACE_MAX 4096
+// tag = 1000·level + phase: 1 residual, 2 sub-mean, 3 jacobi ϵ, 4 increment, 5 restrict, 6 prolong+increment+init, 7 pcg init,
+// 10+3s pcg mult / 11+3s update / 12+3s dir of sweep s, 90 single-block sub-cycle, 95 perBC, 99 start/end
+__device__ __forceinline__ void trace(const FusedParams& p, Run& run, int tag) {
+  if (p.trace && blockIdx.x == 0 && threadIdx.x == 0 && run.trn < VC_TRACE_MAX) {
+    p.trace[2 * run.trn] = (unsigned long long)tag;
+    p.trace[2 * run.trn + 1] = p2p_now();
+    ++run.trn;
+  }
+}
 
 // ---- barriers -----------------------------------------------------------------------------
 __device__ __forceinline__ void grid_barrier(const FusedParams& p, Run& run) {
@@ -268,6 +289,9 @@ __device__ __forceinline__ void increment(const FusedParams& p, Run& run, int l,
   const Lvl& L = p.lv[l];
   if (GRID && p.dist[l]) halo_push(p, run, l, L.eps);
   double acc[1] = {0.0};
+  if (GRID && D == 3 && V == 4 && p.march[l] == 2) {
+    for_columns_even(L.g, p.mg[l], [&](int i, int j, int k0, int k1) { tile_increment(L, p.mg[l], vc_ring, i, j, k0, k1, acc[0]); });
+  } else
   rows<V, GRID>(p, l, [&](int i, int j, int k, int64_t I) {
     const Pack<V> ec = ldp<V>(L.eps + I), ae = mult_w<D, V>(L, L.eps, i, j, k, I, ec, pack_uniform<V>(L, I));
     Pack<V> r = ldp<V>(L.r + I), x = ldp<V>(L.x + I);
@@ -287,6 +311,7 @@ __device__ __forceinline__ void increment(const FusedParams& p, Run& run, int l,
     phase_sync<GRID>(p, run);
   }
   if (GRID && p.dist[l]) post_ready(p, run);
+  if (GRID) trace(p, run, 1000 * l + 4);
 }
 // Jacobi!(l; it=1) (Poisson.jl:110-113)
 template <int D, int V, bool GRID>
@@ -301,6 +326,7 @@ __device__ __forceinline__ void jacobi(const FusedParams& p, Run& run, int l, bo
     stp<V>(L.eps + I, e);
   });
   phase_sync<GRID>(p, run);
+  if (GRID) trace(p, run, 1000 * l + 3);
   increment<D, V, GRID>(p, run, l);
 }
 // pcg!(l; it=6) (Poisson.jl:123-144)
@@ -325,6 +351,7 @@ __device__ __forceinline__ void pcg(const FusedParams& p, Run& run, int l, int i
     });
     reduce<1, GRID>(p, run, dist, acc);
     rho = (float)acc[0];
+    if (GRID) trace(p, run, 1000 * l + 7);
   }
   if (fabsf(rho) < 10 * WL_EPS32) return;
   for (int i = 1; i <= it; ++i) {
@@ -332,6 +359,9 @@ __device__ __forceinline__ void pcg(const FusedParams& p, Run& run, int l, int i
     float alpha;
     {
       double acc[1] = {0.0};
+      if (GRID && D == 3 && V == 4 && p.march[l] == 2) {
+        for_columns_even(L.g, p.mg[l], [&](int ii, int j, int k0, int k1) { tile_pcg_mult(L, p.mg[l], vc_ring, ii, j, k0, k1, acc[0]); });
+      } else
       rows<V, GRID>(p, l, [&](int ii, int j, int k, int64_t I) {
         const Pack<V> ec = ldp<V>(L.eps + I), z = mult_w<D, V>(L, L.eps, ii, j, k, I, ec, pack_uniform<V>(L, I));
 #pragma unroll
@@ -354,6 +384,7 @@ __device__ __forceinline__ void pcg(const FusedParams& p, Run& run, int l, int i
       reduce<1, GRID>(p, run, dist, acc);
       if (dist) post_ready(p, run);
       alpha = rho / (float)acc[0];
+      if (GRID) trace(p, run, 1000 * l + 10 + 3 * i);
     }
     const double aa = fabs((double)alpha);
     if (aa < 1e-2 || aa > 1e2) return;
@@ -373,8 +404,9 @@ __device__ __forceinline__ void pcg(const FusedParams& p, Run& run, int l, int i
         stp<V>(L.x + I, x);
         stp<V>(L.r + I, r);
       });
-      if (i == it && !r2) { phase_sync<GRID>(p, run); return; }  // the dots of the last sweep are never used below level 1
+      if (i == it && !r2) { phase_sync<GRID>(p, run); if (GRID) trace(p, run, 1000 * l + 11 + 3 * i); return; }  // the dots of the last sweep are never used below level 1
       reduce<2, GRID>(p, run, dist, acc);
+      if (GRID) trace(p, run, 1000 * l + 11 + 3 * i);
       if (r2) *r2 = (float)acc[1];
       if (i == it) return;
       rho2 = (float)acc[0];
@@ -390,6 +422,7 @@ __device__ __forceinline__ void pcg(const FusedParams& p, Run& run, int l, int i
       stp<V>(L.eps + I, e);
     });
     phase_sync<GRID>(p, run);
+    if (GRID) trace(p, run, 1000 * l + 12 + 3 * i);
   }
 }
 // restrict!(l → l+1) (MultiLevelPoisson.jl:33) + fill!(x_{l+1},0) (:75); a distributed → replicated
@@ -435,6 +468,7 @@ __device__ __forceinline__ void restrict_to(const FusedParams& p, Run& run, int 
     }
     push_segments(p, run, seg, ns, mask);
   }
+  if (GRID) trace(p, run, 1000 * l + 5);
 }
 // prolongate!(l+1 → l) + increment!(l) + the head of pcg!(l) in one phase (wl_vec.cuh); across slab faces
 // ϵ is the neighbour's coarse x, so the halo that travels is the (4× smaller) coarse one
@@ -452,11 +486,16 @@ __device__ __forceinline__ void prolong_inc_init(const FusedParams& p, Run& run,
   m.nzg = p.nzg0 >> l;
   m.perz_global = p.perz_global;
   double acc[2] = {0.0, 0.0};
-  rows<V, GRID>(p, l, [&](int i, int j, int k, int64_t I) { prolong_increment_init<D, V>(f, c, m, i, j, k, I, acc[0], acc[1]); });
+  if (GRID && D == 3 && V == 4 && p.march[l] >= 1) {
+    for_columns_even(f.g, p.mg[l], [&](int i, int j, int k0, int k1) { tile_prolong(f, c, m, i, j, k0, k1, acc[0], acc[1]); });
+  } else {
+    rows<V, GRID>(p, l, [&](int i, int j, int k, int64_t I) { prolong_increment_init<D, V>(f, c, m, i, j, k, I, acc[0], acc[1]); });
+  }
   reduce<2, GRID>(p, run, fdist, acc);
   if (fdist && cdist) post_ready(p, run);
   rho = (float)acc[0];
   if (r2) *r2 = (float)acc[1];
+  if (GRID) trace(p, run, 1000 * l + 6);
 }
 
 template <int D, bool GRID>
@@ -497,6 +536,7 @@ __device__ __forceinline__ void vcycle_tail(const FusedParams& p, Run& run, int 
       for (int l = last - 1; l >= lb; --l) up_level<D, false>(p, run, l);
     }
     grid_barrier(p, run);
+    trace(p, run, 1000 * lb + 90);
   } else {
     pcg_level<D, true>(p, run, last);
   }
@@ -516,6 +556,9 @@ __device__ __forceinline__ void residual0(const FusedParams& p, Run& run, const 
   // x's periodic neighbours are read through wrapped indices; slab faces need the neighbours' planes
   if (dist && !sa.ghosts_valid) halo_push(p, run, 0, L.x);
   double acc[2] = {0.0, 0.0};
+  if (D == 3 && V == 4 && p.march[0] == 2) {
+    for_columns_even(L.g, p.mg[0], [&](int i, int j, int k0, int k1) { tile_residual(L, p.mg[0], vc_ring, i, j, k0, k1, 1, sa.divu, acc[0], acc[1]); });
+  } else
   rows<V, true>(p, 0, [&](int i, int j, int k, int64_t I) {
     const bool uni = pack_uniform<V>(L, I);
     const Pack<V> xc = ldp<V>(L.x + I), ax = mult_w<D, V>(L, L.x, i, j, k, I, xc, uni), zc = sa.divu ? div_pack<D, V>(L.g, sa.divu, I) : ldp<V>(L.z + I),
@@ -535,6 +578,7 @@ __device__ __forceinline__ void residual0(const FusedParams& p, Run& run, const 
   if (dist && !sa.ghosts_valid) post_ready(p, run);
   const float rmean = (float)acc[0] / (float)L.g.interior_global;
   r2 = (float)acc[1];
+  trace(p, run, 1);
   if (fabsf(rmean) > 2 * WL_EPS32) {
     rows<V, true>(p, 0, [&](int, int, int, int64_t I) {
       Pack<V> r = ldp<V>(L.r + I);
@@ -597,8 +641,10 @@ __global__ void __launch_bounds__(VC_THREADS, MINB) k_vcycle_tail(FusedParams p,
     post_ready(p, run);  // every earlier kernel of this rank has retired
   }
   run.bar_gen = *((volatile unsigned int*)&p.bar[1]);
+  run.trn = 0;
   // every block must have sampled the generation / epochs before anyone moves them
   grid_barrier(p, run);
+  trace(p, run, 99);
   const bool solve = sa.solve != 0;
   const bool v4 = (p.lv[0].g.n[0] - 2) % 4 == 0;
   const int lf = solve ? 1 : p.lf;
@@ -630,6 +676,8 @@ __global__ void __launch_bounds__(VC_THREADS, MINB) k_vcycle_tail(FusedParams p,
   }
   if (solve) {
     per_bc_x0<D>(p, run);
+    trace(p, run, 95);
+    if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) { p.trace[2 * VC_TRACE_MAX] = (unsigned long long)run.trn; }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
       p.lv[0].sc->r2 = r2;
       p.misc->solve_n[sa.slot] = n;
@@ -647,13 +695,14 @@ __global__ void __launch_bounds__(VC_THREADS, MINB) k_vcycle_tail(FusedParams p,
 // Host side: the fused coarse tail replaces pois_vcycle(level ≥ lf-1)'s recursion.
 struct VcycleFused {
   FusedParams p;
+  size_t smem = 0;   // dynamic shared memory: the operand ring of the staged stencil phases
   int grid = 0;
   int minb = 2;
   bool ok = false;
   bool solve = false;  // the whole solver! runs in the kernel (level 1 of the reference included)
 };
 static const void* tail_kernel(int D, int) {
-  return D == 2 ? (const void*)k_vcycle_tail<2, 2> : (const void*)k_vcycle_tail<3, 2>;
+  return D == 2 ? (const void*)k_vcycle_tail<2, WL_VC_MINB> : (const void*)k_vcycle_tail<3, WL_VC_MINB>;
 }
 
 static int ilog2(int v) { int l = 0; while ((1 << (l + 1)) <= v) ++l; return l; }
@@ -704,8 +753,21 @@ int vcycle_fused_setup(Sim& s) {
   }
   const char* e4 = getenv("WL_FUSED_MINB");
   vf->minb = e4 ? atoi(e4) : 2;
+  // z-marching tiles for the levels that are bandwidth-bound (3-D, grid mode, large enough)
+  const char* e6 = getenv("WL_FUSED_MARCH_CELLS");
+  const int64_t march_cells = e6 ? atoll(e6) : (int64_t)1 << 20;
+  vf->smem = 0;
+  for (int l = 0; l < p.nl; ++l) {
+    p.march[l] = 0;
+    p.mg[l] = MarchGeom{};
+    const MarchLaunch ml = march_launch(s.levels[l].g, s.nsm);
+    if (!s.march_on || l >= lb || !ml.ok || s.levels[l].g.interior < march_cells) continue;
+    p.mg[l] = ml.mg;
+    p.march[l] = (ml.staged && s.stage_on) ? 2 : 1;
+    if (p.march[l] == 2) vf->smem = std::max(vf->smem, ml.smem);
+  }
   int per_sm = 0;
-  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tail_kernel(s.D, vf->minb), VC_THREADS, 0);
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tail_kernel(s.D, vf->minb), VC_THREADS, vf->smem);
   if (e != cudaSuccess || per_sm < 1) { cudaGetLastError(); delete vf; return 0; }
   const char* e3 = getenv("WL_FUSED_BLOCKS_PER_SM");
   const int want = e3 ? atoi(e3) : 4;
@@ -718,6 +780,10 @@ int vcycle_fused_setup(Sim& s) {
   if (cudaMalloc(&tmp, sizeof(double) * 2 * vf->grid) != cudaSuccess) { delete vf; return wl_fail(WL_ERR_CUDA, "cudaMalloc partials"); }
   s.allocs.push_back(tmp);
   p.partials = (double*)tmp;
+  p.trace = nullptr;
+  if (getenv("WL_VC_TRACE") && atoi(getenv("WL_VC_TRACE"))) {
+    if (cudaMalloc(&tmp, sizeof(unsigned long long) * (2 * VC_TRACE_MAX + 2)) == cudaSuccess) { s.allocs.push_back(tmp); p.trace = (unsigned long long*)tmp; cudaMemsetAsync(tmp, 0, 8 * (2 * VC_TRACE_MAX + 2), s.stream); }
+  }
   vf->ok = true;
   // whole-solver mode: one launch and no host read per solver! when the finest level is small enough
   // per rank for a 2-blocks-per-SM persistent grid to stream it at full bandwidth
@@ -744,7 +810,7 @@ int vcycle_fused_run(Sim& s) {
   SolveArgs sa{};
   void* args[] = {&vf->p, &sa};
   wl_prof_begin(s, WL_PROF_VCTAIL);
-  cudaError_t e = cudaLaunchCooperativeKernel(tail_kernel(s.D, vf->minb), dim3(vf->grid), dim3(VC_THREADS), args, 0, s.stream);
+  cudaError_t e = cudaLaunchCooperativeKernel(tail_kernel(s.D, vf->minb), dim3(vf->grid), dim3(VC_THREADS), args, vf->smem, s.stream);
   ++s.launches;
   wl_prof_end(s, WL_PROF_VCTAIL, 0.0);
   return wl_cuda_check(s, e, "k_vcycle_tail");
@@ -766,7 +832,21 @@ int vcycle_fused_solve(Sim& s, double tol, int itmx, bool ghosts_valid, int slot
   sa.slot = slot;
   sa.divu = divu;
   void* args[] = {&vf->p, &sa};
-  cudaError_t e = cudaLaunchCooperativeKernel(tail_kernel(s.D, vf->minb), dim3(vf->grid), dim3(VC_THREADS), args, 0, s.stream);
+  cudaError_t e = cudaLaunchCooperativeKernel(tail_kernel(s.D, vf->minb), dim3(vf->grid), dim3(VC_THREADS), args, vf->smem, s.stream);
   ++s.launches;
   return wl_cuda_check(s, e, "k_vcycle_tail (solver!)");
+}
+
+// development aid (WL_VC_TRACE=1): the phase log of the last whole-solver launch → out[2n] = tag, out[2n+1] = globaltimer ns
+int vcycle_fused_trace(Sim& s, unsigned long long* out, int max_pairs, int* n) {
+  VcycleFused* vf = (VcycleFused*)s.vc_fused;
+  *n = 0;
+  if (!vf || !vf->p.trace) return 0;
+  unsigned long long cnt = 0;
+  cudaStreamSynchronize(s.stream);
+  cudaMemcpy(&cnt, vf->p.trace + 2 * VC_TRACE_MAX, sizeof(cnt), cudaMemcpyDeviceToHost);
+  const int m = (int)std::min<unsigned long long>(cnt, (unsigned long long)std::min(max_pairs, VC_TRACE_MAX));
+  cudaMemcpy(out, vf->p.trace, sizeof(unsigned long long) * 2 * m, cudaMemcpyDeviceToHost);
+  *n = m;
+  return 0;
 }

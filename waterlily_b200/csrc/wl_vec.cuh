@@ -125,37 +125,42 @@ template <int V>
 __device__ __forceinline__ Pack<V> mult_vals(const Lvl& l, int64_t I, const Pack<V>& xc, float xm1, float xp4, const Pack<V>& ym, const Pack<V>& yp,
                                              const Pack<V>& zm, const Pack<V>& zp, bool uni) {
   const GridD& g = l.g;
-  const Pack<V> Dc = uni ? splat<V>(l.uD) : ldp<V>(l.Dg + I);
-  Pack<V> s;
+  Pack<V> xm, xp, s;
+  xm.v[0] = xm1;
+#pragma unroll
+  for (int q = 1; q < V; ++q) xm.v[q] = xc.v[q - 1];
+#pragma unroll
+  for (int q = 0; q < V - 1; ++q) xp.v[q] = xc.v[q + 1];
+  xp.v[V - 1] = xp4;
+  if (uni) {  // a branch of its own: the constants are used as scalar operands (a select per coefficient cost 24 moves per pack)
+    const float L = l.uL, Dd = l.uD;
+#pragma unroll
+    for (int q = 0; q < V; ++q) {
+      float t = xc.v[q] * Dd;
+      t += (xm.v[q] * L + xp.v[q] * L);
+      t += (ym.v[q] * L + yp.v[q] * L);
+      t += (zm.v[q] * L + zp.v[q] * L);
+      s.v[q] = t;
+    }
+    return s;
+  }
+  const Pack<V> Dc = ldp<V>(l.Dg + I);
 #pragma unroll
   for (int q = 0; q < V; ++q) s.v[q] = xc.v[q] * Dc.v[q];
   {
-    Pack<V> Lc, Lp;
-    if (uni) { Lc = splat<V>(l.uL); Lp = Lc; }
-    else { Lc = ldp<V>(l.L + I); Lp = ld_xp<V>(l.L + I, Lc); }
-    Pack<V> xm, xp;
-    xm.v[0] = xm1;
-#pragma unroll
-    for (int q = 1; q < V; ++q) xm.v[q] = xc.v[q - 1];
-#pragma unroll
-    for (int q = 0; q < V - 1; ++q) xp.v[q] = xc.v[q + 1];
-    xp.v[V - 1] = xp4;
+    const Pack<V> Lc = ldp<V>(l.L + I), Lp = ld_xp<V>(l.L + I, Lc);
 #pragma unroll
     for (int q = 0; q < V; ++q) s.v[q] += (xm.v[q] * Lc.v[q] + xp.v[q] * Lp.v[q]);
   }
   {
     const float* Li = l.L + g.comp;
-    Pack<V> Lc, Lp;
-    if (uni) { Lc = splat<V>(l.uL); Lp = Lc; }
-    else { Lc = ldp<V>(Li + I); Lp = ldp<V>(Li + I + g.s[1]); }
+    const Pack<V> Lc = ldp<V>(Li + I), Lp = ldp<V>(Li + I + g.s[1]);
 #pragma unroll
     for (int q = 0; q < V; ++q) s.v[q] += (ym.v[q] * Lc.v[q] + yp.v[q] * Lp.v[q]);
   }
   {
     const float* Li = l.L + 2 * g.comp;
-    Pack<V> Lc, Lp;
-    if (uni) { Lc = splat<V>(l.uL); Lp = Lc; }
-    else { Lc = ldp<V>(Li + I); Lp = ldp<V>(Li + I + g.s[2]); }
+    const Pack<V> Lc = ldp<V>(Li + I), Lp = ldp<V>(Li + I + g.s[2]);
 #pragma unroll
     for (int q = 0; q < V; ++q) s.v[q] += (zm.v[q] * Lc.v[q] + zp.v[q] * Lp.v[q]);
   }
@@ -186,16 +191,45 @@ __device__ __forceinline__ int64_t zoff_p(const GridD& g, int k) { return (g.per
 // along z: a thread keeps the packs of planes k-1, k, k+1 of its column in registers (one new load per
 // step), its y-neighbours were loaded one step earlier by the adjacent threads of the same block (L1 hits),
 // and only the tile's perimeter rows come from L2.
-struct MarchGeom { int mx, my, ntx, nty, ntz, zchunk; };
+struct MarchGeom { int mx, my, ntx, nty, ntz, zchunk; };  // mx (a power of two) · my = threads of the block
+// position of the calling thread inside its mx × my tile (blocks may be 1-D: the persistent solver kernel)
+struct TilePos { int tx, ty; };
+__device__ __forceinline__ TilePos tile_pos(const MarchGeom& mg) {
+  const int tid = threadIdx.x + blockDim.x * threadIdx.y;
+  TilePos t; t.tx = tid & (mg.mx - 1); t.ty = tid / mg.mx;
+  return t;
+}
 template <class F>
 __device__ __forceinline__ void for_columns(const GridD& g, const MarchGeom& mg, F&& f) {
   const int ntiles = mg.ntx * mg.nty * mg.ntz;
+  const TilePos tp = tile_pos(mg);
   for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
     const int tx = t % mg.ntx, q = t / mg.ntx;
     const int ty = q % mg.nty, tz = q / mg.nty;
-    const int i = 1 + 4 * (tx * mg.mx + (int)threadIdx.x), j = 1 + ty * mg.my + (int)threadIdx.y;
+    const int i = 1 + 4 * (tx * mg.mx + tp.tx), j = 1 + ty * mg.my + tp.ty;
     const int k0 = 1 + tz * mg.zchunk, k1 = min(k0 + mg.zchunk - 1, g.n[2] - 2);
     if (i <= g.n[0] - 2 && j <= g.n[1] - 2) f(i, j, k0, k1);
+  }
+}
+
+// The persistent solver kernel has a fixed number of blocks: the (tile, plane) pairs are dealt out in equal
+// contiguous runs, planes fastest, so a block marches through ~total/gridDim planes of (at most two) tiles with one
+// pipeline fill per run instead of one per short z-chunk.
+template <class F>
+__device__ __forceinline__ void for_columns_even(const GridD& g, const MarchGeom& mg, F&& f) {
+  const int nz = g.n[2] - 2;
+  const int64_t total = (int64_t)mg.ntx * mg.nty * nz;
+  const int64_t per = (total + gridDim.x - 1) / gridDim.x;
+  int64_t lo = per * blockIdx.x;
+  const int64_t hi = min(total, lo + per);
+  const TilePos tp = tile_pos(mg);
+  while (lo < hi) {
+    const int t = (int)(lo / nz), kz = (int)(lo - (int64_t)t * nz);
+    const int len = (int)min(hi - lo, (int64_t)(nz - kz));
+    const int tx = t % mg.ntx, ty = t / mg.ntx;
+    const int i = 1 + 4 * (tx * mg.mx + tp.tx), j = 1 + ty * mg.my + tp.ty;
+    if (i <= g.n[0] - 2 && j <= g.n[1] - 2) f(i, j, 1 + kz, kz + len);
+    lo += len;
   }
 }
 
@@ -207,7 +241,10 @@ __device__ __forceinline__ void for_columns(const GridD& g, const MarchGeom& mg,
 // two planes ahead of the one being differenced; every neighbour read is then an LDS with a compile-time
 // shape: [my + 2 rows][4 pad | 4·mx | 4 pad floats], the x-halo cells in the inner float of each pad.
 // Each thread copies its own pack; edge threads add the tile's halo rows / cells (periodic wrap in the address).
-#define WL_NST 5
+#ifndef WL_AHEAD
+#define WL_AHEAD 2          // planes in flight beyond the three being read
+#endif
+#define WL_NST (3 + WL_AHEAD)
 __device__ __forceinline__ unsigned int wl_smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cp_async16(float* smem, const float* gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(wl_smem_u32(smem)), "l"(gmem) : "memory");
@@ -218,75 +255,98 @@ __device__ __forceinline__ void cp_async4(float* smem, const float* gmem) {
 __device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// Everything the inner loop needs is kept as running pointers / shared-memory byte addresses that advance by a
+// constant per step: the first version recomputed 64-bit addresses and ring slots (mod 5) from indices every step
+// and spent 270 instructions per step on ~60 of arithmetic — it was issue-bound, not memory-bound.
 struct StageCtx {
-  float* ring;       // WL_NST planes
-  int row, plane;    // floats per staged row / plane
-  int mine;          // offset of this thread's pack inside a staged plane
-  int64_t col;       // i + j*s1 of the thread's pack
-  int64_t colm, colp;  // the same for the y-neighbour rows (wrapped)
-  int64_t xm, xp;    // i-1 / i+4 (wrapped) + j*s1
+  unsigned int ring0;   // shared-memory byte address of this thread's pack in stage 0
+  unsigned int pbytes;  // bytes per staged plane
+  int rowb;             // bytes per staged row
+  int64_t col;          // i + j*s1 of the thread's pack
+  int colm, colp;       // offsets from col to the y-neighbour rows (wrapped)
+  int xm, xp;           // … to cell i-1 / i+4 of the row (wrapped)
   bool ylo, yhi, xlo, xhi;  // this thread also copies the tile's lower/upper halo row, left/right halo cell
 };
-__device__ __forceinline__ StageCtx stage_ctx(const GridD& g, float* ring, int i, int j) {
+__device__ __forceinline__ StageCtx stage_ctx(const GridD& g, const MarchGeom& mg, float* ring, int i, int j) {
   StageCtx c;
-  c.ring = ring;
-  c.row = 4 * blockDim.x + 8;
-  c.plane = (blockDim.y + 2) * c.row;
-  c.mine = (threadIdx.y + 1) * c.row + 4 + 4 * threadIdx.x;
+  const TilePos tp = tile_pos(mg);
+  const int row = 4 * mg.mx + 8;
+  c.rowb = row * (int)sizeof(float);
+  c.pbytes = (unsigned int)((mg.my + 2) * row * sizeof(float));
+  c.ring0 = wl_smem_u32(ring) + (unsigned int)(((tp.ty + 1) * row + 4 + 4 * tp.tx) * sizeof(float));
   const int64_t s1 = g.s[1];
   c.col = i + j * s1;
   const int n1 = g.n[1], n0 = g.n[0];
-  c.colm = i + (int64_t)((g.per[1] && j == 1) ? n1 - 2 : j - 1) * s1;
-  c.colp = i + (int64_t)((g.per[1] && j == n1 - 2) ? 1 : j + 1) * s1;
-  c.xm = ((g.per[0] && i == 1) ? n0 - 2 : i - 1) + j * s1;
-  c.xp = ((g.per[0] && i + 3 == n0 - 2) ? 1 : i + 4) + j * s1;
-  c.ylo = threadIdx.y == 0; c.yhi = threadIdx.y == blockDim.y - 1;
-  c.xlo = threadIdx.x == 0; c.xhi = threadIdx.x == blockDim.x - 1;
+  c.colm = (int)((((g.per[1] && j == 1) ? n1 - 2 : j - 1) - j) * s1);
+  c.colp = (int)((((g.per[1] && j == n1 - 2) ? 1 : j + 1) - j) * s1);
+  c.xm = ((g.per[0] && i == 1) ? n0 - 2 : i - 1) - i;
+  c.xp = ((g.per[0] && i + 3 == n0 - 2) ? 1 : i + 4) - i;
+  c.ylo = tp.ty == 0; c.yhi = tp.ty == mg.my - 1;
+  c.xlo = tp.tx == 0; c.xhi = tp.tx == mg.mx - 1;
   return c;
 }
-// requests plane P (0 … n2-1; wrapped if the level is periodic in z) of field S into ring stage `st`
-__device__ __forceinline__ void stage_issue(const StageCtx& c, const GridD& g, const float* __restrict__ S, int P, int st) {
+__device__ __forceinline__ void cp_async16s(unsigned int smem, const float* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async4s(unsigned int smem, const float* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem), "l"(gmem) : "memory");
+}
+// requests the plane at `src` (pointer to its cell (0,0)) into the stage whose pack address is `dst`
+__device__ __forceinline__ void stage_issue(const StageCtx& c, const float* __restrict__ src, unsigned int dst) {
+  const float* p = src + c.col;
+  cp_async16s(dst, p);
+  if (c.ylo) cp_async16s(dst - c.rowb, p + c.colm);
+  if (c.yhi) cp_async16s(dst + c.rowb, p + c.colp);
+  if (c.xlo) cp_async4s(dst - 4, p + c.xm);
+  if (c.xhi) cp_async4s(dst + 16, p + c.xp);
+}
+// plane P (0 … n2-1) of a field, wrapped if the level is periodic in z
+__device__ __forceinline__ const float* plane_ptr(const GridD& g, const float* __restrict__ S, int P) {
   if (g.per[2]) P = P == 0 ? g.n[2] - 2 : (P == g.n[2] - 1 ? 1 : P);
-  const float* src = S + (int64_t)P * g.s[2];
-  float* dst = c.ring + st * c.plane;
-  cp_async16(dst + c.mine, src + c.col);
-  if (c.ylo) cp_async16(dst + c.mine - c.row, src + c.colm);
-  if (c.yhi) cp_async16(dst + c.mine + c.row, src + c.colp);
-  if (c.xlo) cp_async4(dst + c.mine - 1, src + c.xm);
-  if (c.xhi) cp_async4(dst + c.mine + 4, src + c.xp);
+  return S + (int64_t)P * g.s[2];
 }
-__device__ __forceinline__ Pack<4> lds4(const float* p) {
-  const float4 t = *reinterpret_cast<const float4*>(p);
-  Pack<4> r; r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w; return r;
+__device__ __forceinline__ Pack<4> lds4(unsigned int a) {
+  Pack<4> r;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]) : "r"(a));
+  return r;
 }
-// Marches a column block over planes k0 … k1 with field S staged: body(k, I, xc, Ax-operands…) is called with
-// the seven neighbour values of the thread's pack.  `pre(k, I)` runs before the step's wait + barrier (issue the
-// step's own global loads there: they overlap the wait).  All threads of the block must call it (barriers).
+__device__ __forceinline__ float lds1(unsigned int a) {
+  float r;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(a));
+  return r;
+}
+// Marches a column block over planes k0 … k1 with field S staged: body(k, I, xc, xm1, xp4, ym, yp, zm, zp) is called with
+// the neighbour values of the thread's pack.  `pre(k, I)` runs before the step's wait + barrier (issue the step's own
+// global loads there: they overlap the wait).  All threads of the block must call it (barriers).
 template <class Pre, class Body>
-__device__ __forceinline__ void march_staged(const GridD& g, const float* __restrict__ S, float* ring, int i, int j, int k0, int k1, Pre&& pre, Body&& body) {
-  const StageCtx c = stage_ctx(g, ring, i, j);
-  // planes k0-1, k0, k0+1, k0+2 → stages 0, 1, 2, 3 (one group each)
+__device__ __forceinline__ void march_staged(const GridD& g, const MarchGeom& mg, const float* __restrict__ S, float* ring, int i, int j, int k0, int k1,
+                                             Pre&& pre, Body&& body) {
+  const StageCtx c = stage_ctx(g, mg, ring, i, j);
+  const unsigned int ring_end = c.ring0 + WL_NST * c.pbytes;
+  // planes k0-1 … k0+WL_AHEAD → stages 0 … 1+WL_AHEAD (one group each)
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    if (k0 - 1 + q <= k1 + 1) stage_issue(c, g, S, k0 - 1 + q, q);
+  for (int q = 0; q < 2 + WL_AHEAD; ++q) {
+    if (k0 - 1 + q <= k1 + 1) stage_issue(c, plane_ptr(g, S, k0 - 1 + q), c.ring0 + q * c.pbytes);
     cp_async_commit_group();
   }
-  int st = 1;  // stage of plane k
+  // stages of planes k-1, k, k+1 and of the plane requested at step k (k+1+WL_AHEAD: it takes the stage of plane k-2)
+  unsigned int am = c.ring0, ac = c.ring0 + c.pbytes, ap = c.ring0 + 2 * c.pbytes, ai = c.ring0 + (WL_NST - 1) * c.pbytes;
+  const float* nxt = S + (int64_t)(k0 + 1 + WL_AHEAD) * g.s[2];  // (a periodic wrap can only concern the last plane of the level: handled below)
+  const int klast = k1 - WL_AHEAD;                                // last step that still requests a plane (k+1+WL_AHEAD ≤ k1+1)
   int64_t I = c.col + (int64_t)k0 * g.s[2];
-  for (int k = k0; k <= k1; ++k, I += g.s[2]) {
+#pragma unroll 1
+  for (int k = k0; k <= k1; ++k) {
     pre(k, I);
-    cp_async_wait_group<1>();   // planes ≤ k+1 have landed (the newest group, k+2, may still be in flight)
-    __syncthreads();             // … for every thread of the block; and everyone is done with plane k-2
-    {                            // plane k+3 takes the stage plane k-2 occupied
-      const int P = k + 3;
-      if (P <= k1 + 1) stage_issue(c, g, S, P, (st + 3) % WL_NST);
-      cp_async_commit_group();
-    }
-    const float* pc = c.ring + st * c.plane + c.mine;
-    const float* pm = c.ring + ((st + WL_NST - 1) % WL_NST) * c.plane + c.mine;
-    const float* pp = c.ring + ((st + 1) % WL_NST) * c.plane + c.mine;
-    body(k, I, lds4(pc), pc[-1], pc[4], lds4(pc - c.row), lds4(pc + c.row), lds4(pm), lds4(pp));
-    st = (st + 1) % WL_NST;
+    cp_async_wait_group<WL_AHEAD - 1>();   // planes ≤ k+1 have landed (the newer groups may still be in flight)
+    __syncthreads();                        // … for every thread of the block; and everyone is done with plane k-2
+    if (k <= klast) stage_issue(c, (g.per[2] && k + 1 + WL_AHEAD == g.n[2] - 1) ? S + g.s[2] : nxt, ai);
+    cp_async_commit_group();
+    body(k, I, lds4(ac), lds1(ac - 4), lds1(ac + 16), lds4(ac - c.rowb), lds4(ac + c.rowb), lds4(am), lds4(ap));
+    am = ac; ac = ap;
+    ap += c.pbytes; if (ap == ring_end) ap = c.ring0;
+    ai += c.pbytes; if (ai == ring_end) ai = c.ring0;
+    nxt += g.s[2];
+    I += g.s[2];
   }
   cp_async_wait_group<0>();
   __syncthreads();  // the ring is reused by the block's next tile
@@ -372,6 +432,116 @@ __device__ __forceinline__ void prolong_increment_init(const Lvl& f, const Lvl& 
   stp<V>(f.r + I, r);
   stp<V>(f.x + I, x);
   stp<V>(f.eps + I, en);
+}
+
+// ---- the stencil phases on one column tile (3-D, V = 4) — shared by the per-level kernels (wl_poisson.cu) and
+// ---- the persistent solver kernel (wl_vcycle.cu).  Arithmetic per cell is that of the for_rows kernels.
+// pcg!: z = Aϵ, acc += z·ϵ (Poisson.jl:130-131)
+__device__ __forceinline__ void tile_pcg_mult(const Lvl& l, const MarchGeom& mg, float* ring, int i, int j, int k0, int k1, double& acc) {
+  // the pack-mask byte of the NEXT plane is requested one step early: a load issued and consumed within the same step
+  // exposed a full HBM latency per step (the largest stall of the first profile)
+  bool uni = false, uni_n = false;
+  march_staged(l.g, mg, l.eps, ring, i, j, k0, k1,
+    [&](int k, int64_t I) {
+      uni = k == k0 ? pack_uniform<4>(l, I) : uni_n;
+      uni_n = pack_uniform<4>(l, I + l.g.s[2]);
+    },
+    [&](int, int64_t I, const Pack<4>& ec, float xm1, float xp4, const Pack<4>& ym, const Pack<4>& yp, const Pack<4>& zm, const Pack<4>& zp) {
+      const Pack<4> z = mult_vals<4>(l, I, ec, xm1, xp4, ym, yp, zm, zp, uni);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc += (double)z.v[q] * (double)ec.v[q];
+      stp<4>(l.z + I, z);
+    });
+}
+// increment!: r -= Aϵ, x += ϵ, acc += r·r (Poisson.jl:101-102, :146); r and x of the next plane travel one step ahead too
+__device__ __forceinline__ void tile_increment(const Lvl& l, const MarchGeom& mg, float* ring, int i, int j, int k0, int k1, double& acc) {
+  bool uni = false, uni_n = false;
+  Pack<4> r, x, rn, xn;
+  march_staged(l.g, mg, l.eps, ring, i, j, k0, k1,
+    [&](int k, int64_t I) {
+      if (k == k0) { uni = pack_uniform<4>(l, I); r = ldp<4>(l.r + I); x = ldp<4>(l.x + I); }
+      else { uni = uni_n; r = rn; x = xn; }
+      const int64_t In = I + l.g.s[2];  // plane k1+1 is a ghost / halo plane of the same arrays: readable, never used
+      uni_n = pack_uniform<4>(l, In); rn = ldp<4>(l.r + In); xn = ldp<4>(l.x + In);
+    },
+    [&](int, int64_t I, const Pack<4>& ec, float xm1, float xp4, const Pack<4>& ym, const Pack<4>& yp, const Pack<4>& zm, const Pack<4>& zp) {
+      const Pack<4> ae = mult_vals<4>(l, I, ec, xm1, xp4, ym, yp, zm, zp, uni);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        r.v[q] = r.v[q] - ae.v[q];
+        x.v[q] = x.v[q] + ec.v[q];
+        acc += (double)r.v[q] * (double)r.v[q];
+      }
+      stp<4>(l.r + I, r);
+      stp<4>(l.x + I, x);
+    });
+}
+// residual!: r = iD == 0 ? 0 : z - Ax (z read, or evaluated as div(divu)), a0 += r, a1 += r·r; optionally ϵ = r·iD
+__device__ __forceinline__ void tile_residual(const Lvl& l, const MarchGeom& mg, float* ring, int i, int j, int k0, int k1, int write_eps,
+                                              const float* __restrict__ divu, double& a0, double& a1) {
+  bool uni = false, uni_n = false;
+  Pack<4> zc;
+  march_staged(l.g, mg, l.x, ring, i, j, k0, k1,
+    [&](int k, int64_t I) {
+      uni = k == k0 ? pack_uniform<4>(l, I) : uni_n;
+      uni_n = pack_uniform<4>(l, I + l.g.s[2]);
+      zc = divu ? div_pack<3, 4>(l.g, divu, I) : ldp<4>(l.z + I);
+    },
+    [&](int, int64_t I, const Pack<4>& xc, float xm1, float xp4, const Pack<4>& ym, const Pack<4>& yp, const Pack<4>& zm, const Pack<4>& zp) {
+      const Pack<4> ax = mult_vals<4>(l, I, xc, xm1, xp4, ym, yp, zm, zp, uni), id = ld_iD<4>(l, I, uni);
+      Pack<4> r;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        r.v[q] = id.v[q] == 0.f ? 0.f : zc.v[q] - ax.v[q];
+        a0 += (double)r.v[q];
+        a1 += (double)r.v[q] * (double)r.v[q];
+      }
+      stp<4>(l.r + I, r);
+      if (write_eps) {
+        Pack<4> e;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) e.v[q] = r.v[q] * id.v[q];
+        stp<4>(l.eps + I, e);
+      }
+    });
+}
+// prolongate! + increment! + head of pcg! (see prolong_increment_init): ϵ of a fine pack (i = 1+4t) is {c, c, c', c'}
+// with (c, c') the aligned coarse pair at ci = 1+2t, so a pack costs one 8-byte load per coarse row it touches
+__device__ __forceinline__ Pack<4> pro_pack(const float* __restrict__ crow, int ci) {
+  const float2 c = *reinterpret_cast<const float2*>(crow + ci);
+  Pack<4> e; e.v[0] = c.x; e.v[1] = c.x; e.v[2] = c.y; e.v[3] = c.y;
+  return e;
+}
+__device__ __forceinline__ void tile_prolong(const Lvl& f, const Lvl& c, const ProMap& m, int i, int j, int k0, int k1, double& a0, double& a1) {
+  const GridD& g = f.g;
+  const float* __restrict__ xc = c.x;
+  const int64_t cs1 = c.g.s[1], cs2 = c.g.s[2];
+  int64_t I = i + j * g.s[1] + (int64_t)k0 * g.s[2];
+  const int ci = (i + 1) >> 1;
+  const int cim = pro_cidx(m, 0, i - 1), cip = pro_cidx(m, 0, i + 4);
+  const int64_t Jy = pro_cidx(m, 1, j) * cs1, Jym = pro_cidx(m, 1, j - 1) * cs1, Jyp = pro_cidx(m, 1, j + 1) * cs1;
+  for (int k = k0; k <= k1; ++k, I += g.s[2]) {
+    const int64_t Jz = pro_cidx(m, 2, k) * cs2, Jzm = pro_cidx(m, 2, k - 1) * cs2, Jzp = pro_cidx(m, 2, k + 1) * cs2;
+    const float* row = xc + Jy + Jz;
+    const Pack<4> e = pro_pack(row, ci);
+    const bool uni = pack_uniform<4>(f, I);
+    const Pack<4> s = mult_vals<4>(f, I, e, row[cim], row[cip], pro_pack(xc + Jym + Jz, ci), pro_pack(xc + Jyp + Jz, ci), pro_pack(xc + Jy + Jzm, ci),
+                                   pro_pack(xc + Jy + Jzp, ci), uni);
+    Pack<4> r = ldp<4>(f.r + I), x = ldp<4>(f.x + I);
+    const Pack<4> id = ld_iD<4>(f, I, uni);
+    Pack<4> en;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      r.v[q] = r.v[q] - s.v[q];
+      x.v[q] = x.v[q] + e.v[q];
+      en.v[q] = r.v[q] * id.v[q];
+      a0 += (double)r.v[q] * (double)en.v[q];
+      a1 += (double)r.v[q] * (double)r.v[q];
+    }
+    stp<4>(f.r + I, r);
+    stp<4>(f.x + I, x);
+    stp<4>(f.eps + I, en);
+  }
 }
 
 // interior rows; f(i, j, k, I) is called for the first cell of each V-group
