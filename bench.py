@@ -48,6 +48,14 @@ def workload_name(N):
     return f"3D Taylor-Green vortex {N}^3 periodic, Re=1600, Float32, MultiLevelPoisson"
 
 
+def bench_config(N, gpus):
+    """`config` — identical on both arms for the same command line (the driver compares them); run-dependent details
+    (V-cycle counts, level count, collective count, CPU sample) go into the top-level `details` key."""
+    par = "1 GPU" if gpus == 1 else (f"z-slab x{gpus}: {N // gpus} planes/rank, peer-memory (NVLink) halo exchange and all-reduce from inside "
+                                     "the kernels, NCCL for bootstrap only, coarse levels replicated")
+    return {"workload": workload_name(N), "l2": "working set (~17 GB at 512^3) far exceeds the 126 MB L2; no flush needed", "parallelism": par}
+
+
 def make_tgv(cls, N, **kw):
     ulam, nu = tgv_ulam(N)
     return cls((N, N, N), (0, 0, 0), N, U=1, nu=nu, ulam=ulam, perdir=(1, 2, 3), **kw)
@@ -142,7 +150,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": "Mcell-updates/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.size), "sample": sample},
+        "config": bench_config(args.size, args.gpus), "details": {"sample": sample},
         "cpu_baseline": {"value": val, "unit": "Mcell-updates/s", "cores": cores, "kind": "port", "sample": sample,
                          "note": "the reference is Julia and cannot run in this image; this is the C++/OpenMP oracle, a literal un-fused restatement of it"},
         "e2e": {"value": val, "unit": "Mcell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -295,10 +303,9 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": "Mcell-updates/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(N), "multigrid_levels": eng.nlevels(),
-                   "vcycles_per_solve": ns, "l2": "working set (~17 GB at 512^3) far exceeds the 126 MB L2; no flush needed",
-                   "parallelism": "1 GPU" if world == 1 else f"z-slab x{world}: {info['nz_local']} planes/rank, NCCL halo exchange + all-reduce, coarse levels replicated",
-                   "nccl_calls_per_step": collectives / K if world > 1 else 0},
+        "config": bench_config(N, world),
+        "details": {"multigrid_levels": eng.nlevels(), "vcycles_per_solve": ns, "planes_per_rank": info["nz_local"],
+                    "nccl_calls_per_step": collectives / K if world > 1 else 0},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
     }
     print(json.dumps(line))

@@ -8,4 +8,4 @@ steps = d['steps']
 for k, v in r['kernels'].items():
     gbs = v['GB/s']
     print(f"  {k:18s} {v['ms_total']/steps:8.3f} ms/step  {v['launches']/steps:5.1f} launches/step  {'' if not gbs else f'{gbs:7.0f} GB/s'}")
-print("vcycles", d['config'].get('vcycles_per_solve'))
+print("vcycles", (d.get('details') or d['config']).get('vcycles_per_solve'))

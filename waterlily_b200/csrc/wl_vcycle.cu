@@ -701,8 +701,12 @@ struct VcycleFused {
   bool ok = false;
   bool solve = false;  // the whole solver! runs in the kernel (level 1 of the reference included)
 };
-static const void* tail_kernel(int D, int) {
-  return D == 2 ? (const void*)k_vcycle_tail<2, WL_VC_MINB> : (const void*)k_vcycle_tail<3, WL_VC_MINB>;
+// MINB = resident blocks per SM the register allocation aims for: 2 (128 registers, no spills) is best for the latency-bound
+// coarse tail; the whole-solver mode also streams the finest level, where 3 blocks (80 registers) hide HBM latency better
+// (256³ per rank: 5.30 → 4.96 ms/step)
+static const void* tail_kernel(int D, int minb) {
+  if (D == 2) return (const void*)k_vcycle_tail<2, 2>;
+  return minb >= 3 ? (const void*)k_vcycle_tail<3, 3> : (const void*)k_vcycle_tail<3, 2>;
 }
 
 static int ilog2(int v) { int l = 0; while ((1 << (l + 1)) <= v) ++l; return l; }
@@ -751,8 +755,14 @@ int vcycle_fused_setup(Sim& s) {
     while (bx < nxi / V && bx < 128) bx <<= 1;
     p.bxlog[l] = ilog2(bx);
   }
+  // whole-solver mode: one launch and no host read per solver! when the finest level is small enough per rank that the
+  // launch and host-read latencies of the per-level kernels outweigh their higher streaming bandwidth (measured at 512³:
+  // 8 ranks, 16.7 M cells each: 4.36 vs 4.49 ms/step; 2 ranks, 67 M cells: 11.3 vs 10.1)
+  const char* e5 = getenv("WL_FUSED_SOLVE_CELLS");
+  const int64_t solve_cells = e5 ? atoll(e5) : (int64_t)40 << 20;
+  vf->solve = s.levels[0].g.interior <= solve_cells;
   const char* e4 = getenv("WL_FUSED_MINB");
-  vf->minb = e4 ? atoi(e4) : 2;
+  vf->minb = e4 ? atoi(e4) : (vf->solve ? 3 : 2);
   // z-marching tiles for the levels that are bandwidth-bound (3-D, grid mode, large enough)
   const char* e6 = getenv("WL_FUSED_MARCH_CELLS");
   const int64_t march_cells = e6 ? atoll(e6) : (int64_t)1 << 20;
@@ -785,11 +795,6 @@ int vcycle_fused_setup(Sim& s) {
     if (cudaMalloc(&tmp, sizeof(unsigned long long) * (2 * VC_TRACE_MAX + 2)) == cudaSuccess) { s.allocs.push_back(tmp); p.trace = (unsigned long long*)tmp; cudaMemsetAsync(tmp, 0, 8 * (2 * VC_TRACE_MAX + 2), s.stream); }
   }
   vf->ok = true;
-  // whole-solver mode: one launch and no host read per solver! when the finest level is small enough
-  // per rank for a 2-blocks-per-SM persistent grid to stream it at full bandwidth
-  const char* e5 = getenv("WL_FUSED_SOLVE_CELLS");
-  const int64_t solve_cells = e5 ? atoll(e5) : (int64_t)96 << 20;  // measured: 67 M cells per rank gains 0.4 ms/step, 134 M loses 2.4 ms (2 blocks/SM stream the finest level at lower bandwidth)
-  vf->solve = s.levels[0].g.interior <= solve_cells;
   s.vc_fused = vf;
   s.vc_first = lf;
   s.vc_solve = vf->solve;
