@@ -65,6 +65,36 @@ __device__ __forceinline__ bool pack_uniform(const Lvl& l, int64_t I) {
   if (V != 4 || l.umask == nullptr) return false;
   return l.umask[(I + l.g.lead) >> 2] == 0;
 }
+// The staged marches read the mask byte of their pack once per plane.  The byte is tiny but its load is a full HBM
+// round trip: consumed in the step that issued it (or the next: a step of a fully fed SM is ~0.4 µs, the loaded HBM
+// latency ~1 µs) it was the largest stall of the staged kernels (32 % of the warp samples of k_pcg_mult_s waited on the
+// compare).  MaskPipe keeps the raw byte of the next plane in a register, prefetches the byte WL_MASK_PF planes ahead
+// into L1, and compares only where the flag is used.
+#ifndef WL_MASK_PF
+#define WL_MASK_PF 6
+#endif
+// planes ahead at which the per-step operand loads of the marching tiles (r, x, div u, coarse x) are prefetched into L1
+#ifndef WL_PF
+#define WL_PF 3
+#endif
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+struct MaskPipe {
+  unsigned int cur, nxt;
+  __device__ __forceinline__ unsigned int raw(const Lvl& l, int64_t I) const { return l.umask == nullptr ? 1u : (unsigned int)l.umask[(I + l.g.lead) >> 2]; }
+  // call at the top of step k (plane k, first cell of the pack at I); planes k0 … k1 ≤ n2 - 2
+  __device__ __forceinline__ void step(const Lvl& l, int k, int k0, int64_t I) {
+    const int64_t s2 = l.g.s[2];
+    cur = k == k0 ? raw(l, I) : nxt;
+    nxt = raw(l, I + s2);
+    if (l.umask != nullptr && k + WL_MASK_PF <= l.g.n[2] - 1)
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(l.umask + ((I + WL_MASK_PF * s2 + l.g.lead) >> 2)));
+  }
+  __device__ __forceinline__ bool uni() const {
+    unsigned int m = cur;
+    asm volatile("" : "+r"(m));  // the compare stays at the point of use
+    return m == 0u;
+  }
+};
 template <int V>
 __device__ __forceinline__ Pack<V> splat(float v) {
   Pack<V> r;
@@ -440,14 +470,11 @@ __device__ __forceinline__ void prolong_increment_init(const Lvl& f, const Lvl& 
 __device__ __forceinline__ void tile_pcg_mult(const Lvl& l, const MarchGeom& mg, float* ring, int i, int j, int k0, int k1, double& acc) {
   // the pack-mask byte of the NEXT plane is requested one step early: a load issued and consumed within the same step
   // exposed a full HBM latency per step (the largest stall of the first profile)
-  bool uni = false, uni_n = false;
+  MaskPipe mp;
   march_staged(l.g, mg, l.eps, ring, i, j, k0, k1,
-    [&](int k, int64_t I) {
-      uni = k == k0 ? pack_uniform<4>(l, I) : uni_n;
-      uni_n = pack_uniform<4>(l, I + l.g.s[2]);
-    },
+    [&](int k, int64_t I) { mp.step(l, k, k0, I); },
     [&](int, int64_t I, const Pack<4>& ec, float xm1, float xp4, const Pack<4>& ym, const Pack<4>& yp, const Pack<4>& zm, const Pack<4>& zp) {
-      const Pack<4> z = mult_vals<4>(l, I, ec, xm1, xp4, ym, yp, zm, zp, uni);
+      const Pack<4> z = mult_vals<4>(l, I, ec, xm1, xp4, ym, yp, zm, zp, mp.uni());
 #pragma unroll
       for (int q = 0; q < 4; ++q) acc += (double)z.v[q] * (double)ec.v[q];
       stp<4>(l.z + I, z);
@@ -455,17 +482,19 @@ __device__ __forceinline__ void tile_pcg_mult(const Lvl& l, const MarchGeom& mg,
 }
 // increment!: r -= Aϵ, x += ϵ, acc += r·r (Poisson.jl:101-102, :146); r and x of the next plane travel one step ahead too
 __device__ __forceinline__ void tile_increment(const Lvl& l, const MarchGeom& mg, float* ring, int i, int j, int k0, int k1, double& acc) {
-  bool uni = false, uni_n = false;
+  MaskPipe mp;
   Pack<4> r, x, rn, xn;
   march_staged(l.g, mg, l.eps, ring, i, j, k0, k1,
     [&](int k, int64_t I) {
-      if (k == k0) { uni = pack_uniform<4>(l, I); r = ldp<4>(l.r + I); x = ldp<4>(l.x + I); }
-      else { uni = uni_n; r = rn; x = xn; }
+      mp.step(l, k, k0, I);
+      if (k == k0) { r = ldp<4>(l.r + I); x = ldp<4>(l.x + I); }
+      else { r = rn; x = xn; }
       const int64_t In = I + l.g.s[2];  // plane k1+1 is a ghost / halo plane of the same arrays: readable, never used
-      uni_n = pack_uniform<4>(l, In); rn = ldp<4>(l.r + In); xn = ldp<4>(l.x + In);
+      rn = ldp<4>(l.r + In); xn = ldp<4>(l.x + In);
+      if (WL_PF > 1 && k + WL_PF <= l.g.n[2] - 1) { prefetch_l1(l.r + I + WL_PF * l.g.s[2]); prefetch_l1(l.x + I + WL_PF * l.g.s[2]); }
     },
     [&](int, int64_t I, const Pack<4>& ec, float xm1, float xp4, const Pack<4>& ym, const Pack<4>& yp, const Pack<4>& zm, const Pack<4>& zp) {
-      const Pack<4> ae = mult_vals<4>(l, I, ec, xm1, xp4, ym, yp, zm, zp, uni);
+      const Pack<4> ae = mult_vals<4>(l, I, ec, xm1, xp4, ym, yp, zm, zp, mp.uni());
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         r.v[q] = r.v[q] - ae.v[q];
@@ -479,15 +508,27 @@ __device__ __forceinline__ void tile_increment(const Lvl& l, const MarchGeom& mg
 // residual!: r = iD == 0 ? 0 : z - Ax (z read, or evaluated as div(divu)), a0 += r, a1 += r·r; optionally ϵ = r·iD
 __device__ __forceinline__ void tile_residual(const Lvl& l, const MarchGeom& mg, float* ring, int i, int j, int k0, int k1, int write_eps,
                                               const float* __restrict__ divu, double& a0, double& a1) {
-  bool uni = false, uni_n = false;
+  MaskPipe mp;
   Pack<4> zc;
+  const TilePos tpos = tile_pos(mg);
+  const bool xhi = tpos.tx == mg.mx - 1, yhi = tpos.ty == mg.my - 1;
   march_staged(l.g, mg, l.x, ring, i, j, k0, k1,
     [&](int k, int64_t I) {
-      uni = k == k0 ? pack_uniform<4>(l, I) : uni_n;
-      uni_n = pack_uniform<4>(l, I + l.g.s[2]);
+      mp.step(l, k, k0, I);
       zc = divu ? div_pack<3, 4>(l.g, divu, I) : ldp<4>(l.z + I);
+      // the operands of a later plane's z: own pack of each component (the neighbour threads fetch theirs), the cell
+      // right of / row above the tile by its edge threads; u₃ of plane k+1 is the pack fetched one step later
+      if (WL_PF > 0 && k + WL_PF <= l.g.n[2] - 1) {
+        if (divu) {
+          const float* q = divu + I + WL_PF * l.g.s[2];
+          prefetch_l1(q); prefetch_l1(q + l.g.comp); prefetch_l1(q + 2 * l.g.comp);
+          if (xhi) prefetch_l1(q + 4);
+          if (yhi) prefetch_l1(q + l.g.comp + l.g.s[1]);
+        } else prefetch_l1(l.z + I + WL_PF * l.g.s[2]);
+      }
     },
     [&](int, int64_t I, const Pack<4>& xc, float xm1, float xp4, const Pack<4>& ym, const Pack<4>& yp, const Pack<4>& zm, const Pack<4>& zp) {
+      const bool uni = mp.uni();
       const Pack<4> ax = mult_vals<4>(l, I, xc, xm1, xp4, ym, yp, zm, zp, uni), id = ld_iD<4>(l, I, uni);
       Pack<4> r;
 #pragma unroll
@@ -521,6 +562,7 @@ __device__ __forceinline__ void tile_prolong(const Lvl& f, const Lvl& c, const P
   const int cim = pro_cidx(m, 0, i - 1), cip = pro_cidx(m, 0, i + 4);
   const int64_t Jy = pro_cidx(m, 1, j) * cs1, Jym = pro_cidx(m, 1, j - 1) * cs1, Jyp = pro_cidx(m, 1, j + 1) * cs1;
   for (int k = k0; k <= k1; ++k, I += g.s[2]) {
+    if (WL_PF > 0 && k + WL_PF <= g.n[2] - 1) { prefetch_l1(f.r + I + WL_PF * g.s[2]); prefetch_l1(f.x + I + WL_PF * g.s[2]); }
     const int64_t Jz = pro_cidx(m, 2, k) * cs2, Jzm = pro_cidx(m, 2, k - 1) * cs2, Jzp = pro_cidx(m, 2, k + 1) * cs2;
     const float* row = xc + Jy + Jz;
     const Pack<4> e = pro_pack(row, ci);
