@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(256) k_residual(Lvl l, ReduceWS ws, FinArgs fa
     for (int q = 0; q < V; ++q) {
       r.v[q] = id.v[q] == 0.f ? 0.f : zc.v[q] - ax.v[q];
       acc[0] += (double)r.v[q];
-      acc[1] += (double)r.v[q] * (double)r.v[q];
+      acc[1] = dfma(r.v[q], r.v[q], acc[1]);
     }
     stp<V>(l.r + I, r);
     if (write_eps) {  // ϵ = r·iD of the Jacobi! that opens the V-cycle (Poisson.jl:111): saves its own pass over r, iD
@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(256) k_sub_mean(Lvl l, ReduceWS ws, FinArgs fa
   for_rows<V>(l.g, [&](int, int, int, int64_t I) {
     Pack<V> r = ldp<V>(l.r + I);
 #pragma unroll
-    for (int q = 0; q < V; ++q) { r.v[q] = r.v[q] - s; acc[0] += (double)r.v[q] * (double)r.v[q]; }
+    for (int q = 0; q < V; ++q) { r.v[q] = r.v[q] - s; acc[0] = dfma(r.v[q], r.v[q], acc[0]); }
     stp<V>(l.r + I, r);
     if (write_eps) {
       const Pack<V> id = ld_iD<V>(l, I, pack_uniform<V>(l, I));
@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(256) k_increment(Lvl l, ReduceWS ws, FinArgs f
     for (int q = 0; q < V; ++q) {
       r.v[q] = r.v[q] - ae.v[q];
       x.v[q] = x.v[q] + ec.v[q];
-      acc[0] += (double)r.v[q] * (double)r.v[q];
+      acc[0] = dfma(r.v[q], r.v[q], acc[0]);
     }
     stp<V>(l.r + I, r);
     stp<V>(l.x + I, x);
@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(256) k_residual_m(Lvl l, MarchGeom mg, ReduceW
       for (int q = 0; q < 4; ++q) {
         r.v[q] = id.v[q] == 0.f ? 0.f : zc.v[q] - ax.v[q];
         acc[0] += (double)r.v[q];
-        acc[1] += (double)r.v[q] * (double)r.v[q];
+        acc[1] = dfma(r.v[q], r.v[q], acc[1]);
       }
       stp<4>(l.r + I, r);
       if (write_eps) {
@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(256) k_increment_m(Lvl l, MarchGeom mg, Reduce
       for (int q = 0; q < 4; ++q) {
         r.v[q] = r.v[q] - ae.v[q];
         x.v[q] = x.v[q] + ec.v[q];
-        acc[0] += (double)r.v[q] * (double)r.v[q];
+        acc[0] = dfma(r.v[q], r.v[q], acc[0]);
       }
       stp<4>(l.r + I, r);
       stp<4>(l.x + I, x);
@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(256) k_pcg_mult_m(Lvl l, MarchGeom mg, ReduceW
       const Pack<4> ep = ldp<4>(l.eps + I + zoff_p(g, k));
       const Pack<4> z = mult_zreg<4>(l, l.eps, i, j, I, ec, em, ep, pack_uniform<4>(l, I));
 #pragma unroll
-      for (int q = 0; q < 4; ++q) acc[0] += (double)z.v[q] * (double)ec.v[q];
+      for (int q = 0; q < 4; ++q) acc[0] = dfma(z.v[q], ec.v[q], acc[0]);
       stp<4>(l.z + I, z);
       em = ec; ec = ep;
     }
@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(256, WL_STAGE_MINB) k_residual_s(Lvl l, MarchG
 }
 __global__ void __launch_bounds__(256) k_prolong_increment_init_m(Lvl f, Lvl c, ProMap m, MarchGeom mg, ReduceWS ws, FinArgs fa) {
   double acc[2] = {0.0, 0.0};
-  for_columns(f.g, mg, [&](int i, int j, int k0, int k1) { tile_prolong(f, c, m, i, j, k0, k1, acc[0], acc[1]); });
+  for_columns(f.g, mg, [&](int i, int j, int k0, int k1) { tile_prolong(f, c, m, mg, i, j, k0, k1, acc[0], acc[1]); });
   double tot[2];
   if (grid_reduce<2>(acc, ws, tot)) finish_reduction(FIN_INC_INIT, fa, tot[0], tot[1]);
 }
@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(256) k_pcg_init(Lvl l, ReduceWS ws, FinArgs fa
     const Pack<V> r = ldp<V>(l.r + I), id = ld_iD<V>(l, I, pack_uniform<V>(l, I));
     Pack<V> e;
 #pragma unroll
-    for (int q = 0; q < V; ++q) { e.v[q] = r.v[q] * id.v[q]; acc[0] += (double)r.v[q] * (double)e.v[q]; }
+    for (int q = 0; q < V; ++q) { e.v[q] = r.v[q] * id.v[q]; acc[0] = dfma(r.v[q], e.v[q], acc[0]); }
     stp<V>(l.eps + I, e);
   });
   double tot[1];
@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(256) k_pcg_mult(Lvl l, ReduceWS ws, FinArgs fa
   for_rows<V>(l.g, [&](int i, int j, int k, int64_t I) {
     const Pack<V> ec = ldp<V>(l.eps + I), z = mult_w<D, V>(l, l.eps, i, j, k, I, ec, pack_uniform<V>(l, I));
 #pragma unroll
-    for (int q = 0; q < V; ++q) acc[0] += (double)z.v[q] * (double)ec.v[q];
+    for (int q = 0; q < V; ++q) acc[0] = dfma(z.v[q], ec.v[q], acc[0]);
     stp<V>(l.z + I, z);
   });
   double tot[1];
@@ -388,8 +388,8 @@ __global__ void __launch_bounds__(256) k_pcg_update(Lvl l, ReduceWS ws, FinArgs 
     for (int q = 0; q < V; ++q) {
       x.v[q] += alpha * e.v[q];
       r.v[q] -= alpha * z.v[q];
-      acc[0] += (double)r.v[q] * (double)(r.v[q] * id.v[q]);
-      acc[1] += (double)r.v[q] * (double)r.v[q];
+      acc[0] = dfma(r.v[q], (r.v[q] * id.v[q]), acc[0]);
+      acc[1] = dfma(r.v[q], r.v[q], acc[1]);
     }
     stp<V>(l.x + I, x);
     stp<V>(l.r + I, r);
@@ -438,7 +438,7 @@ __global__ void __launch_bounds__(256) k_dot_rr(Lvl l, ReduceWS ws, FinArgs fa) 
   for_rows<V>(l.g, [&](int, int, int, int64_t I) {
     const Pack<V> r = ldp<V>(l.r + I);
 #pragma unroll
-    for (int q = 0; q < V; ++q) acc[0] += (double)r.v[q] * (double)r.v[q];
+    for (int q = 0; q < V; ++q) acc[0] = dfma(r.v[q], r.v[q], acc[0]);
   });
   double tot[1];
   if (grid_reduce<1>(acc, ws, tot)) finish_reduction(FIN_DOT, fa, tot[0], 0.0);

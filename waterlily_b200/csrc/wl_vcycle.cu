@@ -299,7 +299,7 @@ __device__ __forceinline__ void increment(const FusedParams& p, Run& run, int l,
     for (int q = 0; q < V; ++q) {
       r.v[q] = r.v[q] - ae.v[q];
       x.v[q] = x.v[q] + ec.v[q];
-      acc[0] += (double)r.v[q] * (double)r.v[q];
+      acc[0] = dfma(r.v[q], r.v[q], acc[0]);
     }
     stp<V>(L.r + I, r);
     stp<V>(L.x + I, x);
@@ -346,7 +346,7 @@ __device__ __forceinline__ void pcg(const FusedParams& p, Run& run, int l, int i
       const Pack<V> r = ldp<V>(L.r + I), id = ld_iD<V>(L, I, pack_uniform<V>(L, I));
       Pack<V> e;
 #pragma unroll
-      for (int q = 0; q < V; ++q) { e.v[q] = r.v[q] * id.v[q]; acc[0] += (double)r.v[q] * (double)e.v[q]; }
+      for (int q = 0; q < V; ++q) { e.v[q] = r.v[q] * id.v[q]; acc[0] = dfma(r.v[q], e.v[q], acc[0]); }
       stp<V>(L.eps + I, e);
     });
     reduce<1, GRID>(p, run, dist, acc);
@@ -365,7 +365,7 @@ __device__ __forceinline__ void pcg(const FusedParams& p, Run& run, int l, int i
       rows<V, GRID>(p, l, [&](int ii, int j, int k, int64_t I) {
         const Pack<V> ec = ldp<V>(L.eps + I), z = mult_w<D, V>(L, L.eps, ii, j, k, I, ec, pack_uniform<V>(L, I));
 #pragma unroll
-        for (int q = 0; q < V; ++q) acc[0] += (double)z.v[q] * (double)ec.v[q];
+        for (int q = 0; q < V; ++q) acc[0] = dfma(z.v[q], ec.v[q], acc[0]);
         stp<V>(L.z + I, z);
       });
       if (shell) {
@@ -398,8 +398,8 @@ __device__ __forceinline__ void pcg(const FusedParams& p, Run& run, int l, int i
         for (int q = 0; q < V; ++q) {
           x.v[q] += alpha * e.v[q];
           r.v[q] -= alpha * z.v[q];
-          acc[0] += (double)r.v[q] * (double)(r.v[q] * id.v[q]);
-          acc[1] += (double)r.v[q] * (double)r.v[q];
+          acc[0] = dfma(r.v[q], (r.v[q] * id.v[q]), acc[0]);
+          acc[1] = dfma(r.v[q], r.v[q], acc[1]);
         }
         stp<V>(L.x + I, x);
         stp<V>(L.r + I, r);
@@ -487,7 +487,7 @@ __device__ __forceinline__ void prolong_inc_init(const FusedParams& p, Run& run,
   m.perz_global = p.perz_global;
   double acc[2] = {0.0, 0.0};
   if (GRID && D == 3 && V == 4 && p.march[l] >= 1) {
-    for_columns_even(f.g, p.mg[l], [&](int i, int j, int k0, int k1) { tile_prolong(f, c, m, i, j, k0, k1, acc[0], acc[1]); });
+    for_columns_even(f.g, p.mg[l], [&](int i, int j, int k0, int k1) { tile_prolong(f, c, m, p.mg[l], i, j, k0, k1, acc[0], acc[1]); });
   } else {
     rows<V, GRID>(p, l, [&](int i, int j, int k, int64_t I) { prolong_increment_init<D, V>(f, c, m, i, j, k, I, acc[0], acc[1]); });
   }
@@ -568,7 +568,7 @@ __device__ __forceinline__ void residual0(const FusedParams& p, Run& run, const 
     for (int q = 0; q < V; ++q) {
       r.v[q] = id.v[q] == 0.f ? 0.f : zc.v[q] - ax.v[q];
       acc[0] += (double)r.v[q];
-      acc[1] += (double)r.v[q] * (double)r.v[q];
+      acc[1] = dfma(r.v[q], r.v[q], acc[1]);
       e.v[q] = r.v[q] * id.v[q];
     }
     stp<V>(L.r + I, r);

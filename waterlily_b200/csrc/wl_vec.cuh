@@ -79,15 +79,23 @@ __device__ __forceinline__ bool pack_uniform(const Lvl& l, int64_t I) {
 #endif
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 struct MaskPipe {
+  const unsigned char* p;  // byte of the plane after the one `nxt` belongs to
+  int64_t stp;             // bytes per plane (s2 / 4: rows and planes are multiples of four cells)
   unsigned int cur, nxt;
-  __device__ __forceinline__ unsigned int raw(const Lvl& l, int64_t I) const { return l.umask == nullptr ? 1u : (unsigned int)l.umask[(I + l.g.lead) >> 2]; }
-  // call at the top of step k (plane k, first cell of the pack at I); planes k0 … k1 ≤ n2 - 2
-  __device__ __forceinline__ void step(const Lvl& l, int k, int k0, int64_t I) {
-    const int64_t s2 = l.g.s[2];
-    cur = k == k0 ? raw(l, I) : nxt;
-    nxt = raw(l, I + s2);
-    if (l.umask != nullptr && k + WL_MASK_PF <= l.g.n[2] - 1)
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(l.umask + ((I + WL_MASK_PF * s2 + l.g.lead) >> 2)));
+  int pf;                  // steps that still have a plane WL_MASK_PF ahead inside the array
+  // before the march: I0 = first cell of the pack on plane k0
+  __device__ __forceinline__ void init(const Lvl& l, int64_t I0, int k0) {
+    p = l.umask; cur = 1u; nxt = 1u; stp = l.g.s[2] >> 2; pf = l.g.n[2] - k0 - WL_MASK_PF;
+    if (p != nullptr) { p += (I0 + l.g.lead) >> 2; nxt = *p; p += stp; }
+  }
+  // top of every step, first at plane k0; planes ≤ n2 - 2, so the byte of the next plane exists
+  __device__ __forceinline__ void step() {
+    cur = nxt;
+    if (p == nullptr) return;
+    nxt = *p;
+    if (pf > 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(p + (WL_MASK_PF - 1) * stp));
+    --pf;
+    p += stp;
   }
   __device__ __forceinline__ bool uni() const {
     unsigned int m = cur;
@@ -163,13 +171,16 @@ __device__ __forceinline__ Pack<V> mult_vals(const Lvl& l, int64_t I, const Pack
   for (int q = 0; q < V - 1; ++q) xp.v[q] = xc.v[q + 1];
   xp.v[V - 1] = xp4;
   if (uni) {  // a branch of its own: the constants are used as scalar operands (a select per coefficient cost 24 moves per pack)
+    // uL is a power of two (1 on the finest level, ×2 per restrictL in 3-D): a·L is exact, a·L + b·L = (a + b)·L with the
+    // single rounding of the sum, and t + (…)·L rounds once — (a + b) then fmaf(·, L, t) gives the bits of the
+    // generic expression x[I-δ]·L[I] + x[I+δ]·L[I+δ] in 7 instead of 13 operations per cell
     const float L = l.uL, Dd = l.uD;
 #pragma unroll
     for (int q = 0; q < V; ++q) {
       float t = xc.v[q] * Dd;
-      t += (xm.v[q] * L + xp.v[q] * L);
-      t += (ym.v[q] * L + yp.v[q] * L);
-      t += (zm.v[q] * L + zp.v[q] * L);
+      t = fmaf(xm.v[q] + xp.v[q], L, t);
+      t = fmaf(ym.v[q] + yp.v[q], L, t);
+      t = fmaf(zm.v[q] + zp.v[q], L, t);
       s.v[q] = t;
     }
     return s;
@@ -363,13 +374,15 @@ __device__ __forceinline__ void march_staged(const GridD& g, const MarchGeom& mg
   unsigned int am = c.ring0, ac = c.ring0 + c.pbytes, ap = c.ring0 + 2 * c.pbytes, ai = c.ring0 + (WL_NST - 1) * c.pbytes;
   const float* nxt = S + (int64_t)(k0 + 1 + WL_AHEAD) * g.s[2];  // (a periodic wrap can only concern the last plane of the level: handled below)
   const int klast = k1 - WL_AHEAD;                                // last step that still requests a plane (k+1+WL_AHEAD ≤ k1+1)
+  const int kwrap = g.per[2] ? g.n[2] - 2 - WL_AHEAD : -1;        // the step whose request is the upper ghost plane = image of plane 1
+  const float* const pwrap = S + g.s[2];
   int64_t I = c.col + (int64_t)k0 * g.s[2];
 #pragma unroll 1
   for (int k = k0; k <= k1; ++k) {
     pre(k, I);
     cp_async_wait_group<WL_AHEAD - 1>();   // planes ≤ k+1 have landed (the newer groups may still be in flight)
     __syncthreads();                        // … for every thread of the block; and everyone is done with plane k-2
-    if (k <= klast) stage_issue(c, (g.per[2] && k + 1 + WL_AHEAD == g.n[2] - 1) ? S + g.s[2] : nxt, ai);
+    if (k <= klast) stage_issue(c, k == kwrap ? pwrap : nxt, ai);
     cp_async_commit_group();
     body(k, I, lds4(ac), lds1(ac - 4), lds1(ac + 16), lds4(ac - c.rowb), lds4(ac + c.rowb), lds4(am), lds4(ap));
     am = ac; ac = ap;
@@ -456,8 +469,8 @@ __device__ __forceinline__ void prolong_increment_init(const Lvl& f, const Lvl& 
     r.v[q] = r.v[q] - s.v[q];
     x.v[q] = x.v[q] + e.v[q];
     en.v[q] = r.v[q] * id.v[q];
-    acc_rho += (double)r.v[q] * (double)en.v[q];
-    acc_r2 += (double)r.v[q] * (double)r.v[q];
+    acc_rho = dfma(r.v[q], en.v[q], acc_rho);
+    acc_r2 = dfma(r.v[q], r.v[q], acc_r2);
   }
   stp<V>(f.r + I, r);
   stp<V>(f.x + I, x);
@@ -471,22 +484,24 @@ __device__ __forceinline__ void tile_pcg_mult(const Lvl& l, const MarchGeom& mg,
   // the pack-mask byte of the NEXT plane is requested one step early: a load issued and consumed within the same step
   // exposed a full HBM latency per step (the largest stall of the first profile)
   MaskPipe mp;
+  mp.init(l, i + j * l.g.s[1] + (int64_t)k0 * l.g.s[2], k0);
   march_staged(l.g, mg, l.eps, ring, i, j, k0, k1,
-    [&](int k, int64_t I) { mp.step(l, k, k0, I); },
+    [&](int, int64_t) { mp.step(); },
     [&](int, int64_t I, const Pack<4>& ec, float xm1, float xp4, const Pack<4>& ym, const Pack<4>& yp, const Pack<4>& zm, const Pack<4>& zp) {
       const Pack<4> z = mult_vals<4>(l, I, ec, xm1, xp4, ym, yp, zm, zp, mp.uni());
 #pragma unroll
-      for (int q = 0; q < 4; ++q) acc += (double)z.v[q] * (double)ec.v[q];
+      for (int q = 0; q < 4; ++q) acc = dfma(z.v[q], ec.v[q], acc);
       stp<4>(l.z + I, z);
     });
 }
 // increment!: r -= Aϵ, x += ϵ, acc += r·r (Poisson.jl:101-102, :146); r and x of the next plane travel one step ahead too
 __device__ __forceinline__ void tile_increment(const Lvl& l, const MarchGeom& mg, float* ring, int i, int j, int k0, int k1, double& acc) {
   MaskPipe mp;
+  mp.init(l, i + j * l.g.s[1] + (int64_t)k0 * l.g.s[2], k0);
   Pack<4> r, x, rn, xn;
   march_staged(l.g, mg, l.eps, ring, i, j, k0, k1,
     [&](int k, int64_t I) {
-      mp.step(l, k, k0, I);
+      mp.step();
       if (k == k0) { r = ldp<4>(l.r + I); x = ldp<4>(l.x + I); }
       else { r = rn; x = xn; }
       const int64_t In = I + l.g.s[2];  // plane k1+1 is a ghost / halo plane of the same arrays: readable, never used
@@ -499,7 +514,7 @@ __device__ __forceinline__ void tile_increment(const Lvl& l, const MarchGeom& mg
       for (int q = 0; q < 4; ++q) {
         r.v[q] = r.v[q] - ae.v[q];
         x.v[q] = x.v[q] + ec.v[q];
-        acc += (double)r.v[q] * (double)r.v[q];
+        acc = dfma(r.v[q], r.v[q], acc);
       }
       stp<4>(l.r + I, r);
       stp<4>(l.x + I, x);
@@ -512,9 +527,10 @@ __device__ __forceinline__ void tile_residual(const Lvl& l, const MarchGeom& mg,
   Pack<4> zc;
   const TilePos tpos = tile_pos(mg);
   const bool xhi = tpos.tx == mg.mx - 1, yhi = tpos.ty == mg.my - 1;
+  mp.init(l, i + j * l.g.s[1] + (int64_t)k0 * l.g.s[2], k0);
   march_staged(l.g, mg, l.x, ring, i, j, k0, k1,
     [&](int k, int64_t I) {
-      mp.step(l, k, k0, I);
+      mp.step();
       zc = divu ? div_pack<3, 4>(l.g, divu, I) : ldp<4>(l.z + I);
       // the operands of a later plane's z: own pack of each component (the neighbour threads fetch theirs), the cell
       // right of / row above the tile by its edge threads; u₃ of plane k+1 is the pack fetched one step later
@@ -535,7 +551,7 @@ __device__ __forceinline__ void tile_residual(const Lvl& l, const MarchGeom& mg,
       for (int q = 0; q < 4; ++q) {
         r.v[q] = id.v[q] == 0.f ? 0.f : zc.v[q] - ax.v[q];
         a0 += (double)r.v[q];
-        a1 += (double)r.v[q] * (double)r.v[q];
+        a1 = dfma(r.v[q], r.v[q], a1);
       }
       stp<4>(l.r + I, r);
       if (write_eps) {
@@ -553,8 +569,11 @@ __device__ __forceinline__ Pack<4> pro_pack(const float* __restrict__ crow, int 
   Pack<4> e; e.v[0] = c.x; e.v[1] = c.x; e.v[2] = c.y; e.v[3] = c.y;
   return e;
 }
-__device__ __forceinline__ void tile_prolong(const Lvl& f, const Lvl& c, const ProMap& m, int i, int j, int k0, int k1, double& a0, double& a1) {
+__device__ __forceinline__ void tile_prolong(const Lvl& f, const Lvl& c, const ProMap& m, const MarchGeom& mg, int i, int j, int k0, int k1, double& a0,
+                                             double& a1) {
   const GridD& g = f.g;
+  const TilePos tpos = tile_pos(mg);
+  const bool xlo = tpos.tx == 0, xhi = tpos.tx == mg.mx - 1, ylo = tpos.ty == 0, yhi = tpos.ty == mg.my - 1;
   const float* __restrict__ xc = c.x;
   const int64_t cs1 = c.g.s[1], cs2 = c.g.s[2];
   int64_t I = i + j * g.s[1] + (int64_t)k0 * g.s[2];
@@ -562,7 +581,18 @@ __device__ __forceinline__ void tile_prolong(const Lvl& f, const Lvl& c, const P
   const int cim = pro_cidx(m, 0, i - 1), cip = pro_cidx(m, 0, i + 4);
   const int64_t Jy = pro_cidx(m, 1, j) * cs1, Jym = pro_cidx(m, 1, j - 1) * cs1, Jyp = pro_cidx(m, 1, j + 1) * cs1;
   for (int k = k0; k <= k1; ++k, I += g.s[2]) {
-    if (WL_PF > 0 && k + WL_PF <= g.n[2] - 1) { prefetch_l1(f.r + I + WL_PF * g.s[2]); prefetch_l1(f.x + I + WL_PF * g.s[2]); }
+    // Every load of a step is consumed within the step: without help each step exposes a full memory latency (17 warps
+    // per issue waited on the scoreboard).  r and x of a later plane, and the coarse-x rows that plane will read (own
+    // pair; the tile's edge threads add the rows / cells beyond the tile), are prefetched into L1.
+    if (WL_PF > 0 && k + WL_PF <= g.n[2] - 2) {
+      prefetch_l1(f.r + I + WL_PF * g.s[2]); prefetch_l1(f.x + I + WL_PF * g.s[2]);
+      const float* q = xc + pro_cidx(m, 2, k + WL_PF + 1) * cs2;
+      prefetch_l1(q + Jy + ci);
+      if (ylo) prefetch_l1(q + Jym + ci);
+      if (yhi) prefetch_l1(q + Jyp + ci);
+      if (xlo) prefetch_l1(q + Jy + cim);
+      if (xhi) prefetch_l1(q + Jy + cip);
+    }
     const int64_t Jz = pro_cidx(m, 2, k) * cs2, Jzm = pro_cidx(m, 2, k - 1) * cs2, Jzp = pro_cidx(m, 2, k + 1) * cs2;
     const float* row = xc + Jy + Jz;
     const Pack<4> e = pro_pack(row, ci);
@@ -577,8 +607,8 @@ __device__ __forceinline__ void tile_prolong(const Lvl& f, const Lvl& c, const P
       r.v[q] = r.v[q] - s.v[q];
       x.v[q] = x.v[q] + e.v[q];
       en.v[q] = r.v[q] * id.v[q];
-      a0 += (double)r.v[q] * (double)en.v[q];
-      a1 += (double)r.v[q] * (double)r.v[q];
+      a0 = dfma(r.v[q], en.v[q], a0);
+      a1 = dfma(r.v[q], r.v[q], a1);
     }
     stp<4>(f.r + I, r);
     stp<4>(f.x + I, x);
