@@ -151,6 +151,11 @@ int wl_pois_jacobi(wl_sim* s, int level, int it);
 int wl_pois_pcg(wl_sim* s, int level, int it);
 /* Vcycle!(ml;l=level+1) */
 int wl_pois_vcycle(wl_sim* s, int level);
+/* The head of solver!(ml) on the finest level: residual!(levels[1]) (src/Poisson.jl:91-97) followed by the opening of
+ * the first Vcycle! (src/MultiLevelPoisson.jl:72-75): Jacobi!(fine), restrict!(coarse.r, fine.r), fill!(coarse.x, 0).
+ * The library runs these four reference calls as one pass where the grid allows (wl_resjac.cu); this entry exposes
+ * exactly that group so that it has its own parity test.  MultiLevelPoisson only. */
+int wl_pois_head(wl_sim* s);
 /* solver!(pois;tol,itmx): MultiLevelPoisson (tol=1e-4,itmx=32) or Poisson (tol=1e-4,itmx=1e3);
  * pass tol<0 / itmx<0 for the reference defaults.  n = iterations, also appended to the log. */
 int wl_pois_solve(wl_sim* s, double tol, int itmx, int* n);

@@ -853,6 +853,15 @@ int wlo_pois_vcycle(wl_sim* s, int level) {
   if (level < 0 || level + 1 >= (int)S->levels.size()) return fail(WL_ERR_ARG, "bad level");
   vcycle(*S, (size_t)level); return WL_OK;
 }
+int wlo_pois_head(wl_sim* s) {  // MultiLevelPoisson.jl:88 (residual!) and :72-75 (Jacobi!, restrict!, fill!)
+  if (S->pois_kind != WL_POIS_MULTILEVEL || S->levels.size() < 2) return fail(WL_ERR_ARG, "MultiLevelPoisson with at least two levels required");
+  Pois& fine = S->levels[0]; Pois& coarse = S->levels[1];
+  residual(fine);
+  jacobi(fine);
+  restrict_r(coarse.g, coarse.r, fine.g, fine.r);
+  std::memset(coarse.x, 0, sizeof(float) * coarse.g.cells);
+  return WL_OK;
+}
 int wlo_pois_solve(wl_sim* s, double tol, int itmx, int* n) {
   if (tol < 0) tol = 1e-4;
   if (itmx < 0) itmx = S->pois_kind == WL_POIS_MULTILEVEL ? 32 : 1000;

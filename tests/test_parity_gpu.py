@@ -384,6 +384,123 @@ def test_uniform_mask_goes_stale_with_L():
     assert np.array_equal(ec.level_download(0, "D"), eo.level_download(0, "D"))
 
 
+def _head_case(cls_engine, dims, perdir, mu0, x0, z):
+    e = cls_engine(dims, perdir=perdir, pois_kind=_cabi.POIS_MULTILEVEL)
+    e.upload("mu0", np.asfortranarray(mu0))
+    e.bc("mu0", (0.0, 0.0, 0.0))
+    e.pois_update()
+    e.upload("p", np.asfortranarray(x0))
+    e.per_bc("p", None)
+    e.upload("sigma", np.asfortranarray(z))
+    return e
+
+
+def _head_fields(dims, uniform, mean, seed=3):
+    rng = np.random.default_rng(seed)
+    Ng = tuple(n + 2 for n in dims)
+    mu0 = np.ones(Ng + (3,), dtype=np.float32) if uniform else (0.2 + 0.8 * rng.random(Ng + (3,))).astype(np.float32)
+    x0 = (rng.random(Ng) * 2 - 1).astype(np.float32)
+    z = (rng.random(Ng) * 2 - 1).astype(np.float64)
+    z[1:-1, 1:-1, 1:-1] -= z[1:-1, 1:-1, 1:-1].mean() - mean
+    return mu0, x0, z.astype(np.float32)
+
+
+@pytest.mark.parametrize("dims", [(128, 16, 16), (256, 24, 8)])
+@pytest.mark.parametrize("perdir", [(), (1, 2, 3), (2,), (1, 3)])
+@pytest.mark.parametrize("uniform", [False, True])
+def test_fused_solver_head_is_bit_identical(dims, perdir, uniform, monkeypatch):
+    # wl_resjac.cu: residual! + Jacobi! + restrict! + fill!(coarse.x,0) as one pass (several tiles in x, y and z) against
+    # the four separate kernels: same operations in the same order per cell → the same bits in r, x and the coarse r
+    # (right-hand side with zero mean: residual!'s mean subtraction does not fire)
+    mu0, x0, z = _head_fields(dims, uniform, 0.0)
+    out = []
+    for which in ("0", "1"):
+        monkeypatch.setenv("WL_RESJAC", which)
+        e = _head_case(cuda_engine, dims, perdir, mu0, x0, z)
+        e.pois_head()
+        out.append((e.level_download(0, "r"), e.download("p"), e.level_download(1, "r"), e.level_download(1, "x")))
+    inner = (slice(1, -1),) * 3
+    for a, b in zip(out[0], out[1]):
+        assert np.array_equal(a[inner], b[inner])
+    eo = _head_case(oracle.engine, dims, perdir, mu0, x0, z)
+    eo.pois_head()
+    assert rel_l2(out[1][0][inner], eo.level_download(0, "r")[inner]) < 2e-6
+    assert rel_l2(out[1][1][inner], eo.download("p")[inner]) < 2e-6
+    assert rel_l2(out[1][2][inner], eo.level_download(1, "r")[inner]) < 2e-6
+
+
+@pytest.mark.parametrize("perdir", [(), (1, 2, 3), (2,)])
+@pytest.mark.parametrize("uniform", [False, True])
+def test_fused_solver_head_mean_subtraction(perdir, uniform, monkeypatch):
+    # right-hand side with a (huge) mean: the fused pass runs without residual!'s subtraction and is corrected afterwards
+    # by the exact linear identity (k_resjac_fix) — equal to the separate kernels and the oracle up to rounding
+    dims = (128, 16, 16)
+    mu0, x0, z = _head_fields(dims, uniform, 0.1)
+    inner = (slice(1, -1),) * 3
+    got = []
+    for which in ("oracle", "0", "1"):
+        monkeypatch.setenv("WL_RESJAC", "1" if which == "oracle" else which)
+        e = _head_case(oracle.engine if which == "oracle" else cuda_engine, dims, perdir, mu0, x0, z)
+        e.pois_head()
+        got.append((e.level_download(0, "r")[inner], e.download("p")[inner], e.level_download(1, "r")[inner]))
+    for k in range(3):
+        assert rel_l2(got[2][k], got[1][k]) < 2e-6 and rel_l2(got[2][k], got[0][k]) < 2e-6, k
+
+
+@pytest.mark.parametrize("perdir", [(), (1, 2, 3), (2,), (1, 3)])
+@pytest.mark.parametrize("uniform", [False, True])
+@pytest.mark.parametrize("mean", [0.0, 0.1])
+def test_fused_solver_head_solve(perdir, uniform, mean, monkeypatch):
+    # the whole solver! with the fused head against the separate kernels and against the oracle
+    dims = (128, 16, 16)
+    monkeypatch.setenv("WL_FUSED_SOLVE_CELLS", "0")   # per-level kernels on the finest level
+    mu0, x0, z = _head_fields(dims, uniform, mean)
+    out = []
+    for which in ("oracle", "0", "1"):
+        monkeypatch.setenv("WL_RESJAC", "1" if which == "oracle" else which)
+        e = _head_case(oracle.engine if which == "oracle" else cuda_engine, dims, perdir, mu0, x0, z)
+        l0 = e.launch_count() if which != "oracle" else 0
+        n = e.pois_solve(itmx=2)
+        out.append((n, e.download("p"), e.level_download(0, "r"), (e.launch_count() - l0) if which != "oracle" else 0))
+    (no, xo, ro, _), (n0, xa, ra, la), (n1, xb, rb, lb) = out
+    assert n0 == n1 == no
+    tol = 2e-6 if mean == 0.0 else 2e-5   # with the mean correction the two paths round differently from the first sweep on
+    assert rel_l2(xb, xa) < tol and rel_l2(xb, xo) < 2e-5 and rel_l2(xa, xo) < 2e-5
+    assert lb < la   # the fused pass really ran
+
+
+@pytest.mark.parametrize("make,steps", [(lambda cls: tgv3d(cls, 128), 2), (lambda cls: sphere3d(cls, n=128, m=64, exitBC=True), 3)])
+def test_fused_solver_head_mom_step(make, steps, monkeypatch):
+    monkeypatch.setenv("WL_FUSED_SOLVE_CELLS", "0")
+    monkeypatch.setenv("WL_RESJAC", "0")
+    s0 = make(Simulation)
+    monkeypatch.setenv("WL_RESJAC", "1")
+    s1 = make(Simulation)
+    for _ in range(steps):
+        sim_step(s0, remeasure=False)
+        sim_step(s1, remeasure=False)
+    assert s0.pois.n == s1.pois.n
+    for f in ("u", "p"):
+        assert rel_l2(getattr(s1.flow, f).numpy(), getattr(s0.flow, f).numpy()) < 2e-6, f
+
+
+@pytest.mark.parametrize("make,steps", [(lambda cls: tgv3d(cls, 128), 2), (lambda cls: sphere3d(cls, exitBC=True), 4), (lambda cls: sphere3d(cls, n=128, m=64, exitBC=False), 3)])
+def test_cfl_fused_into_pressure_correction_is_bit_identical(make, steps, monkeypatch):
+    # k_project_correct_cfl + k_cfl_upper (the corrector's project! correction evaluates CFL's σ = flux_out, the corrected
+    # field goes to the spare velocity buffer) against k_project_correct + k_cfl: same operations, same bits, same Δt
+    monkeypatch.setenv("WL_CFL_FUSE", "0")
+    s0 = make(Simulation)
+    monkeypatch.setenv("WL_CFL_FUSE", "1")
+    s1 = make(Simulation)
+    for _ in range(steps):
+        sim_step(s0, remeasure=False)
+        sim_step(s1, remeasure=False)
+    assert s0.pois.n == s1.pois.n
+    assert [float(x) for x in s0.flow.dt] == [float(x) for x in s1.flow.dt]
+    for f in ("u", "p", "sigma", "f"):
+        assert np.array_equal(getattr(s1.flow, f).numpy(), getattr(s0.flow, f).numpy()), f
+
+
 @pytest.mark.parametrize("make,steps", [(lambda cls: tgv3d(cls, 64), 3), (lambda cls: sphere3d(cls, exitBC=True), 4), (lambda cls: sphere3d(cls, n=128, m=64, exitBC=False), 2)])
 @pytest.mark.parametrize("stage", ["0", "1"])   # z-window in registers / operand planes staged in shared memory by cp.async
 def test_z_marching_kernels_match_row_kernels(make, steps, stage, monkeypatch):

@@ -7,7 +7,7 @@ mkdir -p ../variants
 NAME=$1; FILE=$2; FLAGS=$3
 /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -fmad=false -lineinfo -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr $FLAGS -c -o ../variants/${NAME}_${FILE%.cu}.o $FILE
 OBJS=""
-for f in wl_api wl_bc wl_poisson wl_momentum wl_dist wl_vcycle wl_convdiff_tma wl_metrics; do
+for f in wl_api wl_bc wl_poisson wl_momentum wl_dist wl_vcycle wl_convdiff_tma wl_metrics wl_resjac; do
   if [ "$f.cu" == "$FILE" ]; then OBJS="$OBJS ../variants/${NAME}_$f.o"; else OBJS="$OBJS $f.o"; fi
 done
 /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../variants/libwl_$NAME.so $OBJS -lcudart -ldl

@@ -57,6 +57,7 @@ SIGNATURES = {
     "pressure_moment": (C.c_int, [H, c_dbl_p, c_dbl_p, C.c_int64, c_dbl_p]),
     "derived": (C.c_int, [H, C.c_int, C.c_int, c_dbl_p, c_dbl_p, c_dbl_p]),
     "mom_step": (C.c_int, [H, c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p, c_int_p, c_int_p]),
+    "pois_head": (C.c_int, [H]),
     "get_dt": (C.c_int, [H, c_dbl_p]),
     "set_dt": (C.c_int, [H, C.c_double]),
     "launch_count": (C.c_int64, [H]),
@@ -307,6 +308,10 @@ class Engine:
 
     def pois_vcycle(self, level=0):
         self.cabi.check(self.cabi.pois_vcycle(self.h, level))
+
+    def pois_head(self):
+        """residual! + Jacobi! + restrict! + fill!(coarse.x,0): the head of solver!(ml) on the finest level."""
+        self.cabi.check(self.cabi.pois_head(self.h))
 
     def pois_solve(self, tol=-1.0, itmx=-1):
         n = C.c_int(0)

@@ -344,6 +344,8 @@ static int create_impl(wl_sim** out, int D, const int* N, double nu, double dt0,
   { const char* e = getenv("WL_UNIFORM"); a.uniform_path = !(e && atoi(e) == 0); }
   { const char* e = getenv("WL_MARCH"); a.march_on = !(e && atoi(e) == 0); }
   { const char* e = getenv("WL_STAGE"); a.stage_on = !(e && atoi(e) == 0); }
+  { const char* e = getenv("WL_RESJAC"); a.resjac_on = !(e && atoi(e) == 0); }
+  { const char* e = getenv("WL_CFL_FUSE"); a.cflfuse_on = !(e && atoi(e) == 0); }
   { const char* e = getenv("WL_BDIM_FUSE"); a.bdim_fuse = !(e && atoi(e) == 0); }
   if (!rc && cudaMalloc(&tmp, 64) == cudaSuccess) { a.allocs.push_back(tmp); a.ws.ticket = (unsigned int*)tmp; cudaMemsetAsync(tmp, 0, 64, a.stream); } else if (!rc) rc = wl_fail(WL_ERR_CUDA, "cudaMalloc ticket");
   if (!rc && cudaMallocHost((void**)&a.h_pinned, 64 * sizeof(float)) != cudaSuccess) rc = wl_fail(WL_ERR_CUDA, "cudaMallocHost");
@@ -592,6 +594,13 @@ int wl_pois_pcg(wl_sim* s, int level, int it) {
   int rc = mom_materialize_p(S);
   if (!rc) rc = pois_pcg(S, level, it);
   if (!rc) rc = bc_per(S, S.levels[level].g, S.levels[level].eps, S.levels[level].g.per);
+  return rc ? rc : wl_sync(s);
+}
+int wl_pois_head(wl_sim* s) {
+  GUARD(s);
+  if (S.pois_kind != WL_POIS_MULTILEVEL || S.levels.size() < 2) return wl_fail(WL_ERR_ARG, "MultiLevelPoisson with at least two levels required");
+  int rc = mom_materialize_p(S);
+  if (!rc) rc = pois_head(S);
   return rc ? rc : wl_sync(s);
 }
 int wl_pois_vcycle(wl_sim* s, int level) {

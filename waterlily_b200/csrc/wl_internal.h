@@ -80,6 +80,8 @@ struct Sim {
   int p_pend = 0;                      // 0 none, 1 divide by p_pend32 (Float32 dt), 2 divide by p_pend64 (Float64 dt)
   float p_pend32 = 0.f;
   double p_pend64 = 0.0;
+  bool cflfuse_on = true;              // WL_CFL_FUSE=0: the corrector's pressure correction and CFL stay separate kernels
+  bool cfl_fused = false;              // the corrector's project! already produced σ = flux_out and its maximum away from the upper boundaries
   bool last_cd_fused = false;          // the last conv_diff! folded BDIM! stage 2 into its store on the clean tile-planes
   float nu = 0.f;
   std::vector<float> dt;
@@ -113,6 +115,9 @@ struct Sim {
   bool uniform_path = true;          // WL_UNIFORM=0 switches the fast path off (every stencil loads L, D, iD)
   bool march_on = true;              // WL_MARCH=0: the stencil kernels iterate (row-group, plane) units instead of marching in z
   bool stage_on = true;              // WL_STAGE=0: marching kernels keep their z-window in registers instead of a shared-memory ring
+  bool resjac_on = true;             // WL_RESJAC=0: residual!, the first Jacobi! and restrict! of solver! stay separate kernels (wl_resjac.cu)
+  bool head_fused = false;           // solver!: the fused head already ran Jacobi! + restrict! of the first Vcycle! on the finest level
+  bool x_parked = false;             // … and the finest x lives in levels[0].eps until the prolongation pass moves it back
   bool nonuni_known = false;
   unsigned int nonuni0 = 0;
   double uni_frac0 = 0.0;            // fraction of uniform packs on the finest level (profiling: algorithmic bytes)
@@ -173,6 +178,11 @@ int bc_vec(Sim& s, const GridD& g, float* a, const double* A, bool saveexit, con
 int bc_per(Sim& s, const GridD& g, float* a, const int* per, const int* active = nullptr);
 int bc_exit(Sim& s, const double* U, float dt);
 
+// ---- wl_resjac.cu ----
+bool resjac_eligible(const Sim& s);
+int resjac_run(Sim& s);
+int resjac_unpark(Sim& s);  // moves the parked x' from levels[0].eps back into levels[0].x (API inspection only)
+
 // ---- wl_poisson.cu ----
 int pois_set_diag(Sim& s, Lvl& l);
 void pois_invalidate_uniform(Sim& s, int level);
@@ -190,6 +200,7 @@ int pois_residual(Sim& s, Lvl& l, bool need_r2 = true, bool ghosts_valid = false
 int pois_jacobi(Sim& s, Lvl& l, int it);
 int pois_pcg(Sim& s, int level, int it);
 int pois_vcycle(Sim& s, int level);
+int pois_head(Sim& s);  // residual! + Jacobi! + restrict! + fill!(coarse.x,0) on the finest level
 int pois_solve(Sim& s, double tol, int itmx, int* n, bool ghosts_valid = false, int slot = 0, bool defer_count = false, const float* divu = nullptr);
 int pois_materialize_eps(Sim& s, int level);
 int pois_dot_rr(Sim& s, Lvl& l, double* out);
@@ -201,7 +212,8 @@ int mom_accelerate(Sim& s, const double* g);
 int mom_bdim1(Sim& s);
 int mom_bdim2(Sim& s, bool accumulate, float scale, bool fused = false);
 int mom_scale_u(Sim& s, double scale);
-int mom_project(Sim& s, double w, int* n, int slot = 0, bool defer_count = false, bool in_step = false);
+int mom_project(Sim& s, double w, int* n, int slot = 0, bool defer_count = false, bool in_step = false, bool with_cfl = false);
+int mom_div(Sim& s, const float* u, float* z);  // z = div u on the interior (Flow.jl:139)
 int mom_materialize_p(Sim& s);  // applies a pending x ./= dt (see Sim::p_pend)
 int mom_cfl(Sim& s, double* dt);
 int mom_step(Sim& s, const double* U, const double* gp, const double* gc, double* dt_next, int* n_pred, int* n_corr);

@@ -609,6 +609,103 @@ __global__ void __launch_bounds__(256) k_project_correct(Lvl l, float* __restric
     }
   });
 }
+// The corrector's project! correction and CFL's σ = flux_out(I,u) (Flow.jl:141-143, 173, 176-182) in one pass: CFL used
+// to re-read the three components the correction had just written (5 words per cell, 0.53 ms at 512³).  flux_out needs the
+// corrected u_i on the UPPER faces too, i.e. the neighbours' correction: their operands (u, x, L one cell up) are read
+// as well — which rules out the in-place update, so the corrected field goes to a spare velocity buffer and the caller
+// swaps the pointers.  Cells whose upper neighbour is a ghost cell (any coordinate n-2) need the values BC! sets
+// afterwards: they are left to k_cfl_upper and stay out of the maximum here.
+__global__ void __launch_bounds__(256) k_project_correct_cfl(Lvl l, const float* __restrict__ u, float* __restrict__ uo, float* __restrict__ sigma, ReduceWS ws,
+                                                             FinArgs fa) {
+  const GridD& g = l.g;
+  const float* __restrict__ L = l.L;
+  const float* __restrict__ x = l.x;
+  const int64_t s1 = g.s[1], s2 = g.s[2], cp = g.comp;
+  double acc[1] = {0.0};
+  for_rows<4>(g, [&](int i, int j, int k, int64_t I) {
+    const Pack<4> xc = ldp<4>(x + I);
+    const bool uni = pack_uniform<4>(l, I);
+    const Pack<4> one = splat<4>(l.uL);
+    // lower faces: the correction itself (k_project_correct)
+    Pack<4> un[3];
+    {
+      const Pack<4> xm = ld_xm<4>(x + I, xc), Lc = uni ? one : ldp<4>(L + I), uc = ldp<4>(u + I);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) un[0].v[q] = uc.v[q] - Lc.v[q] * (xc.v[q] - xm.v[q]);
+    }
+    {
+      const Pack<4> xm = ldp<4>(x + I - s1), Lc = uni ? one : ldp<4>(L + I + cp), uc = ldp<4>(u + I + cp);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) un[1].v[q] = uc.v[q] - Lc.v[q] * (xc.v[q] - xm.v[q]);
+    }
+    {
+      const Pack<4> xm = ldp<4>(x + I - s2), Lc = uni ? one : ldp<4>(L + I + 2 * cp), uc = ldp<4>(u + I + 2 * cp);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) un[2].v[q] = uc.v[q] - Lc.v[q] * (xc.v[q] - xm.v[q]);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) stp<4>(uo + I + c * cp, un[c]);
+    // upper faces: the corrected value of the neighbour cell, evaluated with its operands in its operation order
+    Pack<4> up[3];
+    {
+      const float x4 = x[I + 4], u4 = u[I + 4], L4 = uni ? l.uL : L[I + 4];
+#pragma unroll
+      for (int q = 0; q < 3; ++q) up[0].v[q] = un[0].v[q + 1];
+      up[0].v[3] = u4 - L4 * (x4 - xc.v[3]);
+    }
+    {
+      const Pack<4> xp = ldp<4>(x + I + s1), Lp = uni ? one : ldp<4>(L + I + cp + s1), uq = ldp<4>(u + I + cp + s1);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) up[1].v[q] = uq.v[q] - Lp.v[q] * (xp.v[q] - xc.v[q]);
+    }
+    {
+      const Pack<4> xp = ldp<4>(x + I + s2), Lp = uni ? one : ldp<4>(L + I + 2 * cp + s2), uq = ldp<4>(u + I + 2 * cp + s2);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) up[2].v[q] = uq.v[q] - Lp.v[q] * (xp.v[q] - xc.v[q]);
+    }
+    Pack<4> o;
+    const bool edge = j == g.n[1] - 2 || k == g.n[2] - 2;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      // max(0., u) on a Float32 u: the Float32 maximum converted is the same Float64 number
+      double sg = 0.0 + ((double)fmaxf(0.f, up[0].v[q]) + (double)fmaxf(0.f, -un[0].v[q]));
+      sg += (double)fmaxf(0.f, up[1].v[q]) + (double)fmaxf(0.f, -un[1].v[q]);
+      sg += (double)fmaxf(0.f, up[2].v[q]) + (double)fmaxf(0.f, -un[2].v[q]);
+      o.v[q] = (float)sg;
+      if (!edge && i + q != g.n[0] - 2) acc[0] = fmax(acc[0], (double)o.v[q]);
+    }
+    stp<4>(sigma + I, o);
+  });
+  double tot[1];
+  if (grid_reduce<1, true>(acc, ws, tot)) finish_reduction(FIN_CFL, fa, tot[0], 0.0);
+}
+// σ = flux_out(I,u) on the interior cells with a coordinate n-2 (their upper neighbour is a ghost cell, final after BC!),
+// folded into the maximum of k_project_correct_cfl.  Edge cells are visited by more than one plane: same value.
+__global__ void __launch_bounds__(256) k_cfl_upper(GridD g, const float* __restrict__ u, float* __restrict__ sigma, ReduceWS ws, FinArgs fa, int64_t shell) {
+  const int m0 = g.n[0] - 2, m1 = g.n[1] - 2, m2 = g.n[2] - 2;
+  const int cA = m1 * m2, cB = m0 * m2, cC = m0 * m1;
+  double acc[1] = {0.0};
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < cA + cB + cC; idx += gridDim.x * blockDim.x) {
+    int c0, c1, c2;
+    if (idx < cA) { c0 = m0; c1 = 1 + idx % m1; c2 = 1 + idx / m1; }
+    else if (idx < cA + cB) { const int t = idx - cA; c0 = 1 + t % m0; c1 = m1; c2 = 1 + t / m0; }
+    else { const int t = idx - cA - cB; c0 = 1 + t % m0; c1 = 1 + t / m0; c2 = m2; }
+    const int64_t I = c0 + c1 * g.s[1] + c2 * g.s[2];
+    double sg = 0.0 + (fmax(0., (double)u[I + 1]) + fmax(0., (double)-u[I]));
+#pragma unroll
+    for (int d = 1; d < 3; ++d) sg += fmax(0., (double)u[I + g.s[d] + d * g.comp]) + fmax(0., (double)-u[I + d * g.comp]);
+    const float o = (float)sg;
+    sigma[I] = o;
+    acc[0] = fmax(acc[0], (double)o);
+  }
+  // … and the ghost shell of σ, which the reference's maximum over the padded array includes (k_shell_max): one reduction for both
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < shell; idx += (int64_t)gridDim.x * blockDim.x) {
+    int c[3];
+    if (shell_decode(g, idx, c) && is_global_ghost(g, c)) acc[0] = fmax(acc[0], (double)sigma[c[0] + c[1] * g.s[1] + c[2] * g.s[2]]);
+  }
+  double tot[1];
+  if (grid_reduce<1, true>(acc, ws, tot)) finish_reduction(FIN_CFL_SHELL, fa, tot[0], 0.0);
+}
 // CFL: σ = flux_out (Flow.jl:173,176-182) + interior max
 template <int D, int V>
 __global__ void __launch_bounds__(256) k_cfl(GridD g, const float* __restrict__ u, float* __restrict__ sigma, ReduceWS ws, FinArgs fa) {
@@ -853,7 +950,7 @@ int mom_materialize_p(Sim& s) {
 // project!(a,b,w) (Flow.jl:137-145)
 // `in_step` (mom_step!): z = div u is evaluated inside residual! instead of by a pass of its own, and the closing
 // x ./= dt is left pending for the next project! (or mom_materialize_p)
-int mom_project(Sim& s, double w, int* n, int slot, bool defer_count, bool in_step) {
+int mom_project(Sim& s, double w, int* n, int slot, bool defer_count, bool in_step, bool with_cfl) {
   const float dt32 = s.dt.back();
   const bool f32 = (w == 1.0);                 // dt = w*Δt: Float32 for the Int w=1, Float64 for w=0.5
   const double dtw = f32 ? (double)dt32 : w * (double)dt32;
@@ -866,19 +963,49 @@ int mom_project(Sim& s, double w, int* n, int slot, bool defer_count, bool in_st
   rc = pois_solve(s, 1e-4, s.pois_kind == WL_POIS_MULTILEVEL ? 32 : 1000, n, true, slot, defer_count, in_step ? s.u : nullptr);
   if (rc) return rc;
   wl_prof_begin(s, WL_PROF_PROJECT);
-  RLAUNCH(s, k_project_correct, s.g, b, s.u);
+  // the corrector's correction also evaluates CFL's σ (k_project_correct_cfl) when a velocity-sized buffer is free to take
+  // the corrected field: after a fused step flow.f is not materialised (f_stale), its array is that buffer
+  const RowLaunch rlc = row_launch(s.g);
+  s.cfl_fused = false;
+  if (with_cfl && s.cflfuse_on && s.D == 3 && rlc.V == 4 && s.f_stale) {
+    const FinArgs fa = fin_misc(s);
+    k_project_correct_cfl<<<wl_grid_for(s, rlc.nunits), rlc.blk, 0, s.stream>>>(b, s.u, s.f, s.sigma, s.ws, fa);
+    ++s.launches;
+    if ((rc = post_reduce(s, FIN_CFL, fa, true))) return rc;
+    if (s.exitBC) {  // BC! rewrites every ghost cell of the new array except the saved exit plane
+      const int64_t cnt = (int64_t)s.g.n[1] * s.g.n[2];
+      k_copy_exit_plane<<<(int)std::min<int64_t>((cnt + 255) / 256, 256), 256, 0, s.stream>>>(s.g, s.f, s.u);
+      ++s.launches;
+    }
+    float* t = s.u; s.u = s.f; s.f = t;
+    s.cfl_fused = true;
+  } else {
+    RLAUNCH(s, k_project_correct, s.g, b, s.u);
+  }
   s.p_pend = f32 ? 1 : 2; s.p_pend32 = (float)dtw; s.p_pend64 = dtw;
   if (!in_step && (rc = mom_materialize_p(s))) return rc;
   wl_prof_end(s, WL_PROF_PROJECT, 4.0 * (double)s.g.interior * (wl_words(s, 3 * s.D + 1, s.D) + (in_step ? 0 : 2)));
   return wl_cuda_check(s, cudaGetLastError(), "project");
 }
+int mom_div(Sim& s, const float* u, float* z) {
+  RLAUNCH(s, k_project_pre, s.g, s.g, u, z);
+  return wl_cuda_check(s, cudaGetLastError(), "k_project_pre");
+}
 // CFL(a) (Flow.jl:172-175)
 int mom_cfl(Sim& s, double* dt) {
   const FinArgs fa = fin_misc(s);
-  RLAUNCH(s, k_cfl, s.g, s.g, s.u, s.sigma, s.ws, fa);
-  int rc = post_reduce(s, FIN_CFL, fa, true);
-  if (rc) return rc;
-  {
+  int rc;
+  if (s.cfl_fused) {
+    // σ and its maximum away from the upper boundaries came with the pressure correction; the rest needs BC!'s ghosts
+    s.cfl_fused = false;
+    const int64_t cnt = (int64_t)(s.g.n[1] - 2) * (s.g.n[2] - 2) + (int64_t)(s.g.n[0] - 2) * (s.g.n[2] - 2) + (int64_t)(s.g.n[0] - 2) * (s.g.n[1] - 2);
+    const int64_t shell = shell_count(s.g);
+    k_cfl_upper<<<(int)std::min<int64_t>((std::max(cnt, shell) + 255) / 256, (int64_t)s.nsm * 8), 256, 0, s.stream>>>(s.g, s.u, s.sigma, s.ws, fa, shell);
+    ++s.launches;
+    if ((rc = post_reduce(s, FIN_CFL_SHELL, fa, true))) return rc;
+  } else {
+    RLAUNCH(s, k_cfl, s.g, s.g, s.u, s.sigma, s.ws, fa);
+    if ((rc = post_reduce(s, FIN_CFL, fa, true))) return rc;
     const int64_t cnt = shell_count(s.g);
     k_shell_max<<<(int)std::min<int64_t>((cnt + 255) / 256, 256), 256, 0, s.stream>>>(s.g, s.sigma, s.ws, fa, cnt);
     ++s.launches;
@@ -939,7 +1066,7 @@ int mom_step(Sim& s, const double* U, const double* gp, const double* gc, double
     for (int k = 0; k < 3; ++k) s.f_g[k] = (gc && k < s.D) ? gc[k] : 0.0;
   }
   if ((rc = bc_vec(s, s.g, s.u, U, s.exitBC, s.g.per, 2))) return rc;
-  if ((rc = mom_project(s, 0.5, n_corr, 1, defer, true))) return rc;
+  if ((rc = mom_project(s, 0.5, n_corr, 1, defer, true, true))) return rc;
   if ((rc = bc_vec(s, s.g, s.u, U, s.exitBC, s.g.per, 2))) return rc;
   double dt;
   if ((rc = mom_cfl(s, &dt))) return rc;

@@ -230,9 +230,9 @@ __global__ void __launch_bounds__(256) k_prolongate(Lvl f, Lvl c, int fzadd) {
 
 // prolongate! + increment! + ϵ = r·iD, ρ = r⋅ϵ of the pcg! that follows (see wl_vec.cuh)
 template <int D, int V>
-__global__ void __launch_bounds__(256) k_prolong_increment_init(Lvl f, Lvl c, ProMap m, ReduceWS ws, FinArgs fa) {
+__global__ void __launch_bounds__(256) k_prolong_increment_init(Lvl f, Lvl c, ProMap m, const float* __restrict__ xsrc, ReduceWS ws, FinArgs fa) {
   double acc[2] = {0.0, 0.0};
-  for_rows<V>(f.g, [&](int i, int j, int k, int64_t I) { prolong_increment_init<D, V>(f, c, m, i, j, k, I, acc[0], acc[1]); });
+  for_rows<V>(f.g, [&](int i, int j, int k, int64_t I) { prolong_increment_init<D, V>(f, c, m, xsrc, i, j, k, I, acc[0], acc[1]); });
   double tot[2];
   if (grid_reduce<2>(acc, ws, tot)) finish_reduction(FIN_INC_INIT, fa, tot[0], tot[1]);
 }
@@ -336,9 +336,9 @@ __global__ void __launch_bounds__(256, WL_STAGE_MINB) k_residual_s(Lvl l, MarchG
   double tot[2];
   if (grid_reduce<2>(acc, ws, tot)) finish_reduction(FIN_RESIDUAL, fa, tot[0], tot[1]);
 }
-__global__ void __launch_bounds__(256) k_prolong_increment_init_m(Lvl f, Lvl c, ProMap m, MarchGeom mg, ReduceWS ws, FinArgs fa) {
+__global__ void __launch_bounds__(256) k_prolong_increment_init_m(Lvl f, Lvl c, ProMap m, MarchGeom mg, const float* __restrict__ xsrc, ReduceWS ws, FinArgs fa) {
   double acc[2] = {0.0, 0.0};
-  for_columns(f.g, mg, [&](int i, int j, int k0, int k1) { tile_prolong(f, c, m, mg, i, j, k0, k1, acc[0], acc[1]); });
+  for_columns(f.g, mg, [&](int i, int j, int k0, int k1) { tile_prolong(f, c, m, mg, xsrc, i, j, k0, k1, acc[0], acc[1]); });
   double tot[2];
   if (grid_reduce<2>(acc, ws, tot)) finish_reduction(FIN_INC_INIT, fa, tot[0], tot[1]);
 }
@@ -677,17 +677,23 @@ int pois_pcg(Sim& s, int level, int it) {
 int pois_vcycle(Sim& s, int level) {
   Lvl& fine = s.levels[level];
   Lvl& coarse = s.levels[level + 1];
-  int rc = pois_jacobi(s, fine, 1);
-  if (rc) return rc;
-  // restrict! + fill!(coarse.x,0); a distributed→replicated transition gathers the planes
+  int rc = 0;
   const bool gather = s.dist.nranks > 1 && s.lvl_dist[level] && !s.lvl_dist[level + 1];
-  int ck0 = 1, ck1 = coarse.g.n[2] - 2, fshift = 0;
-  if (gather) {
-    const int cp = (coarse.g.n[2] - 2) / s.dist.nranks;
-    ck0 = 1 + s.dist.rank * cp; ck1 = ck0 + cp - 1; fshift = -fine.g.zoff;
+  const bool head = level == 0 && s.head_fused;  // Jacobi! + restrict! of this cycle ran inside the fused head of solver! (wl_resjac.cu)
+  if (head) {
+    s.head_fused = false;
+    s.x_parked = true;   // the finest x is in fine.eps until the prolongation pass below
+  } else {
+    if ((rc = pois_jacobi(s, fine, 1))) return rc;
+    // restrict! + fill!(coarse.x,0); a distributed→replicated transition gathers the planes
+    int ck0 = 1, ck1 = coarse.g.n[2] - 2, fshift = 0;
+    if (gather) {
+      const int cp = (coarse.g.n[2] - 2) / s.dist.nranks;
+      ck0 = 1 + s.dist.rank * cp; ck1 = ck0 + cp - 1; fshift = -fine.g.zoff;
+    }
+    RLAUNCH(s, k_restrict, coarse.g, coarse, fine, ck0, ck1, fshift);
+    if (gather && (rc = dist_allgather(s, coarse.r + coarse.g.s[2], (size_t)((coarse.g.n[2] - 2) / s.dist.nranks) * coarse.g.s[2]))) return rc;
   }
-  RLAUNCH(s, k_restrict, coarse.g, coarse, fine, ck0, ck1, fshift);
-  if (gather && (rc = dist_allgather(s, coarse.r + coarse.g.s[2], (size_t)((coarse.g.n[2] - 2) / s.dist.nranks) * coarse.g.s[2]))) return rc;
   if (s.vc_first == level + 1) {
     // the rest of the cycle below this level is one persistent kernel (wl_vcycle.cu)
     if ((rc = vcycle_fused_run(s))) return rc;
@@ -709,8 +715,10 @@ int pois_vcycle(Sim& s, int level) {
     const bool top = level == 0;
     if (top) wl_prof_begin(s, WL_PROF_INCREMENT);
     const MarchLaunch ml = march_for(s, fine.g);
-    if (ml.ok && (coarse.g.n[0] - 2) % 2 == 0) { k_prolong_increment_init_m<<<ml.grid, ml.blk, 0, s.stream>>>(fine, coarse, m, ml.mg, s.ws, fa); ++s.launches; }
-    else RLAUNCH(s, k_prolong_increment_init, fine.g, fine, coarse, m, s.ws, fa);
+    const float* xsrc = (level == 0 && s.x_parked) ? fine.eps : fine.x;  // same cell read and (as the new ϵ) written by one thread: no hazard
+    if (level == 0) s.x_parked = false;
+    if (ml.ok && (coarse.g.n[0] - 2) % 2 == 0) { k_prolong_increment_init_m<<<ml.grid, ml.blk, 0, s.stream>>>(fine, coarse, m, ml.mg, xsrc, s.ws, fa); ++s.launches; }
+    else RLAUNCH(s, k_prolong_increment_init, fine.g, fine, coarse, m, xsrc, s.ws, fa);
     if ((rc = post_reduce(s, FIN_INC_INIT, fa))) return rc;
     if (top) wl_prof_end(s, WL_PROF_INCREMENT, 4.0 * (double)fine.g.interior * wl_words(s, s.D + 7.125, s.D + 2));
     s.pcg_init_done = level;
@@ -718,6 +726,23 @@ int pois_vcycle(Sim& s, int level) {
   }
   RLAUNCH(s, k_prolongate, fine.g, fine, coarse, gather ? fine.g.zoff : 0);
   return pois_increment(s, fine);
+}
+// residual!(fine) and the opening of the first Vcycle! — Jacobi!(fine), restrict!, fill!(coarse.x,0)
+// (MultiLevelPoisson.jl:88,72-75) — as their own entry: the fused pass where the grid allows, else the separate kernels
+int pois_head(Sim& s) {
+  Lvl& fine = s.levels[0];
+  Lvl& coarse = s.levels[1];
+  int rc;
+  if (resjac_eligible(s)) {
+    if ((rc = resjac_run(s))) return rc;
+    s.eps_is_jacobi = false;
+    return resjac_unpark(s);
+  }
+  if ((rc = pois_residual(s, fine, false, false, true, nullptr))) return rc;
+  if ((rc = pois_jacobi(s, fine, 1))) return rc;
+  if (s.dist.nranks > 1 && s.lvl_dist[0] && !s.lvl_dist[1]) return wl_fail(WL_ERR_ARG, "wl_pois_head: not available across a distributed/replicated level transition");
+  RLAUNCH(s, k_restrict, coarse.g, coarse, fine, 1, coarse.g.n[2] - 2, 0);
+  return wl_cuda_check(s, cudaGetLastError(), "k_restrict");
 }
 // solver!(ml;tol,itmx) (MultiLevelPoisson.jl:87-99) / solver!(p::Poisson;tol,itmx) (Poisson.jl:162-172)
 int pois_solve(Sim& s, double tol, int itmx, int* n_out, bool ghosts_valid, int slot, bool defer_count, const float* divu) {
@@ -736,11 +761,23 @@ int pois_solve(Sim& s, double tol, int itmx, int* n_out, bool ghosts_valid, int 
     if (n_out) *n_out = n;
     return 0;
   }
-  int rc = pois_residual(s, p, false, ghosts_valid, s.pois_kind == WL_POIS_MULTILEVEL && itmx > 0, divu);
-  if (rc) return rc;
-  int n = 0;
   static int fuse_env = -1;
   if (fuse_env < 0) { const char* e = getenv("WL_FUSE_PROLONG"); fuse_env = e ? atoi(e) : 1; }
+  int rc;
+  s.head_fused = false;
+  s.x_parked = false;
+  if (s.pois_kind == WL_POIS_MULTILEVEL && itmx > 0 && fuse_env != 0 && resjac_eligible(s)) {
+    // residual! and the Jacobi! + restrict! that open the first Vcycle! as one pass (wl_resjac.cu); it reads z, so
+    // project!'s z = div u is materialised first (x needs no perBC!: the pass wraps its own periodic reads)
+    if (divu && (rc = mom_div(s, divu, p.z))) return rc;
+    if ((rc = resjac_run(s))) return rc;
+    s.eps_is_jacobi = false;
+    s.head_fused = true;
+  } else {
+    rc = pois_residual(s, p, false, ghosts_valid, s.pois_kind == WL_POIS_MULTILEVEL && itmx > 0, divu);
+    if (rc) return rc;
+  }
+  int n = 0;
   s.fuse_prolong = fuse_env != 0;
   s.pcg_init_done = -1;
   while (n < itmx) {

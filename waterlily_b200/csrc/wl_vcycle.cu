@@ -487,9 +487,9 @@ __device__ __forceinline__ void prolong_inc_init(const FusedParams& p, Run& run,
   m.perz_global = p.perz_global;
   double acc[2] = {0.0, 0.0};
   if (GRID && D == 3 && V == 4 && p.march[l] >= 1) {
-    for_columns_even(f.g, p.mg[l], [&](int i, int j, int k0, int k1) { tile_prolong(f, c, m, p.mg[l], i, j, k0, k1, acc[0], acc[1]); });
+    for_columns_even(f.g, p.mg[l], [&](int i, int j, int k0, int k1) { tile_prolong(f, c, m, p.mg[l], f.x, i, j, k0, k1, acc[0], acc[1]); });
   } else {
-    rows<V, GRID>(p, l, [&](int i, int j, int k, int64_t I) { prolong_increment_init<D, V>(f, c, m, i, j, k, I, acc[0], acc[1]); });
+    rows<V, GRID>(p, l, [&](int i, int j, int k, int64_t I) { prolong_increment_init<D, V>(f, c, m, f.x, i, j, k, I, acc[0], acc[1]); });
   }
   reduce<2, GRID>(p, run, fdist, acc);
   if (fdist && cdist) post_ready(p, run);

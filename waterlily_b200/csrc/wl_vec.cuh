@@ -419,8 +419,8 @@ __device__ __forceinline__ int pro_cidx(const ProMap& m, int d, int v) {
   return (v + 1) >> 1;
 }
 template <int D, int V>
-__device__ __forceinline__ void prolong_increment_init(const Lvl& f, const Lvl& c, const ProMap& m, int i, int j, int k, int64_t I,
-                                                       double& acc_rho, double& acc_r2) {
+__device__ __forceinline__ void prolong_increment_init(const Lvl& f, const Lvl& c, const ProMap& m, const float* __restrict__ xsrc, int i, int j, int k,
+                                                       int64_t I, double& acc_rho, double& acc_r2) {
   const float* __restrict__ xc = c.x;
   const int64_t cs1 = c.g.s[1], cs2 = c.g.s[2];
   int ci[V];
@@ -461,7 +461,7 @@ __device__ __forceinline__ void prolong_increment_init(const Lvl& f, const Lvl& 
 #pragma unroll
     for (int q = 0; q < V; ++q) s.v[q] += (xc[Jm + ci[q]] * Lc.v[q] + xc[Jp + ci[q]] * Lp.v[q]);
   }
-  Pack<V> r = ldp<V>(f.r + I), x = ldp<V>(f.x + I);
+  Pack<V> r = ldp<V>(f.r + I), x = ldp<V>(xsrc + I);  // xsrc: f.x, or f.eps when the fused head of solver! parked x there (wl_resjac.cu)
   const Pack<V> id = ld_iD<V>(f, I, uni);
   Pack<V> en;
 #pragma unroll
@@ -569,8 +569,8 @@ __device__ __forceinline__ Pack<4> pro_pack(const float* __restrict__ crow, int 
   Pack<4> e; e.v[0] = c.x; e.v[1] = c.x; e.v[2] = c.y; e.v[3] = c.y;
   return e;
 }
-__device__ __forceinline__ void tile_prolong(const Lvl& f, const Lvl& c, const ProMap& m, const MarchGeom& mg, int i, int j, int k0, int k1, double& a0,
-                                             double& a1) {
+__device__ __forceinline__ void tile_prolong(const Lvl& f, const Lvl& c, const ProMap& m, const MarchGeom& mg, const float* __restrict__ xsrc, int i, int j,
+                                             int k0, int k1, double& a0, double& a1) {
   const GridD& g = f.g;
   const TilePos tpos = tile_pos(mg);
   const bool xlo = tpos.tx == 0, xhi = tpos.tx == mg.mx - 1, ylo = tpos.ty == 0, yhi = tpos.ty == mg.my - 1;
@@ -585,7 +585,7 @@ __device__ __forceinline__ void tile_prolong(const Lvl& f, const Lvl& c, const P
     // per issue waited on the scoreboard).  r and x of a later plane, and the coarse-x rows that plane will read (own
     // pair; the tile's edge threads add the rows / cells beyond the tile), are prefetched into L1.
     if (WL_PF > 0 && k + WL_PF <= g.n[2] - 2) {
-      prefetch_l1(f.r + I + WL_PF * g.s[2]); prefetch_l1(f.x + I + WL_PF * g.s[2]);
+      prefetch_l1(f.r + I + WL_PF * g.s[2]); prefetch_l1(xsrc + I + WL_PF * g.s[2]);
       const float* q = xc + pro_cidx(m, 2, k + WL_PF + 1) * cs2;
       prefetch_l1(q + Jy + ci);
       if (ylo) prefetch_l1(q + Jym + ci);
@@ -599,7 +599,7 @@ __device__ __forceinline__ void tile_prolong(const Lvl& f, const Lvl& c, const P
     const bool uni = pack_uniform<4>(f, I);
     const Pack<4> s = mult_vals<4>(f, I, e, row[cim], row[cip], pro_pack(xc + Jym + Jz, ci), pro_pack(xc + Jyp + Jz, ci), pro_pack(xc + Jy + Jzm, ci),
                                    pro_pack(xc + Jy + Jzp, ci), uni);
-    Pack<4> r = ldp<4>(f.r + I), x = ldp<4>(f.x + I);
+    Pack<4> r = ldp<4>(f.r + I), x = ldp<4>(xsrc + I);
     const Pack<4> id = ld_iD<4>(f, I, uni);
     Pack<4> en;
 #pragma unroll
