@@ -590,13 +590,24 @@ __global__ void __launch_bounds__(256) k_scale_alloc(float4* __restrict__ x, int
 }
 // project!: u[I,i] -= L[I,i]*∂(i,I,x) (Flow.jl:141-143)
 // On a uniform pack (Lvl::umask) L[I,i] is the constant uL = 1 and is not loaded.
+// `xdiv` (inside mom_step!, when the next solver! opens with the fused head of wl_resjac.cu): the closing x ./= dt of
+// project! (Flow.jl:144) is stored for the interior cells into that spare array — one extra word written here instead of a
+// read-modify-write pass of its own; x itself keeps the scaled values with the division pending (Sim::p_pend).
+template <int V>
+__device__ __forceinline__ void store_xdiv(float* __restrict__ xdiv, int64_t I, const Pack<V>& xc, int pre, float pre32, double pre64) {
+  Pack<V> xd;
+#pragma unroll
+  for (int q = 0; q < V; ++q) xd.v[q] = pre == 1 ? xc.v[q] / pre32 : (float)((double)xc.v[q] / pre64);
+  stp<V>(xdiv + I, xd);
+}
 template <int D, int V>
-__global__ void __launch_bounds__(256) k_project_correct(Lvl l, float* __restrict__ u) {
+__global__ void __launch_bounds__(256) k_project_correct(Lvl l, float* __restrict__ u, float* __restrict__ xdiv, int pre, float pre32, double pre64) {
   const GridD& g = l.g;
   const float* __restrict__ L = l.L;
   const float* __restrict__ x = l.x;
   for_rows<V>(g, [&](int, int, int, int64_t I) {
     const Pack<V> xc = ldp<V>(x + I);
+    if (xdiv) store_xdiv<V>(xdiv, I, xc, pre, pre32, pre64);
     const bool uni = pack_uniform<V>(l, I);
 #pragma unroll
     for (int i = 0; i < D; ++i) {
@@ -616,7 +627,7 @@ __global__ void __launch_bounds__(256) k_project_correct(Lvl l, float* __restric
 // swaps the pointers.  Cells whose upper neighbour is a ghost cell (any coordinate n-2) need the values BC! sets
 // afterwards: they are left to k_cfl_upper and stay out of the maximum here.
 __global__ void __launch_bounds__(256) k_project_correct_cfl(Lvl l, const float* __restrict__ u, float* __restrict__ uo, float* __restrict__ sigma, ReduceWS ws,
-                                                             FinArgs fa) {
+                                                             FinArgs fa, float* __restrict__ xdiv, int pre, float pre32, double pre64) {
   const GridD& g = l.g;
   const float* __restrict__ L = l.L;
   const float* __restrict__ x = l.x;
@@ -624,6 +635,7 @@ __global__ void __launch_bounds__(256) k_project_correct_cfl(Lvl l, const float*
   double acc[1] = {0.0};
   for_rows<4>(g, [&](int i, int j, int k, int64_t I) {
     const Pack<4> xc = ldp<4>(x + I);
+    if (xdiv) store_xdiv<4>(xdiv, I, xc, pre, pre32, pre64);
     const bool uni = pack_uniform<4>(l, I);
     const Pack<4> one = splat<4>(l.uL);
     // lower faces: the correction itself (k_project_correct)
