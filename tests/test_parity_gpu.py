@@ -484,6 +484,32 @@ def test_fused_solver_head_mom_step(make, steps, monkeypatch):
         assert rel_l2(getattr(s1.flow, f).numpy(), getattr(s0.flow, f).numpy()) < 2e-6, f
 
 
+@pytest.mark.parametrize("make,steps", [(lambda cls: tgv3d(cls, 128), 4), (lambda cls: sphere3d(cls, n=128, m=64, exitBC=True), 4)])
+def test_head_takes_divided_pressure_and_div_u_on_the_fly_bit_identical(make, steps, monkeypatch):
+    # inside mom_step! the fused head (wl_resjac.cu) evaluates z = div u itself and reads the pressure that the previous
+    # pressure correction stored divided by dt, multiplying by the new dt while staging — against the stored z and the
+    # whole-allocation scaling pass: same operations per cell, same bits.  Looking at p between two steps materialises the
+    # pending division and must not disturb either path.
+    monkeypatch.setenv("WL_FUSED_SOLVE_CELLS", "0")
+    monkeypatch.setenv("WL_XDIV", "0")
+    monkeypatch.setenv("WL_RESJAC_DIV", "0")
+    s0 = make(Simulation)
+    monkeypatch.setenv("WL_XDIV", "1")
+    monkeypatch.setenv("WL_RESJAC_DIV", "1")
+    s1 = make(Simulation)
+    l0 = [s0._eng.launch_count(), s1._eng.launch_count()]
+    for k in range(steps):
+        sim_step(s0, remeasure=False)
+        sim_step(s1, remeasure=False)
+        if k == 1:
+            assert np.array_equal(s1.flow.p.numpy(), s0.flow.p.numpy())
+    assert s0.pois.n == s1.pois.n
+    assert [float(x) for x in s0.flow.dt] == [float(x) for x in s1.flow.dt]
+    for f in ("u", "p"):
+        assert np.array_equal(getattr(s1.flow, f).numpy(), getattr(s0.flow, f).numpy()), f
+    assert s1._eng.launch_count() - l0[1] < s0._eng.launch_count() - l0[0]   # the two passes are really gone
+
+
 @pytest.mark.parametrize("make,steps", [(lambda cls: tgv3d(cls, 128), 2), (lambda cls: sphere3d(cls, exitBC=True), 4), (lambda cls: sphere3d(cls, n=128, m=64, exitBC=False), 3)])
 def test_cfl_fused_into_pressure_correction_is_bit_identical(make, steps, monkeypatch):
     # k_project_correct_cfl + k_cfl_upper (the corrector's project! correction evaluates CFL's σ = flux_out, the corrected

@@ -346,6 +346,8 @@ static int create_impl(wl_sim** out, int D, const int* N, double nu, double dt0,
   { const char* e = getenv("WL_STAGE"); a.stage_on = !(e && atoi(e) == 0); }
   { const char* e = getenv("WL_RESJAC"); a.resjac_on = !(e && atoi(e) == 0); }
   { const char* e = getenv("WL_CFL_FUSE"); a.cflfuse_on = !(e && atoi(e) == 0); }
+  { const char* e = getenv("WL_XDIV"); a.xdiv_on = e && atoi(e) != 0; }
+  { const char* e = getenv("WL_RESJAC_DIV"); a.resjac_div = e && atoi(e) != 0; }
   { const char* e = getenv("WL_BDIM_FUSE"); a.bdim_fuse = !(e && atoi(e) == 0); }
   if (!rc && cudaMalloc(&tmp, 64) == cudaSuccess) { a.allocs.push_back(tmp); a.ws.ticket = (unsigned int*)tmp; cudaMemsetAsync(tmp, 0, 64, a.stream); } else if (!rc) rc = wl_fail(WL_ERR_CUDA, "cudaMalloc ticket");
   if (!rc && cudaMallocHost((void**)&a.h_pinned, 64 * sizeof(float)) != cudaSuccess) rc = wl_fail(WL_ERR_CUDA, "cudaMallocHost");
@@ -471,7 +473,7 @@ int wl_upload(wl_sim* s, int field, const float* host, int64_t count) {
   if (field == WL_V || field == WL_MU0 || field == WL_MU1) S.mask_dirty = true;
   if (field == WL_MU0) pois_invalidate_uniform(S, 0);  // levels[1].L ≡ μ₀: stale until update!
   int rc = 0;
-  if (field == WL_P) S.p_pend = 0;                                        // replaced wholesale
+  if (field == WL_P) { S.p_pend = 0; S.xdiv_valid = false; }              // replaced wholesale
   if (field == WL_F) S.f_stale = false;                                   // replaced wholesale
   else if (field == WL_U0 || field == WL_V) rc = mom_materialize_f(S);     // inputs of the on-demand f are about to change
   if (rc) return rc;
@@ -505,6 +507,7 @@ int wl_level_upload(wl_sim* s, int level, int lf, const float* host, int64_t cou
   const int nzg = nz_padded_global(S, level);
   if (count != (int64_t)g.n[0] * g.n[1] * nzg * nc) return wl_fail(WL_ERR_ARG, "wl_level_upload: bad size");
   if (level == 0 && lf == WL_LVL_X) S.p_pend = 0;         // levels[1].x ≡ p, replaced wholesale
+  if (level == 0) S.xdiv_valid = false;                   // x or ϵ may be the one replaced
   if (level == 0 && lf == WL_LVL_L) S.mask_dirty = true;  // levels[1].L ≡ μ₀
   if (lf == WL_LVL_L || lf == WL_LVL_D || lf == WL_LVL_ID) pois_invalidate_uniform(S, level);
   int rc = copy_field(S, g, d, const_cast<float*>(host), nc, true, nzg);

@@ -80,6 +80,15 @@ struct Sim {
   int p_pend = 0;                      // 0 none, 1 divide by p_pend32 (Float32 dt), 2 divide by p_pend64 (Float64 dt)
   float p_pend32 = 0.f;
   double p_pend64 = 0.0;
+  // … and, when the next solver! opens with the fused head (wl_resjac.cu), the divided pressure of the interior cells
+  // already sits in levels[0].eps (written by the pressure correction): the head reads x from there, applies the next
+  // project!'s x .*= dt while staging and writes the smoothed x straight into the x array — no scaling pass at all
+  bool xdiv_valid = false;
+  bool xdiv_on = false;                // WL_XDIV=1 switches this on.  Measured at 512³ (profiles/r02_ab_fusions.txt): the divisions cost the two pressure
+                                       // corrections more (+0.24 ms each) than the scaling pass they replace (0.21 ms) — off by default
+  int xmul_op = 0;                     // set by project! for the head it is about to run: 0 x is read as is, 1 ·xmul32 (Float32 dt), 2 ·xmul64 (Float64 dt)
+  float xmul32 = 0.f;
+  double xmul64 = 0.0;
   bool cflfuse_on = true;              // WL_CFL_FUSE=0: the corrector's pressure correction and CFL stay separate kernels
   bool cfl_fused = false;              // the corrector's project! already produced σ = flux_out and its maximum away from the upper boundaries
   bool last_cd_fused = false;          // the last conv_diff! folded BDIM! stage 2 into its store on the clean tile-planes
@@ -116,6 +125,8 @@ struct Sim {
   bool march_on = true;              // WL_MARCH=0: the stencil kernels iterate (row-group, plane) units instead of marching in z
   bool stage_on = true;              // WL_STAGE=0: marching kernels keep their z-window in registers instead of a shared-memory ring
   bool resjac_on = true;             // WL_RESJAC=0: residual!, the first Jacobi! and restrict! of solver! stay separate kernels (wl_resjac.cu)
+  bool resjac_div = false;           // WL_RESJAC_DIV=1: the fused head evaluates project!'s z = div u itself instead of reading the z a pass of its own stored.
+                                     // Measured at 512³: the head slows down by 0.52 ms, the pass it replaces takes 0.42 ms — off by default
   bool head_fused = false;           // solver!: the fused head already ran Jacobi! + restrict! of the first Vcycle! on the finest level
   bool x_parked = false;             // … and the finest x lives in levels[0].eps until the prolongation pass moves it back
   bool nonuni_known = false;
@@ -180,7 +191,8 @@ int bc_exit(Sim& s, const double* U, float dt);
 
 // ---- wl_resjac.cu ----
 bool resjac_eligible(const Sim& s);
-int resjac_run(Sim& s);
+bool pois_head_fusable(const Sim& s);  // solver!(ml) on this handle opens with the fused head
+int resjac_run(Sim& s, const float* divu = nullptr);
 int resjac_unpark(Sim& s);  // moves the parked x' from levels[0].eps back into levels[0].x (API inspection only)
 
 // ---- wl_poisson.cu ----

@@ -147,8 +147,14 @@ __global__ void __launch_bounds__(256) k_conv_diff(CDArgs a) {
 // The shell is walked as three groups with 32-bit index arithmetic and x fastest wherever a group has
 // an x extent: full z-planes outside the core's z-range, then the 4 outer y-rows of every core plane,
 // then the 4 outer x-cells of every remaining row.
+#ifndef WL_SHELL_MINB
+#define WL_SHELL_MINB 5  // 48 registers (a few spills): the shell is latency-bound, 40 resident warps instead of 32 (512³: 0.33 → 0.17 ms per launch)
+#endif
+#ifndef WL_PCC_MINB
+#define WL_PCC_MINB 5    // k_project_correct_cfl: 48 instead of 54 registers, five resident blocks (512³: 1.03 → 0.95 ms)
+#endif
 template <int D>
-__global__ void __launch_bounds__(256) k_conv_diff_shell(CDArgs a, unsigned int nZ, unsigned int nY, unsigned int nX, int xlow) {
+__global__ void __launch_bounds__(256, WL_SHELL_MINB) k_conv_diff_shell(CDArgs a, unsigned int nZ, unsigned int nY, unsigned int nX, int xlow) {
   const GridD& g = a.g;
   const int n0 = g.n[0], n1 = g.n[1], n2 = g.n[2];
   const int zc0 = g.zlo_halo ? 1 : 2, zc1 = g.zhi_halo ? n2 - 2 : n2 - 3;  // core z-range
@@ -626,7 +632,7 @@ __global__ void __launch_bounds__(256) k_project_correct(Lvl l, float* __restric
 // as well — which rules out the in-place update, so the corrected field goes to a spare velocity buffer and the caller
 // swaps the pointers.  Cells whose upper neighbour is a ghost cell (any coordinate n-2) need the values BC! sets
 // afterwards: they are left to k_cfl_upper and stay out of the maximum here.
-__global__ void __launch_bounds__(256) k_project_correct_cfl(Lvl l, const float* __restrict__ u, float* __restrict__ uo, float* __restrict__ sigma, ReduceWS ws,
+__global__ void __launch_bounds__(256, WL_PCC_MINB) k_project_correct_cfl(Lvl l, const float* __restrict__ u, float* __restrict__ uo, float* __restrict__ sigma, ReduceWS ws,
                                                              FinArgs fa, float* __restrict__ xdiv, int pre, float pre32, double pre64) {
   const GridD& g = l.g;
   const float* __restrict__ L = l.L;
@@ -872,7 +878,9 @@ int mom_conv_diff(Sim& s, const float* src, bool fuse_bdim1, const double* gacc,
       const int xlow = used_tma ? convdiff_tma_core_x0(s) : 2;
       const unsigned int nX = (unsigned int)(xlow + 2) * (unsigned int)(g.n[1] - 4) * (unsigned int)nzc;
       const int64_t cnt = (int64_t)nZ + nY + nX;
-      k_conv_diff_shell<3><<<(int)std::min<int64_t>((cnt + 255) / 256, s.nsm * 16), 256, 0, s.stream>>>(a, nZ, nY, nX, xlow);
+      static int bps = 0;
+      if (!bps) { const char* e = getenv("WL_SHELL_BPS"); bps = std::max(1, e ? atoi(e) : 16); }
+      k_conv_diff_shell<3><<<(int)std::min<int64_t>((cnt + 255) / 256, (int64_t)s.nsm * bps), 256, 0, s.stream>>>(a, nZ, nY, nX, xlow);
       ++s.launches;
     }
   } else {
@@ -956,8 +964,25 @@ static int scale_pressure(Sim& s, int op, float f32v, double f64v) {
 // the pressure as the reference leaves it after project! (x ./= dt applied): on demand, before anything outside
 // mom_step! looks at it
 int mom_materialize_p(Sim& s) {
+  s.xdiv_valid = false;  // every entry point that may touch x or ϵ outside mom_step! comes through here first
   if (!s.p_pend) return 0;
   return scale_pressure(s, 0, 0.f, 0.0);
+}
+// The row kernels that read their stencil neighbours through the L1 (no shared-memory staging) ask for the largest L1 the SM
+// can give them; without the hint the split follows whatever the driver derives from the kernels that ran before.
+template <class K> static void prefer_l1(K kern) {
+  static const bool off = [] { const char* e = getenv("WL_MAXL1"); return e && atoi(e) == 0; }();
+  if (!off) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxL1);
+}
+static void momentum_kernel_attributes() {
+  static bool done = false;
+  if (done) return;
+  done = true;
+  prefer_l1(k_project_correct<3, 4>);
+  prefer_l1(k_project_correct_cfl);
+  prefer_l1(k_project_pre<3, 4>);
+  prefer_l1(k_cfl<3, 4>);
+  cudaGetLastError();
 }
 // project!(a,b,w) (Flow.jl:137-145)
 // `in_step` (mom_step!): z = div u is evaluated inside residual! instead of by a pass of its own, and the closing
@@ -968,20 +993,28 @@ int mom_project(Sim& s, double w, int* n, int slot, bool defer_count, bool in_st
   const double dtw = f32 ? (double)dt32 : w * (double)dt32;
   Lvl& b = s.levels[0];
   int rc;
+  // inside mom_step! with the fused solver head: the pressure correction of the previous project! left x ./ dt of the interior
+  // cells in the ϵ array (xdiv_valid) and the head applies x .*= dt while it stages x from there — no scaling pass
+  momentum_kernel_attributes();
+  const bool head = in_step && s.xdiv_on && pois_head_fusable(s);
+  const bool from_div = head && s.xdiv_valid;
+  s.xdiv_valid = false;
   wl_prof_begin(s, WL_PROF_PROJECT);
   if (!in_step) RLAUNCH(s, k_project_pre, s.g, s.g, s.u, b.z);
-  if ((rc = scale_pressure(s, f32 ? 1 : 2, (float)dtw, dtw))) return rc;
-  wl_prof_end(s, WL_PROF_PROJECT, 4.0 * (double)s.g.interior * ((in_step ? 0 : s.D + 1) + 2));
+  if (from_div) { s.xmul_op = f32 ? 1 : 2; s.xmul32 = (float)dtw; s.xmul64 = dtw; }
+  else if ((rc = scale_pressure(s, f32 ? 1 : 2, (float)dtw, dtw))) return rc;
+  wl_prof_end(s, WL_PROF_PROJECT, 4.0 * (double)s.g.interior * ((in_step ? 0 : s.D + 1) + (from_div ? 0 : 2)));
   rc = pois_solve(s, 1e-4, s.pois_kind == WL_POIS_MULTILEVEL ? 32 : 1000, n, true, slot, defer_count, in_step ? s.u : nullptr);
   if (rc) return rc;
   wl_prof_begin(s, WL_PROF_PROJECT);
   // the corrector's correction also evaluates CFL's σ (k_project_correct_cfl) when a velocity-sized buffer is free to take
   // the corrected field: after a fused step flow.f is not materialised (f_stale), its array is that buffer
   const RowLaunch rlc = row_launch(s.g);
+  float* xdiv = head ? b.eps : nullptr;  // ϵ is free between two solver! calls
   s.cfl_fused = false;
   if (with_cfl && s.cflfuse_on && s.D == 3 && rlc.V == 4 && s.f_stale) {
     const FinArgs fa = fin_misc(s);
-    k_project_correct_cfl<<<wl_grid_for(s, rlc.nunits), rlc.blk, 0, s.stream>>>(b, s.u, s.f, s.sigma, s.ws, fa);
+    k_project_correct_cfl<<<wl_grid_for(s, rlc.nunits), rlc.blk, 0, s.stream>>>(b, s.u, s.f, s.sigma, s.ws, fa, xdiv, f32 ? 1 : 2, (float)dtw, dtw);
     ++s.launches;
     if ((rc = post_reduce(s, FIN_CFL, fa, true))) return rc;
     if (s.exitBC) {  // BC! rewrites every ghost cell of the new array except the saved exit plane
@@ -992,11 +1025,12 @@ int mom_project(Sim& s, double w, int* n, int slot, bool defer_count, bool in_st
     float* t = s.u; s.u = s.f; s.f = t;
     s.cfl_fused = true;
   } else {
-    RLAUNCH(s, k_project_correct, s.g, b, s.u);
+    RLAUNCH(s, k_project_correct, s.g, b, s.u, xdiv, f32 ? 1 : 2, (float)dtw, dtw);
   }
   s.p_pend = f32 ? 1 : 2; s.p_pend32 = (float)dtw; s.p_pend64 = dtw;
+  s.xdiv_valid = xdiv != nullptr;
   if (!in_step && (rc = mom_materialize_p(s))) return rc;
-  wl_prof_end(s, WL_PROF_PROJECT, 4.0 * (double)s.g.interior * (wl_words(s, 3 * s.D + 1, s.D) + (in_step ? 0 : 2)));
+  wl_prof_end(s, WL_PROF_PROJECT, 4.0 * (double)s.g.interior * (wl_words(s, 3 * s.D + 1, s.D) + (in_step ? 0 : 2) + (xdiv ? 1 : 0)));
   return wl_cuda_check(s, cudaGetLastError(), "project");
 }
 int mom_div(Sim& s, const float* u, float* z) {

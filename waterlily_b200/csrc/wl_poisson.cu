@@ -336,7 +336,10 @@ __global__ void __launch_bounds__(256, WL_STAGE_MINB) k_residual_s(Lvl l, MarchG
   double tot[2];
   if (grid_reduce<2>(acc, ws, tot)) finish_reduction(FIN_RESIDUAL, fa, tot[0], tot[1]);
 }
-__global__ void __launch_bounds__(256) k_prolong_increment_init_m(Lvl f, Lvl c, ProMap m, MarchGeom mg, const float* __restrict__ xsrc, ReduceWS ws, FinArgs fa) {
+#ifndef WL_PROLONG_MINB
+#define WL_PROLONG_MINB 5  // 48 instead of 64 registers, five resident blocks: the pass is latency-bound on its L1-served coarse-x reads (512³: 0.65 → 0.54 ms)
+#endif
+__global__ void __launch_bounds__(256, WL_PROLONG_MINB) k_prolong_increment_init_m(Lvl f, Lvl c, ProMap m, MarchGeom mg, const float* __restrict__ xsrc, ReduceWS ws, FinArgs fa) {
   double acc[2] = {0.0, 0.0};
   for_columns(f.g, mg, [&](int i, int j, int k0, int k1) { tile_prolong(f, c, m, mg, xsrc, i, j, k0, k1, acc[0], acc[1]); });
   double tot[2];
@@ -376,8 +379,11 @@ __global__ void __launch_bounds__(256) k_pcg_mult(Lvl l, ReduceWS ws, FinArgs fa
 }
 // :133-139  x += αϵ ; r -= αz ; [last sweep → return] ; z = r·iD ; ρ₂ = r⋅z ; |ρ₂|<10eps → return ;
 // β = ρ₂/ρ ; ρ = ρ₂
+#ifndef WL_UPD_MINB
+#define WL_UPD_MINB 1
+#endif
 template <int D, int V>
-__global__ void __launch_bounds__(256) k_pcg_update(Lvl l, ReduceWS ws, FinArgs fa, int last) {
+__global__ void __launch_bounds__(256, WL_UPD_MINB) k_pcg_update(Lvl l, ReduceWS ws, FinArgs fa, int last) {
   if (!l.sc->active) return;
   const float alpha = l.sc->alpha;
   double acc[2] = {0.0, 0.0};
@@ -681,8 +687,7 @@ int pois_vcycle(Sim& s, int level) {
   const bool gather = s.dist.nranks > 1 && s.lvl_dist[level] && !s.lvl_dist[level + 1];
   const bool head = level == 0 && s.head_fused;  // Jacobi! + restrict! of this cycle ran inside the fused head of solver! (wl_resjac.cu)
   if (head) {
-    s.head_fused = false;
-    s.x_parked = true;   // the finest x is in fine.eps until the prolongation pass below
+    s.head_fused = false;  // (s.x_parked, set by the head: the finest x is in fine.eps until the prolongation pass below)
   } else {
     if ((rc = pois_jacobi(s, fine, 1))) return rc;
     // restrict! + fill!(coarse.x,0); a distributed→replicated transition gathers the planes
@@ -717,6 +722,13 @@ int pois_vcycle(Sim& s, int level) {
     const MarchLaunch ml = march_for(s, fine.g);
     const float* xsrc = (level == 0 && s.x_parked) ? fine.eps : fine.x;  // same cell read and (as the new ϵ) written by one thread: no hazard
     if (level == 0) s.x_parked = false;
+    static bool l1_done = false;
+    if (!l1_done) {
+      l1_done = true;
+      const char* e = getenv("WL_MAXL1");
+      if (!(e && atoi(e) == 0)) cudaFuncSetAttribute(k_prolong_increment_init_m, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxL1);
+      cudaGetLastError();
+    }
     if (ml.ok && (coarse.g.n[0] - 2) % 2 == 0) { k_prolong_increment_init_m<<<ml.grid, ml.blk, 0, s.stream>>>(fine, coarse, m, ml.mg, xsrc, s.ws, fa); ++s.launches; }
     else RLAUNCH(s, k_prolong_increment_init, fine.g, fine, coarse, m, xsrc, s.ws, fa);
     if ((rc = post_reduce(s, FIN_INC_INIT, fa))) return rc;
@@ -736,6 +748,7 @@ int pois_head(Sim& s) {
   if (resjac_eligible(s)) {
     if ((rc = resjac_run(s))) return rc;
     s.eps_is_jacobi = false;
+    s.x_parked = false;
     return resjac_unpark(s);
   }
   if ((rc = pois_residual(s, fine, false, false, true, nullptr))) return rc;
@@ -743,6 +756,14 @@ int pois_head(Sim& s) {
   if (s.dist.nranks > 1 && s.lvl_dist[0] && !s.lvl_dist[1]) return wl_fail(WL_ERR_ARG, "wl_pois_head: not available across a distributed/replicated level transition");
   RLAUNCH(s, k_restrict, coarse.g, coarse, fine, 1, coarse.g.n[2] - 2, 0);
   return wl_cuda_check(s, cudaGetLastError(), "k_restrict");
+}
+static int fuse_prolong_env() {
+  static int fuse_env = -1;
+  if (fuse_env < 0) { const char* e = getenv("WL_FUSE_PROLONG"); fuse_env = e ? atoi(e) : 1; }
+  return fuse_env;
+}
+bool pois_head_fusable(const Sim& s) {
+  return s.pois_kind == WL_POIS_MULTILEVEL && !s.vc_solve && fuse_prolong_env() != 0 && resjac_eligible(s);
 }
 // solver!(ml;tol,itmx) (MultiLevelPoisson.jl:87-99) / solver!(p::Poisson;tol,itmx) (Poisson.jl:162-172)
 int pois_solve(Sim& s, double tol, int itmx, int* n_out, bool ghosts_valid, int slot, bool defer_count, const float* divu) {
@@ -761,16 +782,15 @@ int pois_solve(Sim& s, double tol, int itmx, int* n_out, bool ghosts_valid, int 
     if (n_out) *n_out = n;
     return 0;
   }
-  static int fuse_env = -1;
-  if (fuse_env < 0) { const char* e = getenv("WL_FUSE_PROLONG"); fuse_env = e ? atoi(e) : 1; }
+  const int fuse_env = fuse_prolong_env();
   int rc;
   s.head_fused = false;
   s.x_parked = false;
-  if (s.pois_kind == WL_POIS_MULTILEVEL && itmx > 0 && fuse_env != 0 && resjac_eligible(s)) {
-    // residual! and the Jacobi! + restrict! that open the first Vcycle! as one pass (wl_resjac.cu); it reads z, so
-    // project!'s z = div u is materialised first (x needs no perBC!: the pass wraps its own periodic reads)
-    if (divu && (rc = mom_div(s, divu, p.z))) return rc;
-    if ((rc = resjac_run(s))) return rc;
+  if (itmx > 0 && pois_head_fusable(s)) {
+    // residual! and the Jacobi! + restrict! that open the first Vcycle! as one pass (wl_resjac.cu); project!'s z = div u is
+    // evaluated inside it (x needs no perBC!: the pass wraps its own periodic reads)
+    if (divu && !s.resjac_div) { if ((rc = mom_div(s, divu, p.z))) return rc; divu = nullptr; }
+    if ((rc = resjac_run(s, divu))) return rc;
     s.eps_is_jacobi = false;
     s.head_fused = true;
   } else {

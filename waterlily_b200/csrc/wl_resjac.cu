@@ -39,6 +39,10 @@ constexpr int RJ_XPLB = (RJ_MY + 4) * RJ_RWB;   // bytes per x stage (halo of tw
 constexpr int RJ_ZPLB = (RJ_MY + 2) * RJ_RWB;   // bytes per z / ϵ stage (halo of one row)
 constexpr int RJ_XBB = (RJ_MY / 2) * 4 * RJ_MX * 4;  // restrict!: r of the odd rows handed to the even rows
 constexpr int RJ_SMEM = RJ_NXS * RJ_XPLB + 2 * RJ_NZS * RJ_ZPLB + RJ_XBB;
+constexpr int RJ_SMEM_DIVU = RJ_SMEM - RJ_NZS * RJ_ZPLB;  // no z ring
+#ifndef RJ_PF
+#define RJ_PF 1                                 // planes ahead of the L1 prefetch of the velocity field
+#endif
 
 __device__ __forceinline__ void sts4(unsigned int a, const Pack<4>& v) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.v[0]), "f"(v.v[1]), "f"(v.v[2]), "f"(v.v[3]) : "memory");
@@ -59,13 +63,19 @@ __device__ __forceinline__ bool rj_dead(int v, int n, int per) { return !per && 
 // residual of V cells at tile position (c, rr) of plane p: r = iD == 0 ? 0 : z − A x (Poisson.jl:93), e = r·iD (:111).
 // xm/xc/xp: byte addresses of the x stages of planes p-1, p, p+1; zc: the z stage of plane p; Iw: (wrapped) cell index
 // for the coefficient loads of a non-uniform pack.
+// zc: the z stage of plane p, or — divu given — z = div u (Flow.jl:11-17, 138) is evaluated here from the velocity field
+// (its lines were prefetched into L1 one plane earlier), with the operations of k_project_pre.
 template <int V>
-__device__ __forceinline__ void rj_residual(const Lvl& l, unsigned int xm, unsigned int xc, unsigned int xp, unsigned int zc, int c, int rr, int64_t Iw, bool uni,
-                                            bool dead, Pack<V>& r, Pack<V>& e) {
+__device__ __forceinline__ void rj_residual(const Lvl& l, unsigned int xm, unsigned int xc, unsigned int xp, unsigned int zc, const float* __restrict__ divu, int c,
+                                            int rr, int64_t Iw, bool uni, bool dead, Pack<V>& r, Pack<V>& e) {
   const unsigned int xo = (unsigned int)(((rr + 2) * RJ_RW + 4 + c) * 4), zo = (unsigned int)(((rr + 1) * RJ_RW + 4 + c) * 4);
+  Pack<V> zz;
+  if (divu) {
+    if (!dead) zz = div_pack<3, V>(l.g, divu, Iw);
+  } else zz = ldsp<V>(zc + zo);
   const Pack<V> x0 = ldsp<V>(xc + xo);
   const float xm1 = lds1(xc + xo - 4), xp4 = lds1(xc + xo + 4 * V);
-  const Pack<V> ym = ldsp<V>(xc + xo - RJ_RWB), yp = ldsp<V>(xc + xo + RJ_RWB), zm = ldsp<V>(xm + xo), zp = ldsp<V>(xp + xo), zz = ldsp<V>(zc + zo);
+  const Pack<V> ym = ldsp<V>(xc + xo - RJ_RWB), yp = ldsp<V>(xc + xo + RJ_RWB), zm = ldsp<V>(xm + xo), zp = ldsp<V>(xp + xo);
   if (dead) {
 #pragma unroll
     for (int q = 0; q < V; ++q) { r.v[q] = 0.f; e.v[q] = 0.f; }
@@ -81,13 +91,24 @@ __device__ __forceinline__ void rj_residual(const Lvl& l, unsigned int xm, unsig
   }
 }
 
-__global__ void __launch_bounds__(256, 3) k_resjac(Lvl l, Lvl cl, float* __restrict__ xout, MarchGeom mg, ReduceWS ws, FinArgs fa, const unsigned int* __restrict__ nonuni) {
+// project!'s x .*= dt (Flow.jl:139) applied to a staged value: dt is Float32 for w = 1, Float64 for w = 0.5
+__device__ __forceinline__ float rj_mul(float v, int op, float m32, double m64) { return op == 1 ? v * m32 : (float)((double)v * m64); }
+
+// xin: where the pressure is read from — the x array, or (mul_op != 0, inside mom_step!) the array that holds the divided
+// pressure of the last project!, which gets the new project!'s x .*= dt while it is staged.  xout ≠ xin.
+template <bool DIVU, int MULOP>
+__global__ void __launch_bounds__(256, 3) k_resjac(Lvl l, Lvl cl, const float* __restrict__ xin, float* __restrict__ xout, float mul32, double mul64,
+                                                    const float* __restrict__ divu_, MarchGeom mg, ReduceWS ws, FinArgs fa,
+                                                    const unsigned int* __restrict__ nonuni) {
   extern __shared__ __align__(16) float rj_smem[];
+  const float* __restrict__ const divu = DIVU ? divu_ : nullptr;  // compile-time switches: no registers spent on them
+  constexpr int mul_op = MULOP;
   const GridD& g = l.g;
   const int n0 = g.n[0], n1 = g.n[1], n2 = g.n[2];
   const int64_t s1 = g.s[1], s2 = g.s[2];
   const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
-  const unsigned int XR = wl_smem_u32(rj_smem), ZR = XR + RJ_NXS * RJ_XPLB, ER = ZR + RJ_NZS * RJ_ZPLB, XB = ER + RJ_NZS * RJ_ZPLB;
+  // (no z ring when z is evaluated from divu: the launch then asks for less shared memory, which stays with the L1)
+  const unsigned int XR = wl_smem_u32(rj_smem), ZR = XR + RJ_NXS * RJ_XPLB, ER = divu ? ZR : ZR + RJ_NZS * RJ_ZPLB, XB = ER + RJ_NZS * RJ_ZPLB;
   // every pack of the level uniform (no body, no wall: the periodic benchmark): no mask traffic at all
   const bool has_mask = l.umask != nullptr;
   const bool all_uni = has_mask && *nonuni == 0u;
@@ -122,10 +143,25 @@ __global__ void __launch_bounds__(256, 3) k_resjac(Lvl l, Lvl cl, float* __restr
     }
     const unsigned int d_xown = (unsigned int)(((ty + 2) * RJ_RW + 4 + 4 * tx) * 4), d_zown = (unsigned int)(((ty + 1) * RJ_RW + 4 + 4 * tx) * 4);
     auto issue_x = [&](int P, unsigned int stage) {
-      const float* b = l.x + (int64_t)rj_wrap(P, n2, g.per[2]) * s2;
+      const float* b = xin + (int64_t)rj_wrap(P, n2, g.per[2]) * s2;
       cp_async16s(stage + d_xown, b + o_own);
       if (tid < 128) cp_async16s(stage + d_xh, b + o_xh);
       else if (tid < 168) cp_async4s(stage + d_xh, b + o_xh);
+    };
+    // x .*= dt on what this thread itself copied into a stage (its cp.async group has completed: visible to the thread)
+    auto scale_x = [&](unsigned int stage) {
+      Pack<4> v = lds4(stage + d_xown);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) v.v[q] = rj_mul(v.v[q], mul_op, mul32, mul64);
+      sts4(stage + d_xown, v);
+      if (tid < 128) {
+        Pack<4> h = lds4(stage + d_xh);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) h.v[q] = rj_mul(h.v[q], mul_op, mul32, mul64);
+        sts4(stage + d_xh, h);
+      } else if (tid < 168) {
+        sts1(stage + d_xh, rj_mul(lds1(stage + d_xh), mul_op, mul32, mul64));
+      }
     };
     auto issue_z = [&](int P, unsigned int stage) {
       const float* b = l.z + (int64_t)rj_wrap(P, n2, g.per[2]) * s2;
@@ -141,7 +177,7 @@ __global__ void __launch_bounds__(256, 3) k_resjac(Lvl l, Lvl cl, float* __restr
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       issue_x(k0 - 2 + q, XR + q * RJ_XPLB);
-      if (q >= 2) issue_z(k0 - 3 + q, ZR + (q - 2) * RJ_ZPLB);
+      if (q >= 2 && !divu) issue_z(k0 - 3 + q, ZR + (q - 2) * RJ_ZPLB);
       cp_async_commit_group();
     }
     unsigned int xa_m = XR, xa_c = XR + RJ_XPLB, xa_p = XR + 2 * RJ_XPLB, xa_i = XR + 4 * RJ_XPLB;  // x stages of planes s-1, s, s+1, s+3
@@ -159,10 +195,33 @@ __global__ void __launch_bounds__(256, 3) k_resjac(Lvl l, Lvl cl, float* __restr
       const unsigned int m_cur = m_next;
       if (has_mask && !all_uni && s <= k1) m_next = mbase[(int64_t)rj_wrap(s + 1, n2, g.per[2]) * mstp];
       cp_async_wait_group<1>();   // x planes ≤ s+1 and z planes ≤ s have landed
+      if (mul_op) {
+        if (s == k0 - 1) { scale_x(xa_m); scale_x(xa_c); }
+        scale_x(xa_p);            // plane s+1, complete since this wait
+      }
       __syncthreads();            // … for every thread; everyone is done with the stages about to be refilled
       if (s + 3 <= k1 + 2) issue_x(s + 3, xa_i);
-      if (s + 2 <= k1 + 1) issue_z(s + 2, ZR + (zs == 0 ? 2 : zs - 1) * RJ_ZPLB);
+      if (s + 2 <= k1 + 1 && !divu) issue_z(s + 2, ZR + (zs == 0 ? 2 : zs - 1) * RJ_ZPLB);
       cp_async_commit_group();
+      if (divu && s + RJ_PF <= k1 + 1) {
+        // the velocity lines the R phase of plane s+RJ_PF will read: own pack of each component; the tile's edge threads
+        // add the halo ring (rows -1, 8 and u₂'s row 9; the packs left and right of the tile).  u₃ of the plane above
+        // is the own pack of the following step.  Addresses of cells outside the array are clamped: never used.
+        const int kp = rj_wrap(s + RJ_PF, n2, g.per[2]);
+        const float* q = divu + o_own + (int64_t)kp * s2;
+        prefetch_l1(q); prefetch_l1(q + g.comp); prefetch_l1(q + 2 * g.comp);
+        if (s + RJ_PF == k1 + 1) prefetch_l1(q + 2 * g.comp + s2);
+        if (ty == 0 || ty == RJ_MY - 1) {
+          const int jw = rj_wrap(ty == 0 ? j0 - 1 : j0 + RJ_MY, n1, g.per[1]);
+          const float* qr = divu + (i0 + 4 * tx) + jw * s1 + (int64_t)kp * s2;
+          prefetch_l1(qr); prefetch_l1(qr + g.comp); prefetch_l1(qr + 2 * g.comp);
+          if (ty == RJ_MY - 1) prefetch_l1(qr + g.comp + s1);
+        }
+        if (tx == 0 || tx == 31) {
+          const float* qc = divu + rj_wrap(tx == 0 ? i0 - 1 : i0 + 4 * RJ_MX, n0, g.per[0]) + j * s1 + (int64_t)kp * s2;
+          prefetch_l1(qc); prefetch_l1(qc + g.comp); prefetch_l1(qc + 2 * g.comp);
+        }
+      }
       // ---- restrict! of the plane finished in the previous step (MultiLevelPoisson.jl:33: Σ over the 2×2×2 block, x fastest) ----
       if (pend && (ty & 1) == 0) {
         const Pack<4> pr = lds4(XB + (unsigned int)(((ty >> 1) * 4 * RJ_MX + 4 * tx) * 4));
@@ -184,7 +243,7 @@ __global__ void __launch_bounds__(256, 3) k_resjac(Lvl l, Lvl cl, float* __restr
       {
         uni_cur = all_uni || (has_mask && m_cur == 0u);
         Pack<4> e;
-        rj_residual<4>(l, xa_m, xa_c, xa_p, zst, 4 * tx, ty, o_own + (int64_t)kw * s2, uni_cur, pdead, r_cur, e);
+        rj_residual<4>(l, xa_m, xa_c, xa_p, zst, divu, 4 * tx, ty, o_own + (int64_t)kw * s2, uni_cur, pdead, r_cur, e);
         sts4(est + d_zown, e);
         if (s >= k0 && s <= k1) {
 #pragma unroll
@@ -198,7 +257,7 @@ __global__ void __launch_bounds__(256, 3) k_resjac(Lvl l, Lvl cl, float* __restr
         const bool dead = pdead || rj_dead(j0 + rr, n1, g.per[1]);
         const bool uni = all_uni || (has_mask && !dead && l.umask[(Iw + g.lead) >> 2] == 0);
         Pack<4> r, e;
-        rj_residual<4>(l, xa_m, xa_c, xa_p, zst, 4 * lane, rr, Iw, uni, dead, r, e);
+        rj_residual<4>(l, xa_m, xa_c, xa_p, zst, divu, 4 * lane, rr, Iw, uni, dead, r, e);
         sts4(est + (unsigned int)(((rr + 1) * RJ_RW + 4 + 4 * lane) * 4), e);
       } else if (ty == ((hw + 2) & 7) && lane < 16) {
         const int h = lane >> 3, rr = lane & 7, c = h == 0 ? -1 : 4 * RJ_MX, iw = rj_wrap(i0 + c, n0, g.per[0]);
@@ -206,7 +265,7 @@ __global__ void __launch_bounds__(256, 3) k_resjac(Lvl l, Lvl cl, float* __restr
         const bool dead = pdead || rj_dead(i0 + c, n0, g.per[0]);
         const bool uni = all_uni || (has_mask && !dead && l.umask[(Iw - ((iw - 1) & 3) + g.lead) >> 2] == 0);
         Pack<1> r, e;
-        rj_residual<1>(l, xa_m, xa_c, xa_p, zst, c, rr, Iw, uni, dead, r, e);
+        rj_residual<1>(l, xa_m, xa_c, xa_p, zst, divu, c, rr, Iw, uni, dead, r, e);
         sts1(est + (unsigned int)(((rr + 1) * RJ_RW + 4 + c) * 4), e.v[0]);
       }
       __syncthreads();  // ϵ of plane s complete
@@ -316,15 +375,22 @@ bool resjac_eligible(const Sim& s) {
   return c.n[0] - 2 == nxi / 2 && c.n[1] - 2 == nyi / 2 && c.n[2] - 2 == nzi / 2;
 }
 
-// residual!(fine) + Jacobi!(fine) + restrict!(fine → coarse) + fill!(coarse.x, 0); z must hold div u (interior).
-// Leaves r' in fine.r, x' PARKED in fine.ϵ, the coarse residual in levels[1].r.
-int resjac_run(Sim& s) {
+// residual!(fine) + Jacobi!(fine) + restrict!(fine → coarse) + fill!(coarse.x, 0); z holds the source term (interior), or —
+// divu given (project! inside mom_step!) — it is div(divu), evaluated on the fly and never stored.
+// Leaves r' in fine.r, the coarse residual in levels[1].r, and x' PARKED in fine.ϵ (Sim::x_parked) — or, when project! asked
+// for its x .*= dt to be applied on the way (Sim::xmul_op: x is then read from fine.ϵ, see Sim::xdiv_valid), in fine.x.
+int resjac_run(Sim& s, const float* divu) {
   Lvl& l = s.levels[0];
   Lvl& c = s.levels[1];
   const GridD& g = l.g;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(k_resjac, cudaFuncAttributeMaxDynamicSharedMemorySize, RJ_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(k_resjac<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, RJ_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_resjac<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, RJ_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_resjac<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, RJ_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_resjac<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, RJ_SMEM_DIVU);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_resjac<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, RJ_SMEM_DIVU);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_resjac<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, RJ_SMEM_DIVU);
     if (e != cudaSuccess) return wl_cuda_check(s, e, "cudaFuncSetAttribute(k_resjac)");
     attr_done = true;
   }
@@ -333,7 +399,9 @@ int resjac_run(Sim& s) {
   mg.ntx = (g.n[0] - 2) / (4 * RJ_MX);
   mg.nty = (g.n[1] - 2) / RJ_MY;
   const int nzi = g.n[2] - 2;
-  int zc = 64;
+  static int zc_env = -1;
+  if (zc_env < 0) { const char* e = getenv("WL_RJ_ZCHUNK"); zc_env = e ? std::max(8, atoi(e)) : 64; }
+  int zc = zc_env;
   while (zc > 8 && (int64_t)mg.ntx * mg.nty * ((nzi + zc - 1) / zc) < (int64_t)s.nsm * 6) zc >>= 1;
   mg.zchunk = zc;
   mg.ntz = (nzi + zc - 1) / zc;
@@ -341,17 +409,26 @@ int resjac_run(Sim& s) {
   const int grid = (int)std::min<int64_t>(ntiles, WL_MAXBLOCKS);
   const FinArgs fa = fin_level(s, 0);
   wl_prof_begin(s, WL_PROF_RESIDUAL);
-  k_resjac<<<grid, 256, RJ_SMEM, s.stream>>>(l, c, l.eps, mg, s.ws, fa, s.d_nonuni);
+  const bool from_div = s.xmul_op != 0;
+  const float* xin = from_div ? l.eps : l.x;
+  float* xout = from_div ? l.x : l.eps;
+#define RJ_LAUNCH(DV, MO) k_resjac<DV, MO><<<grid, 256, DV ? RJ_SMEM_DIVU : RJ_SMEM, s.stream>>>(l, c, xin, xout, s.xmul32, s.xmul64, divu, mg, s.ws, fa, s.d_nonuni)
+  if (divu) { if (s.xmul_op == 0) RJ_LAUNCH(true, 0); else if (s.xmul_op == 1) RJ_LAUNCH(true, 1); else RJ_LAUNCH(true, 2); }
+  else { if (s.xmul_op == 0) RJ_LAUNCH(false, 0); else if (s.xmul_op == 1) RJ_LAUNCH(false, 1); else RJ_LAUNCH(false, 2); }
+#undef RJ_LAUNCH
+  s.xmul_op = 0;
+  s.x_parked = !from_div;
   ++s.launches;
   int rc = wl_cuda_check(s, cudaGetLastError(), "k_resjac");
   if (rc) return rc;
   if ((rc = post_reduce(s, FIN_RESIDUAL, fa))) return rc;
-  RLAUNCH(s, k_resjac_fix, l.g, l, l.eps);
+  RLAUNCH(s, k_resjac_fix, l.g, l, xout);
   {
     const RowLaunch rl = row_launch(c.g);
     k_resjac_rerestrict<<<wl_grid_for(s, rl.nunits), rl.blk, 0, s.stream>>>(c, l);
     ++s.launches;
   }
-  wl_prof_end(s, WL_PROF_RESIDUAL, 4.0 * (double)g.interior * 4.125);
+  // algorithmic words per cell: read x, z (or the three velocity components), write r, x', ⅛ coarse r
+  wl_prof_end(s, WL_PROF_RESIDUAL, 4.0 * (double)g.interior * (divu ? 6.125 : 4.125));
   return wl_cuda_check(s, cudaGetLastError(), "k_resjac_fix");
 }
