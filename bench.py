@@ -241,17 +241,18 @@ def run_ours(args):
     dom = max(kern, key=lambda k: kern[k]["ms"])
     d = kern[dom]
     achieved = d["bytes"] / (d["ms"] * 1e-3) / 1e9
-    # dram__bytes_read.sum + dram__bytes_write.sum per launch from ncu captures at 512^3 on one GPU
-    # (profiles/r01_launches_tgv512_1gpu_v4.txt, profiles/r01_ncu_full_increment_512.txt).  The "increment" class is
-    # k_increment (9 words/cell, 5.61 GB per launch) and k_prolong_increment_init (10.1 words, 6.01 GB), one each per solve
-    ncu_traffic = {"increment": 0.5 * (5.61e9 + 6.01e9), "conv_diff+bdim1": 0.5 * (5.05e9 + 6.73e9), "pcg_update": 3.78e9, "pcg_mult": 4.00e9,
-                   "residual": 5.65e9}
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch from one `ncu --set full` capture at 512^3 on one GPU
+    # (profiles/r02_ncu_full_top_kernels_512_c.txt, profiles/r02_launches_tgv512_1gpu_c.txt).  A class with two kernels
+    # (conv_diff!: predictor / corrector launch) carries their mean, like `achieved`.
+    ncu_traffic = {"conv_diff+bdim1": 0.5 * ((1.839e9 + 1.574e9) + (3.518e9 + 1.606e9)), "pcg_update": 2.216e9 + 1.050e9, "pcg_mult": 0.607e9 + 0.507e9,
+                   "residual": 1.172e9 + 1.200e9, "increment": 1.262e9 + 1.577e9}
     traffic = ncu_traffic.get(dom) if (N == 512 and world == 1) else None
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src,
-                "note": "dominant kernel = the profiling class with the largest device time in the timed region; conv_diff! (k_conv_diff3_tma2) is "
-                        "bound by instruction issue, not HBM (300 warp instructions per 32 cells at 75 % issue-slot utilisation, "
-                        "profiles/r01_ncu_full_conv_diff3_tma2_384.txt); the solver kernels are HBM-bound (kernels{})", "launches": d["launches"], "avg_ms": d["ms"] / d["launches"],
+                "note": "dominant kernel = the profiling class with the largest device time in the timed region; conv_diff! (k_conv_diff3_tma2, BDIM! folded "
+                        "into its store: 6 / 9 algorithmic words per cell) is bound by instruction issue, not HBM (1.1e9 warp instructions per launch at 64 % "
+                        "issue-slot utilisation, ALU pipe 51 %, profiles/r02_ncu_full_top_kernels_512_c.txt); the streaming solver kernels run at "
+                        "84-96 % of the measured HBM peak (kernels{})", "launches": d["launches"], "avg_ms": d["ms"] / d["launches"],
                 "share_of_step": d["ms"] / prof["mom_step"]["ms"] if prof["mom_step"]["ms"] else None,
                 "kernels": {k: {"GB/s": (v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] else None, "ms_total": v["ms"], "launches": v["launches"]} for k, v in prof.items()}}
 

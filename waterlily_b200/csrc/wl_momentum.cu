@@ -968,22 +968,6 @@ int mom_materialize_p(Sim& s) {
   if (!s.p_pend) return 0;
   return scale_pressure(s, 0, 0.f, 0.0);
 }
-// The row kernels that read their stencil neighbours through the L1 (no shared-memory staging) ask for the largest L1 the SM
-// can give them; without the hint the split follows whatever the driver derives from the kernels that ran before.
-template <class K> static void prefer_l1(K kern) {
-  static const bool off = [] { const char* e = getenv("WL_MAXL1"); return e && atoi(e) == 0; }();
-  if (!off) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxL1);
-}
-static void momentum_kernel_attributes() {
-  static bool done = false;
-  if (done) return;
-  done = true;
-  prefer_l1(k_project_correct<3, 4>);
-  prefer_l1(k_project_correct_cfl);
-  prefer_l1(k_project_pre<3, 4>);
-  prefer_l1(k_cfl<3, 4>);
-  cudaGetLastError();
-}
 // project!(a,b,w) (Flow.jl:137-145)
 // `in_step` (mom_step!): z = div u is evaluated inside residual! instead of by a pass of its own, and the closing
 // x ./= dt is left pending for the next project! (or mom_materialize_p)
@@ -995,7 +979,6 @@ int mom_project(Sim& s, double w, int* n, int slot, bool defer_count, bool in_st
   int rc;
   // inside mom_step! with the fused solver head: the pressure correction of the previous project! left x ./ dt of the interior
   // cells in the ϵ array (xdiv_valid) and the head applies x .*= dt while it stages x from there — no scaling pass
-  momentum_kernel_attributes();
   const bool head = in_step && s.xdiv_on && pois_head_fusable(s);
   const bool from_div = head && s.xdiv_valid;
   s.xdiv_valid = false;

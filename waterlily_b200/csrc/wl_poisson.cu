@@ -722,13 +722,6 @@ int pois_vcycle(Sim& s, int level) {
     const MarchLaunch ml = march_for(s, fine.g);
     const float* xsrc = (level == 0 && s.x_parked) ? fine.eps : fine.x;  // same cell read and (as the new ϵ) written by one thread: no hazard
     if (level == 0) s.x_parked = false;
-    static bool l1_done = false;
-    if (!l1_done) {
-      l1_done = true;
-      const char* e = getenv("WL_MAXL1");
-      if (!(e && atoi(e) == 0)) cudaFuncSetAttribute(k_prolong_increment_init_m, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxL1);
-      cudaGetLastError();
-    }
     if (ml.ok && (coarse.g.n[0] - 2) % 2 == 0) { k_prolong_increment_init_m<<<ml.grid, ml.blk, 0, s.stream>>>(fine, coarse, m, ml.mg, xsrc, s.ws, fa); ++s.launches; }
     else RLAUNCH(s, k_prolong_increment_init, fine.g, fine, coarse, m, xsrc, s.ws, fa);
     if ((rc = post_reduce(s, FIN_INC_INIT, fa))) return rc;
