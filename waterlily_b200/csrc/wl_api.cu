@@ -208,6 +208,9 @@ int wl_read_scalars(Sim& s, const void* dptr, size_t bytes) {
 
 extern "C" {
 
+#ifndef WL_DIST_REPL_CELLS_DEFAULT
+#define WL_DIST_REPL_CELLS_DEFAULT (1 << 21)  // 128³: measured at 512³ on 4 GPUs 6.16 → 6.01 ms/step, on 8 GPUs 4.24 → 4.22 (profiles/r02_bench_{4,8}gpu_*)
+#endif
 // Which multigrid levels are z-distributed (1) and which are replicated on every rank (0).
 static int plan_levels(int D, const int* N, int nranks, const std::vector<std::vector<int>>& dims, std::vector<int>& lvl_dist) {
   lvl_dist.assign(dims.size(), 0);
@@ -217,11 +220,16 @@ static int plan_levels(int D, const int* N, int nranks, const std::vector<std::v
     return wl_fail(WL_ERR_ARG, "wl_create_dist: N[3] must split into an even number of z-planes per rank");
   const char* e = getenv("WL_DIST_MIN_NZ");
   const int min_nz = e ? atoi(e) : 16;  // coarser levels are agglomerated: replicated on every rank
+  // … and so is every level small enough that one GPU works it off faster than the ranks can shake hands about it: a
+  // distributed level costs a peer-memory halo or all-reduce (6–9 µs) in most of its ≈21 phases per V-cycle
+  const char* e2 = getenv("WL_DIST_REPL_CELLS");
+  const long long repl_cells = e2 ? atoll(e2) : WL_DIST_REPL_CELLS_DEFAULT;
   lvl_dist[0] = 1;
   for (size_t l = 1; l < dims.size(); ++l) {
     const int nz = dims[l][2] - 2;
     const int nzf_loc = (dims[l - 1][2] - 2) / nranks;
-    lvl_dist[l] = lvl_dist[l - 1] && nz % nranks == 0 && nz / nranks >= min_nz && nzf_loc % 2 == 0;
+    const long long cells = (long long)(dims[l][0] - 2) * (dims[l][1] - 2) * nz;
+    lvl_dist[l] = lvl_dist[l - 1] && nz % nranks == 0 && nz / nranks >= min_nz && nzf_loc % 2 == 0 && cells > repl_cells;
   }
   for (size_t l = 1; l < dims.size(); ++l)
     if (lvl_dist[l - 1] && !lvl_dist[l] && (((dims[l - 1][2] - 2) / nranks) % 2 != 0 || (dims[l][2] - 2) % nranks != 0))

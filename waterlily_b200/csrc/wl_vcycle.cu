@@ -11,7 +11,7 @@
 //       up:    prolongate!(l+1 → l) ; increment!(l) ; pcg!(l)                    l = nl-2 … lf
 //   solve mode — the whole solver!(ml; tol, itmx): residual! (+ mean subtraction), then
 //       { Jacobi!(1) ; restrict! ; the tail ; prolongate! ; increment! ; pcg!(1) ; L₂ test } until
-//       converged, then perBC!(x); chosen when the finest level has ≤ 96 M cells per rank.
+//       converged, then perBC!(x); chosen when the finest level has ≤ 24 M cells per rank (WL_FUSED_SOLVE_CELLS).
 //
 // Phases are separated by a grid barrier (~1-2 µs) instead of a kernel boundary, every scalar
 // decision of pcg! (|ρ|<10eps, |α|∉[1e-2,1e2]) and of solver! (L₂ < tol) is taken redundantly and
@@ -756,10 +756,10 @@ int vcycle_fused_setup(Sim& s) {
     p.bxlog[l] = ilog2(bx);
   }
   // whole-solver mode: one launch and no host read per solver! when the finest level is small enough per rank that the
-  // launch and host-read latencies of the per-level kernels outweigh their higher streaming bandwidth (measured at 512³:
-  // 8 ranks, 16.7 M cells each: 4.36 vs 4.49 ms/step; 2 ranks, 67 M cells: 11.3 vs 10.1)
+  // launch and host-read latencies of the per-level kernels outweigh their higher streaming bandwidth (measured at 512³,
+  // round 2: 8 ranks, 16.8 M cells each: 4.22 vs 4.39 ms/step; 4 ranks, 33.5 M cells: 6.27 vs 6.01; 2 ranks, 67 M cells: 11.3 vs 10.1)
   const char* e5 = getenv("WL_FUSED_SOLVE_CELLS");
-  const int64_t solve_cells = e5 ? atoll(e5) : (int64_t)40 << 20;
+  const int64_t solve_cells = e5 ? atoll(e5) : (int64_t)24 << 20;
   vf->solve = s.levels[0].g.interior <= solve_cells;
   const char* e4 = getenv("WL_FUSED_MINB");
   vf->minb = e4 ? atoi(e4) : (vf->solve ? 3 : 2);
