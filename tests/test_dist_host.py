@@ -23,14 +23,20 @@ def test_plan_covers_domain_and_agglomerates():
             d = plans[0][l]["distributed"]
             assert all(p[l]["distributed"] == d for p in plans)
             if d:
-                assert R > 1 and nzg // R >= 16
+                assert R > 1 and nzg // R >= 16 and nzg ** 3 > 1 << 21   # enough planes per rank, and more than 128³ cells in all
                 assert [p[l]["zoff"] for p in plans] == [r * (nzg // R) for r in range(R)]   # disjoint cover
                 assert sum(p[l]["nz_local"] for p in plans) == nzg
                 assert all(p[l]["zlo_halo"] and p[l]["zhi_halo"] for p in plans)               # periodic ring
             else:
                 assert all(p[l]["nz_local"] == nzg and p[l]["zoff"] == 0 for p in plans)
         if R == 8:
-            assert [p["distributed"] for p in plans[0]] == [1, 1, 1, 0, 0, 0, 0, 0, 0]       # 64,32,16 planes/rank; 8 and fewer are replicated
+            assert [p["distributed"] for p in plans[0]] == [1, 1, 0, 0, 0, 0, 0, 0, 0]       # 64, 32 planes/rank; the 128³ level and below are replicated
+    # the plane criterion alone (WL_DIST_REPL_CELLS=0): 64, 32, 16 planes/rank are distributed, 8 and fewer replicated
+    os.environ["WL_DIST_REPL_CELLS"] = "0"
+    try:
+        assert [p["distributed"] for p in _cabi.dist_plan(L, (512, 512, 512), (1, 2, 3), 0, 8)] == [1, 1, 1, 0, 0, 0, 0, 0, 0]
+    finally:
+        del os.environ["WL_DIST_REPL_CELLS"]
     # non-periodic z: end ranks keep a physical boundary
     plans = [_cabi.dist_plan(L, (256, 128, 128), (), r, 4) for r in range(4)]
     assert [p[0]["zlo_halo"] for p in plans] == [0, 1, 1, 1] and [p[0]["zhi_halo"] for p in plans] == [1, 1, 1, 0]
