@@ -77,10 +77,9 @@ __global__ void __launch_bounds__(256) k_bc_vec(GridD g, float* __restrict__ a, 
 __global__ void __launch_bounds__(256) k_per_bc(GridD g, float* __restrict__ a, int p0, int p1, int p2, int64_t count, const int* active) {
   if (active && !*active) return;
   const int per[3] = {p0, p1, p2};
-  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < count; idx += (int64_t)gridDim.x * blockDim.x) {
-    int c0[3];
-    if (!planes_decode(g, idx, 2, c0)) continue;
-    if (g.D > 2 && ((c0[2] == 0 && g.zlo_halo) || (c0[2] == g.n[2] - 1 && g.zhi_halo))) continue;
+  // every ghost cell of the global domain takes the value of its fully wrapped image — what the reference's ordered
+  // per-direction slice copies leave behind (edges and corners included); ghost cells of non-periodic directions only stay
+  for_global_ghosts(g, blockIdx.x * (int64_t)blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x, [&](const int (&c0)[3]) {
     int c[3] = {c0[0], c0[1], c0[2]};
     bool written = false;
     for (int j = g.D - 1; j >= 0; --j) {
@@ -89,7 +88,7 @@ __global__ void __launch_bounds__(256) k_per_bc(GridD g, float* __restrict__ a, 
       else if (c[j] == g.n[j] - 1) { c[j] = 1; written = true; }
     }
     if (written) a[c0[0] + c0[1] * g.s[1] + c0[2] * g.s[2]] = a[c[0] + c[1] * g.s[1] + c[2] * g.s[2]];
-  }
+  });
 }
 
 // exitBC! (util.jl:216-222): 1-D convective update of the exit plane + its mean
@@ -145,7 +144,7 @@ int bc_per(Sim& s, const GridD& g, float* a, const int* per, const int* active) 
   bool any = false;
   for (int k = 0; k < g.D; ++k) any |= per[k] != 0;
   if (any) {  // perBC!(a,::Tuple{}) = nothing
-    const int64_t cnt = planes_count(g, 2);
+    const int64_t cnt = global_ghost_count(g);
     k_per_bc<<<flat_grid(cnt, s.nsm * 8), 256, 0, s.stream>>>(g, a, per[0], g.D > 1 ? per[1] : 0, g.D > 2 ? per[2] : 0, cnt, active);
     ++s.launches;
     const int rc = wl_cuda_check(s, cudaGetLastError(), "k_per_bc");

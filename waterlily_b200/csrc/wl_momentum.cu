@@ -717,10 +717,8 @@ __global__ void __launch_bounds__(256) k_cfl_upper(GridD g, const float* __restr
     acc[0] = fmax(acc[0], (double)o);
   }
   // … and the ghost shell of σ, which the reference's maximum over the padded array includes (k_shell_max): one reduction for both
-  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < shell; idx += (int64_t)gridDim.x * blockDim.x) {
-    int c[3];
-    if (shell_decode(g, idx, c) && is_global_ghost(g, c)) acc[0] = fmax(acc[0], (double)sigma[c[0] + c[1] * g.s[1] + c[2] * g.s[2]]);
-  }
+  for_global_ghosts(g, blockIdx.x * (int64_t)blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x,
+                    [&](const int (&c)[3]) { acc[0] = fmax(acc[0], (double)sigma[c[0] + c[1] * g.s[1] + c[2] * g.s[2]]); });
   double tot[1];
   if (grid_reduce<1, true>(acc, ws, tot)) finish_reduction(FIN_CFL_SHELL, fa, tot[0], 0.0);
 }
@@ -753,10 +751,8 @@ __global__ void __launch_bounds__(256) k_cfl(GridD g, const float* __restrict__ 
 // holds the corrector's stale Φ.  Shell = cells with any coordinate on a boundary.
 __global__ void __launch_bounds__(256) k_shell_max(GridD g, const float* __restrict__ sigma, ReduceWS ws, FinArgs fa, int64_t count) {
   double acc[1] = {-1e300};
-  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < count; idx += (int64_t)gridDim.x * blockDim.x) {
-    int c[3];
-    if (shell_decode(g, idx, c) && is_global_ghost(g, c)) acc[0] = fmax(acc[0], (double)sigma[c[0] + c[1] * g.s[1] + c[2] * g.s[2]]);
-  }
+  for_global_ghosts(g, blockIdx.x * (int64_t)blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x,
+                    [&](const int (&c)[3]) { acc[0] = fmax(acc[0], (double)sigma[c[0] + c[1] * g.s[1] + c[2] * g.s[2]]); });
   double tot[1];
   if (grid_reduce<1, true>(acc, ws, tot)) finish_reduction(FIN_CFL_SHELL, fa, tot[0], 0.0);
 }
@@ -1028,15 +1024,15 @@ int mom_cfl(Sim& s, double* dt) {
     // σ and its maximum away from the upper boundaries came with the pressure correction; the rest needs BC!'s ghosts
     s.cfl_fused = false;
     const int64_t cnt = (int64_t)(s.g.n[1] - 2) * (s.g.n[2] - 2) + (int64_t)(s.g.n[0] - 2) * (s.g.n[2] - 2) + (int64_t)(s.g.n[0] - 2) * (s.g.n[1] - 2);
-    const int64_t shell = shell_count(s.g);
+    const int64_t shell = global_ghost_count(s.g);
     k_cfl_upper<<<(int)std::min<int64_t>((std::max(cnt, shell) + 255) / 256, (int64_t)s.nsm * 8), 256, 0, s.stream>>>(s.g, s.u, s.sigma, s.ws, fa, shell);
     ++s.launches;
     if ((rc = post_reduce(s, FIN_CFL_SHELL, fa, true))) return rc;
   } else {
     RLAUNCH(s, k_cfl, s.g, s.g, s.u, s.sigma, s.ws, fa);
     if ((rc = post_reduce(s, FIN_CFL, fa, true))) return rc;
-    const int64_t cnt = shell_count(s.g);
-    k_shell_max<<<(int)std::min<int64_t>((cnt + 255) / 256, 256), 256, 0, s.stream>>>(s.g, s.sigma, s.ws, fa, cnt);
+    const int64_t cnt = global_ghost_count(s.g);
+    k_shell_max<<<(int)std::min<int64_t>((cnt + 255) / 256, (int64_t)s.nsm * 4), 256, 0, s.stream>>>(s.g, s.sigma, s.ws, fa, cnt);
     ++s.launches;
     if ((rc = post_reduce(s, FIN_CFL_SHELL, fa, true))) return rc;
   }

@@ -423,17 +423,14 @@ __global__ void __launch_bounds__(256) k_pcg_dir(Lvl l) {
 __global__ void __launch_bounds__(256) k_shell_dot(Lvl l, ReduceWS ws, FinArgs fa, int64_t count) {
   if (!l.sc->active) return;
   double acc[1] = {0.0};
-  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < count; idx += (int64_t)gridDim.x * blockDim.x) {
-    int c[3];
-    if (shell_decode(l.g, idx, c) && is_global_ghost(l.g, c)) {
-      const int64_t I = c[0] + c[1] * l.g.s[1] + c[2] * l.g.s[2];
-      // ϵ's periodic ghosts are not materialised (the stencils wrap their index): read the image perBC! would copy
-      int w[3] = {c[0], c[1], c[2]};
-      for (int d = 0; d < l.g.D; ++d)
-        if (l.g.per[d]) w[d] = c[d] == 0 ? l.g.n[d] - 2 : (c[d] == l.g.n[d] - 1 ? 1 : c[d]);
-      acc[0] += (double)l.z[I] * (double)l.eps[w[0] + w[1] * l.g.s[1] + w[2] * l.g.s[2]];
-    }
-  }
+  for_global_ghosts(l.g, blockIdx.x * (int64_t)blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x, [&](const int (&c)[3]) {
+    const int64_t I = c[0] + c[1] * l.g.s[1] + c[2] * l.g.s[2];
+    // ϵ's periodic ghosts are not materialised (the stencils wrap their index): read the image perBC! would copy
+    int w[3] = {c[0], c[1], c[2]};
+    for (int d = 0; d < l.g.D; ++d)
+      if (l.g.per[d]) w[d] = c[d] == 0 ? l.g.n[d] - 2 : (c[d] == l.g.n[d] - 1 ? 1 : c[d]);
+    acc[0] += (double)l.z[I] * (double)l.eps[w[0] + w[1] * l.g.s[1] + w[2] * l.g.s[2]];
+  });
   double tot[1];
   if (grid_reduce<1>(acc, ws, tot)) finish_reduction(FIN_GHOST_DOT, fa, tot[0], 0.0);
 }
@@ -649,8 +646,8 @@ int pois_pcg(Sim& s, int level, int it) {
       if (ghosts) {
         if ((rc = dist_halo(s, l.g, l.eps, 1, 1))) return rc;  // perBC!(ϵ) (:129), see pois_increment
         if (fine) {  // only level 1 has non-zero z ghosts (z ≡ σ)
-          const int64_t cnt = shell_count(l.g);
-          k_shell_dot<<<(int)std::min<int64_t>((cnt + 255) / 256, 256), 256, 0, s.stream>>>(l, s.ws, fa, cnt);
+          const int64_t cnt = global_ghost_count(l.g);
+          k_shell_dot<<<(int)std::min<int64_t>((cnt + 255) / 256, (int64_t)s.nsm * 4), 256, 0, s.stream>>>(l, s.ws, fa, cnt);
           ++s.launches;  // multi-rank: its partial is parked next to the z⋅ϵ partial and shares that all-reduce
         }
       }

@@ -370,16 +370,12 @@ __device__ __forceinline__ void pcg(const FusedParams& p, Run& run, int l, int i
       });
       if (shell) {
         const GridD& g = L.g;
-        const int64_t cnt = shell_count(g);
-        for (int64_t idx = blockIdx.x * (int64_t)VC_THREADS + threadIdx.x; idx < cnt; idx += (int64_t)gridDim.x * VC_THREADS) {
-          int c[3];
-          if (shell_decode(g, idx, c) && is_global_ghost(g, c)) {
-            int w[3] = {c[0], c[1], c[2]};
-            for (int d = 0; d < g.D; ++d)
-              if (g.per[d]) w[d] = c[d] == 0 ? g.n[d] - 2 : (c[d] == g.n[d] - 1 ? 1 : c[d]);
-            acc[0] += (double)L.z[c[0] + c[1] * g.s[1] + c[2] * g.s[2]] * (double)L.eps[w[0] + w[1] * g.s[1] + w[2] * g.s[2]];
-          }
-        }
+        for_global_ghosts(g, blockIdx.x * (int64_t)VC_THREADS + threadIdx.x, (int64_t)gridDim.x * VC_THREADS, [&](const int (&c)[3]) {
+          int w[3] = {c[0], c[1], c[2]};
+          for (int d = 0; d < g.D; ++d)
+            if (g.per[d]) w[d] = c[d] == 0 ? g.n[d] - 2 : (c[d] == g.n[d] - 1 ? 1 : c[d]);
+          acc[0] += (double)L.z[c[0] + c[1] * g.s[1] + c[2] * g.s[2]] * (double)L.eps[w[0] + w[1] * g.s[1] + w[2] * g.s[2]];
+        });
       }
       reduce<1, GRID>(p, run, dist, acc);
       if (dist) post_ready(p, run);
@@ -600,11 +596,7 @@ __device__ __forceinline__ void per_bc_x0(const FusedParams& p, Run& run) {
   bool any_per = false;
   for (int d = 0; d < D; ++d) any_per |= g.per[d] != 0;
   if (any_per) {
-    const int64_t cnt = planes_count(g, 2);
-    for (int64_t idx = blockIdx.x * (int64_t)VC_THREADS + threadIdx.x; idx < cnt; idx += (int64_t)gridDim.x * VC_THREADS) {
-      int c0[3];
-      if (!planes_decode(g, idx, 2, c0)) continue;
-      if (D > 2 && ((c0[2] == 0 && g.zlo_halo) || (c0[2] == g.n[2] - 1 && g.zhi_halo))) continue;
+    for_global_ghosts(g, blockIdx.x * (int64_t)VC_THREADS + threadIdx.x, (int64_t)gridDim.x * VC_THREADS, [&](const int (&c0)[3]) {
       int c[3] = {c0[0], c0[1], c0[2]};
       bool written = false;
       for (int j = D - 1; j >= 0; --j) {
@@ -613,7 +605,7 @@ __device__ __forceinline__ void per_bc_x0(const FusedParams& p, Run& run) {
         else if (c[j] == g.n[j] - 1) { c[j] = 1; written = true; }
       }
       if (written) L.x[c0[0] + c0[1] * g.s[1] + c0[2] * g.s[2]] = L.x[c[0] + c[1] * g.s[1] + c[2] * g.s[2]];
-    }
+    });
   }
   if (p.dist[0]) {
     grid_barrier(p, run);
