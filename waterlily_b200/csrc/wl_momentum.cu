@@ -969,8 +969,15 @@ int mom_materialize_p(Sim& s) {
 // x ./= dt is left pending for the next project! (or mom_materialize_p)
 int mom_project(Sim& s, double w, int* n, int slot, bool defer_count, bool in_step, bool with_cfl) {
   const float dt32 = s.dt.back();
-  const bool f32 = (w == 1.0);                 // dt = w*Δt: Float32 for the Int w=1, Float64 for w=0.5
-  const double dtw = f32 ? (double)dt32 : w * (double)dt32;
+  // dt = w*Δt: Float32 for the Int w=1, Float64 for w=0.5 — the reference then evaluates Float32(Float64(x)·dt) and
+  // Float32(Float64(x)/dt).  When that Float64 dt is itself a Float32 number (always for w = 0.5: halving is exact) these
+  // equal the Float32 operations x·dt and x/dt bit for bit: the product of two Float32 numbers is exact in Float64, and a
+  // Float64 quotient rounded to Float32 is the correctly rounded Float32 quotient (double rounding is innocuous for
+  // division when the wider format has ≥ 2·24+2 bits).  So only a dt that is not a Float32 number takes the Float64 path.
+  static const bool exact32 = [] { const char* e = getenv("WL_SCALE_F64"); return !(e && atoi(e) != 0); }();
+  const double dtw_ref = (w == 1.0) ? (double)dt32 : w * (double)dt32;
+  const bool f32 = (w == 1.0) || (exact32 && (double)(float)dtw_ref == dtw_ref && fabs(dtw_ref) > 1e-30);
+  const double dtw = dtw_ref;
   Lvl& b = s.levels[0];
   int rc;
   // inside mom_step! with the fused solver head: the pressure correction of the previous project! left x ./ dt of the interior
