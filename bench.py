@@ -266,15 +266,14 @@ def run_ours(args):
     t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    sim.flow.u.set(u_np)
-    sim.flow.u0.set(u_np)
-    sim.flow.p.set(p_np)
+    sim.flow.u.set(u_np)               # the state a user hands over: velocity and pressure (u⁰ is not an input: the reference's Flow
+    sim.flow.p.set(p_np)               # constructor makes it on the device with copy(u), and mom_step! opens with u⁰ .= u, Flow.jl:155)
     sim.flow.dt[:] = [np.float32(0.25)]
     eng.set_dt(0.25)
     for _ in range(K):
         sim_step(sim)                      # default remeasure=True: measure! (NoBody → no-op) + update!(pois) + mom_step!
     frac = (info["nz_local"] + 2) / Ng[2]   # a slab handle copies only its own planes of the global host array
-    h2d = sum_over_ranks((2 * u_host.numel() + p_host.numel()) * 4 * frac)
+    h2d = sum_over_ranks((u_host.numel() + p_host.numel()) * 4 * frac)
     # results back into pinned host memory
     import ctypes
     eng.cabi.check(eng.cabi.download(eng.h, _cabi.U, ctypes.cast(out_u.data_ptr(), _cabi.c_flt_p), out_u.numel()))
@@ -286,7 +285,7 @@ def run_ours(args):
     d2h = sum_over_ranks((out_u.numel() + out_p.numel()) * 4 * frac)
     e2e = {"value": N ** 3 * K / (e2e_ms * 1e-3) / 1e6, "unit": "Mcell-updates/s",
            "h2d_bytes_per_step": h2d / K + 24, "d2h_bytes_per_step": d2h / K + 16,
-           "what": "pinned-host upload of u,u0,p + K x sim_step(sim) (Python API -> C ABI, dt/n read back every step) + download of u,p; max(CUDA events, wall clock)",
+           "what": "pinned-host upload of u,p + K x sim_step(sim) (Python API -> C ABI, dt/n read back every step) + download of u,p; max(CUDA events, wall clock)",
            "vcycles": list(sim.pois.n[-2 * K:])}
 
     # ---- CPU baseline on a bounded sample --------------------------------------------------------

@@ -53,3 +53,16 @@ class OracleSimulation(_SimulationBase):
     @classmethod
     def _lib(cls):
         return load()
+
+
+def debug_flux(which: str, f, I: int = 0, Ip: int = 0, u: float = 0.0) -> float:
+    """The oracle's flux helpers on a 1-D vector, 1-based indices like the reference (`quick`, `phi`, `phiu`, `phiuP`,
+    `phiuL`, `phiuR` = quick, ϕ, ϕu, ϕuP, ϕuL, ϕuR of src/Flow.jl:3-9) — for the pins of maintests.jl:120-155."""
+    import ctypes
+    import numpy as np
+    fn = load().lib.wlo_debug_flux
+    fn.restype = ctypes.c_double
+    fn.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_float), ctypes.c_int, ctypes.c_int, ctypes.c_double]
+    a = np.ascontiguousarray(f, dtype=np.float32)
+    k = ["quick", "phi", "phiu", "phiuP", "phiuL", "phiuR"].index(which)
+    return float(fn(k, a.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), int(I) - 1, int(Ip) - 1, float(u)))

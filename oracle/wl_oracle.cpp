@@ -218,6 +218,12 @@ inline float median(float a, float b, float c) {
 inline float quick(float u, float c, float d) { return median((5 * c + 2 * d - u) / 6, c, median(10 * c - 9 * u, c, d)); }
 // ϕ(a,I,f) (Flow.jl:3): Float32 add, then ×0.5 promotes to Float64
 inline double phi(const float* f, int64_t I, int64_t sa) { return (double)(f[I] + f[I - sa]) * 0.5; }
+// ϕu, ϕuP, ϕuL, ϕuR (Flow.jl:6-9) with λ = quick; `u` is the Float64 face velocity ϕ(i,CI(I,j),u), sa the stride of direction a,
+// Ip the linear index of the upwind-upwind sample of the periodic variant
+inline double phiu(const float* f, int64_t I, int64_t sa, double u) { return u > 0 ? u * quick(f[I - 2 * sa], f[I - sa], f[I]) : u * quick(f[I + sa], f[I], f[I - sa]); }
+inline double phiuP(const float* f, int64_t Ip, int64_t I, int64_t sa, double u) { return u > 0 ? u * quick(f[Ip], f[I - sa], f[I]) : u * quick(f[I + sa], f[I], f[I - sa]); }
+inline double phiuL(const float* f, int64_t I, int64_t sa, double u) { return u > 0 ? u * phi(f, I, sa) : u * quick(f[I + sa], f[I], f[I - sa]); }
+inline double phiuR(const float* f, int64_t I, int64_t sa, double u) { return u < 0 ? u * phi(f, I, sa) : u * quick(f[I - 2 * sa], f[I - sa], f[I]); }
 
 // conv_diff!(r,u,Φ;ν,perdir) Flow.jl:36-60
 void conv_diff(const Grid& g, float* r, const float* u, float* Phi, float nu, const bool* per) {
@@ -231,21 +237,21 @@ void conv_diff(const Grid& g, float* r, const float* u, float* Phi, float nu, co
       const int64_t wrap = (int64_t)(Nj - 2 - 2) * sj;  // CIj(j,I,N[j]-2) from I_j=2
       loop(g, r_slice(g, 2, j, 2), [&](int64_t I, int, int, int) {
         const double uf = phi(uj, I, si);
-        const double flux = uf > 0 ? uf * quick(ui[I + wrap], ui[I - sj], ui[I]) : uf * quick(ui[I + sj], ui[I], ui[I - sj]);
+        const double flux = phiuP(ui, I + wrap, I, sj, uf);
         Phi[I] = (float)(flux - (double)(nu * (ui[I] - ui[I - sj])));
         ri[I] += Phi[I];
       });
     } else {
       loop(g, r_slice(g, 2, j, 2), [&](int64_t I, int, int, int) {
         const double uf = phi(uj, I, si);
-        const double flux = uf > 0 ? uf * phi(ui, I, sj) : uf * quick(ui[I + sj], ui[I], ui[I - sj]);  // ϕuL
+        const double flux = phiuL(ui, I, sj, uf);
         ri[I] = (float)((double)ri[I] + (flux - (double)(nu * (ui[I] - ui[I - sj]))));
       });
     }
     // inner cells (Flow.jl:45-47)
     loop(g, r_inside_u(g, j), [&](int64_t I, int, int, int) {
       const double uf = phi(uj, I, si);
-      const double flux = uf > 0 ? uf * quick(ui[I - 2 * sj], ui[I - sj], ui[I]) : uf * quick(ui[I + sj], ui[I], ui[I - sj]);  // ϕu
+      const double flux = phiu(ui, I, sj, uf);
       Phi[I] = (float)(flux - (double)(nu * (ui[I] - ui[I - sj])));
       ri[I] += Phi[I];
     });
@@ -257,7 +263,7 @@ void conv_diff(const Grid& g, float* r, const float* u, float* Phi, float nu, co
     } else {
       loop(g, r_slice(g, Nj, j, 2), [&](int64_t I, int, int, int) {
         const double uf = phi(uj, I, si);
-        const double flux = uf < 0 ? uf * phi(ui, I, sj) : uf * quick(ui[I - 2 * sj], ui[I - sj], ui[I]);  // ϕuR
+        const double flux = phiuR(ui, I, sj, uf);
         ri[I - sj] = (float)((double)ri[I - sj] + (-flux + (double)(nu * (ui[I] - ui[I - sj]))));
       });
     }
@@ -900,6 +906,18 @@ int wlo_profile_read(wl_sim*, int, double* ms, int64_t* launches, double* bytes)
   return WL_OK;
 }
 int wlo_set_sum_mode(int mode) { g_sum_mode = mode; return WL_OK; }
+// the flux helpers on a 1-D Float32 vector (0-based index I, unit stride) — the reference pins them directly (maintests.jl:120-155).
+// which: 0 quick(f[0],f[1],f[2]), 1 ϕ(1,I,f), 2 ϕu(1,I,f,u), 3 ϕuP(1,Ip,I,f,u), 4 ϕuL(1,I,f,u), 5 ϕuR(1,I,f,u)
+double wlo_debug_flux(int which, const float* f, int I, int Ip, double u) {
+  switch (which) {
+    case 0: return (double)quick(f[0], f[1], f[2]);
+    case 1: return phi(f, I, 1);
+    case 2: return phiu(f, I, 1, u);
+    case 3: return phiuP(f, Ip, I, 1, u);
+    case 4: return phiuL(f, I, 1, u);
+    default: return phiuR(f, I, 1, u);
+  }
+}
 int wlo_profile_count(void) { return 0; }
 const char* wlo_profile_name(int) { return ""; }
 // torchrun exports OMP_NUM_THREADS=1 to its workers: bench.py --impl reference asks for all host cores explicitly

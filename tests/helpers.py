@@ -36,3 +36,27 @@ def rel_l2(a, b):
     b = np.asarray(b, dtype=np.float64)
     den = np.sqrt((b ** 2).sum())
     return float(np.sqrt(((a - b) ** 2).sum()) / (den if den > 0 else 1.0))
+
+
+def check_accelerating_circle(cls):
+    """"Circle in accelerating flow", maintests.jl:304-316: `make_accel_circle(radius=32, H=16)` — a 1024² grid, u_BC = (t, 0),
+    a circle of radius 32 in the centre.  After one step the pressure force is the added-mass force −π L² (inertial coefficient
+    1 of a circle), the flow past the shoulder is ≈ 2U, and the solver needs at most two V-cycles per projection afterwards."""
+    import numpy as np
+    import torch
+    from waterlily_b200 import AutoBody, pressure_force, sim_step
+    radius, H = 32, 16
+
+    def u_bc(i, t):
+        return t if i == 1 else 0 * t
+    sim = cls((2 * H * radius, 2 * H * radius), u_bc, radius, U=1,
+              body=AutoBody(lambda x, t: torch.sqrt(((x - H * radius) ** 2).sum(-1)) - radius))
+    sim_step(sim)
+    force = np.asarray(pressure_force(sim)) / (np.pi * sim.L ** 2)
+    assert np.allclose(force, [-1.0, 0.0], atol=0.04), force                                    # :310
+    u = sim.flow.u.numpy()
+    assert u.max() / u[1, 1, 0] > 1.91                                                          # :311  (≈ 2U)
+    for _ in range(3):
+        sim_step(sim)
+    assert all(n <= 2 for n in sim.pois.n), sim.pois.n                                          # :313
+    return sim

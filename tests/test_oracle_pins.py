@@ -129,6 +129,32 @@ def test_accelerating_flow():
     assert L2(u[:, :, 0] - uFinal) < 1e-4 and L2(u[:, :, 1]) < 1e-4                                       # :297-300
 
 
+def test_flux_helper_pins():
+    # maintests.jl:126-153 — the boundary variants of the QUICK flux on 1-D vectors (exact comparisons, as there)
+    fl = oracle.debug_flux
+    quick = lambda u, c, d: fl("quick", [u, c, d])
+    v = [0.0, 0.5, 2.0]
+    assert fl("phiuL", v, I=2, u=1) == fl("phi", v, I=2)                        # inlet with positive flux -> CD            :132
+    assert fl("phiuL", v, I=2, u=-1) == -quick(2.0, 0.5, 0.0)                   # inlet negative flux -> backward QUICK     :134
+    assert fl("phiuR", v, I=3, u=1) == quick(0.0, 0.5, 2.0)                     # outlet, positive flux -> standard QUICK   :136
+    assert fl("phiuR", v, I=3, u=-1) == -fl("phi", v, I=3)                      # outlet, negative flux -> backward CD      :138
+    assert fl("phiu", v, I=3, u=1) == fl("phiuP", v, Ip=1, I=3, u=1)            # ϕu == ϕuP with I-2δ given explicitly     :146
+    assert fl("phiu", v, I=2, u=-1) == fl("phiuP", v, Ip=0 + 1, I=2, u=-1)      # negative flux: Ip is not read             :148
+    f = [1.0, 1.25, 1.5, 1.75, 2.0]
+    assert fl("phiuP", f, Ip=1, I=3, u=1) == quick(f[0], f[1], f[2])            # :153
+    Ip = len(f) - 2                                                             # CIj(1,I,length(f)-2): the periodic image  :154
+    assert fl("phiuP", f, Ip=Ip, I=3, u=1) == quick(f[Ip - 1], f[1], f[2])      # :155
+    # quick itself: the median form against its definition on a monotone and a non-monotone triple (Flow.jl:4)
+    assert quick(0.0, 0.5, 2.0) == np.float32(np.median([np.float32((5 * 0.5 + 2 * 2.0 - 0.0) / 6), 0.5, np.median([10 * 0.5 - 9 * 0.0, 0.5, 2.0])]))
+    assert quick(1.0, 0.0, 1.0) == 0.0
+
+
+def test_accelerating_circle_added_mass():
+    # maintests.jl:304-316
+    from helpers import check_accelerating_circle
+    check_accelerating_circle(OracleSimulation)
+
+
 def test_body_kernel_pins():
     # maintests.jl:183-187
     assert mu0_of(3, 6) == mu0_of(0.5, 1)

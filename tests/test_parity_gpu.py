@@ -246,6 +246,16 @@ def test_accelerating_flow_and_g():
     assert rel_l2(u, so.flow.u.numpy()) < 1e-5
 
 
+def test_accelerating_circle_added_mass_on_cuda():
+    # test/maintests.jl:304-316 on the CUDA path (1024² grid, time-dependent u_BC, pressure_force), and against the oracle
+    from helpers import check_accelerating_circle
+    sc = check_accelerating_circle(Simulation)
+    so = check_accelerating_circle(OracleSimulation)
+    assert all(abs(a - b) <= 1 for a, b in zip(sc.pois.n, so.pois.n)), (sc.pois.n, so.pois.n)
+    for f in ("u", "p"):
+        assert rel_l2(getattr(sc.flow, f).numpy(), getattr(so.flow, f).numpy()) < 1e-4, f
+
+
 def test_moving_body_pins_on_cuda():
     # test/maintests.jl:398-400: accelerating circle, pois.n == [2,1]
     radius = 8
