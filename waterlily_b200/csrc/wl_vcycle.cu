@@ -311,7 +311,7 @@ __device__ __forceinline__ void increment(const FusedParams& p, Run& run, int l,
     phase_sync<GRID>(p, run);
   }
   if (GRID && p.dist[l]) post_ready(p, run);
-  if (GRID) trace(p, run, 1000 * l + 4);
+  trace(p, run, 1000 * l + 4);
 }
 // Jacobi!(l; it=1) (Poisson.jl:110-113)
 template <int D, int V, bool GRID>
@@ -326,7 +326,7 @@ __device__ __forceinline__ void jacobi(const FusedParams& p, Run& run, int l, bo
     stp<V>(L.eps + I, e);
   });
   phase_sync<GRID>(p, run);
-  if (GRID) trace(p, run, 1000 * l + 3);
+  trace(p, run, 1000 * l + 3);
   increment<D, V, GRID>(p, run, l);
 }
 // pcg!(l; it=6) (Poisson.jl:123-144)
@@ -351,7 +351,7 @@ __device__ __forceinline__ void pcg(const FusedParams& p, Run& run, int l, int i
     });
     reduce<1, GRID>(p, run, dist, acc);
     rho = (float)acc[0];
-    if (GRID) trace(p, run, 1000 * l + 7);
+    trace(p, run, 1000 * l + 7);
   }
   if (fabsf(rho) < 10 * WL_EPS32) return;
   for (int i = 1; i <= it; ++i) {
@@ -380,7 +380,7 @@ __device__ __forceinline__ void pcg(const FusedParams& p, Run& run, int l, int i
       reduce<1, GRID>(p, run, dist, acc);
       if (dist) post_ready(p, run);
       alpha = rho / (float)acc[0];
-      if (GRID) trace(p, run, 1000 * l + 10 + 3 * i);
+      trace(p, run, 1000 * l + 10 + 3 * i);
     }
     const double aa = fabs((double)alpha);
     if (aa < 1e-2 || aa > 1e2) return;
@@ -400,9 +400,9 @@ __device__ __forceinline__ void pcg(const FusedParams& p, Run& run, int l, int i
         stp<V>(L.x + I, x);
         stp<V>(L.r + I, r);
       });
-      if (i == it && !r2) { phase_sync<GRID>(p, run); if (GRID) trace(p, run, 1000 * l + 11 + 3 * i); return; }  // the dots of the last sweep are never used below level 1
+      if (i == it && !r2) { phase_sync<GRID>(p, run); trace(p, run, 1000 * l + 11 + 3 * i); return; }  // the dots of the last sweep are never used below level 1
       reduce<2, GRID>(p, run, dist, acc);
-      if (GRID) trace(p, run, 1000 * l + 11 + 3 * i);
+      trace(p, run, 1000 * l + 11 + 3 * i);
       if (r2) *r2 = (float)acc[1];
       if (i == it) return;
       rho2 = (float)acc[0];
@@ -418,7 +418,7 @@ __device__ __forceinline__ void pcg(const FusedParams& p, Run& run, int l, int i
       stp<V>(L.eps + I, e);
     });
     phase_sync<GRID>(p, run);
-    if (GRID) trace(p, run, 1000 * l + 12 + 3 * i);
+    trace(p, run, 1000 * l + 12 + 3 * i);
   }
 }
 // restrict!(l → l+1) (MultiLevelPoisson.jl:33) + fill!(x_{l+1},0) (:75); a distributed → replicated
@@ -464,7 +464,7 @@ __device__ __forceinline__ void restrict_to(const FusedParams& p, Run& run, int 
     }
     push_segments(p, run, seg, ns, mask);
   }
-  if (GRID) trace(p, run, 1000 * l + 5);
+  trace(p, run, 1000 * l + 5);
 }
 // prolongate!(l+1 → l) + increment!(l) + the head of pcg!(l) in one phase (wl_vec.cuh); across slab faces
 // ϵ is the neighbour's coarse x, so the halo that travels is the (4× smaller) coarse one
@@ -491,7 +491,7 @@ __device__ __forceinline__ void prolong_inc_init(const FusedParams& p, Run& run,
   if (fdist && cdist) post_ready(p, run);
   rho = (float)acc[0];
   if (r2) *r2 = (float)acc[1];
-  if (GRID) trace(p, run, 1000 * l + 6);
+  trace(p, run, 1000 * l + 6);
 }
 
 template <int D, bool GRID>
