@@ -442,9 +442,18 @@ __device__ __forceinline__ void restrict_to(const FusedParams& p, Run& run, int 
     for (int d = 0; d < D; ++d) { lo[d] = 2 * cc[d] - 1; hi[d] = 2 * cc[d]; }
     if (D > 2) { lo[2] += fshift; hi[2] += fshift; }
     float s = 0.f;
-    for (int z = lo[2]; z <= hi[2]; ++z)
-      for (int y = lo[1]; y <= hi[1]; ++y)
-        for (int x = lo[0]; x <= hi[0]; ++x) s += f.r[x + y * f.g.s[1] + z * f.g.s[2]];
+    if (D == 3) {
+      // the two x-cells of a fine row are one aligned 8-byte load (fine x = 2·i0−1 sits 2·i0+2 floats into a 16-byte aligned
+      // row); four independent loads, then the additions in the reference's order (x fastest, then y, then z)
+      const float* b = f.r + lo[0] + (int64_t)lo[1] * f.g.s[1] + (int64_t)lo[2] * f.g.s[2];
+      const float2 v00 = *reinterpret_cast<const float2*>(b), v01 = *reinterpret_cast<const float2*>(b + f.g.s[1]);
+      const float2 v10 = *reinterpret_cast<const float2*>(b + f.g.s[2]), v11 = *reinterpret_cast<const float2*>(b + f.g.s[1] + f.g.s[2]);
+      s += v00.x; s += v00.y; s += v01.x; s += v01.y; s += v10.x; s += v10.y; s += v11.x; s += v11.y;
+    } else {
+      for (int z = lo[2]; z <= hi[2]; ++z)
+        for (int y = lo[1]; y <= hi[1]; ++y)
+          for (int x = lo[0]; x <= hi[0]; ++x) s += f.r[x + y * f.g.s[1] + z * f.g.s[2]];
+    }
     c.r[I] = s;
   });
   phase_sync<GRID>(p, run);
@@ -729,7 +738,9 @@ int vcycle_fused_setup(Sim& s) {
   while (lf < p.nl - 1 && s.levels[lf].g.interior > max_cells) ++lf;
   p.lf = lf;
   const char* e2 = getenv("WL_FUSED_BLOCK_CELLS");
-  const int64_t blk_cells = e2 ? atoll(e2) : 4096;
+  // measured (profiles/r02_solver_kernel_phase_trace_256.txt): one block needs 7–18 µs per phase on a 16³ level, the whole grid
+  // 4–5 µs including its barrier; from 8³ down the single block wins
+  const int64_t blk_cells = e2 ? atoll(e2) : 512;
   int lb = p.nl;
   for (int l = p.nl - 1; l >= lf; --l) {
     const bool dist = s.dist.nranks > 1 && s.lvl_dist[l];
